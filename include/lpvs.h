@@ -1,0 +1,166 @@
+/*
+ * lpvs.h -- C ABI of liblpvs.so: B200 (sm_100a) least-squares spectral estimation.
+ *
+ * Drop-in boundary for the hot path of baggepinnen/LPVSpectral.jl.  The reference has no FFI layer of
+ * its own; the contract is its exported Julia signatures (src/LPVSpectral.jl:82-97).  Each entry point
+ * below names the reference function whose body it replaces.  A thin Julia shim (julia/LPVSpectralB200.jl,
+ * see INTEGRATION.md) `ccall`s these; the tests and bench drive the identical ABI through ctypes.
+ *
+ * Conventions
+ *  - every pointer is HOST memory owned by the caller unless the function name ends in `_dev`
+ *    (then array arguments are DEVICE pointers on the context's GPU);
+ *  - the library never retains a caller pointer after return; every call is synchronous;
+ *  - complex outputs are interleaved (re,im) doubles;
+ *  - return value: 0 = ok, negative = error code below; message via lpvs_last_error();
+ *  - one lpvs_ctx per GPU (one process per GPU); calls on one ctx are serialised internally;
+ *  - there is NO CPU fallback: every entry point that computes fails with LPVS_E_CUDA without a GPU.
+ */
+#ifndef LPVS_H
+#define LPVS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lpvs_ctx lpvs_ctx;
+typedef struct lpvs_admm lpvs_admm;
+
+enum lpvs_status {
+    LPVS_OK = 0,
+    LPVS_E_BAD_ARG = -1,     /* reference: ArgumentError / @assert sites (src/lsfft.jl:22, src/windows.jl:31,96, src/lasso.jl:143) */
+    LPVS_E_NOT_SPD = -2,     /* Cholesky breakdown; *info = 1-based failing pivot */
+    LPVS_E_NONFINITE = -3,
+    LPVS_E_CUDA = -4,
+    LPVS_E_NCCL = -5,
+    LPVS_E_UNSUPPORTED = -6, /* e.g. sparse LPV with coulomb=true */
+    LPVS_E_NOMEM = -7
+};
+
+enum lpvs_window_kind { LPVS_WIN_PSD = 0, LPVS_WIN_CSD = 1, LPVS_WIN_COHERE = 2 };
+enum lpvs_prox_kind { LPVS_PROX_L1 = 0, LPVS_PROX_L0 = 1, LPVS_PROX_BALL_L0 = 2, LPVS_PROX_GROUP_L2 = 3 };
+enum lpvs_phase_mode {
+    LPVS_PHASE_AUTO = 0,  /* chain when f is a uniform grid, else direct */
+    LPVS_PHASE_CHAIN = 1, /* exact anchors + angle-addition chains (fast path) */
+    LPVS_PHASE_DIRECT = 2 /* per-element sincos of fl(fl(2*pi*f)*t), the reference's rounding (src/lsfft.jl:41) */
+};
+enum lpvs_option {
+    LPVS_OPT_PHASE_MODE = 0,   /* lpvs_phase_mode */
+    LPVS_OPT_WINDOW_BATCH = 1, /* windows factorised per batch (bounds workspace), default auto */
+    LPVS_OPT_JITTER = 2,       /* 1 (default): on Cholesky breakdown of the UNWEIGHTED ls_spectral re-factor on device
+                                  with ridge max(lambda^2, Nreg*eps*max diag G) and set *info=1; 0: fail */
+    LPVS_OPT_ADMM_CHECK_EVERY = 3 /* residual test cadence inside the device loop; 1 (default) = every iteration (Q12) */
+};
+
+/* info flags returned by solvers */
+#define LPVS_INFO_JITTER 1
+
+int lpvs_version(void);
+int lpvs_device_count(void);
+int lpvs_init(int device, lpvs_ctx** ctx);
+void lpvs_destroy(lpvs_ctx* ctx);
+const char* lpvs_last_error(const lpvs_ctx* ctx);
+int lpvs_set_option(lpvs_ctx* ctx, int key, double value);
+/* cumulative number of kernels this context launched (bench.py's gpu_launches) */
+int64_t lpvs_launch_count(const lpvs_ctx* ctx);
+/* device time [ms] and launch count of the Gram kernel(s) during the last API call (bench.py's roofline) */
+int lpvs_last_gram_timing(const lpvs_ctx* ctx, double* ms, int64_t* launches, double* flops);
+/* cudaMalloc/cudaFree/cudaMemcpy wrappers so a host language without CUDA bindings can keep inputs resident */
+int lpvs_dev_alloc(lpvs_ctx* ctx, int64_t bytes, void** dptr);
+int lpvs_dev_free(lpvs_ctx* ctx, void* dptr);
+int lpvs_dev_upload(lpvs_ctx* ctx, void* dptr, const void* hptr, int64_t bytes);
+int lpvs_dev_download(lpvs_ctx* ctx, void* hptr, const void* dptr, int64_t bytes);
+int lpvs_sync(lpvs_ctx* ctx);
+
+/* ---- window bookkeeping: DSP.arraysplit semantics used by Windows2/Windows3 (src/windows.jl:27-36,94-104) ---- */
+/* K = N >= n ? (N-n) div (n-noverlap) + 1 : 0 ; noverlap < 0 means n>>1 */
+int64_t lpvs_window_count(int64_t N, int n, int noverlap);
+
+/* ---- get_fourier_regressor + Gram (src/lsfft.jl:26-49, :77) -- parity/bench entry ----
+ * G (Nreg x Nreg, full symmetric, reference column order: cos block then -sin block) = A' diag(W) A,
+ * b (Nreg) = A' diag(W) y.  W and y may be NULL (W=1, b not produced). Nreg = 2Nf - (f[0]==0). */
+int lpvs_gram_fourier(lpvs_ctx* ctx, const double* y, const double* t, int64_t N, const double* f, int Nf,
+                      const double* W, double* G, double* b);
+
+/* ---- ls_spectral(y,t,f; lambda) and ls_spectral(y,t,f,W; lambda)  (src/lsfft.jl:62-80) ----
+ * W == NULL: x = (A'A + lambda^2 I)^-1 A'y  (fourier_solve, src/utilities.jl:56-60)
+ * W != NULL: x = (A'WA + lambda I)^-1 A'Wy  (src/lsfft.jl:77)
+ * x: Nf complex (fourier2complex, src/utilities.jl:62-73). */
+int lpvs_ls_spectral(lpvs_ctx* ctx, const double* y, const double* t, int64_t N, const double* f, int Nf,
+                     const double* W, double lambda, double* x, int* info);
+
+/* ---- ls_windowpsd / ls_windowcsd / ls_cohere (src/lsfft.jl:112-126, 140-156, 176-193) ----
+ * One weighted ls_spectral per window (window weights W[n], shared), reduced on device.
+ * `sums` holds the raw cross-window sums for windows [k_begin,k_end) (multi-GPU: ranks take disjoint ranges and
+ * add their sums before finalising):
+ *   PSD:    Nf   doubles  sum |x|^2
+ *   CSD:    2Nf  doubles  [Re sum xy conj(xu) | Im ...]
+ *   COHERE: 4Nf  doubles  [Syy | Suu | Re Syu | Im Syu]
+ * lpvs_ls_window_finalize applies /K^2 (PSD), /K (CSD) or |Syu|^2/(Suu Syy) (COHERE) with Julia's abs2 order. */
+int lpvs_ls_window_sums(lpvs_ctx* ctx, int kind, const double* y, const double* u, const double* t, int64_t N,
+                        const double* f, int Nf, const double* W, int n, int noverlap, double lambda,
+                        int64_t k_begin, int64_t k_end, double* sums, int* info);
+int lpvs_ls_window_sums_dev(lpvs_ctx* ctx, int kind, const double* d_y, const double* d_u, const double* d_t,
+                            int64_t N, const double* f, int Nf, const double* W, int n, int noverlap,
+                            double lambda, int64_t k_begin, int64_t k_end, double* sums, int* info);
+int lpvs_ls_window_finalize(int kind, const double* sums, int Nf, int64_t K, double* out);
+/* all windows on this GPU + finalize; out: PSD Nf reals, CSD Nf complex, COHERE Nf reals; *K = window count */
+int lpvs_ls_window(lpvs_ctx* ctx, int kind, const double* y, const double* u, const double* t, int64_t N,
+                   const double* f, int Nf, const double* W, int n, int noverlap, double lambda, double* out,
+                   int64_t* K, int* info);
+
+/* ---- ls_spectral_lpv (src/lsfft.jl:239-259; basis src/utilities.jl:23-36, src/lsfft.jl:195-207) ----
+ * params: Nf*Nvv complex (Nvv = coulomb ? 2Nv : Nv), column order f + k*Nf.
+ * Sigma (may be NULL): (2 Nf Nvv)^2 doubles = var(e) * inv(Ar'Ar + lambda I).  fva: fraction of variance explained. */
+int lpvs_ls_spectral_lpv(lpvs_ctx* ctx, const double* Y, const double* X, const double* V, int64_t N,
+                         const double* w, int Nf, int Nv, double lambda, int coulomb, int normalize,
+                         double* params, double* Sigma, double* fva, int* info);
+
+/* ---- ADMM (src/lasso.jl:136-171) behind ls_sparse_spectral / ls_sparse_spectral_lpv (src/lasso.jl:27-126) ----
+ * create: builds the Gram on device, factorises (G + I/mu), keeps everything resident.
+ *   W == NULL  -> LeastSquares(A,y):   x-update solves (G + I/mu) x = A'y + (z-u)/mu
+ *   W != NULL  -> Quadratic(A'WA,A'Wy): x-update solves (Q + I/mu) x = (z-u)/mu - q   (sign quirk Q13 kept)
+ *   x0 (Nreg, reference order) may be NULL (zeros).  init != 0: x0 = ridge LS with ridge lambda_init^2 (Q14).
+ * run: up to max_iters more iterations on device without host sync; stops when ||x-z||_2 < tol.
+ * The shim loops run(printerval) to reproduce the reference's prints / callback. */
+int lpvs_admm_create_fourier(lpvs_ctx* ctx, const double* y, const double* t, int64_t N, const double* f, int Nf,
+                             const double* W, int prox_kind, double prox_param, double mu, const double* x0,
+                             int init, double lambda_init, lpvs_admm** h);
+int lpvs_admm_create_lpv(lpvs_ctx* ctx, const double* y, const double* X, const double* V, int64_t N,
+                         const double* w, int Nf, int Nv, int coulomb, int normalize, double lambda, double mu,
+                         lpvs_admm** h);
+int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_done, double* residual,
+                  int* converged);
+int lpvs_admm_size(const lpvs_admm* h); /* length of x / z in reference order */
+int lpvs_admm_get(lpvs_admm* h, double* x, double* z);
+/* fourier2complex(z) (Nf complex) or LPV params (Nf*Nv complex, un-permuted as src/lasso.jl:67-68) */
+int lpvs_admm_result(lpvs_admm* h, double* out);
+/* device time [ms] of the last lpvs_admm_run loop kernel and its algorithmic bytes per iteration */
+int lpvs_admm_last_timing(const lpvs_admm* h, double* ms, double* bytes_per_iter);
+void lpvs_admm_free(lpvs_admm* h);
+
+/* one-shot conveniences mirroring the Julia functions */
+int lpvs_ls_sparse_spectral(lpvs_ctx* ctx, const double* y, const double* t, int64_t N, const double* f, int Nf,
+                            const double* W, int prox_kind, double prox_param, double mu, int init,
+                            double lambda_init, int64_t iters, double tol, double* x, int64_t* iters_done,
+                            double* residual);
+int lpvs_ls_sparse_spectral_lpv(lpvs_ctx* ctx, const double* y, const double* X, const double* V, int64_t N,
+                                const double* w, int Nf, int Nv, int coulomb, int normalize, double lambda,
+                                double mu, int64_t iters, double tol, double* params, int64_t* iters_done,
+                                double* residual);
+
+/* ---- row-sharded Gram for very tall problems: partial packed Gram on DEVICE so the host can
+ * all-reduce it (NCCL via torch.distributed / ncclAllReduce) before lpvs_solve_packed_dev ----
+ * d_packed: Np*Np + 2*Np doubles (internal tiled layout, lower tiles + 2 rhs), see lpvs_packed_size. */
+int64_t lpvs_packed_size(int Nf);
+int lpvs_gram_partial_dev(lpvs_ctx* ctx, const double* d_y, const double* d_u, const double* d_t,
+                          const double* d_W, int64_t N, const double* f, int Nf, double* d_packed);
+/* x: nrhs * Nf complex; ridge is added as given (caller picks lambda or lambda^2) */
+int lpvs_solve_packed_dev(lpvs_ctx* ctx, double* d_packed, const double* f, int Nf, int nrhs, double ridge,
+                          double* x, int* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPVS_H */

@@ -1,0 +1,732 @@
+// C ABI of liblpvs.so (see include/lpvs.h): context, Fourier LS estimators, windowed estimators.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "ctx.h"
+
+namespace lpvs {
+
+int fail(lpvs_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+void* ws_raw(lpvs_ctx* c, int slot, size_t bytes) {
+    DevBuf& b = c->buf[slot];
+    if (bytes == 0) bytes = 16;
+    if (b.cap < bytes) {
+        if (b.p) {
+            cudaStreamSynchronize(c->st);
+            cudaFree(b.p);
+        }
+        b.p = nullptr;
+        b.cap = 0;
+        size_t want = bytes + bytes / 8;
+        if (cudaMalloc(&b.p, want) != cudaSuccess) {
+            cudaGetLastError();
+            if (cudaMalloc(&b.p, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            want = bytes;
+        }
+        b.cap = want;
+    }
+    return b.p;
+}
+
+void gram_timer_reset(lpvs_ctx* c) {
+    c->ev_used = 0;
+    c->gram_ms = 0.0;
+    c->gram_launches = 0;
+    c->gram_flops = 0.0;
+}
+void gram_timer_begin(lpvs_ctx* c) {
+    if ((int)c->ev.size() < c->ev_used + 2) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        c->ev.push_back(a);
+        c->ev.push_back(b);
+    }
+    cudaEventRecord(c->ev[c->ev_used], c->st);
+}
+void gram_timer_end(lpvs_ctx* c, double flops, int launches) {
+    cudaEventRecord(c->ev[c->ev_used + 1], c->st);
+    c->ev_used += 2;
+    c->gram_flops += flops;
+    c->gram_launches += launches;
+}
+int gram_timer_resolve(lpvs_ctx* c) {
+    double ms = 0.0;
+    for (int i = 0; i < c->ev_used; i += 2) {
+        float m = 0.f;
+        if (cudaEventElapsedTime(&m, c->ev[i], c->ev[i + 1]) == cudaSuccess) ms += m;
+    }
+    c->gram_ms = ms;
+    return 0;
+}
+
+int make_fourier_plan(lpvs_ctx* c, const double* f, int Nf, FourierPlan* pl) {
+    if (!f || Nf <= 0) return fail(c, LPVS_E_BAD_ARG, "empty frequency vector");
+    for (int k = 0; k < Nf; k++) {
+        if (!isfinite(f[k])) return fail(c, LPVS_E_NONFINITE, "non-finite frequency at index %d", k);
+        if (k > 0 && f[k] == 0.0)  // src/lsfft.jl:20-24
+            return fail(c, LPVS_E_BAD_ARG, "If zero frequency is included it must be the first frequency");
+    }
+    pl->Nf = Nf;
+    pl->zero_first = (f[0] == 0.0);
+    pl->Nreg = 2 * Nf - pl->zero_first;
+    pl->nblk = (Nf + FB - 1) / FB;
+    pl->Np = pl->nblk * TB;
+    pl->ngroups = pl->nblk * (FB / GRP);
+    pl->dd = 1.0 / sqrt(2.0 * (double)Nf);  // src/lsfft.jl:35
+    pl->f0 = f[0];
+    pl->df = Nf > 1 ? (f[Nf - 1] - f[0]) / (double)(Nf - 1) : 0.0;
+    double fmaxabs = 0.0, dev = 0.0;
+    for (int k = 0; k < Nf; k++) {
+        fmaxabs = std::max(fmaxabs, fabs(f[k]));
+        dev = std::max(dev, fabs(f[k] - (pl->f0 + k * pl->df)));
+    }
+    bool uniform = dev <= 8.0 * 2.220446049250313e-16 * fmaxabs;
+    int mode = c->phase_mode;
+    if (mode == LPVS_PHASE_AUTO) mode = uniform ? LPVS_PHASE_CHAIN : LPVS_PHASE_DIRECT;
+    if (mode == LPVS_PHASE_CHAIN && !uniform)
+        return fail(c, LPVS_E_BAD_ARG, "LPVS_PHASE_CHAIN requires a uniformly spaced frequency grid");
+    pl->mode = (mode == LPVS_PHASE_CHAIN) ? GRAM_CHAIN : GRAM_DIRECT;
+    double* d_f = ws<double>(c, BUF_F, Nf);
+    if (!d_f) return fail(c, LPVS_E_NOMEM, "out of device memory (f)");
+    LPVS_CU(c, cudaMemcpyAsync(d_f, f, sizeof(double) * Nf, cudaMemcpyHostToDevice, c->st));
+    pl->d_f = d_f;
+    return LPVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small kernels: partial reduction, layout gathers, window accumulation
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_reduce_parts(double* __restrict__ out, const double* __restrict__ parts, long long count,
+                               long long stride, int nparts, int accumulate) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double s = accumulate ? out[i] : 0.0;
+    for (int p = 0; p < nparts; p++) s += parts[(long long)p * stride + i];
+    out[i] = s;
+}
+
+// internal x ([nrhs][Np]) -> interleaved complex [nrhs][Nf]   (fourier2complex, src/utilities.jl:62-73)
+__global__ void k_x_to_complex(const double* __restrict__ X, int Np, int Nf, int zero_first, int nrhs,
+                               double* __restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Nf) return;
+    int pc = (k >> 6) * 128 + (k & 63);
+    for (int r = 0; r < nrhs; r++) {
+        double re = X[(long long)r * Np + pc];
+        double im = (zero_first && k == 0) ? 0.0 : X[(long long)r * Np + pc + 64];
+        out[((long long)r * Nf + k) * 2] = re;
+        out[((long long)r * Nf + k) * 2 + 1] = im;
+    }
+}
+
+// internal lower-tile G -> reference-ordered full symmetric Nreg x Nreg; internal b -> reference order
+__device__ __forceinline__ int ref_to_internal(int j, int Nf, int zero_first) {
+    if (j < Nf) return (j >> 6) * 128 + (j & 63);
+    int k = j - Nf + zero_first;
+    return (k >> 6) * 128 + 64 + (k & 63);
+}
+__global__ void k_gather_ref(const double* __restrict__ G, const double* __restrict__ B, int Np, int Nf,
+                             int zero_first, int Nreg, double* __restrict__ Gout, double* __restrict__ bout) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j >= Nreg) return;
+    int pi = ref_to_internal(i, Nf, zero_first), pj = ref_to_internal(j, Nf, zero_first);
+    int a = max(pi, pj), b = min(pi, pj);
+    double v = G[(long long)a * Np + b];  // always the lower element: bit-symmetric output
+    Gout[(long long)i * Nreg + j] = v;
+    if (bout && i == 0) bout[j] = B[pj];
+}
+__global__ void k_scatter_ref_vec(const double* __restrict__ xin, int Nf, int zero_first, int Nreg, int Np,
+                                  double* __restrict__ xout) {
+    // reference-ordered vector -> internal layout (dummies zero)
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Np) return;
+    int q = p >> 7, r = p & 127, part = r >> 6, cc = q * 64 + (r & 63);
+    double v = 0.0;
+    if (cc < Nf && !(zero_first && part == 1 && cc == 0)) {
+        int j = part == 0 ? cc : (Nf + cc - zero_first);
+        v = xin[j];
+    }
+    xout[p] = v;
+}
+
+// Cross-window accumulation in window order (the reference's serial `S .+= ...`, src/lsfft.jl:122,153,187-189),
+// one thread per frequency; products are kept unfused so identical channels give coherence == 1 exactly (Q8/H7).
+__global__ void k_window_accum(int kind, const double* __restrict__ X, long long strideB, int Np, int nwin, int Nf,
+                               int zero_first, double* __restrict__ sums) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Nf) return;
+    int pc = (k >> 6) * 128 + (k & 63);
+    bool noim = zero_first && k == 0;
+    if (kind == LPVS_WIN_PSD) {
+        double s = sums[k];
+        for (int wdx = 0; wdx < nwin; wdx++) {
+            const double* x = X + (long long)wdx * strideB;
+            double re = x[pc], im = noim ? 0.0 : x[pc + 64];
+            s = __dadd_rn(s, __dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im)));
+        }
+        sums[k] = s;
+    } else if (kind == LPVS_WIN_CSD) {
+        double sr = sums[k], si = sums[Nf + k];
+        for (int wdx = 0; wdx < nwin; wdx++) {
+            const double* x = X + (long long)wdx * strideB;
+            double ar = x[pc], ai = noim ? 0.0 : x[pc + 64];
+            double br = x[Np + pc], bi = noim ? 0.0 : x[Np + pc + 64];
+            sr = __dadd_rn(sr, __dadd_rn(__dmul_rn(ar, br), __dmul_rn(ai, bi)));
+            si = __dadd_rn(si, __dsub_rn(__dmul_rn(ai, br), __dmul_rn(ar, bi)));
+        }
+        sums[k] = sr;
+        sums[Nf + k] = si;
+    } else {
+        double syy = sums[k], suu = sums[Nf + k], sr = sums[2 * Nf + k], si = sums[3 * Nf + k];
+        for (int wdx = 0; wdx < nwin; wdx++) {
+            const double* x = X + (long long)wdx * strideB;
+            double ar = x[pc], ai = noim ? 0.0 : x[pc + 64];
+            double br = x[Np + pc], bi = noim ? 0.0 : x[Np + pc + 64];
+            sr = __dadd_rn(sr, __dadd_rn(__dmul_rn(ar, br), __dmul_rn(ai, bi)));
+            si = __dadd_rn(si, __dsub_rn(__dmul_rn(ai, br), __dmul_rn(ar, bi)));
+            syy = __dadd_rn(syy, __dadd_rn(__dmul_rn(ar, ar), __dmul_rn(ai, ai)));
+            suu = __dadd_rn(suu, __dadd_rn(__dmul_rn(br, br), __dmul_rn(bi, bi)));
+        }
+        sums[k] = syy;
+        sums[Nf + k] = suu;
+        sums[2 * Nf + k] = sr;
+        sums[3 * Nf + k] = si;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// single-problem Gram (with sample splitting) and factor/solve
+// ---------------------------------------------------------------------------------------------------------
+static void fill_basis_args(const FourierPlan& pl, GramArgs& g) {
+    g.ncc = pl.Nf;
+    g.nblk = pl.nblk;
+    g.f = pl.d_f;
+    g.gscale = pl.dd * pl.dd;
+    g.bscale = pl.dd;
+    g.E = nullptr;
+    g.Kt = nullptr;
+    g.lpv_nf = 1;
+}
+
+int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const double* d_y, const double* d_u,
+                const double* d_W, int64_t N, int nrhs, double* d_G, double* d_B) {
+    const long long Np = pl.Np;
+    const int ntiles = pl.nblk * (pl.nblk + 1) / 2;
+    // split over samples when tiles alone cannot fill the machine; each split >= 2048 samples
+    int nsplit = 1;
+    if (ntiles < 4 * c->sms) {
+        long long want = (4LL * c->sms + ntiles - 1) / ntiles;
+        long long maxs = std::max<long long>(1, N / 2048);
+        nsplit = (int)std::min(want, maxs);
+    }
+    // segment the sample axis so the anchor table stays below ~2 GiB
+    long long seg_cap = N;
+    if (pl.mode == GRAM_CHAIN) {
+        long long per_sample = (long long)(pl.ngroups + 1) * sizeof(double2);
+        seg_cap = std::max<long long>(65536, (2LL << 30) / per_sample);
+    }
+    int nseg = (int)((N + seg_cap - 1) / seg_cap);
+    if (nseg < 1) nseg = 1;
+    long long seg_len = (N + nseg - 1) / nseg;
+    int split_per_seg = std::max(1, nsplit / nseg);
+    const bool direct_out = (nseg == 1 && split_per_seg == 1);
+    double* parts = nullptr;
+    const long long part_stride = Np * Np + 2 * Np;
+    if (!direct_out) {
+        parts = ws<double>(c, BUF_PART, (size_t)split_per_seg * part_stride);
+        if (!parts) return fail(c, LPVS_E_NOMEM, "out of device memory (Gram partials)");
+    }
+    double2* anc = nullptr;
+    double2* del = nullptr;
+    for (int sgi = 0; sgi < nseg; sgi++) {
+        long long s0 = sgi * seg_len, s1 = std::min<long long>(N, s0 + seg_len);
+        if (s1 <= s0) break;
+        long long ns = s1 - s0;
+        if (pl.mode == GRAM_CHAIN) {
+            anc = ws<double2>(c, BUF_ANC, (size_t)pl.ngroups * ns);
+            del = ws<double2>(c, BUF_DEL, (size_t)ns);
+            if (!anc || !del) return fail(c, LPVS_E_NOMEM, "out of device memory (anchor table)");
+            launch_anchor_table(d_t, s0, ns, pl.d_f, pl.Nf, pl.ngroups, pl.f0, pl.df, anc, del, c->st);
+            c->launches++;
+        }
+        long long n_split = (ns + split_per_seg - 1) / split_per_seg;
+        n_split = (n_split + KC - 1) / KC * KC;
+        int nprob = (int)((ns + n_split - 1) / n_split);
+        GramArgs g{};
+        fill_basis_args(pl, g);
+        g.t = d_t;
+        g.y = d_y;
+        g.u = d_u;
+        g.W = d_W;
+        g.w_abs = 1;
+        g.start0 = s0;
+        g.hop = n_split;
+        g.n = (int)n_split;
+        g.s_end = s1;
+        g.nrhs = nrhs;
+        g.anc = anc;
+        g.del = del;
+        g.tbl_base = s0;
+        g.tbl_ns = ns;
+        if (direct_out) {
+            g.G = d_G;
+            g.strideG = 0;
+            g.B = d_B;
+            g.strideB = 0;
+        } else {
+            g.G = parts;
+            g.strideG = part_stride;
+            g.B = parts + Np * Np;
+            g.strideB = part_stride;
+        }
+        gram_timer_begin(c);
+        launch_gram(pl.mode, g, nprob, c->st);
+        gram_timer_end(c, (double)ns * pl.Nreg * (pl.Nreg + 1.0), 1);
+        c->launches++;
+        if (!direct_out) {
+            k_reduce_parts<<<(unsigned)((Np * Np + 255) / 256), 256, 0, c->st>>>(d_G, parts, Np * Np, part_stride,
+                                                                                 nprob, sgi > 0);
+            if (d_B)
+                k_reduce_parts<<<(unsigned)((2 * Np + 255) / 256), 256, 0, c->st>>>(d_B, parts + Np * Np, 2 * Np,
+                                                                                    part_stride, nprob, sgi > 0);
+            c->launches += 2;
+        }
+    }
+    LPVS_CU(c, cudaGetLastError());
+    return LPVS_OK;
+}
+
+int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, double* d_B, int nrhs, double ridge,
+                 int nproblems, int* info_host) {
+    const int nb = Np / TB;
+    CholArgs ca{};
+    ca.G = d_G;
+    ca.strideG = (long long)Np * Np;
+    ca.Y = nullptr;
+    ca.strideY = 0;
+    ca.Linv = ws<double>(c, BUF_LINV, (size_t)nproblems * nb * TB * TB);
+    ca.strideLinv = (long long)nb * TB * TB;
+    ca.info = ws<int>(c, BUF_INFO, (size_t)nproblems);
+    ca.Np = Np;
+    ca.nb = nb;
+    if (!ca.Linv || !ca.info) return fail(c, LPVS_E_NOMEM, "out of device memory (factor workspace)");
+    LPVS_CU(c, cudaMemsetAsync(ca.info, 0, sizeof(int) * nproblems, c->st));
+    launch_diag_prepare(d_G, ca.strideG, Np, ncc, zero_first, nullptr, ridge, nproblems, c->st);
+    c->launches += 1 + potrf(ca, nproblems, c->sms, c->st);
+    if (d_B && nrhs > 0) {
+        launch_trsv(ca, d_B, 2LL * Np, nrhs, nproblems, c->st);
+        c->launches++;
+    }
+    LPVS_CU(c, cudaGetLastError());
+    if (info_host)
+        LPVS_CU(c, cudaMemcpyAsync(info_host, ca.info, sizeof(int) * nproblems, cudaMemcpyDeviceToHost, c->st));
+    return LPVS_OK;
+}
+
+static int upload(lpvs_ctx* c, int slot, const double* h, int64_t n, double** d) {
+    *d = nullptr;
+    if (!h) return LPVS_OK;
+    double* p = ws<double>(c, slot, (size_t)n);
+    if (!p) return fail(c, LPVS_E_NOMEM, "out of device memory (input upload, %lld doubles)", (long long)n);
+    LPVS_CU(c, cudaMemcpyAsync(p, h, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+    *d = p;
+    return LPVS_OK;
+}
+
+}  // namespace lpvs
+
+using namespace lpvs;
+
+extern "C" {
+
+int lpvs_version(void) { return 100; }
+
+int lpvs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int lpvs_init(int device, lpvs_ctx** out) {
+    if (!out) return LPVS_E_BAD_ARG;
+    *out = nullptr;
+    int n = lpvs_device_count();
+    if (n <= 0 || device < 0 || device >= n) return LPVS_E_CUDA;  // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return LPVS_E_CUDA;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return LPVS_E_CUDA;
+    if (p.major < 10) return LPVS_E_UNSUPPORTED;  // sm_100a only
+    lpvs_ctx* c = new lpvs_ctx();
+    c->device = device;
+    c->sms = p.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return LPVS_E_CUDA;
+    }
+    *out = c;
+    return LPVS_OK;
+}
+
+void lpvs_destroy(lpvs_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    for (auto& b : c->buf)
+        if (b.p) cudaFree(b.p);
+    for (auto e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->st);
+    delete c;
+}
+
+const char* lpvs_last_error(const lpvs_ctx* c) { return c ? c->err.c_str() : "no context (no CUDA device?)"; }
+
+int lpvs_set_option(lpvs_ctx* c, int key, double value) {
+    if (!c) return LPVS_E_BAD_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    switch (key) {
+        case LPVS_OPT_PHASE_MODE: c->phase_mode = (int)value; break;
+        case LPVS_OPT_WINDOW_BATCH: c->window_batch = (int)value; break;
+        case LPVS_OPT_JITTER: c->jitter = (int)value; break;
+        case LPVS_OPT_ADMM_CHECK_EVERY: c->admm_check_every = std::max(1, (int)value); break;
+        default: return fail(c, LPVS_E_BAD_ARG, "unknown option %d", key);
+    }
+    return LPVS_OK;
+}
+
+int64_t lpvs_launch_count(const lpvs_ctx* c) { return c ? c->launches : 0; }
+
+int lpvs_last_gram_timing(const lpvs_ctx* c, double* ms, int64_t* launches, double* flops) {
+    if (!c) return LPVS_E_BAD_ARG;
+    if (ms) *ms = c->gram_ms;
+    if (launches) *launches = c->gram_launches;
+    if (flops) *flops = c->gram_flops;
+    return LPVS_OK;
+}
+
+int lpvs_dev_alloc(lpvs_ctx* c, int64_t bytes, void** dptr) {
+    if (!c || !dptr) return LPVS_E_BAD_ARG;
+    cudaSetDevice(c->device);
+    LPVS_CU(c, cudaMalloc(dptr, (size_t)bytes));
+    return LPVS_OK;
+}
+int lpvs_dev_free(lpvs_ctx* c, void* dptr) {
+    if (!c) return LPVS_E_BAD_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    LPVS_CU(c, cudaFree(dptr));
+    return LPVS_OK;
+}
+int lpvs_dev_upload(lpvs_ctx* c, void* dptr, const void* hptr, int64_t bytes) {
+    if (!c) return LPVS_E_BAD_ARG;
+    cudaSetDevice(c->device);
+    LPVS_CU(c, cudaMemcpyAsync(dptr, hptr, (size_t)bytes, cudaMemcpyHostToDevice, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    return LPVS_OK;
+}
+int lpvs_dev_download(lpvs_ctx* c, void* hptr, const void* dptr, int64_t bytes) {
+    if (!c) return LPVS_E_BAD_ARG;
+    cudaSetDevice(c->device);
+    LPVS_CU(c, cudaMemcpyAsync(hptr, dptr, (size_t)bytes, cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    return LPVS_OK;
+}
+int lpvs_sync(lpvs_ctx* c) {
+    if (!c) return LPVS_E_BAD_ARG;
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    return LPVS_OK;
+}
+
+int64_t lpvs_window_count(int64_t N, int n, int noverlap) {
+    if (n <= 0) return 0;
+    if (noverlap < 0) noverlap = n >> 1;
+    if (noverlap >= n) return -1;
+    return N >= n ? (N - n) / (n - noverlap) + 1 : 0;
+}
+
+int lpvs_gram_fourier(lpvs_ctx* c, const double* y, const double* t, int64_t N, const double* f, int Nf,
+                      const double* W, double* G, double* b) {
+    if (!c) return LPVS_E_BAD_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    if (!t || N <= 0 || !G) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
+    gram_timer_reset(c);
+    FourierPlan pl;
+    int rc = make_fourier_plan(c, f, Nf, &pl);
+    if (rc) return rc;
+    double *d_t, *d_y, *d_W;
+    if ((rc = upload(c, BUF_T, t, N, &d_t))) return rc;
+    if ((rc = upload(c, BUF_Y, y, N, &d_y))) return rc;
+    if ((rc = upload(c, BUF_W, W, N, &d_W))) return rc;
+    const long long Np = pl.Np;
+    double* d_G = ws<double>(c, BUF_G, (size_t)Np * Np);
+    double* d_B = ws<double>(c, BUF_B, (size_t)2 * Np);
+    if (!d_G || !d_B) return fail(c, LPVS_E_NOMEM, "out of device memory (G)");
+    if ((rc = gram_single(c, pl, d_t, d_y, nullptr, d_W, N, y ? 1 : 0, d_G, d_B))) return rc;
+    double* d_out = ws<double>(c, BUF_MISC, (size_t)pl.Nreg * pl.Nreg + pl.Nreg);
+    if (!d_out) return fail(c, LPVS_E_NOMEM, "out of device memory (G out)");
+    dim3 grid((pl.Nreg + 127) / 128, pl.Nreg);
+    k_gather_ref<<<grid, 128, 0, c->st>>>(d_G, (y && b) ? d_B : nullptr, pl.Np, pl.Nf, pl.zero_first, pl.Nreg, d_out,
+                                          (y && b) ? d_out + (size_t)pl.Nreg * pl.Nreg : nullptr);
+    c->launches++;
+    LPVS_CU(c, cudaMemcpyAsync(G, d_out, sizeof(double) * pl.Nreg * pl.Nreg, cudaMemcpyDeviceToHost, c->st));
+    if (y && b)
+        LPVS_CU(c, cudaMemcpyAsync(b, d_out + (size_t)pl.Nreg * pl.Nreg, sizeof(double) * pl.Nreg,
+                                   cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    gram_timer_resolve(c);
+    return LPVS_OK;
+}
+
+// shared by lpvs_ls_spectral and the ADMM init path: solve one ridge LS on device arrays, x internal in BUF_B
+static int ls_solve_dev(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const double* d_y, const double* d_u,
+                        const double* d_W, int64_t N, int nrhs, double ridge, bool allow_jitter, double** d_x,
+                        int* info) {
+    const long long Np = pl.Np;
+    double* d_G = ws<double>(c, BUF_G, (size_t)Np * Np);
+    double* d_B = ws<double>(c, BUF_B, (size_t)2 * Np);
+    double* d_md = ws<double>(c, BUF_SUMS, 8);
+    if (!d_G || !d_B || !d_md) return fail(c, LPVS_E_NOMEM, "out of device memory (G)");
+    int rc;
+    if (info) *info = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((rc = gram_single(c, pl, d_t, d_y, d_u, d_W, N, nrhs, d_G, d_B))) return rc;
+        double maxdiag = 0.0;
+        if (attempt == 0 && allow_jitter) {
+            launch_max_diag(d_G, Np * Np, pl.Np, pl.Nf, pl.zero_first, d_md, 1, c->st);
+            c->launches++;
+        }
+        int pinfo = 0;
+        if ((rc = factor_solve(c, pl.Nf, pl.zero_first, pl.Np, d_G, d_B, nrhs, ridge, 1, &pinfo))) return rc;
+        if (attempt == 0 && allow_jitter)
+            LPVS_CU(c, cudaMemcpyAsync(&maxdiag, d_md, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        LPVS_CU(c, cudaStreamSynchronize(c->st));
+        if (pinfo == 0) break;
+        if (attempt == 0 && allow_jitter) {
+            // numerically rank-deficient Gram -> re-factor on device with a jitter ridge
+            double jr = (double)pl.Nreg * 2.220446049250313e-16 * maxdiag;
+            ridge = std::max(ridge, jr);
+            if (info) *info = LPVS_INFO_JITTER;
+            continue;
+        }
+        if (info) *info = pinfo;
+        return fail(c, LPVS_E_NOT_SPD, "Cholesky breakdown at internal pivot %d (A'WA + ridge not positive definite)",
+                    pinfo);
+    }
+    *d_x = d_B;
+    return LPVS_OK;
+}
+
+int lpvs_ls_spectral(lpvs_ctx* c, const double* y, const double* t, int64_t N, const double* f, int Nf,
+                     const double* W, double lambda, double* x, int* info) {
+    if (!c) return LPVS_E_BAD_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    if (!y || !t || !x || N <= 0) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
+    gram_timer_reset(c);
+    FourierPlan pl;
+    int rc = make_fourier_plan(c, f, Nf, &pl);
+    if (rc) return rc;
+    double *d_t, *d_y, *d_W;
+    if ((rc = upload(c, BUF_T, t, N, &d_t))) return rc;
+    if ((rc = upload(c, BUF_Y, y, N, &d_y))) return rc;
+    if ((rc = upload(c, BUF_W, W, N, &d_W))) return rc;
+    // ridge: lambda^2 unweighted (src/utilities.jl:58), lambda weighted (src/lsfft.jl:77)
+    double ridge = W ? lambda : lambda * lambda;
+    double* d_x;
+    if ((rc = ls_solve_dev(c, pl, d_t, d_y, nullptr, d_W, N, 1, ridge, !W && c->jitter, &d_x, info))) return rc;
+    double* d_out = ws<double>(c, BUF_X, (size_t)2 * Nf);
+    if (!d_out) return fail(c, LPVS_E_NOMEM, "out of device memory (x)");
+    k_x_to_complex<<<(Nf + 127) / 128, 128, 0, c->st>>>(d_x, pl.Np, Nf, pl.zero_first, 1, d_out);
+    c->launches++;
+    LPVS_CU(c, cudaMemcpyAsync(x, d_out, sizeof(double) * 2 * Nf, cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    gram_timer_resolve(c);
+    return LPVS_OK;
+}
+
+static int sums_len(int kind, int Nf) { return kind == LPVS_WIN_PSD ? Nf : (kind == LPVS_WIN_CSD ? 2 * Nf : 4 * Nf); }
+
+int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const double* d_u, const double* d_t,
+                            int64_t N, const double* f, int Nf, const double* W, int n, int noverlap, double lambda,
+                            int64_t k_begin, int64_t k_end, double* sums, int* info) {
+    if (!c) return LPVS_E_BAD_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    if (info) *info = 0;
+    if (kind < 0 || kind > 2) return fail(c, LPVS_E_BAD_ARG, "bad window kind %d", kind);
+    if (!d_y || !d_t || !W || !sums || n <= 0) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
+    if (kind != LPVS_WIN_PSD && !d_u) return fail(c, LPVS_E_BAD_ARG, "second signal required");
+    if (noverlap < 0) noverlap = n >> 1;  // src/windows.jl:29
+    if (noverlap >= n) return fail(c, LPVS_E_BAD_ARG, "noverlap must be < n");
+    const int64_t K = lpvs_window_count(N, n, noverlap);
+    if (k_begin < 0 || k_end > K || k_begin > k_end) return fail(c, LPVS_E_BAD_ARG, "window range out of bounds");
+    gram_timer_reset(c);
+    FourierPlan pl;
+    int rc = make_fourier_plan(c, f, Nf, &pl);
+    if (rc) return rc;
+    const int nrhs = kind == LPVS_WIN_PSD ? 1 : 2;
+    const int slen = sums_len(kind, Nf);
+    double* d_sums = ws<double>(c, BUF_SUMS, (size_t)slen);
+    double* d_W;
+    if ((rc = upload(c, BUF_W, W, n, &d_W))) return rc;
+    if (!d_sums) return fail(c, LPVS_E_NOMEM, "out of device memory");
+    LPVS_CU(c, cudaMemsetAsync(d_sums, 0, sizeof(double) * slen, c->st));
+    const long long Np = pl.Np, hop = n - noverlap;
+    // batch: keep the per-batch Gram workspace <= ~6 GiB
+    int64_t batch = c->window_batch > 0 ? c->window_batch : std::max<int64_t>(1, (6LL << 30) / (Np * Np * 8));
+    batch = std::min<int64_t>(batch, std::max<int64_t>(1, k_end - k_begin));
+    std::vector<int> hinfo((size_t)batch);
+    int bad = 0;
+    int64_t bad_window = -1;
+    for (int64_t k0 = k_begin; k0 < k_end; k0 += batch) {
+        const int nw = (int)std::min<int64_t>(batch, k_end - k0);
+        const long long s0 = k0 * hop, ns = (long long)(nw - 1) * hop + n;
+        double* d_G = ws<double>(c, BUF_G, (size_t)nw * Np * Np);
+        double* d_B = ws<double>(c, BUF_B, (size_t)nw * 2 * Np);
+        if (!d_G || !d_B) return fail(c, LPVS_E_NOMEM, "out of device memory (window batch of %d)", nw);
+        GramArgs g{};
+        fill_basis_args(pl, g);
+        if (pl.mode == GRAM_CHAIN) {
+            double2* anc = ws<double2>(c, BUF_ANC, (size_t)pl.ngroups * ns);
+            double2* del = ws<double2>(c, BUF_DEL, (size_t)ns);
+            if (!anc || !del) return fail(c, LPVS_E_NOMEM, "out of device memory (anchor table)");
+            launch_anchor_table(d_t, s0, ns, pl.d_f, pl.Nf, pl.ngroups, pl.f0, pl.df, anc, del, c->st);
+            c->launches++;
+            g.anc = anc;
+            g.del = del;
+        }
+        g.t = d_t;
+        g.y = d_y;
+        g.u = nrhs > 1 ? d_u : nullptr;
+        g.W = d_W;
+        g.w_abs = 0;
+        g.start0 = s0;
+        g.hop = hop;
+        g.n = n;
+        g.s_end = N;
+        g.nrhs = nrhs;
+        g.tbl_base = s0;
+        g.tbl_ns = ns;
+        g.G = d_G;
+        g.strideG = Np * Np;
+        g.B = d_B;
+        g.strideB = 2 * Np;
+        gram_timer_begin(c);
+        launch_gram(pl.mode, g, nw, c->st);
+        gram_timer_end(c, (double)nw * n * pl.Nreg * (pl.Nreg + 1.0), 1);
+        c->launches++;
+        // always the weighted estimator: ridge lambda (src/lsfft.jl:121 -> :77)
+        if ((rc = factor_solve(c, pl.Nf, pl.zero_first, pl.Np, d_G, d_B, nrhs, lambda, nw, hinfo.data()))) return rc;
+        k_window_accum<<<(Nf + 127) / 128, 128, 0, c->st>>>(kind, d_B, 2 * Np, pl.Np, nw, Nf, pl.zero_first, d_sums);
+        c->launches++;
+        LPVS_CU(c, cudaStreamSynchronize(c->st));
+        for (int i = 0; i < nw && !bad; i++)
+            if (hinfo[i]) {
+                bad = hinfo[i];
+                bad_window = k0 + i;
+            }
+    }
+    LPVS_CU(c, cudaMemcpyAsync(sums, d_sums, sizeof(double) * slen, cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    gram_timer_resolve(c);
+    if (bad) {
+        if (info) *info = bad;
+        return fail(c, LPVS_E_NOT_SPD, "Cholesky breakdown in window %lld at internal pivot %d", (long long)bad_window,
+                    bad);
+    }
+    return LPVS_OK;
+}
+
+int lpvs_ls_window_sums(lpvs_ctx* c, int kind, const double* y, const double* u, const double* t, int64_t N,
+                        const double* f, int Nf, const double* W, int n, int noverlap, double lambda, int64_t k_begin,
+                        int64_t k_end, double* sums, int* info) {
+    if (!c) return LPVS_E_BAD_ARG;
+    if (!y || !t || N <= 0 || n <= 0) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
+    if (noverlap < 0) noverlap = n >> 1;
+    if (noverlap >= n) return fail(c, LPVS_E_BAD_ARG, "noverlap must be < n");
+    double *d_t, *d_y, *d_u;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        cudaSetDevice(c->device);
+        // only this rank's sample range travels to the device
+        const int64_t K = lpvs_window_count(N, n, noverlap);
+        if (k_begin < 0 || k_end > K || k_begin > k_end) return fail(c, LPVS_E_BAD_ARG, "window range out of bounds");
+        int rc;
+        if (k_end == k_begin) {
+            memset(sums, 0, sizeof(double) * sums_len(kind, Nf));
+            return LPVS_OK;
+        }
+        const int64_t hop = n - noverlap, s0 = k_begin * hop, s1 = (k_end - 1) * hop + n;
+        if ((rc = upload(c, BUF_T, t + s0, s1 - s0, &d_t))) return rc;
+        if ((rc = upload(c, BUF_Y, y + s0, s1 - s0, &d_y))) return rc;
+        if ((rc = upload(c, BUF_U, u ? u + s0 : nullptr, s1 - s0, &d_u))) return rc;
+        N = s1 - s0;
+        k_end -= k_begin;
+        k_begin = 0;
+    }
+    return lpvs_ls_window_sums_dev(c, kind, d_y, d_u, d_t, N, f, Nf, W, n, noverlap, lambda, k_begin, k_end, sums,
+                                   info);
+}
+
+int lpvs_ls_window_finalize(int kind, const double* sums, int Nf, int64_t K, double* out) {
+    if (!sums || !out || Nf <= 0) return LPVS_E_BAD_ARG;
+    if (kind == LPVS_WIN_PSD) {
+        double k2 = (double)K * (double)K;  // S./nw^2  (src/lsfft.jl:125)
+        for (int k = 0; k < Nf; k++) out[k] = sums[k] / k2;
+    } else if (kind == LPVS_WIN_CSD) {
+        double kk = (double)K;  // S./nw (src/lsfft.jl:155)
+        for (int k = 0; k < Nf; k++) {
+            out[2 * k] = sums[k] / kk;
+            out[2 * k + 1] = sums[Nf + k] / kk;
+        }
+    } else if (kind == LPVS_WIN_COHERE) {
+        for (int k = 0; k < Nf; k++) {  // abs2.(Syu)./(Suu.*Syy) (src/lsfft.jl:191)
+            volatile double rr = sums[2 * Nf + k] * sums[2 * Nf + k];
+            volatile double ii = sums[3 * Nf + k] * sums[3 * Nf + k];
+            volatile double den = sums[Nf + k] * sums[k];
+            out[k] = (rr + ii) / den;
+        }
+    } else {
+        return LPVS_E_BAD_ARG;
+    }
+    return LPVS_OK;
+}
+
+int lpvs_ls_window(lpvs_ctx* c, int kind, const double* y, const double* u, const double* t, int64_t N,
+                   const double* f, int Nf, const double* W, int n, int noverlap, double lambda, double* out,
+                   int64_t* Kout, int* info) {
+    if (!c) return LPVS_E_BAD_ARG;
+    if (n <= 0 || Nf <= 0) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
+    int64_t K = lpvs_window_count(N, n, noverlap);
+    if (K < 0) return fail(c, LPVS_E_BAD_ARG, "noverlap must be < n");
+    if (Kout) *Kout = K;
+    std::vector<double> sums((size_t)sums_len(kind, Nf), 0.0);
+    if (K > 0) {
+        int rc = lpvs_ls_window_sums(c, kind, y, u, t, N, f, Nf, W, n, noverlap, lambda, 0, K, sums.data(), info);
+        if (rc) return rc;
+    }
+    return lpvs_ls_window_finalize(kind, sums.data(), Nf, K, out);
+}
+
+}  // extern "C"

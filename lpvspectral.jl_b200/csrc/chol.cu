@@ -1,0 +1,536 @@
+// Blocked FP64 Cholesky, triangular inverse and SPD inverse on 128x128 tiles.  See chol.cuh.
+#include "chol.cuh"
+
+namespace lpvs {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// in-smem DMMA GEMM helper: C[MxN] = beta*C + alpha*A[MxK]*op(B); all operands in shared memory, row-major.
+// BT: B is stored [N][K]; else [K][N].  M,N multiples of 8, K multiple of 4.  Tiles are spread over the warps.
+// `lower`: skip 8x8 tiles strictly above the diagonal of C.
+// ------------------------------------------------------------------------------------------------------------
+template <bool BT>
+__device__ __forceinline__ void smem_gemm(double* C, int ldc, const double* A, int lda, const double* B, int ldb,
+                                          int M, int N, int K, double alpha, double beta, bool lower) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int tm = M >> 3, tn = N >> 3;
+    const int r = lane >> 2, q = lane & 3;
+    for (int tile = warp; tile < tm * tn; tile += nwarps) {
+        int ti = tile / tn, tj = tile - ti * tn;
+        if (lower && tj > ti) continue;
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+        const double* pa = A + (8 * ti + r) * lda + q;
+        const double* pb = BT ? (B + (8 * tj + r) * ldb + q) : (B + q * ldb + 8 * tj + r);
+        int k0 = 0;
+        for (; k0 + 8 <= K; k0 += 8) {  // two independent accumulator chains
+            double a0 = pa[k0], a1 = pa[k0 + 4];
+            double b0 = BT ? pb[k0] : pb[k0 * ldb];
+            double b1 = BT ? pb[k0 + 4] : pb[(k0 + 4) * ldb];
+            dmma884(c0, c1, a0, b0);
+            dmma884(d0, d1, a1, b1);
+        }
+        for (; k0 < K; k0 += 4) {
+            double a0 = pa[k0];
+            double b0 = BT ? pb[k0] : pb[k0 * ldb];
+            dmma884(c0, c1, a0, b0);
+        }
+        c0 += d0;
+        c1 += d1;
+        double* pc = C + (8 * ti + r) * ldc + 8 * tj + 2 * q;
+        if (beta == 0.0) {
+            pc[0] = alpha * c0;
+            pc[1] = alpha * c1;
+        } else {
+            pc[0] = beta * pc[0] + alpha * c0;
+            pc[1] = beta * pc[1] + alpha * c1;
+        }
+    }
+}
+
+constexpr int LDS = 132;  // 128x128 block stride (== 4 mod 16)
+constexpr int PB = 16;    // inner panel width
+constexpr int LDP = 20;   // stride of 16-wide panels
+constexpr int LDH = 68;   // stride of the 64x64 temp
+
+// smem layout of k_potf2: S[128*LDS] | tmp[max(128*LDP, 64*LDH)] | dinv[8][16*LDP]
+constexpr int POTF2_TMP = (128 * LDP > 64 * LDH) ? 128 * LDP : 64 * LDH;
+constexpr int POTF2_SMEM_D = 128 * LDS + POTF2_TMP + 8 * PB * LDP;
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ CholArgs a, int k) {
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;
+    double* T = sm + 128 * LDS;
+    double* Dinv = T + POTF2_TMP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int prob = blockIdx.x;
+    double* Gd = a.G + (long long)prob * a.strideG + ((long long)k * TB) * a.Np + (long long)k * TB;
+
+    // load the lower triangle of the diagonal block
+    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+        int r = idx >> 7, c = idx & 127;
+        S[r * LDS + c] = (c <= r) ? Gd[(long long)r * a.Np + c] : 0.0;
+    }
+    __syncthreads();
+
+    for (int p = 0; p < TB / PB; p++) {
+        const int j0 = p * PB;
+        double* D = S + j0 * LDS + j0;
+        double* Di = Dinv + p * PB * LDP;
+        if (warp == 0) {
+            // unblocked 16x16 factor, lane = row
+            for (int c = 0; c < PB; c++) {
+                double d = D[c * LDS + c];
+                if (!(d > 0.0) || !isfinite(d)) {
+                    if (lane == 0) atomicCAS(&a.info[prob], 0, k * TB + j0 + c + 1);
+                    d = (fabs(d) > 0.0 && isfinite(d)) ? fabs(d) : 1.0;
+                }
+                double sd = sqrt(d);
+                __syncwarp();
+                if (lane == c) D[c * LDS + c] = sd;
+                if (lane > c && lane < PB) D[lane * LDS + c] = D[lane * LDS + c] / sd;
+                __syncwarp();
+                if (lane > c && lane < PB) {
+                    double l = D[lane * LDS + c];
+                    for (int c2 = c + 1; c2 <= lane; c2++) D[lane * LDS + c2] -= l * D[c2 * LDS + c];
+                }
+                __syncwarp();
+            }
+            // inverse of the 16x16 triangle, lane = column
+            if (lane < PB) {
+                const int c = lane;
+                for (int i = 0; i < c; i++) Di[i * LDP + c] = 0.0;
+                Di[c * LDP + c] = 1.0 / D[c * LDS + c];
+                for (int i = c + 1; i < PB; i++) {
+                    double s = 0.0;
+                    for (int m = c; m < i; m++) s += D[i * LDS + m] * Di[m * LDP + c];
+                    Di[i * LDP + c] = -s / D[i * LDS + i];
+                }
+            }
+        }
+        __syncthreads();
+        const int rem = TB - j0 - PB;
+        if (rem > 0) {
+            // panel: T = P * Dinv'   (P = S[j0+16.., j0..j0+16))
+            smem_gemm<true>(T, LDP, S + (j0 + PB) * LDS + j0, LDS, Di, LDP, rem, PB, PB, 1.0, 0.0, false);
+            __syncthreads();
+            for (int idx = tid; idx < rem * PB; idx += NTHREADS) {
+                int r = idx >> 4, c = idx & 15;
+                S[(j0 + PB + r) * LDS + j0 + c] = T[r * LDP + c];
+            }
+            // trailing update (lower tiles): S22 -= T T'
+            smem_gemm<true>(S + (j0 + PB) * LDS + j0 + PB, LDS, T, LDP, T, LDP, rem, rem, PB, -1.0, 1.0, true);
+            __syncthreads();
+        }
+    }
+
+    // write L_kk back (strictly-upper part of the block zeroed)
+    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+        int r = idx >> 7, c = idx & 127;
+        Gd[(long long)r * a.Np + c] = (c <= r) ? S[r * LDS + c] : 0.0;
+    }
+    __syncthreads();
+
+    // in-place inverse: diagonal 16x16 blocks first, then recursive doubling X21 = -X22 (L21 X11)
+    for (int idx = tid; idx < (TB / PB) * PB * PB; idx += NTHREADS) {
+        int p = idx >> 8, r = (idx >> 4) & 15, c = idx & 15;
+        S[(p * PB + r) * LDS + p * PB + c] = (c <= r) ? Dinv[p * PB * LDP + r * LDP + c] : 0.0;
+    }
+    __syncthreads();
+    for (int h = PB; h < TB; h <<= 1) {
+        for (int o = 0; o < TB; o += 2 * h) {
+            double* X11 = S + o * LDS + o;
+            double* X22 = S + (o + h) * LDS + o + h;
+            double* L21 = S + (o + h) * LDS + o;
+            smem_gemm<false>(T, LDH, L21, LDS, X11, LDS, h, h, h, 1.0, 0.0, false);
+            __syncthreads();
+            smem_gemm<false>(L21, LDS, X22, LDS, T, LDH, h, h, h, -1.0, 0.0, false);
+            __syncthreads();
+        }
+    }
+    double* Li = a.Linv + (long long)prob * a.strideLinv + (long long)k * TB * TB;
+    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+        int r = idx >> 7, c = idx & 127;
+        Li[idx] = (c <= r) ? S[r * LDS + c] : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// global-memory NT GEMM tile: acc += A[128 x K] * B[128 x K]' with cp.async double buffering
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_tile_async(double* dst, const double* src, long long ld, int tid) {
+#pragma unroll
+    for (int i = 0; i < (TB * KC / 2) / NTHREADS; i++) {
+        int q = tid + i * NTHREADS;
+        int row = q >> 4, seg = q & 15;
+        cp_async16(dst + row * LDT + 2 * seg, src + (long long)row * ld + 2 * seg);
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const __grid_constant__ CholArgs a, int mode, int k) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wm = w & 3, wn = w >> 2;
+    const int prob = blockIdx.y;
+    const int t = blockIdx.x;
+    const long long Np = a.Np;
+    double* G = a.G + (long long)prob * a.strideG;
+    double* Y = a.Y ? a.Y + (long long)prob * a.strideY : nullptr;
+    const double* Linv = a.Linv + (long long)prob * a.strideLinv;
+
+    const double *A, *B;
+    double* C;
+    long long lda, ldb;
+    int K;
+    double alpha, beta;
+    switch (mode) {
+        case GM_TRSM: {
+            int i = k + 1 + t;
+            A = G + (long long)i * TB * Np + (long long)k * TB; lda = Np;
+            B = Linv + (long long)k * TB * TB; ldb = TB;
+            C = G + (long long)i * TB * Np + (long long)k * TB;
+            K = TB; alpha = 1.0; beta = 0.0;
+        } break;
+        case GM_SYRK_RIGHT: {
+            int ii, jj;
+            tile_ij(t, ii, jj);
+            int i = k + 1 + ii, j = k + 1 + jj;
+            A = G + (long long)i * TB * Np + (long long)k * TB; lda = Np;
+            B = G + (long long)j * TB * Np + (long long)k * TB; ldb = Np;
+            C = G + (long long)i * TB * Np + (long long)j * TB;
+            K = TB; alpha = -1.0; beta = 1.0;
+        } break;
+        case GM_SYRK_LEFT: {
+            int i = k + t;
+            A = G + (long long)i * TB * Np; lda = Np;
+            B = G + (long long)k * TB * Np; ldb = Np;
+            C = G + (long long)i * TB * Np + (long long)k * TB;
+            K = k * TB; alpha = -1.0; beta = 1.0;
+        } break;
+        case GM_TRTRI_A: {
+            int kb = t;  // kb < k (k plays the role of block column i)
+            A = Y + (long long)kb * TB * Np + (long long)kb * TB; lda = Np;
+            B = G + (long long)k * TB * Np + (long long)kb * TB; ldb = Np;
+            C = Y + (long long)kb * TB * Np + (long long)k * TB;
+            K = (k - kb) * TB; alpha = 1.0; beta = 0.0;
+        } break;
+        case GM_TRTRI_B: {
+            int kb = t;
+            A = Y + (long long)kb * TB * Np + (long long)k * TB; lda = Np;
+            B = Linv + (long long)k * TB * TB; ldb = TB;
+            C = Y + (long long)kb * TB * Np + (long long)k * TB;
+            K = TB; alpha = -1.0; beta = 0.0;
+        } break;
+        default: {  // GM_LAUUM
+            int ia, ib;
+            tile_ij(t, ia, ib);
+            A = Y + (long long)ia * TB * Np + (long long)ia * TB; lda = Np;
+            B = Y + (long long)ib * TB * Np + (long long)ia * TB; ldb = Np;
+            C = G + (long long)ia * TB * Np + (long long)ib * TB;
+            K = (a.nb - ia) * TB; alpha = 1.0; beta = 0.0;
+        } break;
+    }
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int nchunks = K / KC;
+    double* st0 = sm;
+    double* st1 = sm + 2 * TILE_D;
+    if (nchunks > 0) {
+        load_tile_async(st0, A, lda, tid);
+        load_tile_async(st0 + TILE_D, B, ldb, tid);
+    }
+    cp_async_commit();
+    const int fragA = (32 * wm + (lane >> 2)) * LDT + (lane & 3);
+    const int fragB = (64 * wn + (lane >> 2)) * LDT + (lane & 3);
+    for (int c = 0; c < nchunks; c++) {
+        double* cur = (c & 1) ? st1 : st0;
+        double* nxt = (c & 1) ? st0 : st1;
+        if (c + 1 < nchunks) {
+            load_tile_async(nxt, A + (long long)(c + 1) * KC, lda, tid);
+            load_tile_async(nxt + TILE_D, B + (long long)(c + 1) * KC, ldb, tid);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const double* pa = cur + fragA;
+        const double* pb = cur + TILE_D + fragB;
+#pragma unroll
+        for (int kk = 0; kk < KC / 4; kk++) mma_step(pa, pb, kk, acc);
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int row = 32 * wm + 8 * i + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int col = 64 * wn + 8 * j + 2 * (lane & 3);
+            double2* pc = reinterpret_cast<double2*>(C + (long long)row * Np + col);
+            double2 v = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+            if (beta != 0.0) {
+                double2 o = *pc;
+                v.x += beta * o.x;
+                v.y += beta * o.y;
+            }
+            *pc = v;
+        }
+    }
+}
+
+__global__ void k_diag_prepare(double* G, long long strideG, int Np, int ncc, int zero_first,
+                               const double* __restrict__ ridge_dev, double ridge) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np) return;
+    int prob = blockIdx.y;
+    double* g = G + (long long)prob * strideG + (long long)i * Np + i;
+    double rg = ridge_dev ? ridge_dev[prob] : ridge;
+    *g = is_dummy_col(i, ncc, zero_first) ? 1.0 : (*g + rg);
+}
+
+__global__ void k_max_diag(const double* __restrict__ G, long long strideG, int Np, int ncc, int zero_first,
+                           double* out) {
+    __shared__ double red[256];
+    int prob = blockIdx.x;
+    const double* g = G + (long long)prob * strideG;
+    double m = 0.0;
+    for (int i = threadIdx.x; i < Np; i += blockDim.x)
+        if (!is_dummy_col(i, ncc, zero_first)) m = fmax(m, fabs(g[(long long)i * Np + i]));
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[prob] = red[0];
+}
+
+__global__ void k_init_y(const __grid_constant__ CholArgs a) {
+    // Y_kk = Linv_kk'
+    int kb = blockIdx.x, prob = blockIdx.y;
+    const double* Li = a.Linv + (long long)prob * a.strideLinv + (long long)kb * TB * TB;
+    double* Yd = a.Y + (long long)prob * a.strideY + (long long)kb * TB * a.Np + (long long)kb * TB;
+    __shared__ double tile[32][33];
+    for (int br = 0; br < TB; br += 32)
+        for (int bc = 0; bc < TB; bc += 32) {
+            int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 256 threads: 8 rows at a time
+            for (int r = ty; r < 32; r += 8) tile[r][tx] = Li[(br + r) * TB + bc + tx];
+            __syncthreads();
+            for (int r = ty; r < 32; r += 8) Yd[(long long)(bc + r) * a.Np + br + tx] = tile[tx][r];
+            __syncthreads();
+        }
+}
+
+__global__ void k_symmetrize(double* G, long long strideG, int Np) {
+    // copy lower 32x32 tiles to upper
+    int bi = blockIdx.x, bj = blockIdx.y, prob = blockIdx.z;
+    if (bj >= bi) return;
+    double* g = G + (long long)prob * strideG;
+    __shared__ double tile[32][33];
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) tile[r][tx] = g[(long long)(bi * 32 + r) * Np + bj * 32 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) g[(long long)(bj * 32 + r) * Np + bi * 32 + tx] = tile[tx][r];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// blocked TRSV with the pre-inverted diagonal blocks; one CTA per problem, up to 2 right-hand sides
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_trsv(const __grid_constant__ CholArgs a, double* Bm,
+                                                      long long strideB, int nrhs) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int prob = blockIdx.x;
+    const long long Np = a.Np;
+    const double* L = a.G + (long long)prob * a.strideG;
+    const double* Linv = a.Linv + (long long)prob * a.strideLinv;
+    double* b = Bm + (long long)prob * strideB;  // [nrhs][Np], solved in place
+    __shared__ double rbuf[2][TB];
+    __shared__ double part[2][2][TB];
+
+    // forward: L y = b
+    for (int kb = 0; kb < a.nb; kb++) {
+        for (int rr = warp; rr < TB; rr += 8) {
+            const double* row = L + (long long)(kb * TB + rr) * Np;
+            double s0 = 0.0, s1 = 0.0;
+            for (int c = lane; c < kb * TB; c += 32) {
+                double l = row[c];
+                s0 += l * __ldcg(b + c);
+                if (nrhs > 1) s1 += l * __ldcg(b + Np + c);
+            }
+            s0 = warp_sum(s0);
+            s1 = warp_sum(s1);
+            if (lane == 0) {
+                rbuf[0][rr] = __ldcg(b + kb * TB + rr) - s0;
+                if (nrhs > 1) rbuf[1][rr] = __ldcg(b + Np + kb * TB + rr) - s1;
+            }
+        }
+        __syncthreads();
+        const double* Li = Linv + (long long)kb * TB * TB;
+        for (int rr = warp; rr < TB; rr += 8) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int c = lane; c <= rr; c += 32) {
+                double l = Li[rr * TB + c];
+                s0 += l * rbuf[0][c];
+                if (nrhs > 1) s1 += l * rbuf[1][c];
+            }
+            s0 = warp_sum(s0);
+            s1 = warp_sum(s1);
+            if (lane == 0) {
+                b[kb * TB + rr] = s0;
+                if (nrhs > 1) b[Np + kb * TB + rr] = s1;
+            }
+        }
+        __syncthreads();
+    }
+    // backward: L' x = y
+    const int c = tid & 127, h = tid >> 7;
+    for (int kb = a.nb - 1; kb >= 0; kb--) {
+        double s0 = 0.0, s1 = 0.0;
+        for (long long r = (long long)(kb + 1) * TB + h; r < Np; r += 2) {
+            double l = L[r * Np + kb * TB + c];
+            s0 += l * __ldcg(b + r);
+            if (nrhs > 1) s1 += l * __ldcg(b + Np + r);
+        }
+        part[0][h][c] = s0;
+        part[1][h][c] = s1;
+        __syncthreads();
+        if (h == 0) {
+            rbuf[0][c] = __ldcg(b + kb * TB + c) - (part[0][0][c] + part[0][1][c]);
+            if (nrhs > 1) rbuf[1][c] = __ldcg(b + Np + kb * TB + c) - (part[1][0][c] + part[1][1][c]);
+        }
+        __syncthreads();
+        const double* Li = Linv + (long long)kb * TB * TB;
+        s0 = 0.0;
+        s1 = 0.0;
+        for (int m = c + h; m < TB; m += 2) {
+            double l = Li[m * TB + c];
+            s0 += l * rbuf[0][m];
+            if (nrhs > 1) s1 += l * rbuf[1][m];
+        }
+        part[0][h][c] = s0;
+        part[1][h][c] = s1;
+        __syncthreads();
+        if (h == 0) {
+            b[kb * TB + c] = part[0][0][c] + part[0][1][c];
+            if (nrhs > 1) b[Np + kb * TB + c] = part[1][0][c] + part[1][1][c];
+        }
+        __syncthreads();
+    }
+}
+
+bool attrs_done = false;
+void set_attrs() {
+    if (attrs_done) return;
+    cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(POTF2_SMEM_D * sizeof(double)));
+    cudaFuncSetAttribute(k_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * TILE_D * sizeof(double)));
+    attrs_done = true;
+}
+
+}  // namespace
+
+size_t potf2_smem_bytes() { return POTF2_SMEM_D * sizeof(double); }
+size_t gemm_smem_bytes() { return 4 * TILE_D * sizeof(double); }
+
+void launch_diag_prepare(double* G, long long strideG, int Np, int ncc, int zero_first, const double* ridge_dev,
+                         double ridge, int nproblems, cudaStream_t st) {
+    for (int p0 = 0; p0 < nproblems; p0 += 32768) {
+        int np = nproblems - p0 < 32768 ? nproblems - p0 : 32768;
+        dim3 grid((Np + 255) / 256, np);
+        k_diag_prepare<<<grid, 256, 0, st>>>(G + (long long)p0 * strideG, strideG, Np, ncc, zero_first,
+                                             ridge_dev ? ridge_dev + p0 : nullptr, ridge);
+    }
+}
+
+void launch_max_diag(const double* G, long long strideG, int Np, int ncc, int zero_first, double* out,
+                     int nproblems, cudaStream_t st) {
+    k_max_diag<<<nproblems, 256, 0, st>>>(G, strideG, Np, ncc, zero_first, out);
+}
+
+void launch_potf2(const CholArgs& a, int k, int nproblems, cudaStream_t st) {
+    set_attrs();
+    k_potf2<<<nproblems, NTHREADS, potf2_smem_bytes(), st>>>(a, k);
+}
+
+static CholArgs offset_args(const CholArgs& a, int p0) {
+    CholArgs b = a;
+    b.G = a.G + (long long)p0 * a.strideG;
+    if (a.Y) b.Y = a.Y + (long long)p0 * a.strideY;
+    b.Linv = a.Linv + (long long)p0 * a.strideLinv;
+    b.info = a.info + p0;
+    return b;
+}
+
+void launch_gemm(int mode, const CholArgs& a, int k, int ntiles, int nproblems, cudaStream_t st) {
+    set_attrs();
+    if (ntiles <= 0) return;
+    for (int p0 = 0; p0 < nproblems; p0 += 32768) {
+        int np = nproblems - p0 < 32768 ? nproblems - p0 : 32768;
+        dim3 grid(ntiles, np);
+        k_gemm<<<grid, NTHREADS, gemm_smem_bytes(), st>>>(offset_args(a, p0), mode, k);
+    }
+}
+
+void launch_init_y(const CholArgs& a, int nproblems, cudaStream_t st) {
+    dim3 grid(a.nb, nproblems);
+    k_init_y<<<grid, 256, 0, st>>>(a);
+}
+
+void launch_symmetrize(double* G, long long strideG, int Np, int nproblems, cudaStream_t st) {
+    dim3 grid(Np / 32, Np / 32, nproblems);
+    k_symmetrize<<<grid, 256, 0, st>>>(G, strideG, Np);
+}
+
+void launch_trsv(const CholArgs& a, double* B, long long strideB, int nrhs, int nproblems, cudaStream_t st) {
+    k_trsv<<<nproblems, NTHREADS, 0, st>>>(a, B, strideB, nrhs);
+}
+
+int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st) {
+    int launches = 0;
+    const int nb = a.nb;
+    const bool left = (long long)nproblems * nb >= 2LL * sms;
+    for (int k = 0; k < nb; k++) {
+        if (left && k > 0) {
+            launch_gemm(GM_SYRK_LEFT, a, k, nb - k, nproblems, st);
+            launches++;
+        }
+        launch_potf2(a, k, nproblems, st);
+        launches++;
+        if (k + 1 < nb) {
+            launch_gemm(GM_TRSM, a, k, nb - k - 1, nproblems, st);
+            launches++;
+            if (!left) {
+                int m = nb - k - 1;
+                launch_gemm(GM_SYRK_RIGHT, a, k, m * (m + 1) / 2, nproblems, st);
+                launches++;
+            }
+        }
+    }
+    return launches;
+}
+
+int potri(const CholArgs& a, int nproblems, cudaStream_t st) {
+    int launches = 0;
+    launch_init_y(a, nproblems, st);
+    launches++;
+    for (int i = 1; i < a.nb; i++) {
+        launch_gemm(GM_TRTRI_A, a, i, i, nproblems, st);
+        launch_gemm(GM_TRTRI_B, a, i, i, nproblems, st);
+        launches += 2;
+    }
+    launch_gemm(GM_LAUUM, a, 0, a.nb * (a.nb + 1) / 2, nproblems, st);
+    launch_symmetrize(a.G, a.strideG, a.Np, nproblems, st);
+    return launches + 2;
+}
+
+}  // namespace lpvs

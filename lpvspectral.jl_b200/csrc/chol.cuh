@@ -1,0 +1,61 @@
+// Blocked FP64 Cholesky / triangular solves / SPD inverse on the internal tiled layout (Np = 128*nb, row-major,
+// lower triangle).  Replaces the reference's dense solves: svd([A;lam I])\ (src/utilities.jl:58), the N-rhs LU
+// (src/lsfft.jl:77), pivoted QR (src/utilities.jl:52), inv(AA'AA+lam I) (src/lsfft.jl:254) and the CG x-update
+// (src/lasso.jl:151), all on the Gram matrix.
+#pragma once
+#include "common.cuh"
+
+namespace lpvs {
+
+enum GemmMode {
+    GM_TRSM = 0,       // A_ik <- A_ik * Linv_kk'                       (i > k)
+    GM_SYRK_RIGHT = 1, // A_ij -= A_ik A_jk'                            (i >= j > k)
+    GM_SYRK_LEFT = 2,  // A_ik -= sum_{j<k} A_ij A_kj'                  (i >= k)
+    GM_TRTRI_A = 3,    // Y_ki  = Y[k, k:i) * L[i, k:i)'                (k < i)
+    GM_TRTRI_B = 4,    // Y_ki <- -Y_ki * Linv_ii'
+    GM_LAUUM = 5       // M_ab  = Y[a, a:nb) * Y[b, a:nb)'              (a >= b), M written into G
+};
+
+struct CholArgs {
+    double* G;  // per problem Np x Np row-major (lower)
+    long long strideG;
+    double* Y;  // inverse-transpose workspace (upper), same shape
+    long long strideY;
+    double* Linv;  // per problem nb blocks of 128x128 (ld 128)
+    long long strideLinv;
+    int* info;  // per problem: 0 ok, else 1-based failing pivot (internal index)
+    int Np, nb;
+};
+
+size_t potf2_smem_bytes();
+size_t gemm_smem_bytes();
+
+// diagonal: G[i][i] = dummy(i) ? 1 : G[i][i] + ridge[prob or 0]
+void launch_diag_prepare(double* G, long long strideG, int Np, int ncc, int zero_first, const double* ridge_dev,
+                         double ridge, int nproblems, cudaStream_t st);
+void launch_potf2(const CholArgs& a, int k, int nproblems, cudaStream_t st);
+void launch_gemm(int mode, const CholArgs& a, int k, int ntiles, int nproblems, cudaStream_t st);
+// Y_kk = Linv_kk' for all k
+void launch_init_y(const CholArgs& a, int nproblems, cudaStream_t st);
+// mirror lower tiles of G into the upper triangle
+void launch_symmetrize(double* G, long long strideG, int Np, int nproblems, cudaStream_t st);
+// B[p][r][Np] <- (L L')^{-1} B, nrhs <= 2, one CTA per problem
+void launch_trsv(const CholArgs& a, double* B, long long strideB, int nrhs, int nproblems, cudaStream_t st);
+// max_i G[i][i] over non-dummy i  -> out[prob]
+void launch_max_diag(const double* G, long long strideG, int Np, int ncc, int zero_first, double* out,
+                     int nproblems, cudaStream_t st);
+
+// full factorisation driver (left-looking when batched, right-looking for few large problems); returns launches
+int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st);
+// after potrf: M = (L L')^{-1} written (full symmetric) into G; uses Y. returns launches
+int potri(const CholArgs& a, int nproblems, cudaStream_t st);
+
+__host__ __device__ inline bool is_dummy_col(int p, int ncc, int zero_first) {
+    int q = p >> 7, r = p & 127;
+    int part = r >> 6;
+    int cc = q * 64 + (r & 63);
+    if (cc >= ncc) return true;
+    return zero_first && part == 1 && cc == 0;
+}
+
+}  // namespace lpvs

@@ -1,0 +1,92 @@
+// Internal context / workspace definitions for liblpvs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lpvs.h"
+#include "chol.cuh"
+#include "gram.cuh"
+
+namespace lpvs {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+enum BufSlot {
+    BUF_T = 0, BUF_Y, BUF_U, BUF_W, BUF_F, BUF_ANC, BUF_DEL, BUF_G, BUF_B, BUF_LINV, BUF_INFO, BUF_PART, BUF_SUMS,
+    BUF_X, BUF_MISC, BUF_YINV, BUF_E, BUF_K, BUF_V, BUF_CENT, BUF_COUNT
+};
+
+}  // namespace lpvs
+
+struct lpvs_ctx {
+    int device = 0;
+    int sms = 148;
+    cudaStream_t st = nullptr;
+    std::string err;
+    std::mutex mu;
+    int phase_mode = LPVS_PHASE_AUTO;
+    int window_batch = 0;
+    int jitter = 1;
+    int admm_check_every = 1;
+    lpvs::DevBuf buf[lpvs::BUF_COUNT];
+    int64_t launches = 0;
+    // Gram kernel timing of the last API call
+    std::vector<cudaEvent_t> ev;
+    int ev_used = 0;
+    double gram_ms = 0.0;
+    int64_t gram_launches = 0;
+    double gram_flops = 0.0;
+};
+
+namespace lpvs {
+
+int fail(lpvs_ctx* c, int code, const char* fmt, ...);
+
+#define LPVS_CU(ctx, call)                                                                      \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return lpvs::fail(ctx, LPVS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                              __FILE__, __LINE__);                                              \
+    } while (0)
+
+// grow-only workspace
+void* ws_raw(lpvs_ctx* c, int slot, size_t bytes);
+template <class T>
+inline T* ws(lpvs_ctx* c, int slot, size_t count) {
+    return reinterpret_cast<T*>(ws_raw(c, slot, count * sizeof(T)));
+}
+
+// description of a Fourier basis on the internal tiled layout
+struct FourierPlan {
+    int Nf = 0, Nreg = 0, nblk = 0, Np = 0, ngroups = 0;
+    int zero_first = 0;
+    int mode = GRAM_CHAIN;
+    double f0 = 0.0, df = 0.0, dd = 1.0;
+    const double* d_f = nullptr;
+};
+int make_fourier_plan(lpvs_ctx* c, const double* f, int Nf, FourierPlan* plan);
+inline int pcol(int k) { return (k >> 6) * 128 + (k & 63); }
+
+void gram_timer_begin(lpvs_ctx* c);
+void gram_timer_end(lpvs_ctx* c, double flops, int launches);
+void gram_timer_reset(lpvs_ctx* c);
+int gram_timer_resolve(lpvs_ctx* c);
+
+// G (Np x Np lower tiles) and B ([2][Np]) for ONE problem over samples [0,N) of device arrays; split over samples
+// when the tile count alone cannot fill the GPU.  d_W indexed by absolute sample (nullable).
+int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const double* d_y, const double* d_u,
+                const double* d_W, int64_t N, int nrhs, double* d_G, double* d_B);
+
+// factor + solve one problem in place: d_G -> L, d_B -> x (internal layout); returns pivot info in *info_host
+int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, double* d_B, int nrhs, double ridge,
+                 int nproblems, int* info_host /* nproblems or null */);
+
+}  // namespace lpvs

@@ -1,0 +1,61 @@
+// Gram formation with on-the-fly basis synthesis: G = A' diag(W) A, b = A' diag(W) [y u].
+// A is never materialised in HBM: each CTA synthesises its [128 functions] x [32 samples] basis tiles in
+// shared memory and feeds them to FP64 DMMA.  Replaces get_fourier_regressor + A'Wd*A (src/lsfft.jl:26-49,77),
+// the LPV row loop (src/lsfft.jl:244-248) and the LeastSquares constructor's A'A (src/lasso.jl:51,98).
+#pragma once
+#include "common.cuh"
+
+namespace lpvs {
+
+enum GramMode { GRAM_CHAIN = 0, GRAM_DIRECT = 1, GRAM_LPV = 2 };
+
+// Internal column layout (size Np = 128*nblk): block q holds "complex columns" cc = 64q .. 64q+63;
+// internal index p = 128q + (cc%64) for the real part (cos, or Re A for LPV) and 128q + 64 + (cc%64) for the
+// second part (-sin, or Im A).  Fourier: cc = frequency index.  LPV: cc = f + k*Nf (reference order).
+// Columns with cc >= ncc, and the -sin column of a zero frequency, are identically zero ("dummy"): the
+// factorisation gives them a unit diagonal so they decouple.
+struct GramArgs {
+    const double* t;  // sample positions, absolute index
+    const double* y;  // rhs 0 (nullable)
+    const double* u;  // rhs 1 (nullable)
+    const double* W;  // weights (nullable = 1)
+    int w_abs;        // 0: W indexed by in-problem sample index (shared window weights); 1: by absolute index
+    long long start0; // problem p covers absolute samples [start0 + p*hop, start0 + p*hop + n)
+    long long hop;
+    int n;
+    long long s_end;  // samples >= s_end are invalid (ragged last split)
+    int ncc;  // valid complex columns (Nf, or Nf*Nvv for LPV)
+    int nblk; // Np / 128
+    int nrhs;
+    // GRAM_CHAIN tables, indexed [g * tbl_ns + (s - tbl_base)]
+    const double2* anc;
+    const double2* del;
+    long long tbl_base;
+    long long tbl_ns;
+    // GRAM_DIRECT
+    const double* f;
+    // GRAM_LPV tables: E[fi * tbl_ns + s'], Kt[ki * tbl_ns + s']
+    const double2* E;
+    const double* Kt;
+    int lpv_nf;
+    // output
+    double gscale, bscale;
+    double* G;  // per problem Np x Np row-major, lower tiles written (full 128x128 tiles on the diagonal)
+    long long strideG;
+    double* B;  // per problem [2][Np]
+    long long strideB;
+};
+
+size_t gram_smem_bytes();
+// grid = (nblk*(nblk+1)/2, nproblems)
+void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st);
+
+// anchors every GRP frequencies + per-sample step rotation, exact phase (double-double turns)
+void launch_anchor_table(const double* t, long long s0, long long ns, const double* f, int Nf, int ngroups,
+                         double f0, double df, double2* anc, double2* del, cudaStream_t st);
+// LPV factor tables: E[fi][s] = (cos, -sin)(w_fi * X_s) (reference rounding), Kt[ki][s] = RBF activations
+void launch_lpv_tables(const double* X, const double* V, long long N, const double* w, int Nf, int Nvv,
+                       const double* centers, double gamma, int coulomb, int normalize, double2* E, double* Kt,
+                       cudaStream_t st);
+
+}  // namespace lpvs

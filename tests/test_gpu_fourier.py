@@ -1,0 +1,122 @@
+"""GPU parity: Fourier LS estimators through the C ABI vs the oracle (-m gpu).
+
+Tolerances: coefficients <= 1e-9 relative l2 on well-conditioned FP64 problems (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from oracle import lpvs_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(b)
+
+
+def signal(N, seed, tones=((20.0, 1.0, 0.0), (55.0, 0.5, 1.0)), noise=0.1, T=10.0):
+    rng = np.random.default_rng(seed)
+    t = np.sort(T * rng.random(N))
+    y = sum(a * np.cos(2 * np.pi * f * t + p) for f, a, p in tones) + noise * rng.standard_normal(N)
+    return t, y
+
+
+@pytest.mark.parametrize("phase", [1, 2])
+@pytest.mark.parametrize("N,Nf,zero", [(1000, 100, True), (777, 70, False), (300, 129, True)])
+def test_gram_matches_oracle(ctx, phase, N, Nf, zero):
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+
+    t, y = signal(N, 11)
+    f = (np.arange(Nf) + (0 if zero else 1)) * 0.37
+    W = 0.5 + np.random.default_rng(5).random(N)
+    ctx.set_option(L.OPT_PHASE_MODE, phase)
+    try:
+        G, b = lp.gram_fourier(t, f, W, y, ctx=ctx)
+    finally:
+        ctx.set_option(L.OPT_PHASE_MODE, 0)
+    A, _ = o.get_fourier_regressor(t, f)
+    Gr = (A.T * W) @ A
+    br = (A.T * W) @ y
+    assert np.abs(G - Gr).max() <= 2e-13 * np.abs(Gr).max()
+    assert np.abs(b - br).max() <= 2e-13 * np.abs(br).max()
+    assert np.array_equal(G, G.T)
+
+
+def test_parity1_unweighted_and_weighted(ctx):
+    """SURVEY 8(d) PARITY-1: N=4096, f=default_freqs(t)[:1024], cond(A)=285."""
+    import lpvspectral_jl_b200 as lp
+
+    t, y = signal(4096, 1)
+    f = o.default_freqs(t)[:1024]
+    x, _ = lp.ls_spectral(y, t, f, ctx=ctx)
+    xr, _ = o.ls_spectral(y, t, f, mode="literal")
+    assert rel(x, xr) <= TOL
+    # Hann weights halve the resolution: spacing 2/T keeps the weighted problem well conditioned
+    # (cond(A'WA) = 1e3; at spacing 1/T it is 4e8 and even the oracle's two CPU modes differ by 2e-9).
+    W = o.hanning(4096)
+    f2 = f[::2]
+    xw, _ = lp.ls_spectral(y, t, f2, W, ctx=ctx)
+    xwr, _ = o.ls_spectral(y, t, f2, W, mode="literal")
+    assert rel(xw, xwr) <= TOL
+    # ill-conditioned variant: bounded by cond * phase-rounding differences, documented looser bar
+    xw, _ = lp.ls_spectral(y, t, f, W, ctx=ctx)
+    xwr, _ = o.ls_spectral(y, t, f, W, mode="literal")
+    assert rel(xw, xwr) <= 1e-7
+
+
+def test_reference_kats(ctx):
+    """test/runtests.jl:186-208 through the GPU path."""
+    import lpvspectral_jl_b200 as lp
+
+    t = np.arange(1000) * 0.1
+    f = lp.default_freqs(t)
+    y = np.sin(2 * np.pi * t)
+    x, fr, info = lp.ls_spectral(y, t, ctx=ctx, return_info=True)  # rank-deficient 1000x1001 (H1)
+    a = x.real ** 2 + x.imag ** 2
+    assert a.argmax() + 1 == 101 and abs(a.max() - 2.0 * len(fr)) < 1e-4
+    x, _ = lp.ls_spectral(y, t, f, np.ones(len(y)), ctx=ctx)
+    a = x.real ** 2 + x.imag ** 2
+    assert a.argmax() + 1 == 101 and abs(a.max() - 2.0 * len(f)) < 1e-4
+    S, fr = lp.ls_windowpsd(y, t, noverlap=0, ctx=ctx)
+    assert S.argmax() + 1 == 13
+    S, fr = lp.ls_windowpsd(y, t, nw=16, noverlap=0, ctx=ctx)
+    assert np.abs(S).argmax() + 1 == 7
+    S, fr = lp.ls_windowcsd(y, y, t, noverlap=0, ctx=ctx)
+    assert np.abs(S).argmax() + 1 == 11 and abs(np.abs(S).max() - 2.0 * len(fr)) < 1e-4
+    Cxy, _ = lp.ls_cohere(y, y, t, ctx=ctx)
+    assert np.all(Cxy == 1)
+
+
+@pytest.mark.parametrize("kind", ["psd", "csd", "cohere"])
+def test_windowed_parity(ctx, kind):
+    import lpvspectral_jl_b200 as lp
+
+    N, nw = 6000, 10
+    t, y = signal(N, 3, tones=((30.0, 1.0, 0.0), (70.0, 0.7, 0.4)))
+    rng = np.random.default_rng(9)
+    u = 0.7 * np.roll(y, 3) + 0.5 * rng.standard_normal(N)
+    n = N // nw
+    fs = 1.0 / np.mean(np.diff(t))
+    f = np.arange(40) * 2 * fs / n
+    if kind == "psd":
+        S, _ = lp.ls_windowpsd(y, t, f, nw=nw, window_func=lp.hanning, ctx=ctx)
+        Sr, _ = o.ls_windowpsd(y, t, f, nw=nw, window_func=o.hanning)
+    elif kind == "csd":
+        S, _ = lp.ls_windowcsd(y, u, t, f, nw=nw, window_func=lp.hanning, ctx=ctx)
+        Sr, _ = o.ls_windowcsd(y, u, t, f, nw=nw, window_func=o.hanning)
+    else:
+        S, _ = lp.ls_cohere(y, u, t, f, nw=nw, ctx=ctx)
+        Sr, _ = o.ls_cohere(y, u, t, f, nw=nw)
+    assert rel(S, Sr) <= TOL
+
+
+def test_errors(ctx):
+    import lpvspectral_jl_b200 as lp
+
+    t, y = signal(100, 2)
+    with pytest.raises(ValueError):
+        lp.ls_spectral(y, t, np.array([1.0, 0.0, 2.0]), ctx=ctx)
+    with pytest.raises(ValueError):
+        lp.ls_spectral(y[:-1], t, np.array([1.0, 2.0]), ctx=ctx)
