@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the windowed least-squares spectral estimation hot path (BASELINE.json configs[1]).
+
+workload "cfg2_windowpsd": ls_windowpsd on 2^22 irregular samples, nw=1024 (n=4096, noverlap=2048, K=2047
+windows), hanning window, 256 frequencies per window.  One *step* = one full pass over all K windows of one
+2^22-sample record.  Multi-GPU: windows shard with no data-path collective -- every rank owns one 2^22-sample
+segment (weak scaling, per-GPU work fixed) and only the Nf-long accumulators are all-reduced once per step.
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload cfg2_windowpsd|cfg3_admm]
+
+Prints ONE JSON line (rank 0).  `value` = windows/s with inputs resident in HBM; `e2e` = the same metric through
+the public host-buffer API (H2D of y,t and D2H of the spectrum inside the timed region); `roofline` = the Gram
+kernel's FP64 tensor-pipe fraction measured live with CUDA events on the library's stream; `cpu_baseline` = the
+oracle's reference-literal algorithm on the host cores for a bounded sample of the same windows.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NSAMP = 1 << 22
+NW = 1024
+NF = 256
+LAMBDA = 1e-10
+FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+
+
+def make_cfg2(seed=2, nsamp=NSAMP, nw=NW, nf=NF):
+    """t=sort(10*U^N), two tones at f[40], f[100] + 0.1 noise, f=(0:nf-1)*2fs/n."""
+    rng = np.random.default_rng(seed)
+    t = np.sort(10.0 * rng.random(nsamp))
+    n = nsamp // nw
+    fs = 1.0 / np.mean(np.diff(t))
+    f = np.arange(nf, dtype=np.float64) * (2.0 * fs / n)
+    y = np.sin(2 * np.pi * f[40] * t) + 0.5 * np.cos(2 * np.pi * f[100] * t + 1.0) + 0.1 * rng.standard_normal(nsamp)
+    return t, y, f, n
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        top = sorted(sm)[len(sm) // 2:]  # under-load half
+        return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def fp64_peak():
+    try:
+        with open(FP64_PEAK_FILE) as fh:
+            d = json.load(fh)
+        return float(d["dmma_tflops"]), "profiles/fp64_peak_r01.json (tools/fp64_probe.cu, DMMA.8x8x4 issue peak measured on this pool's B200; MEASURED_PEAKS.json has no FP64 line; cuBLAS DGEMM 8192^3 = %.2f)" % d["dgemm_tflops"]
+    except Exception:
+        return 37.0, "nominal 37 TFLOP/s (fallback: profiles/fp64_peak_r01.json missing)"
+
+
+def cpu_baseline_windows(t, y, f, n, nwin, threads=None):
+    """Reference-literal CPU algorithm (oracle) on `nwin` windows of the workload; returns windows/s."""
+    from oracle import lpvs_oracle as o
+
+    W = o.hanning(n)
+    hop = n - (n >> 1)
+    t0 = time.perf_counter()
+    S = np.zeros(len(f))
+    for k in range(nwin):
+        sl = slice(k * hop, k * hop + n)
+        x, _ = o.ls_spectral(y[sl], t[sl], f, W, lam=LAMBDA, mode="literal")
+        S += x.real ** 2 + x.imag ** 2
+    dt = time.perf_counter() - t0
+    return nwin / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; Julia is not installed) on host cores."""
+    if rank != 0:
+        return
+    t, y, f, n = make_cfg2()
+    nwin = 24
+    for _ in range(args.warmup):
+        cpu_baseline_windows(t, y, f, n, 2)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_baseline_windows(t, y, f, n, nwin)
+    dt = time.perf_counter() - t0
+    val = args.steps * nwin / dt
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "windowed LS spectra/sec", "value": val, "unit": "windows/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2_windowpsd", "samples": NSAMP, "nw": NW, "n": n, "noverlap": n >> 1,
+                   "windows": 2 * NW - 1, "freqs": NF, "window": "hanning"},
+        "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": "port",
+                         "sample": f"{nwin} of {2 * NW - 1} windows per step, oracle reference-literal mode "
+                                   f"(numpy/OpenBLAS, all host threads); Julia is not installed"},
+        "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--cpu-windows", type=int, default=96)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+    import ctypes as C
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = lp.Context(local)
+
+    # every rank owns one 2^22-sample segment (its own seed): weak scaling, no data-path collective
+    t, y, f, n = make_cfg2(seed=2 + rank)
+    noverlap = n >> 1
+    W = lp.hanning(n)
+    K = lp.window_count(NSAMP, n, noverlap)
+    # resident inputs (torch owns the allocation; the library takes raw device pointers)
+    d_t = torch.from_numpy(t).cuda()
+    d_y = torch.from_numpy(y).cuda()
+    # pinned host copies for the e2e leg
+    h_t = torch.from_numpy(t).pin_memory()
+    h_y = torch.from_numpy(y).pin_memory()
+    sums = np.zeros(NF)
+    info = C.c_int(0)
+    fptr, wptr, sptr = f.ctypes.data_as(C.c_void_p), W.ctypes.data_as(C.c_void_p), sums.ctypes.data_as(C.c_void_p)
+    acc = torch.zeros(NF, dtype=torch.float64, device="cuda")
+
+    def step_resident():
+        ctx.check(ctx.lib.lpvs_ls_window_sums_dev(ctx.h, L.WIN_PSD, C.c_void_p(d_y.data_ptr()), None,
+                                                  C.c_void_p(d_t.data_ptr()), NSAMP, fptr, NF, wptr, n, noverlap,
+                                                  LAMBDA, 0, K, sptr, C.byref(info)))
+        ms = ctx.last_call_ms()
+        gms, gl, gfl = ctx.gram_timing()
+        if world > 1:  # cross-rank reduction of the accumulators (Nf doubles), then /K_total^2 on the host
+            acc.copy_(torch.from_numpy(sums))
+            dist.all_reduce(acc)
+        return ms, gms, gfl
+
+    def step_e2e():
+        ctx.check(ctx.lib.lpvs_ls_window_sums(ctx.h, L.WIN_PSD, C.c_void_p(h_y.data_ptr()), None,
+                                              C.c_void_p(h_t.data_ptr()), NSAMP, fptr, NF, wptr, n, noverlap, LAMBDA,
+                                              0, K, sptr, C.byref(info)))
+        ms = ctx.last_call_ms()
+        if world > 1:
+            acc.copy_(torch.from_numpy(sums))
+            dist.all_reduce(acc)
+        return ms
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.check(ctx.lib.lpvs_sync(ctx.h))
+
+    def allmax(v):
+        if world == 1:
+            return v
+        tt = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---- resident leg ----
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    launches0 = ctx.launches
+    barrier()
+    if rank == 0:
+        sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms = gram_ms = gram_fl = 0.0
+    for _ in range(args.steps):
+        ms, gms, gfl = step_resident()
+        dev_ms += ms
+        gram_ms += gms
+        gram_fl += gfl
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    dev_ms = allmax(dev_ms)
+    wall = allmax(wall)
+    ms_per_step = dev_ms / args.steps
+    value = world * K / (ms_per_step * 1e-3)
+
+    # ---- e2e leg (host buffers through the public C ABI) ----
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    e2e_ms = 0.0
+    e2e_steps = max(3, args.steps // 2)
+    ew0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_ms += step_e2e()
+    barrier()
+    e2e_wall = allmax(time.perf_counter() - ew0)
+    e2e_ms = allmax(e2e_ms)
+    e2e_value = world * K / (max(e2e_ms / e2e_steps, e2e_wall / e2e_steps * 1e3) * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = fp64_peak()
+        achieved = gram_fl / (gram_ms * 1e-3) / 1e12
+        nreg = 2 * NF - 1
+        cpu_val, cpu_dt = cpu_baseline_windows(t, y, f, n, args.cpu_windows)
+        line = {
+            "metric": "windowed LS spectra/sec", "value": value, "unit": "windows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2_windowpsd", "samples_per_gpu": NSAMP, "nw": NW, "n": n,
+                       "noverlap": noverlap, "windows_per_gpu": K, "freqs": NF, "nreg": nreg, "window": "hanning",
+                       "l2": "inputs+Gram workspace (4.3 GB/step) larger than L2, no flush needed",
+                       "timing": "CUDA events on the library stream per call, summed over steps, max over ranks",
+                       "wall_ms_per_step": wall / args.steps * 1e3},
+            "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(2 * NSAMP * 8 + n * 8 + NF * 8),
+                    "d2h_bytes_per_step": int(NF * 8), "steps": e2e_steps,
+                    "api": "lpvs_ls_window_sums (host pointers, pinned)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "kernel": "k_gram<GRAM_CHAIN>",
+                         "flops_per_window": float(n) * nreg * (nreg + 1), "windows_per_launch": K,
+                         "gram_ms_per_step": gram_ms / args.steps, "gram_share_of_step": gram_ms / dev_ms if world == 1 else None,
+                         "peak_source": peak_src},
+            "cpu_baseline": {"value": cpu_val, "unit": "windows/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{args.cpu_windows} of {K} windows in {cpu_dt:.1f} s, oracle reference-literal "
+                                       "mode (N-rhs LU per window, numpy/OpenBLAS all threads)"},
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,9 @@ int lpvs_set_option(lpvs_ctx* ctx, int key, double value);
 int64_t lpvs_launch_count(const lpvs_ctx* ctx);
 /* device time [ms] and launch count of the Gram kernel(s) during the last API call (bench.py's roofline) */
 int lpvs_last_gram_timing(const lpvs_ctx* ctx, double* ms, int64_t* launches, double* flops);
+/* device time [ms] between the first and last operation the last compute call enqueued on the context's stream
+ * (H2D/D2H copies of the host-pointer entry points included) */
+int lpvs_last_call_ms(const lpvs_ctx* ctx, double* ms);
 /* cudaMalloc/cudaFree/cudaMemcpy wrappers so a host language without CUDA bindings can keep inputs resident */
 int lpvs_dev_alloc(lpvs_ctx* ctx, int64_t bytes, void** dptr);
 int lpvs_dev_free(lpvs_ctx* ctx, void* dptr);

@@ -65,6 +65,11 @@ class Context:
         self.lib.lpvs_last_gram_timing(self.h, C.byref(ms), C.byref(n), C.byref(fl))
         return ms.value, n.value, fl.value
 
+    def last_call_ms(self) -> float:
+        ms = C.c_double()
+        self.check(self.lib.lpvs_last_call_ms(self.h, C.byref(ms)))
+        return ms.value
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.lpvs_destroy(self.h)

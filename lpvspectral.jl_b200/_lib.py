@@ -34,6 +34,7 @@ _PROTOS = {
     "lpvs_set_option": (C.c_int, [_vp, C.c_int, C.c_double]),
     "lpvs_launch_count": (C.c_int64, [_vp]),
     "lpvs_last_gram_timing": (C.c_int, [_vp, _dp, _i64p, _dp]),
+    "lpvs_last_call_ms": (C.c_int, [_vp, _dp]),
     "lpvs_dev_alloc": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "lpvs_dev_free": (C.c_int, [_vp, _vp]),
     "lpvs_dev_upload": (C.c_int, [_vp, _vp, _vp, C.c_int64]),

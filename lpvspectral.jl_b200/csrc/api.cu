@@ -384,6 +384,8 @@ int lpvs_init(int device, lpvs_ctx** out) {
         delete c;
         return LPVS_E_CUDA;
     }
+    cudaEventCreate(&c->ev_call0);
+    cudaEventCreate(&c->ev_call1);
     *out = c;
     return LPVS_OK;
 }
@@ -395,6 +397,8 @@ void lpvs_destroy(lpvs_ctx* c) {
     for (auto& b : c->buf)
         if (b.p) cudaFree(b.p);
     for (auto e : c->ev) cudaEventDestroy(e);
+    cudaEventDestroy(c->ev_call0);
+    cudaEventDestroy(c->ev_call1);
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -421,6 +425,17 @@ int lpvs_last_gram_timing(const lpvs_ctx* c, double* ms, int64_t* launches, doub
     if (ms) *ms = c->gram_ms;
     if (launches) *launches = c->gram_launches;
     if (flops) *flops = c->gram_flops;
+    return LPVS_OK;
+}
+
+int lpvs_last_call_ms(const lpvs_ctx* c, double* ms) {
+    if (!c || !ms) return LPVS_E_BAD_ARG;
+    float m = 0.f;
+    if (cudaEventSynchronize(c->ev_call1) != cudaSuccess || cudaEventElapsedTime(&m, c->ev_call0, c->ev_call1) != cudaSuccess) {
+        cudaGetLastError();
+        return LPVS_E_CUDA;
+    }
+    *ms = m;
     return LPVS_OK;
 }
 
@@ -467,6 +482,7 @@ int64_t lpvs_window_count(int64_t N, int n, int noverlap) {
 int lpvs_gram_fourier(lpvs_ctx* c, const double* y, const double* t, int64_t N, const double* f, int Nf,
                       const double* W, double* G, double* b) {
     if (!c) return LPVS_E_BAD_ARG;
+    CallTimer call_timer(c);
     std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (!t || N <= 0 || !G) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
@@ -540,6 +556,7 @@ static int ls_solve_dev(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, c
 int lpvs_ls_spectral(lpvs_ctx* c, const double* y, const double* t, int64_t N, const double* f, int Nf,
                      const double* W, double lambda, double* x, int* info) {
     if (!c) return LPVS_E_BAD_ARG;
+    CallTimer call_timer(c);
     std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (!y || !t || !x || N <= 0) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
@@ -571,6 +588,7 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
                             int64_t N, const double* f, int Nf, const double* W, int n, int noverlap, double lambda,
                             int64_t k_begin, int64_t k_end, double* sums, int* info) {
     if (!c) return LPVS_E_BAD_ARG;
+    CallTimer call_timer(c);
     std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (info) *info = 0;
@@ -662,6 +680,7 @@ int lpvs_ls_window_sums(lpvs_ctx* c, int kind, const double* y, const double* u,
                         const double* f, int Nf, const double* W, int n, int noverlap, double lambda, int64_t k_begin,
                         int64_t k_end, double* sums, int* info) {
     if (!c) return LPVS_E_BAD_ARG;
+    CallTimer call_timer(c);
     if (!y || !t || N <= 0 || n <= 0) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
     if (noverlap < 0) noverlap = n >> 1;
     if (noverlap >= n) return fail(c, LPVS_E_BAD_ARG, "noverlap must be < n");

@@ -43,11 +43,24 @@ struct lpvs_ctx {
     double gram_ms = 0.0;
     int64_t gram_launches = 0;
     double gram_flops = 0.0;
+    cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
+    int call_depth = 0;
 };
 
 namespace lpvs {
 
 int fail(lpvs_ctx* c, int code, const char* fmt, ...);
+
+// brackets a public compute call with events on the context stream (outermost call only)
+struct CallTimer {
+    lpvs_ctx* c;
+    explicit CallTimer(lpvs_ctx* ctx) : c(ctx) {
+        if (c && c->call_depth++ == 0) cudaEventRecord(c->ev_call0, c->st);
+    }
+    ~CallTimer() {
+        if (c && --c->call_depth == 0) cudaEventRecord(c->ev_call1, c->st);
+    }
+};
 
 #define LPVS_CU(ctx, call)                                                                      \
     do {                                                                                        \
