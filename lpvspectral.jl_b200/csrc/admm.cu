@@ -1,14 +1,660 @@
-// placeholder until the ADMM loop lands (next commit)
+// Device-resident ADMM (src/lasso.jl:136-171) for ls_sparse_spectral / ls_sparse_spectral_lpv.
+//
+// Setup (once): Gram G (fused synthesis kernel), M = (G + I/mu)^-1 from the blocked Cholesky factor (potrf+potri).
+// Loop (persistent cooperative kernel, no host sync): per iteration
+//     x  = M * rhs,          rhs = A'y + (z-u)/mu   (LeastSquares)   or   (z-u)/mu - q   (Quadratic, Q13)
+//     z  = prox_{mu g}(x+u),  u += x - z,  ||x-z||_2 checked on device every iteration (Q12)
+// The x-update is an HBM-bound GEMV over the full symmetric M (8*Np^2 bytes/iteration); the prox, the dual
+// update, the next right-hand side and the residual partial sums are fused into the GEMV epilogue of the CTA that
+// owns the rows, so element-wise prox operators need ONE grid barrier per iteration.  Group-L2 and top-r (IndBallL0)
+// need the whole x first: they run as a second, tiny phase after a barrier.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "ctx.h"
-extern "C" {
-int lpvs_admm_create_fourier(lpvs_ctx* c, const double*, const double*, int64_t, const double*, int, const double*, int, double, double, const double*, int, double, lpvs_admm**) { return lpvs::fail(c, LPVS_E_UNSUPPORTED, "admm not built yet"); }
-int lpvs_admm_create_lpv(lpvs_ctx* c, const double*, const double*, const double*, int64_t, const double*, int, int, int, int, double, double, lpvs_admm**) { return lpvs::fail(c, LPVS_E_UNSUPPORTED, "admm not built yet"); }
-int lpvs_admm_run(lpvs_admm*, int64_t, double, int64_t*, double*, int*) { return LPVS_E_UNSUPPORTED; }
-int lpvs_admm_size(const lpvs_admm*) { return 0; }
-int lpvs_admm_get(lpvs_admm*, double*, double*) { return LPVS_E_UNSUPPORTED; }
-int lpvs_admm_result(lpvs_admm*, double*) { return LPVS_E_UNSUPPORTED; }
-int lpvs_admm_last_timing(const lpvs_admm*, double*, double*) { return LPVS_E_UNSUPPORTED; }
-void lpvs_admm_free(lpvs_admm*) {}
-int lpvs_ls_sparse_spectral(lpvs_ctx* c, const double*, const double*, int64_t, const double*, int, const double*, int, double, double, int, double, int64_t, double, double*, int64_t*, double*) { return lpvs::fail(c, LPVS_E_UNSUPPORTED, "admm not built yet"); }
-int lpvs_ls_sparse_spectral_lpv(lpvs_ctx* c, const double*, const double*, const double*, int64_t, const double*, int, int, int, int, double, double, int64_t, double, double*, int64_t*, double*) { return lpvs::fail(c, LPVS_E_UNSUPPORTED, "admm not built yet"); }
+
+namespace cg = cooperative_groups;
+
+namespace lpvs {
+
+constexpr int ADMM_THREADS = 512;
+constexpr int ADMM_WARPS = ADMM_THREADS / 32;
+
+struct AdmmArgs {
+    const double* M;
+    int Np;
+    const double* q;
+    double *x, *z, *u, *v;  // Np each (v = x+u scratch for non-elementwise prox)
+    double* r;              // [2][Np] right-hand side, double buffered
+    double mu;
+    int quad;
+    int prox;
+    double pparam;
+    // group prox: members of group g are gmem[goff[g] .. goff[g+1])
+    const int* goff;
+    const int* gmem;
+    int ngroups;
+    double* part;  // [2][grid] residual partial sums
+    long long max_iters;
+    double tol;
+    int check_every;
+    int rbuf0;  // which r buffer holds the current rhs at entry
+    // outputs
+    long long* iters_out;
+    double* res_out;
+    int* conv_out;
+    int* rbuf_out;
+    // ball-L0 scratch
+    unsigned long long* sel_key;
+};
+
+__device__ __forceinline__ double prox_elem(int kind, double v, double gl, double thr0) {
+    if (kind == LPVS_PROX_L1) {  // sign(v) max(|v| - mu*lambda, 0)
+        double a = fabs(v) - gl;
+        return a > 0.0 ? copysign(a, v) : 0.0;
+    }
+    // NormL0: keep v iff |v| > sqrt(2 mu lambda)
+    return fabs(v) > thr0 ? v : 0.0;
 }
+
+__device__ __forceinline__ double next_rhs(const AdmmArgs& a, int i, double z, double u) {
+    double w = (z - u) / a.mu;
+    return a.quad ? (w - a.q[i]) : (a.q[i] + w);
+}
+
+template <bool STREAM>
+__device__ __forceinline__ double2 ldm(const double* p) {
+    return STREAM ? __ldcs(reinterpret_cast<const double2*>(p)) : __ldg(reinterpret_cast<const double2*>(p));
+}
+
+// STREAM: M does not fit in L2 -> evict-first loads; otherwise let L2 keep it across iterations
+template <bool STREAM>
+__global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const __grid_constant__ AdmmArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) double sm[];
+    double* rs = sm;                      // Np
+    double* red = sm + a.Np;              // [rows_max][ADMM_WARPS]
+    __shared__ double wsum[ADMM_WARPS];
+    __shared__ double s_nxz;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nblocks = gridDim.x, b = blockIdx.x;
+    const int Np = a.Np;
+    // contiguous row ownership
+    const int base = Np / nblocks, extra = Np % nblocks;
+    const int r0 = b * base + min(b, extra);
+    const int nrows = base + (b < extra ? 1 : 0);
+    // column chunks of 64 handled by this warp: chunk c = w, w+16, ...
+    const int nchunks = Np >> 6;  // Np is a multiple of 128
+    const bool elementwise = (a.prox == LPVS_PROX_L1 || a.prox == LPVS_PROX_L0);
+    const double gl = a.mu * a.pparam;
+    const double thr0 = sqrt(2.0 * a.mu * a.pparam);
+
+    int cur = a.rbuf0;
+    long long it = 0;
+    int converged = 0;
+    double nxz = 0.0;
+    for (; it < a.max_iters; it++) {
+        const double* rc = a.r + (long long)cur * Np;
+        double* rn = a.r + (long long)(cur ^ 1) * Np;
+        for (int i = tid; i < Np; i += ADMM_THREADS) rs[i] = __ldcg(rc + i);
+        __syncthreads();
+        // ---- x rows = M[rows,:] * r, two rows per pass, column chunks striped over the warps ----
+        for (int rr = 0; rr < nrows; rr += 2) {
+            const bool two = rr + 1 < nrows;
+            const double* m0 = a.M + (long long)(r0 + rr) * Np + 2 * lane;
+            const double* m1 = two ? m0 + Np : m0;
+            double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+            int c = w;
+            for (; c + 3 * ADMM_WARPS < nchunks; c += 4 * ADMM_WARPS) {
+                double2 a0 = ldm<STREAM>(m0 + 64 * c);
+                double2 a1 = ldm<STREAM>(m0 + 64 * (c + ADMM_WARPS));
+                double2 a2 = ldm<STREAM>(m0 + 64 * (c + 2 * ADMM_WARPS));
+                double2 a3 = ldm<STREAM>(m0 + 64 * (c + 3 * ADMM_WARPS));
+                double2 b0 = ldm<STREAM>(m1 + 64 * c);
+                double2 b1 = ldm<STREAM>(m1 + 64 * (c + ADMM_WARPS));
+                double2 b2 = ldm<STREAM>(m1 + 64 * (c + 2 * ADMM_WARPS));
+                double2 b3 = ldm<STREAM>(m1 + 64 * (c + 3 * ADMM_WARPS));
+                double2 v0 = *reinterpret_cast<const double2*>(rs + 64 * c + 2 * lane);
+                double2 v1 = *reinterpret_cast<const double2*>(rs + 64 * (c + ADMM_WARPS) + 2 * lane);
+                double2 v2 = *reinterpret_cast<const double2*>(rs + 64 * (c + 2 * ADMM_WARPS) + 2 * lane);
+                double2 v3 = *reinterpret_cast<const double2*>(rs + 64 * (c + 3 * ADMM_WARPS) + 2 * lane);
+                s0 = fma(a0.x, v0.x, s0); t0 = fma(a0.y, v0.y, t0);
+                s1 = fma(b0.x, v0.x, s1); t1 = fma(b0.y, v0.y, t1);
+                s0 = fma(a1.x, v1.x, s0); t0 = fma(a1.y, v1.y, t0);
+                s1 = fma(b1.x, v1.x, s1); t1 = fma(b1.y, v1.y, t1);
+                s0 = fma(a2.x, v2.x, s0); t0 = fma(a2.y, v2.y, t0);
+                s1 = fma(b2.x, v2.x, s1); t1 = fma(b2.y, v2.y, t1);
+                s0 = fma(a3.x, v3.x, s0); t0 = fma(a3.y, v3.y, t0);
+                s1 = fma(b3.x, v3.x, s1); t1 = fma(b3.y, v3.y, t1);
+            }
+            for (; c < nchunks; c += ADMM_WARPS) {
+                double2 a0 = ldm<STREAM>(m0 + 64 * c);
+                double2 b0 = ldm<STREAM>(m1 + 64 * c);
+                double2 v0 = *reinterpret_cast<const double2*>(rs + 64 * c + 2 * lane);
+                s0 = fma(a0.x, v0.x, s0); t0 = fma(a0.y, v0.y, t0);
+                s1 = fma(b0.x, v0.x, s1); t1 = fma(b0.y, v0.y, t1);
+            }
+            s0 += t0;
+            s1 += t1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            }
+            if (lane == 0) {
+                red[rr * ADMM_WARPS + w] = s0;
+                if (two) red[(rr + 1) * ADMM_WARPS + w] = s1;
+            }
+        }
+        __syncthreads();
+        // ---- epilogue for the owned rows ----
+        double d2 = 0.0;
+        if (tid < nrows) {
+            const int i = r0 + tid;
+            double xi = 0.0;
+#pragma unroll
+            for (int k = 0; k < ADMM_WARPS; k++) xi += red[tid * ADMM_WARPS + k];
+            a.x[i] = xi;
+            double ui = a.u[i];
+            double vi = xi + ui;
+            if (elementwise) {
+                double zi = prox_elem(a.prox, vi, gl, thr0);
+                double di = xi - zi;
+                ui += di;
+                a.z[i] = zi;
+                a.u[i] = ui;
+                rn[i] = next_rhs(a, i, zi, ui);
+                d2 = di * di;
+            } else {
+                a.v[i] = vi;
+            }
+        }
+        if (!elementwise) {
+            grid.sync();
+            d2 = 0.0;
+            if (a.prox == LPVS_PROX_GROUP_L2) {
+                // warp per group: z_g = max(0, 1 - mu*lambda/||v_g||) v_g ; ungrouped entries stay z = 0
+                for (int g = b * ADMM_WARPS + w; g <= a.ngroups; g += nblocks * ADMM_WARPS) {
+                    const int lo = a.goff[g], hi = (g < a.ngroups) ? a.goff[g + 1] : a.goff[g];
+                    if (g == a.ngroups) {
+                        // pseudo group: entries not covered by any group (Q16) -> z = 0
+                        const int lo2 = a.goff[a.ngroups], hi2 = a.goff[a.ngroups + 1];
+                        for (int m = lo2 + lane; m < hi2; m += 32) {
+                            int i = a.gmem[m];
+                            double xi = __ldcg(a.x + i), ui = a.u[i];
+                            double di = xi;
+                            ui += di;
+                            a.z[i] = 0.0;
+                            a.u[i] = ui;
+                            rn[i] = next_rhs(a, i, 0.0, ui);
+                            d2 += di * di;
+                        }
+                        continue;
+                    }
+                    double ss = 0.0;
+                    for (int m = lo + lane; m < hi; m += 32) {
+                        double vi = __ldcg(a.v + a.gmem[m]);
+                        ss += vi * vi;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                    double nrm = sqrt(ss);
+                    double scale = nrm > 0.0 ? fmax(0.0, 1.0 - gl / nrm) : 0.0;
+                    for (int m = lo + lane; m < hi; m += 32) {
+                        int i = a.gmem[m];
+                        double vi = __ldcg(a.v + i), xi = __ldcg(a.x + i), ui = a.u[i];
+                        double zi = scale * vi;
+                        double di = xi - zi;
+                        ui += di;
+                        a.z[i] = zi;
+                        a.u[i] = ui;
+                        rn[i] = next_rhs(a, i, zi, ui);
+                        d2 += di * di;
+                    }
+                }
+            } else {  // LPVS_PROX_BALL_L0: keep the r largest |v| (ties -> lower index); block 0 only
+                if (b == 0) {
+                    __shared__ unsigned hist[256];
+                    __shared__ unsigned long long s_prefix;
+                    __shared__ unsigned s_want;
+                    const unsigned rkeep = (unsigned)a.pparam;
+                    if (tid == 0) {
+                        s_prefix = 0ull;
+                        s_want = rkeep;
+                    }
+                    __syncthreads();
+                    // radix select (MSB first) of the rkeep-th largest key = bits(|v|)
+                    for (int pass = 7; pass >= 0 && rkeep > 0 && rkeep < (unsigned)Np; pass--) {
+                        for (int k = tid; k < 256; k += ADMM_THREADS) hist[k] = 0;
+                        __syncthreads();
+                        const unsigned long long hi_mask = pass == 7 ? 0ull : (~0ull << (8 * (pass + 1)));
+                        const unsigned long long prefix = s_prefix;
+                        for (int i = tid; i < Np; i += ADMM_THREADS) {
+                            unsigned long long key = (unsigned long long)__double_as_longlong(fabs(__ldcg(a.v + i)));
+                            if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255], 1u);
+                        }
+                        __syncthreads();
+                        if (tid == 0) {
+                            unsigned want = s_want, accn = 0;
+                            int d = 255;
+                            for (; d > 0; d--) {
+                                if (accn + hist[d] >= want) break;
+                                accn += hist[d];
+                            }
+                            s_want = want - accn;
+                            s_prefix = prefix | ((unsigned long long)d << (8 * pass));
+                        }
+                        __syncthreads();
+                    }
+                    const unsigned long long kth = s_prefix;  // key of the r-th largest
+                    unsigned ties_to_take = s_want;           // how many entries equal to kth are kept (lowest index)
+                    // serial-by-chunk tie handling: thread 0 walks ties in index order (rare path, Np small)
+                    __shared__ int s_tie_cut;
+                    if (tid == 0) {
+                        int cut = -1;
+                        if (rkeep > 0 && rkeep < (unsigned)Np) {
+                            unsigned seen = 0;
+                            for (int i = 0; i < Np && seen < ties_to_take; i++) {
+                                unsigned long long key =
+                                    (unsigned long long)__double_as_longlong(fabs(__ldcg(a.v + i)));
+                                if (key == kth) {
+                                    seen++;
+                                    cut = i;
+                                }
+                            }
+                        }
+                        s_tie_cut = cut;
+                    }
+                    __syncthreads();
+                    const int cut = s_tie_cut;
+                    for (int i = tid; i < Np; i += ADMM_THREADS) {
+                        double vi = __ldcg(a.v + i), xi = __ldcg(a.x + i), ui = a.u[i];
+                        unsigned long long key = (unsigned long long)__double_as_longlong(fabs(vi));
+                        bool keep;
+                        if (rkeep == 0) keep = false;
+                        else if (rkeep >= (unsigned)Np) keep = true;
+                        else keep = key > kth || (key == kth && i <= cut);
+                        double zi = keep ? vi : 0.0;
+                        double di = xi - zi;
+                        ui += di;
+                        a.z[i] = zi;
+                        a.u[i] = ui;
+                        rn[i] = next_rhs(a, i, zi, ui);
+                        d2 += di * di;
+                    }
+                }
+            }
+        }
+        // ---- residual partial of this CTA (fixed-order tree) ----
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        if (lane == 0) wsum[w] = d2;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int k = 0; k < ADMM_WARPS; k++) s += wsum[k];
+            a.part[(it & 1) * nblocks + b] = s;
+        }
+        grid.sync();
+        cur ^= 1;
+        if ((it + 1) % a.check_every == 0 || it + 1 == a.max_iters) {
+            if (tid == 0) {
+                double s = 0.0;
+                for (int k = 0; k < nblocks; k++) s += __ldcg(a.part + (it & 1) * nblocks + k);
+                s_nxz = sqrt(s);
+            }
+            __syncthreads();
+            nxz = s_nxz;
+            if (nxz < a.tol) {
+                converged = 1;
+                it++;
+                break;
+            }
+        }
+    }
+    if (b == 0 && tid == 0) {
+        *a.iters_out = it;
+        *a.res_out = nxz;
+        *a.conv_out = converged;
+        *a.rbuf_out = cur;
+    }
+}
+
+__global__ void k_admm_init(const double* __restrict__ q, const double* __restrict__ x0, int Np, double mu,
+                            int quad, double* x, double* z, double* u, double* r) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np) return;
+    double v = x0 ? x0[i] : 0.0;
+    x[i] = v;
+    z[i] = v;  // z = copy(x), u = 0 (src/lasso.jl:146-147)
+    u[i] = 0.0;
+    double w = v / mu;
+    r[i] = quad ? (w - q[i]) : (q[i] + w);
+}
+
+// internal vector -> reference order (Fourier: cos block then -sin block; LPV: column-major [Re|Im] un-permuted)
+__global__ void k_gather_vec(const double* __restrict__ xin, int nref, int half, int zero_first,
+                             double* __restrict__ out) {
+    // reference index j: j < half -> real part of complex column j; else imaginary part of column j-half+zero_first
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nref) return;
+    int cc, part;
+    if (j < half) {
+        cc = j;
+        part = 0;
+    } else {
+        cc = j - half + zero_first;
+        part = 1;
+    }
+    out[j] = xin[(cc >> 6) * 128 + part * 64 + (cc & 63)];
+}
+
+}  // namespace lpvs
+
+using namespace lpvs;
+
+struct lpvs_admm {
+    lpvs_ctx* ctx = nullptr;
+    int kind = 0;  // 0 fourier, 1 lpv
+    int Np = 0, ncc = 0, zero_first = 0, nref = 0, half = 0;
+    int prox = 0;
+    double pparam = 0.0, mu = 0.05;
+    int quad = 0;
+    // LPV bookkeeping for the result permutation
+    int lpv_nf = 0, lpv_nvv = 0;
+    double* M = nullptr;
+    double* vecs = nullptr;  // q, x, z, u, v, r[2]
+    int* goff = nullptr;
+    int* gmem = nullptr;
+    int ngroups = 0;
+    double* part = nullptr;
+    long long* d_iters = nullptr;  // [iters][res as double bits][conv][rbuf] packed below
+    double* d_res = nullptr;
+    int* d_flags = nullptr;
+    unsigned long long* sel = nullptr;
+    int rbuf = 0;
+    int grid = 0;
+    int64_t iters_total = 0;
+    double residual = INFINITY;
+    int converged = 0;
+    double last_ms = 0.0;
+    int64_t last_iters = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+namespace lpvs {
+
+static void admm_release(lpvs_admm* h) {
+    if (!h) return;
+    cudaSetDevice(h->ctx->device);
+    cudaStreamSynchronize(h->ctx->st);
+    cudaFree(h->M);
+    cudaFree(h->vecs);
+    cudaFree(h->goff);
+    cudaFree(h->gmem);
+    cudaFree(h->part);
+    cudaFree(h->d_iters);
+    cudaFree(h->d_res);
+    cudaFree(h->d_flags);
+    cudaFree(h->sel);
+    if (h->e0) cudaEventDestroy(h->e0);
+    if (h->e1) cudaEventDestroy(h->e1);
+    delete h;
+}
+
+static size_t admm_smem(int Np, int rows_max) { return sizeof(double) * ((size_t)Np + (size_t)rows_max * ADMM_WARPS); }
+
+// Factor (G + I/mu), invert, allocate loop state.  d_G: Np x Np lower tiles (consumed), d_q: Np.
+int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q, const double* d_x0) {
+    const int Np = h->Np, nb = Np / TB;
+    const long long NN = (long long)Np * Np;
+    h->M = d_G;  // owned by the handle from here on (freed by admm_release on any failure)
+    // M = (G + I/mu)^-1 in place of G
+    double* Y = nullptr;
+    if (cudaMalloc(&Y, sizeof(double) * NN) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, LPVS_E_NOMEM, "out of device memory (inverse workspace %lld MB)", (long long)(NN * 8 >> 20));
+    }
+    CholArgs ca{};
+    ca.G = d_G;
+    ca.strideG = NN;
+    ca.Y = Y;
+    ca.strideY = NN;
+    ca.Linv = ws<double>(c, BUF_LINV, (size_t)nb * TB * TB);
+    ca.strideLinv = (long long)nb * TB * TB;
+    ca.info = ws<int>(c, BUF_INFO, 1);
+    ca.Np = Np;
+    ca.nb = nb;
+    if (!ca.Linv || !ca.info) {
+        cudaFree(Y);
+        return fail(c, LPVS_E_NOMEM, "out of device memory (factor workspace)");
+    }
+    cudaMemsetAsync(ca.info, 0, sizeof(int), c->st);
+    launch_diag_prepare(d_G, NN, Np, h->ncc, h->zero_first, nullptr, 1.0 / h->mu, 1, c->st);
+    c->launches += 1 + potrf(ca, 1, c->sms, c->st);
+    int pinfo = 0;
+    cudaMemcpyAsync(&pinfo, ca.info, sizeof(int), cudaMemcpyDeviceToHost, c->st);
+    cudaError_t e = cudaStreamSynchronize(c->st);
+    if (e != cudaSuccess) {
+        cudaFree(Y);
+        return fail(c, LPVS_E_CUDA, "factorisation failed: %s", cudaGetErrorString(e));
+    }
+    if (pinfo) {
+        cudaFree(Y);
+        return fail(c, LPVS_E_NOT_SPD, "Cholesky breakdown of (G + I/mu) at internal pivot %d", pinfo);
+    }
+    c->launches += potri(ca, 1, c->st);
+    e = cudaStreamSynchronize(c->st);
+    cudaFree(Y);
+    if (e != cudaSuccess) return fail(c, LPVS_E_CUDA, "inverse failed: %s", cudaGetErrorString(e));
+    // loop state
+    if (cudaMalloc(&h->vecs, sizeof(double) * 7 * Np) != cudaSuccess) return fail(c, LPVS_E_NOMEM, "out of memory");
+    double* q = h->vecs;
+    LPVS_CU(c, cudaMemcpyAsync(q, d_q, sizeof(double) * Np, cudaMemcpyDeviceToDevice, c->st));
+    // cooperative grid: one CTA per SM, never more CTAs than rows/2
+    int maxb = 0;
+    int grid = std::min(c->sms, std::max(1, Np / 8));
+    int rows_max = (Np + grid - 1) / grid;
+    size_t smem = admm_smem(Np, rows_max + 1);
+    if (smem > 220 * 1024) return fail(c, LPVS_E_UNSUPPORTED, "ADMM problem too large for the resident rhs (Np=%d)", Np);
+    LPVS_CU(c, cudaFuncSetAttribute(k_admm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LPVS_CU(c, cudaFuncSetAttribute(k_admm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LPVS_CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&maxb, k_admm<true>, ADMM_THREADS, smem));
+    if (maxb < 1) return fail(c, LPVS_E_UNSUPPORTED, "ADMM kernel does not fit on an SM");
+    h->grid = grid;
+    LPVS_CU(c, cudaMalloc(&h->part, sizeof(double) * 2 * grid));
+    LPVS_CU(c, cudaMalloc(&h->d_iters, sizeof(long long)));
+    LPVS_CU(c, cudaMalloc(&h->d_res, sizeof(double)));
+    LPVS_CU(c, cudaMalloc(&h->d_flags, sizeof(int) * 2));
+    LPVS_CU(c, cudaMalloc(&h->sel, sizeof(unsigned long long) * 4));
+    LPVS_CU(c, cudaEventCreate(&h->e0));
+    LPVS_CU(c, cudaEventCreate(&h->e1));
+    k_admm_init<<<(Np + 255) / 256, 256, 0, c->st>>>(q, d_x0, Np, h->mu, h->quad, h->vecs + Np, h->vecs + 2 * Np,
+                                                    h->vecs + 3 * Np, h->vecs + 5 * Np);
+    c->launches++;
+    h->rbuf = 0;
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    return LPVS_OK;
+}
+
+}  // namespace lpvs
+
+extern "C" {
+
+int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_done, double* residual,
+                  int* converged) {
+    if (!h) return LPVS_E_BAD_ARG;
+    lpvs_ctx* c = h->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    if (iters_done) *iters_done = 0;
+    if (max_iters <= 0 || h->converged) {
+        if (residual) *residual = h->residual;
+        if (converged) *converged = h->converged;
+        return LPVS_OK;
+    }
+    const int Np = h->Np;
+    AdmmArgs a{};
+    a.M = h->M;
+    a.Np = Np;
+    a.q = h->vecs;
+    a.x = h->vecs + Np;
+    a.z = h->vecs + 2 * Np;
+    a.u = h->vecs + 3 * Np;
+    a.v = h->vecs + 4 * Np;
+    a.r = h->vecs + 5 * Np;
+    a.mu = h->mu;
+    a.quad = h->quad;
+    a.prox = h->prox;
+    a.pparam = h->pparam;
+    a.goff = h->goff;
+    a.gmem = h->gmem;
+    a.ngroups = h->ngroups;
+    a.part = h->part;
+    a.max_iters = max_iters;
+    a.tol = tol;
+    a.check_every = c->admm_check_every;
+    a.rbuf0 = h->rbuf;
+    a.iters_out = h->d_iters;
+    a.res_out = h->d_res;
+    a.conv_out = h->d_flags;
+    a.rbuf_out = h->d_flags + 1;
+    a.sel_key = h->sel;
+    int rows_max = (Np + h->grid - 1) / h->grid;
+    size_t smem = admm_smem(Np, rows_max + 1);
+    void* args[] = {&a};
+    LPVS_CU(c, cudaEventRecord(h->e0, c->st));
+    const bool stream = 8.0 * Np * (double)Np > 96.0 * 1024 * 1024;  // M larger than what L2 can keep
+    void* kfn = stream ? (void*)k_admm<true> : (void*)k_admm<false>;
+    LPVS_CU(c, cudaLaunchCooperativeKernel(kfn, dim3(h->grid), dim3(ADMM_THREADS), args, smem, c->st));
+    LPVS_CU(c, cudaEventRecord(h->e1, c->st));
+    c->launches++;
+    long long its = 0;
+    double res = 0.0;
+    int flags[2] = {0, 0};
+    LPVS_CU(c, cudaMemcpyAsync(&its, h->d_iters, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaMemcpyAsync(&res, h->d_res, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaMemcpyAsync(flags, h->d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->e0, h->e1);
+    h->last_ms = ms;
+    h->last_iters = its;
+    h->iters_total += its;
+    h->residual = res;
+    h->converged = flags[0];
+    h->rbuf = flags[1];
+    if (iters_done) *iters_done = its;
+    if (residual) *residual = res;
+    if (converged) *converged = flags[0];
+    return LPVS_OK;
+}
+
+int lpvs_admm_size(const lpvs_admm* h) { return h ? h->nref : 0; }
+
+int lpvs_admm_get(lpvs_admm* h, double* x, double* z) {
+    if (!h) return LPVS_E_BAD_ARG;
+    lpvs_ctx* c = h->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    double* tmp = ws<double>(c, BUF_X, (size_t)2 * h->nref);
+    if (!tmp) return fail(c, LPVS_E_NOMEM, "out of device memory");
+    const int Np = h->Np;
+    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(h->vecs + Np, h->nref, h->half, h->zero_first, tmp);
+    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(h->vecs + 2 * Np, h->nref, h->half, h->zero_first,
+                                                           tmp + h->nref);
+    c->launches += 2;
+    if (x) LPVS_CU(c, cudaMemcpyAsync(x, tmp, sizeof(double) * h->nref, cudaMemcpyDeviceToHost, c->st));
+    if (z) LPVS_CU(c, cudaMemcpyAsync(z, tmp + h->nref, sizeof(double) * h->nref, cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    if (h->kind == 1) {
+        // reference order of the LPV ADMM vector is the group-permuted one (src/lasso.jl:47-50):
+        // position p = f*2Nvv + k  <->  un-permuted f + k*Nf, k = 0..2Nvv-1 over [Re | Im] columns
+        const int Nf = h->lpv_nf, n2 = h->nref;
+        std::vector<double> t((size_t)n2);
+        for (double* vec : {x, z}) {
+            if (!vec) continue;
+            for (int j = 0; j < n2; j++) {
+                int f = j % Nf, k = j / Nf;
+                t[(size_t)f * (n2 / Nf) + k] = vec[j];
+            }
+            std::copy(t.begin(), t.end(), vec);
+        }
+    }
+    return LPVS_OK;
+}
+
+int lpvs_admm_result(lpvs_admm* h, double* out) {
+    if (!h || !out) return LPVS_E_BAD_ARG;
+    lpvs_ctx* c = h->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    // complex column cc -> (z_re, z_im); Fourier zero frequency has no imaginary coefficient
+    const int Np = h->Np, ncx = h->half;
+    double* tmp = ws<double>(c, BUF_X, (size_t)2 * h->nref + 2);
+    if (!tmp) return fail(c, LPVS_E_NOMEM, "out of device memory");
+    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(h->vecs + 2 * Np, h->nref, h->half, h->zero_first, tmp);
+    c->launches++;
+    std::vector<double> z((size_t)h->nref);
+    LPVS_CU(c, cudaMemcpyAsync(z.data(), tmp, sizeof(double) * h->nref, cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    for (int k = 0; k < ncx; k++) {
+        out[2 * k] = z[k];
+        int j = ncx + k - h->zero_first;
+        out[2 * k + 1] = (h->zero_first && k == 0) ? 0.0 : z[j];
+    }
+    return LPVS_OK;
+}
+
+int lpvs_admm_last_timing(const lpvs_admm* h, double* ms, double* bytes_per_iter) {
+    if (!h) return LPVS_E_BAD_ARG;
+    if (ms) *ms = h->last_ms;
+    if (bytes_per_iter) *bytes_per_iter = 8.0 * (double)h->Np * (double)h->Np;
+    return LPVS_OK;
+}
+
+void lpvs_admm_free(lpvs_admm* h) {
+    if (!h) return;
+    lpvs_ctx* c = h->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    admm_release(h);
+}
+
+}  // extern "C"
+
+namespace lpvs {
+lpvs_admm* admm_new(lpvs_ctx* c) {
+    lpvs_admm* h = new lpvs_admm();
+    h->ctx = c;
+    return h;
+}
+void admm_delete(lpvs_admm* h) { admm_release(h); }
+void admm_set_problem(lpvs_admm* h, int kind, int Np, int ncc, int zero_first, int nref, int half, int prox,
+                      double pparam, double mu, int quad, int lpv_nf, int lpv_nvv) {
+    h->kind = kind;
+    h->Np = Np;
+    h->ncc = ncc;
+    h->zero_first = zero_first;
+    h->nref = nref;
+    h->half = half;
+    h->prox = prox;
+    h->pparam = pparam;
+    h->mu = mu;
+    h->quad = quad;
+    h->lpv_nf = lpv_nf;
+    h->lpv_nvv = lpv_nvv;
+}
+int admm_set_groups(lpvs_ctx* c, lpvs_admm* h, const std::vector<int>& goff, const std::vector<int>& gmem) {
+    h->ngroups = (int)goff.size() - 2;
+    LPVS_CU(c, cudaMalloc(&h->goff, sizeof(int) * goff.size()));
+    LPVS_CU(c, cudaMalloc(&h->gmem, sizeof(int) * std::max<size_t>(1, gmem.size())));
+    LPVS_CU(c, cudaMemcpyAsync(h->goff, goff.data(), sizeof(int) * goff.size(), cudaMemcpyHostToDevice, c->st));
+    if (!gmem.empty())
+        LPVS_CU(c, cudaMemcpyAsync(h->gmem, gmem.data(), sizeof(int) * gmem.size(), cudaMemcpyHostToDevice, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    return LPVS_OK;
+}
+}  // namespace lpvs

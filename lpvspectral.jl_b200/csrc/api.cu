@@ -215,7 +215,7 @@ __global__ void k_window_accum(int kind, const double* __restrict__ X, long long
 // ---------------------------------------------------------------------------------------------------------
 // single-problem Gram (with sample splitting) and factor/solve
 // ---------------------------------------------------------------------------------------------------------
-static void fill_basis_args(const FourierPlan& pl, GramArgs& g) {
+void fill_basis_args(const FourierPlan& pl, GramArgs& g) {
     g.ncc = pl.Nf;
     g.nblk = pl.nblk;
     g.f = pl.d_f;
@@ -341,7 +341,7 @@ int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, doub
     return LPVS_OK;
 }
 
-static int upload(lpvs_ctx* c, int slot, const double* h, int64_t n, double** d) {
+int upload(lpvs_ctx* c, int slot, const double* h, int64_t n, double** d) {
     *d = nullptr;
     if (!h) return LPVS_OK;
     double* p = ws<double>(c, slot, (size_t)n);
@@ -515,7 +515,10 @@ int lpvs_gram_fourier(lpvs_ctx* c, const double* y, const double* t, int64_t N, 
 }
 
 // shared by lpvs_ls_spectral and the ADMM init path: solve one ridge LS on device arrays, x internal in BUF_B
-static int ls_solve_dev(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const double* d_y, const double* d_u,
+}  // extern "C"
+
+namespace lpvs {
+int ls_solve_dev(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const double* d_y, const double* d_u,
                         const double* d_W, int64_t N, int nrhs, double ridge, bool allow_jitter, double** d_x,
                         int* info) {
     const long long Np = pl.Np;
@@ -552,6 +555,28 @@ static int ls_solve_dev(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, c
     *d_x = d_B;
     return LPVS_OK;
 }
+void reduce_parts(lpvs_ctx* c, double* out, const double* parts, long long count, long long stride, int nparts,
+                  int accumulate) {
+    k_reduce_parts<<<(unsigned)((count + 255) / 256), 256, 0, c->st>>>(out, parts, count, stride, nparts, accumulate);
+    c->launches++;
+}
+void launch_gather_ref(lpvs_ctx* c, const double* G, const double* B, int Np, int half, int zero_first, int nref,
+                       double* Gout, double* bout) {
+    dim3 grid((nref + 127) / 128, nref);
+    k_gather_ref<<<grid, 128, 0, c->st>>>(G, B, Np, half, zero_first, nref, Gout, bout);
+    c->launches++;
+}
+void launch_x_to_complex(lpvs_ctx* c, const double* X, int Np, int ncx, int zero_first, int nrhs, double* out) {
+    k_x_to_complex<<<(ncx + 127) / 128, 128, 0, c->st>>>(X, Np, ncx, zero_first, nrhs, out);
+    c->launches++;
+}
+void launch_scatter_ref_vec(lpvs_ctx* c, const double* xin, int half, int zero_first, int nref, int Np, double* xout) {
+    k_scatter_ref_vec<<<(Np + 255) / 256, 256, 0, c->st>>>(xin, half, zero_first, nref, Np, xout);
+    c->launches++;
+}
+}  // namespace lpvs
+
+extern "C" {
 
 int lpvs_ls_spectral(lpvs_ctx* c, const double* y, const double* t, int64_t N, const double* f, int Nf,
                      const double* W, double lambda, double* x, int* info) {

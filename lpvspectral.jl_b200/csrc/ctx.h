@@ -102,4 +102,39 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
 int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, double* d_B, int nrhs, double ridge,
                  int nproblems, int* info_host /* nproblems or null */);
 
+// shared helpers (api.cu)
+int upload(lpvs_ctx* c, int slot, const double* h, int64_t n, double** d);
+void fill_basis_args(const FourierPlan& pl, GramArgs& g);
+// ridge LS on device arrays; on return *d_x points at the internal-layout solution ([nrhs][Np], BUF_B)
+int ls_solve_dev(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const double* d_y, const double* d_u,
+                 const double* d_W, int64_t N, int nrhs, double ridge, bool allow_jitter, double** d_x, int* info);
+// out[i] (+)= sum_p parts[p*stride + i]
+void reduce_parts(lpvs_ctx* c, double* out, const double* parts, long long count, long long stride, int nparts,
+                  int accumulate);
+void launch_gather_ref(lpvs_ctx* c, const double* G, const double* B, int Np, int half, int zero_first, int nref,
+                       double* Gout, double* bout);
+void launch_x_to_complex(lpvs_ctx* c, const double* X, int Np, int ncx, int zero_first, int nrhs, double* out);
+void launch_scatter_ref_vec(lpvs_ctx* c, const double* xin, int half, int zero_first, int nref, int Np, double* xout);
+
+// LPV basis (lpv.cu)
+struct LpvPlan {
+    int Nf = 0, Nv = 0, Nvv = 0, ncc = 0, nblk = 0, Np = 0;
+    int coulomb = 0, normalize = 1;
+    int64_t N = 0;
+    const double2* d_E = nullptr;
+    const double* d_K = nullptr;
+};
+int lpv_prepare(lpvs_ctx* c, const double* X, const double* V, int64_t N, const double* w, int Nf, int Nv,
+                int coulomb, int normalize, LpvPlan* pl);
+// G (Np x Np lower tiles), B[0] = Ar'y for one LPV problem
+int lpv_gram(lpvs_ctx* c, const LpvPlan& pl, const double* d_y, double* d_G, double* d_B);
+
+// ADMM plumbing (admm.cu)
+lpvs_admm* admm_new(lpvs_ctx* c);
+void admm_delete(lpvs_admm* h);
+void admm_set_problem(lpvs_admm* h, int kind, int Np, int ncc, int zero_first, int nref, int half, int prox,
+                      double pparam, double mu, int quad, int lpv_nf, int lpv_nvv);
+int admm_set_groups(lpvs_ctx* c, lpvs_admm* h, const std::vector<int>& goff, const std::vector<int>& gmem);
+int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q, const double* d_x0);
+
 }  // namespace lpvs
