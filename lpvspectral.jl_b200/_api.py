@@ -253,7 +253,7 @@ def _windowed(kind, y, u, t, freqs, nw, noverlap, window_func, estimator, ctx, k
     if kind == L.WIN_PSD:
         return Syy / float(K) ** 2, freqs
     if kind == L.WIN_CSD:
-        return Syu / K, freqs
+        return (Syu.real / K) + 1j * (Syu.imag / K), freqs
     return (Syu.real * Syu.real + Syu.imag * Syu.imag) / (Suu * Syy), freqs
 
 

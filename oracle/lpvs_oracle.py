@@ -288,7 +288,7 @@ def ls_windowcsd(y, u, t, freqs=None, nw=10, noverlap=-1, window_func=rect, esti
         xy = est(yi, ti, freqs, win.W, **kw)[0]
         xu = est(ui, ti, freqs, win.W, **kw)[0]
         S = S + _mul_conj(xy, xu)
-    return S / K, freqs
+    return (S.real / K) + 1j * (S.imag / K), freqs  # Julia Complex/Real is component-wise
 
 
 def ls_cohere(y, u, t, freqs=None, nw=10, noverlap=-1, estimator=None, mode="literal", **kw):
