@@ -53,9 +53,59 @@ constexpr int PB = 16;    // inner panel width
 constexpr int LDP = 20;   // stride of 16-wide panels
 constexpr int LDH = 68;   // stride of the 64x64 temp
 
-// smem layout of k_potf2: S[128*LDS] | tmp[max(128*LDP, 64*LDH)] | dinv[8][16*LDP]
-constexpr int POTF2_TMP = (128 * LDP > 64 * LDH) ? 128 * LDP : 64 * LDH;
-constexpr int POTF2_SMEM_D = 128 * LDS + POTF2_TMP + 8 * PB * LDP;
+// smem layout of k_potf2: S[128*LDS] | tmp[max(112*LDP, 64*LDH)] | dinv[8][16*LDP]
+constexpr int POTF2_TMP = (112 * LDP > 64 * LDH) ? 112 * LDP : 64 * LDH;
+constexpr int POTF2_SMEM_D = 128 * LDS + POTF2_TMP + (TB / PB) * PB * LDP;
+
+// One warp factorises a 16x16 SPD block held in registers (lane = row, lanes 16..31 idle) with shuffles, then
+// inverts the triangle (lane = column).  No divisions on the critical path: one rsqrt per column, and the same
+// reciprocals are the diagonal of the inverse.  Kept at 16x16 so the unrolled code stays I-cache resident
+// (a 32x32 version was 9.4K straight-line instructions and ran at instruction-fetch speed, ncu potf2_r01).
+__device__ __forceinline__ void warp_potf2_inv(double* D, int ldd, double* Di, int ldi, int lane, int* info,
+                                               int pivot_base) {
+    const unsigned full = 0xffffffffu;
+    const int row = lane & (PB - 1);
+    double d[PB], rinv[PB];
+#pragma unroll
+    for (int c = 0; c < PB; c++) d[c] = (c <= row) ? D[row * ldd + c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < PB; c++) {
+        double piv = __shfl_sync(full, d[c], c);
+        if (!(piv > 0.0) || !isfinite(piv)) {
+            if (lane == 0) atomicCAS(info, 0, pivot_base + c + 1);
+            piv = (fabs(piv) > 0.0 && isfinite(piv)) ? fabs(piv) : 1.0;
+        }
+        const double ri = rsqrt(piv);
+        rinv[c] = ri;
+        d[c] = (row == c) ? piv * ri : d[c] * ri;
+#pragma unroll
+        for (int c2 = c + 1; c2 < PB; c2++) {
+            double l2 = __shfl_sync(full, d[c], c2);
+            if (row >= c2) d[c2] = fma(-d[c], l2, d[c2]);
+        }
+    }
+    // inverse, lane = column: x[m] final once all s[m] updates from columns < m are in
+    double sacc[PB], x[PB];
+#pragma unroll
+    for (int i = 0; i < PB; i++) sacc[i] = 0.0;
+#pragma unroll
+    for (int m = 0; m < PB; m++) {
+        const double xm = (m == row) ? rinv[m] : ((m > row) ? -sacc[m] * rinv[m] : 0.0);
+        x[m] = xm;
+#pragma unroll
+        for (int i = m + 1; i < PB; i++) {
+            double lim = __shfl_sync(full, d[m], i);
+            sacc[i] = fma(lim, xm, sacc[i]);
+        }
+    }
+    if (lane < PB) {
+#pragma unroll
+        for (int c = 0; c < PB; c++) {
+            if (c <= row) D[row * ldd + c] = d[c];
+            Di[c * ldi + row] = x[c];
+        }
+    }
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ CholArgs a, int k) {
     extern __shared__ __align__(16) double sm[];
@@ -75,39 +125,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ C
 
     for (int p = 0; p < TB / PB; p++) {
         const int j0 = p * PB;
-        double* D = S + j0 * LDS + j0;
         double* Di = Dinv + p * PB * LDP;
-        if (warp == 0) {
-            // unblocked 16x16 factor, lane = row
-            for (int c = 0; c < PB; c++) {
-                double d = D[c * LDS + c];
-                if (!(d > 0.0) || !isfinite(d)) {
-                    if (lane == 0) atomicCAS(&a.info[prob], 0, k * TB + j0 + c + 1);
-                    d = (fabs(d) > 0.0 && isfinite(d)) ? fabs(d) : 1.0;
-                }
-                double sd = sqrt(d);
-                __syncwarp();
-                if (lane == c) D[c * LDS + c] = sd;
-                if (lane > c && lane < PB) D[lane * LDS + c] = D[lane * LDS + c] / sd;
-                __syncwarp();
-                if (lane > c && lane < PB) {
-                    double l = D[lane * LDS + c];
-                    for (int c2 = c + 1; c2 <= lane; c2++) D[lane * LDS + c2] -= l * D[c2 * LDS + c];
-                }
-                __syncwarp();
-            }
-            // inverse of the 16x16 triangle, lane = column
-            if (lane < PB) {
-                const int c = lane;
-                for (int i = 0; i < c; i++) Di[i * LDP + c] = 0.0;
-                Di[c * LDP + c] = 1.0 / D[c * LDS + c];
-                for (int i = c + 1; i < PB; i++) {
-                    double s = 0.0;
-                    for (int m = c; m < i; m++) s += D[i * LDS + m] * Di[m * LDP + c];
-                    Di[i * LDP + c] = -s / D[i * LDS + i];
-                }
-            }
-        }
+        if (warp == 0) warp_potf2_inv(S + j0 * LDS + j0, LDS, Di, LDP, lane, &a.info[prob], k * TB + j0);
         __syncthreads();
         const int rem = TB - j0 - PB;
         if (rem > 0) {

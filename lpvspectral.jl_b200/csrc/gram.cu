@@ -14,7 +14,7 @@ namespace lpvs {
 
 namespace {
 
-constexpr int STAGE_D = 2 * TILE_D + 8 * LDT;  // I tile, J tile, rhs tile (8 rows)
+constexpr int STAGE_D = 2 * TILE_D;  // I tile, J tile (J = weighted copy)
 
 struct Pref {
     double2 aI, aJ, d;  // chain: anchors + step rotation
@@ -37,7 +37,6 @@ __device__ __forceinline__ Pref load_pref(const GramArgs& a, int c, long long s_
     if (a.W) wt = a.W[a.w_abs ? s : (long long)idc];
     p.wt = valid ? wt : 0.0;
     p.yv = 0.0;
-    if (DIAG && w < a.nrhs) p.yv = (w == 0 ? a.y : a.u)[s] * p.wt;
     if (MODE == GRAM_CHAIN) {
         p.aI = a.anc[(long long)(I * (FB / GRP) + w) * a.tbl_ns + p.si];
         if (!DIAG) p.aJ = a.anc[(long long)(J * (FB / GRP) + w) * a.tbl_ns + p.si];
@@ -61,6 +60,8 @@ __device__ __forceinline__ double2 synth_elem(const GramArgs& a, const Pref& p, 
     }
 }
 
+// DIAG tiles (I == J) compute only the three lower 64x64 sub-blocks (0,0), (1,0), (1,1): warp tile 16x32 per
+// sub-block, 24 DMMAs per k4-step instead of 32.
 template <int MODE, bool DIAG>
 __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int prob, double* smem) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -68,24 +69,15 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     const long long s_begin = a.start0 + (long long)prob * a.hop;
     const int nchunks = (a.n + KC - 1) / KC;
 
-    double acc[4][8][2];
+    double acc[4][8][2];   // off-diagonal: [i][j][e]; diagonal: viewed as [sb(3)][i(2)][j(4)][e(2)] = 48 used
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    double accb[4][2];
-#pragma unroll
-    for (int i = 0; i < 4; i++) accb[i][0] = accb[i][1] = 0.0;
-
-    // zero the rhs tiles once (rows >= nrhs stay zero)
-    for (int q = tid; q < 8 * LDT; q += NTHREADS) {
-        smem[2 * TILE_D + q] = 0.0;
-        smem[STAGE_D + 2 * TILE_D + q] = 0.0;
-    }
 
     const int ccI0 = I * FB + w * GRP, ccJ0 = J * FB + w * GRP;
-    const int rowc = (w * GRP) * LDT + lane;         // smem offset of the real-part row for j = 0
-    const int rows = (FB + w * GRP) * LDT + lane;    // second-part row
+    const int rowc = (w * GRP) * LDT + lane;       // smem offset of the real-part row for j = 0
+    const int rows = (FB + w * GRP) * LDT + lane;  // second-part row
 
     // synthesise element j (of 8) of a chunk into stage buffer `st`
     auto synth_step = [&](const Pref& p, double2& zI, double2& zJ, int j, double* st) {
@@ -115,9 +107,6 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
             }
         }
     };
-    auto synth_rhs = [&](const Pref& p, double* st) {
-        if (DIAG && w < a.nrhs) st[2 * TILE_D + w * LDT + lane] = p.yv;
-    };
 
     // prologue: chunk 0 into stage 0
     Pref p1 = load_pref<MODE, DIAG>(a, 0, s_begin, lane, w, I, J);
@@ -125,14 +114,13 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
         double2 zI = p1.aI, zJ = p1.aJ;
 #pragma unroll
         for (int j = 0; j < GRP; j++) synth_step(p1, zI, zJ, j, smem);
-        synth_rhs(p1, smem);
     }
     if (nchunks > 1) p1 = load_pref<MODE, DIAG>(a, 1, s_begin, lane, w, I, J);
     __syncthreads();
 
-    const int fragA = (32 * wm + (lane >> 2)) * LDT + (lane & 3);
-    const int fragB = (64 * wn + (lane >> 2)) * LDT + (lane & 3);
-    const int fragY = (lane >> 2) * LDT + (lane & 3);
+    // fragment bases: off-diagonal 32(M) x 64(N) warp tile; diagonal 16 x 32 per 64x64 sub-block
+    const int fragA = DIAG ? (16 * wm + (lane >> 2)) * LDT + (lane & 3) : (32 * wm + (lane >> 2)) * LDT + (lane & 3);
+    const int fragB = DIAG ? (32 * wn + (lane >> 2)) * LDT + (lane & 3) : (64 * wn + (lane >> 2)) * LDT + (lane & 3);
 
     for (int c = 0; c < nchunks; c++) {
         double* cur = smem + (c & 1) * STAGE_D;
@@ -146,14 +134,24 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
 #pragma unroll
         for (int kk = 0; kk < KC / 4; kk++) {
             if (have_next) synth_step(p1, zI, zJ, kk, nxt);
-            mma_step(pa, pb, kk, acc);
-            if (DIAG && wn == 0) {
-                double by = cur[2 * TILE_D + fragY + 4 * kk];
+            if (!DIAG) {
+                mma_step(pa, pb, kk, acc);
+            } else {
+                double fa[4], fb[8];  // fa: rows {0,8} of half 0 then half 1; fb: cols {0,8,16,24} of half 0 then half 1
 #pragma unroll
-                for (int i = 0; i < 4; i++) dmma884(accb[i][0], accb[i][1], pa[i * 8 * LDT + 4 * kk], by);
+                for (int i = 0; i < 4; i++) fa[i] = pa[((i >> 1) * 64 + (i & 1) * 8) * LDT + 4 * kk];
+#pragma unroll
+                for (int j = 0; j < 8; j++) fb[j] = pb[((j >> 2) * 64 + (j & 3) * 8) * LDT + 4 * kk];
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        dmma884(acc[0][i * 4 + j][0], acc[0][i * 4 + j][1], fa[i], fb[j]);          // (0,0)
+                        dmma884(acc[1][i * 4 + j][0], acc[1][i * 4 + j][1], fa[2 + i], fb[j]);      // (1,0)
+                        dmma884(acc[2][i * 4 + j][0], acc[2][i * 4 + j][1], fa[2 + i], fb[4 + j]);  // (1,1)
+                    }
             }
         }
-        if (have_next) synth_rhs(p1, nxt);
         p1 = p2;
         __syncthreads();
     }
@@ -161,28 +159,87 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     // epilogue
     const int Np = a.nblk * TB;
     double* Gp = a.G + (long long)prob * a.strideG;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        int row = I * TB + 32 * wm + 8 * i + (lane >> 2);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            int col = J * TB + 64 * wn + 8 * j + 2 * (lane & 3);
-            double2 v = make_double2(acc[i][j][0] * a.gscale, acc[i][j][1] * a.gscale);
-            *reinterpret_cast<double2*>(Gp + (long long)row * Np + col) = v;
-        }
-    }
-    if (DIAG && wn == 0 && a.B) {
-        double* Bp = a.B + (long long)prob * a.strideB;
+    if (!DIAG) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             int row = I * TB + 32 * wm + 8 * i + (lane >> 2);
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                int r = 2 * (lane & 3) + e;
-                if (r < a.nrhs) Bp[(long long)r * Np + row] = accb[i][e] * a.bscale;
+            for (int j = 0; j < 8; j++) {
+                int col = J * TB + 64 * wn + 8 * j + 2 * (lane & 3);
+                double2 v = make_double2(acc[i][j][0] * a.gscale, acc[i][j][1] * a.gscale);
+                *reinterpret_cast<double2*>(Gp + (long long)row * Np + col) = v;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int sb = 0; sb < 3; sb++) {
+            const int sr = sb > 0, sc = sb > 1;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                int row = I * TB + 64 * sr + 16 * wm + 8 * i + (lane >> 2);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    int col = I * TB + 64 * sc + 32 * wn + 8 * j + 2 * (lane & 3);
+                    double2 v = make_double2(acc[sb][i * 4 + j][0] * a.gscale, acc[sb][i * 4 + j][1] * a.gscale);
+                    *reinterpret_cast<double2*>(Gp + (long long)row * Np + col) = v;
+                }
             }
         }
     }
+}
+
+// b = A' diag(W) [y u]: one CTA per (64-frequency block, problem); warp = chain group, lane = sample.
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS) k_gram_rhs(const __grid_constant__ GramArgs a) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int I = blockIdx.x, prob = blockIdx.y;
+    const long long s_begin = a.start0 + (long long)prob * a.hop;
+    const int nchunks = (a.n + KC - 1) / KC;
+    const int cc0 = I * FB + w * GRP;
+    double sc[2][GRP], ss[2][GRP];
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int j = 0; j < GRP; j++) sc[r][j] = ss[r][j] = 0.0;
+    for (int c = 0; c < nchunks; c++) {
+        Pref p = load_pref<MODE, true>(a, c, s_begin, lane, w, I, I);
+        long long s = p.si + a.tbl_base;
+        double y0 = a.y ? a.y[s] * p.wt : 0.0;
+        double y1 = (a.nrhs > 1 && a.u) ? a.u[s] * p.wt : 0.0;
+        double2 z = p.aI;
+#pragma unroll
+        for (int j = 0; j < GRP; j++) {
+            double2 v = z;
+            if (MODE != GRAM_CHAIN) v = (cc0 + j < a.ncc) ? synth_elem<MODE>(a, p, cc0 + j) : make_double2(0.0, 0.0);
+            sc[0][j] = fma(v.x, y0, sc[0][j]);
+            ss[0][j] = fma(v.y, y0, ss[0][j]);
+            sc[1][j] = fma(v.x, y1, sc[1][j]);
+            ss[1][j] = fma(v.y, y1, ss[1][j]);
+            if (MODE == GRAM_CHAIN) {
+                double nx = z.x * p.d.x - z.y * p.d.y;
+                double ny = z.x * p.d.y + z.y * p.d.x;
+                z = make_double2(nx, ny);
+            }
+        }
+    }
+    const int Np = a.nblk * TB;
+    double* Bp = a.B + (long long)prob * a.strideB;
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int j = 0; j < GRP; j++) {
+            double vc = sc[r][j], vs = ss[r][j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                vc += __shfl_xor_sync(0xffffffffu, vc, o);
+                vs += __shfl_xor_sync(0xffffffffu, vs, o);
+            }
+            if (lane == 0 && r < a.nrhs) {
+                bool ok = cc0 + j < a.ncc;
+                Bp[(long long)r * Np + I * TB + w * GRP + j] = ok ? vc * a.bscale : 0.0;
+                Bp[(long long)r * Np + I * TB + FB + w * GRP + j] = ok ? vs * a.bscale : 0.0;
+            }
+        }
 }
 
 template <int MODE>
@@ -262,12 +319,18 @@ void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
         b.G = a.G + (long long)p0 * a.strideG;
         if (a.B) b.B = a.B + (long long)p0 * a.strideB;
         dim3 grid(ntiles, np);
-        if (mode == GRAM_CHAIN)
+        dim3 grid_rhs(a.nblk, np);
+        const bool rhs = a.B && a.nrhs > 0 && a.y;
+        if (mode == GRAM_CHAIN) {
             k_gram<GRAM_CHAIN><<<grid, NTHREADS, smem, st>>>(b);
-        else if (mode == GRAM_DIRECT)
+            if (rhs) k_gram_rhs<GRAM_CHAIN><<<grid_rhs, NTHREADS, 0, st>>>(b);
+        } else if (mode == GRAM_DIRECT) {
             k_gram<GRAM_DIRECT><<<grid, NTHREADS, smem, st>>>(b);
-        else
+            if (rhs) k_gram_rhs<GRAM_DIRECT><<<grid_rhs, NTHREADS, 0, st>>>(b);
+        } else {
             k_gram<GRAM_LPV><<<grid, NTHREADS, smem, st>>>(b);
+            if (rhs) k_gram_rhs<GRAM_LPV><<<grid_rhs, NTHREADS, 0, st>>>(b);
+        }
     }
 }
 
