@@ -62,6 +62,9 @@ int lpvs_init(int device, lpvs_ctx** ctx);
 void lpvs_destroy(lpvs_ctx* ctx);
 const char* lpvs_last_error(const lpvs_ctx* ctx);
 int lpvs_set_option(lpvs_ctx* ctx, int key, double value);
+/* enqueue all work of this context on the caller's CUDA stream (cudaStream_t as void*; NULL = the context's own
+ * stream).  Lets a host framework order the library's kernels with its own work and time them with its events. */
+int lpvs_set_stream(lpvs_ctx* ctx, void* stream);
 /* cumulative number of kernels this context launched (bench.py's gpu_launches) */
 int64_t lpvs_launch_count(const lpvs_ctx* ctx);
 /* device time [ms] and launch count of the Gram kernel(s) during the last API call (bench.py's roofline) */

@@ -1,0 +1,230 @@
+# LPVSpectralB200.jl -- drop-in Julia shim over liblpvs.so (include/lpvs.h).
+#
+# Same names / signatures / kwargs as LPVSpectral.jl's least-squares estimators
+# (src/lsfft.jl:62-80,112-126,140-156,176-193,239-259; src/lasso.jl:27-126), but every flop runs in the
+# sm_100a CUDA library.  The shim only marshals: collect ranges into Vector{Float64}, validate exactly where the
+# reference validates, evaluate window_func on the host, map proxg objects to (kind, param), allocate outputs,
+# `ccall`, and wrap results.  There is NO CPU fallback: unsupported `estimator`/`proxg` throw ArgumentError.
+#
+# NOTE: Julia is not installed in the build image or on the GPU box, so this file is syntax-reviewed only; the
+# identical C ABI is exercised end to end from Python ctypes (lpvspectral.jl_b200/_api.py mirrors this file line
+# for line) by tests/ and bench.py.
+module LPVSpectralB200
+
+using LinearAlgebra, Statistics, Printf
+import LPVSpectral: SpectralExt, default_freqs, check_freq   # host-side pieces stay untouched Julia
+import DSP: rect, hanning
+
+export ls_spectral, ls_windowpsd, ls_windowcsd, ls_cohere, ls_sparse_spectral, ls_spectral_lpv,
+       ls_sparse_spectral_lpv
+
+const liblpvs = get(ENV, "LIBLPVS", "liblpvs")
+const WIN_PSD, WIN_CSD, WIN_COHERE = Cint(0), Cint(1), Cint(2)
+const PROX_L1, PROX_L0, PROX_BALL_L0 = Cint(0), Cint(1), Cint(2)
+
+mutable struct Ctx
+    h::Ptr{Cvoid}
+end
+const CTX = Ref{Union{Nothing,Ctx}}(nothing)
+
+function ctx()
+    if CTX[] === nothing
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        dev = parse(Int, get(ENV, "LOCAL_RANK", "0"))
+        rc = ccall((:lpvs_init, liblpvs), Cint, (Cint, Ptr{Ptr{Cvoid}}), dev, h)
+        rc == 0 || error("lpvs_init failed ($rc): no usable B200 (there is no CPU fallback)")
+        c = Ctx(h[])
+        finalizer(c -> ccall((:lpvs_destroy, liblpvs), Cvoid, (Ptr{Cvoid},), c.h), c)
+        CTX[] = c
+    end
+    CTX[].h
+end
+
+lasterr() = unsafe_string(ccall((:lpvs_last_error, liblpvs), Cstring, (Ptr{Cvoid},), ctx()))
+function check(rc)
+    rc == 0 && return
+    msg = lasterr()
+    rc == -1 && throw(ArgumentError(msg))
+    rc == -2 && throw(PosDefException(1))
+    error("liblpvs error $rc: $msg")
+end
+
+vecf(x) = collect(Float64, x)
+nullable(x) = x === nothing ? Ptr{Float64}(C_NULL) : pointer(x)
+
+# ---- ls_spectral (src/lsfft.jl:62-80) ---------------------------------------------------------------------
+function ls_spectral(y, t, f=default_freqs(t); λ=1e-10, verbose=false)
+    _ls_spectral(y, t, f, nothing, λ)
+end
+function ls_spectral(y, t, f, W::AbstractVector; λ=1e-10, verbose=false)
+    _ls_spectral(y, t, f, W, λ)
+end
+function _ls_spectral(y, t, f, W, λ)
+    check_freq(f)                                    # ArgumentError site, src/lsfft.jl:22
+    yv, tv, fv = vecf(y), vecf(t), vecf(f)
+    length(yv) == length(tv) || throw(ArgumentError("y and t has to be the same length"))
+    Wv = W === nothing ? nothing : vecf(W)
+    x = Vector{ComplexF64}(undef, length(fv))
+    info = Ref{Cint}(0)
+    GC.@preserve yv tv fv Wv x begin
+        check(ccall((:lpvs_ls_spectral, liblpvs), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Float64,
+             Ptr{ComplexF64}, Ptr{Cint}),
+            ctx(), yv, tv, length(yv), fv, length(fv), nullable(Wv), Float64(λ), x, info))
+    end
+    info[] == 1 && @warn "Gram matrix numerically rank deficient: solved with a jitter ridge (see DESIGN.md H1)"
+    x, f                                             # the caller's own f object, untouched
+end
+
+# ---- windowed estimators (src/lsfft.jl:112-193) -----------------------------------------------------------
+function _windowed(kind, y, u, t, freqs, nw, noverlap, window_func, estimator, kwargs)
+    n = length(y) ÷ nw                               # src/lsfft.jl:113
+    freqs === nothing && (freqs = default_freqs(t, n))
+    check_freq(freqs)
+    estimator === ls_spectral ||
+        return _windowed_generic(kind, y, u, t, freqs, n, noverlap, window_func, estimator, kwargs)
+    λ = get(kwargs, :λ, 1e-10)
+    yv, tv, fv = vecf(y), vecf(t), vecf(freqs)
+    uv = u === nothing ? nothing : vecf(u)
+    length(yv) == length(tv) || throw(AssertionError("y and t has to be the same length"))  # src/windows.jl:31
+    noverlap < 0 && (noverlap = n >> 1)
+    Wv = vecf(window_func(n))
+    out = kind == WIN_CSD ? Vector{ComplexF64}(undef, length(fv)) : Vector{Float64}(undef, length(fv))
+    K = Ref{Int64}(0); info = Ref{Cint}(0)
+    GC.@preserve yv uv tv fv Wv out begin
+        check(ccall((:lpvs_ls_window, liblpvs), Cint,
+            (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Ptr{Float64},
+             Cint, Cint, Float64, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cint}),
+            ctx(), kind, yv, nullable(uv), tv, length(yv), fv, length(fv), Wv, n, noverlap, Float64(λ), out, K, info))
+    end
+    out, freqs
+end
+
+# estimator = ls_sparse_spectral: one device ADMM solve per window (test/test_lasso.jl:36)
+function _windowed_generic(kind, y, u, t, freqs, n, noverlap, window_func, estimator, kwargs)
+    estimator === ls_sparse_spectral ||
+        throw(ArgumentError("estimator must be ls_spectral or ls_sparse_spectral (no CPU fallback)"))
+    noverlap < 0 && (noverlap = n >> 1)
+    W = vecf(window_func(n)); hop = n - noverlap
+    K = length(y) >= n ? (length(y) - n) ÷ hop + 1 : 0
+    Syy = zeros(length(freqs)); Suu = zeros(length(freqs)); Syu = zeros(ComplexF64, length(freqs))
+    for k in 0:K-1
+        r = k*hop+1:k*hop+n
+        xy = estimator(y[r], t[r], freqs, W; kwargs...)[1]
+        Syy .+= abs2.(xy)
+        if u !== nothing
+            xu = estimator(u[r], t[r], freqs, W; kwargs...)[1]
+            Suu .+= abs2.(xu); Syu .+= xy .* conj.(xu)
+        end
+    end
+    kind == WIN_PSD && return Syy ./ K^2, freqs
+    kind == WIN_CSD && return Syu ./ K, freqs
+    abs2.(Syu) ./ (Suu .* Syy), freqs
+end
+
+ls_windowpsd(y, t, freqs=nothing; nw=8, noverlap=-1, window_func=rect, estimator=ls_spectral, kwargs...) =
+    _windowed(WIN_PSD, y, nothing, t, freqs, nw, noverlap, window_func, estimator, kwargs)
+ls_windowcsd(y, u, t, freqs=nothing; nw=10, noverlap=-1, window_func=rect, estimator=ls_spectral, kwargs...) =
+    _windowed(WIN_CSD, y, u, t, freqs, nw, noverlap, window_func, estimator, kwargs)
+ls_cohere(y, u, t, freqs=nothing; nw=10, noverlap=-1, estimator=ls_spectral, kwargs...) =
+    _windowed(WIN_COHERE, y, u, t, freqs, nw, noverlap, hanning, estimator, kwargs)   # hanning hard-coded (:182)
+
+# ---- LPV (src/lsfft.jl:239-259) -----------------------------------------------------------------------------
+function ls_spectral_lpv(Y::AbstractVector, X::AbstractVector, V::AbstractVector, w, Nv::Integer;
+                         λ=1e-8, coulomb=false, normalize=true)
+    Yv, Xv, Vv, wv = vecf(Y), vecf(X), vecf(V), vecf(w[:])
+    ncc = length(wv) * (coulomb ? 2Nv : Nv)
+    params = Vector{ComplexF64}(undef, ncc)
+    Σ = Matrix{Float64}(undef, 2ncc, 2ncc)
+    fva = Ref{Float64}(0.0); info = Ref{Cint}(0)
+    GC.@preserve Yv Xv Vv wv params Σ begin
+        check(ccall((:lpvs_ls_spectral_lpv, liblpvs), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Cint, Float64, Cint,
+             Cint, Ptr{ComplexF64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+            ctx(), Yv, Xv, Vv, length(Yv), wv, length(wv), Nv, Float64(λ), coulomb, normalize, params, Σ, fva, info))
+    end
+    fva[] < 0.9 && @warn("Fraction of variance explained = $(fva[])")       # src/lsfft.jl:256
+    SpectralExt(Y, X, V, wv, Nv, λ, coulomb, normalize, params, Σ)
+end
+
+# ---- ADMM-backed sparse estimators (src/lasso.jl) ---------------------------------------------------------------
+# proxg objects are ProximalOperators types; only their (kind, parameter) crosses the ABI.
+proxdesc(p) = begin
+    T = string(nameof(typeof(p)))
+    T == "NormL1" && return PROX_L1, Float64(p.lambda)
+    T == "NormL0" && return PROX_L0, Float64(p.lambda)
+    T == "IndBallL0" && return PROX_BALL_L0, Float64(p.r)
+    throw(ArgumentError("proxg must be NormL1, NormL0 or IndBallL0 (no CPU fallback for other operators)"))
+end
+
+# Drives the device loop in chunks of `printerval` so prints and cb(x,z) match src/lasso.jl:158-167 (SURVEY H6).
+function run_admm(h, n; iters=10000, tol=1e-5, printerval=100, cb=nothing, μ=nothing)
+    done = 0; res = Ref{Float64}(Inf); conv = Ref{Cint}(0); it = Ref{Int64}(0)
+    while done < iters && conv[] == 0
+        chunk = min(printerval - done % printerval, iters - done)
+        check(ccall((:lpvs_admm_run, liblpvs), Cint, (Ptr{Cvoid}, Int64, Float64, Ptr{Int64}, Ptr{Float64}, Ptr{Cint}),
+                    h, chunk, Float64(tol), it, res, conv))
+        done += it[]
+        if conv[] != 0 || done % printerval == 0
+            @printf("%d ||x-z||₂ %.10f\n", done, res[])
+            if cb !== nothing && done % printerval == 0
+                x = Vector{Float64}(undef, n); z = similar(x)
+                check(ccall((:lpvs_admm_get, liblpvs), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h, x, z))
+                cb(x, z)
+            end
+        end
+    end
+    conv[] != 0 && @info("||x-z||₂ ≤ tol")
+end
+
+function ls_sparse_spectral(y::AbstractArray{T}, t, f=default_freqs(t), W=nothing;
+                            init=false, λ=T(1), proxg=nothing, μ=T(0.05), kwargs...) where T
+    @assert 0 ≤ μ ≤ 1 "μ should be ≤ 1"                                  # src/lasso.jl:143
+    check_freq(f)
+    kind, param = proxg === nothing ? (PROX_L1, Float64(λ)) : proxdesc(proxg)   # Q15
+    yv, tv, fv = vecf(y), vecf(t), vecf(f)
+    Wv = W === nothing ? nothing : vecf(W)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve yv tv fv Wv begin
+        check(ccall((:lpvs_admm_create_fourier, liblpvs), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Float64, Float64,
+             Ptr{Float64}, Cint, Float64, Ptr{Ptr{Cvoid}}),
+            ctx(), yv, tv, length(yv), fv, length(fv), nullable(Wv), kind, param, Float64(μ), C_NULL, init,
+            Float64(λ), h))
+    end
+    params = Vector{ComplexF64}(undef, length(fv))
+    try
+        run_admm(h[], ccall((:lpvs_admm_size, liblpvs), Cint, (Ptr{Cvoid},), h[]); kwargs...)
+        check(ccall((:lpvs_admm_result, liblpvs), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), h[], params))
+    finally
+        ccall((:lpvs_admm_free, liblpvs), Cvoid, (Ptr{Cvoid},), h[])
+    end
+    params, f
+end
+
+function ls_sparse_spectral_lpv(y::AbstractVector{S}, X::AbstractVector{S}, V::AbstractVector{S}, w, Nv::Integer;
+                                λ=1, coulomb=false, normalize=true, μ=S(0.05), kwargs...) where S
+    yv, Xv, Vv, wv = vecf(y), vecf(X), vecf(V), vecf(w[:])
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve yv Xv Vv wv begin
+        check(ccall((:lpvs_admm_create_lpv, liblpvs), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Cint, Cint, Cint,
+             Float64, Float64, Ptr{Ptr{Cvoid}}),
+            ctx(), yv, Xv, Vv, length(yv), wv, length(wv), Nv, coulomb, normalize, Float64(λ), Float64(μ), h))
+    end
+    params = Vector{ComplexF64}(undef, length(wv) * (coulomb ? 2Nv : Nv))
+    try
+        try
+            run_admm(h[], ccall((:lpvs_admm_size, liblpvs), Cint, (Ptr{Cvoid},), h[]); kwargs...)
+        catch e
+            e isa InterruptException || rethrow(e)                          # src/lasso.jl:57-66 (Q17)
+            @info "Aborting"
+        end
+        check(ccall((:lpvs_admm_result, liblpvs), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), h[], params))
+    finally
+        ccall((:lpvs_admm_free, liblpvs), Cvoid, (Ptr{Cvoid},), h[])
+    end
+    SpectralExt(y, X, V, wv, Nv, λ, coulomb, normalize, params, nothing)
+end
+
+end # module

@@ -56,6 +56,10 @@ class Context:
     def set_option(self, key, value):
         self.check(self.lib.lpvs_set_option(self.h, key, float(value)))
 
+    def set_stream(self, cuda_stream_ptr):
+        """Run on the caller's CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``); 0/None = own stream."""
+        self.check(self.lib.lpvs_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
     @property
     def launches(self) -> int:
         return int(self.lib.lpvs_launch_count(self.h))

@@ -32,6 +32,7 @@ _PROTOS = {
     "lpvs_destroy": (None, [_vp]),
     "lpvs_last_error": (C.c_char_p, [_vp]),
     "lpvs_set_option": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "lpvs_set_stream": (C.c_int, [_vp, _vp]),
     "lpvs_launch_count": (C.c_int64, [_vp]),
     "lpvs_last_gram_timing": (C.c_int, [_vp, _dp, _i64p, _dp]),
     "lpvs_last_call_ms": (C.c_int, [_vp, _dp]),

@@ -380,10 +380,11 @@ int lpvs_init(int device, lpvs_ctx** out) {
     lpvs_ctx* c = new lpvs_ctx();
     c->device = device;
     c->sms = p.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&c->own_st, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return LPVS_E_CUDA;
     }
+    c->st = c->own_st;
     cudaEventCreate(&c->ev_call0);
     cudaEventCreate(&c->ev_call1);
     *out = c;
@@ -399,7 +400,7 @@ void lpvs_destroy(lpvs_ctx* c) {
     for (auto e : c->ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev_call0);
     cudaEventDestroy(c->ev_call1);
-    cudaStreamDestroy(c->st);
+    cudaStreamDestroy(c->own_st);
     delete c;
 }
 
@@ -415,6 +416,15 @@ int lpvs_set_option(lpvs_ctx* c, int key, double value) {
         case LPVS_OPT_ADMM_CHECK_EVERY: c->admm_check_every = std::max(1, (int)value); break;
         default: return fail(c, LPVS_E_BAD_ARG, "unknown option %d", key);
     }
+    return LPVS_OK;
+}
+
+int lpvs_set_stream(lpvs_ctx* c, void* stream) {
+    if (!c) return LPVS_E_BAD_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    c->st = stream ? (cudaStream_t)stream : c->own_st;
     return LPVS_OK;
 }
 

@@ -28,7 +28,8 @@ enum BufSlot {
 struct lpvs_ctx {
     int device = 0;
     int sms = 148;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;      // stream in use
+    cudaStream_t own_st = nullptr;  // the context's own stream
     std::string err;
     std::mutex mu;
     int phase_mode = LPVS_PHASE_AUTO;

@@ -120,3 +120,69 @@ def test_errors(ctx):
         lp.ls_spectral(y, t, np.array([1.0, 0.0, 2.0]), ctx=ctx)
     with pytest.raises(ValueError):
         lp.ls_spectral(y[:-1], t, np.array([1.0, 2.0]), ctx=ctx)
+
+
+def test_window_ranges_add_up(ctx):
+    """Sharding unit: sums over disjoint window ranges add to the full-range sums (what ranks all-reduce)."""
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+
+    N, nw = 8192, 16
+    t, y = signal(N, 21)
+    u = np.roll(y, 1)
+    n = N // nw
+    f = np.arange(24) * 2.0 / (t[n] - t[0])
+    W = lp.hanning(n)
+    K = lp.window_count(N, n, -1)
+    for kind in (L.WIN_PSD, L.WIN_CSD, L.WIN_COHERE):
+        uu = None if kind == L.WIN_PSD else u
+        full = lp.window_sums(kind, y, uu, t, f, W, n, n >> 1, 1e-10, 0, K, ctx=ctx)
+        a = lp.window_sums(kind, y, uu, t, f, W, n, n >> 1, 1e-10, 0, 11, ctx=ctx)
+        b = lp.window_sums(kind, y, uu, t, f, W, n, n >> 1, 1e-10, 11, K, ctx=ctx)
+        assert np.allclose(a + b, full, rtol=1e-12, atol=1e-300)
+    # small batches (forces several factorisation batches) give bit-identical sums
+    ctx.set_option(L.OPT_WINDOW_BATCH, 5)
+    try:
+        small = lp.window_sums(L.WIN_PSD, y, None, t, f, W, n, n >> 1, 1e-10, 0, K, ctx=ctx)
+    finally:
+        ctx.set_option(L.OPT_WINDOW_BATCH, 0)
+    assert np.array_equal(small, lp.window_sums(L.WIN_PSD, y, None, t, f, W, n, n >> 1, 1e-10, 0, K, ctx=ctx))
+
+
+def test_rowsharded_single_rank_equals_ls_spectral(ctx):
+    """lpvs_gram_partial_dev + lpvs_solve_packed_dev (the row-sharded path) at world size 1, incl. sample splits."""
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _dist as D
+
+    N = 100000
+    t, y = signal(N, 22)
+    u = np.roll(y, 3)
+    f = np.arange(96) * 0.5
+    W = 0.5 + np.random.default_rng(1).random(N)
+    xs = D.ls_spectral_rowsharded(y, t, f, W, u=u, lam=1e-10, ctx=ctx)
+    xy, _ = lp.ls_spectral(y, t, f, W, ctx=ctx)
+    xu, _ = lp.ls_spectral(u, t, f, W, ctx=ctx)
+    assert rel(xs[0], xy) <= 1e-12 and rel(xs[1], xu) <= 1e-12
+    A, _ = o.get_fourier_regressor(t[:20000], f)
+    xr, _ = o.ls_spectral(y[:20000], t[:20000], f, W[:20000], mode="gram")
+    xg = D.ls_spectral_rowsharded(y[:20000], t[:20000], f, W[:20000], lam=1e-10, ctx=ctx)
+    assert rel(xg, xr) <= TOL
+
+
+def test_ragged_and_tiny_inputs(ctx):
+    """Edge cases: n not a multiple of the 32-sample chunk, Nf = 1, a window longer than the signal (K = 0)."""
+    import lpvspectral_jl_b200 as lp
+
+    t, y = signal(333, 23)
+    f = np.array([0.0])
+    x, _ = lp.ls_spectral(y, t, f, ctx=ctx)
+    xr, _ = o.ls_spectral(y, t, f, mode="literal")
+    assert rel(x, xr) <= TOL
+    f = np.arange(1, 8) * 0.7
+    x, _ = lp.ls_spectral(y, t, f, np.ones(333), ctx=ctx)
+    xr, _ = o.ls_spectral(y, t, f, np.ones(333), mode="literal")
+    assert rel(x, xr) <= TOL
+    S, _ = lp.ls_windowpsd(y, t, f, nw=3, noverlap=7, ctx=ctx)  # n = 111 (ragged chunks), K = 3
+    Sr, _ = o.ls_windowpsd(y, t, f, nw=3, noverlap=7)
+    assert rel(S, Sr) <= TOL
+    assert lp.window_count(10, 20, 0) == 0
