@@ -50,7 +50,9 @@ enum lpvs_option {
     LPVS_OPT_WINDOW_BATCH = 1, /* windows factorised per batch (bounds workspace), default auto */
     LPVS_OPT_JITTER = 2,       /* 1 (default): on Cholesky breakdown of the UNWEIGHTED ls_spectral re-factor on device
                                   with ridge max(lambda^2, Nreg*eps*max diag G) and set *info=1; 0: fail */
-    LPVS_OPT_ADMM_CHECK_EVERY = 3 /* residual test cadence inside the device loop; 1 (default) = every iteration (Q12) */
+    LPVS_OPT_ADMM_CHECK_EVERY = 3, /* residual test cadence inside the device loop; 1 (default) = every iteration (Q12) */
+    LPVS_OPT_ADMM_SYMV = 4         /* x-update kernel: -1 auto (default), 0 GEMV over the full symmetric inverse (8 Np^2 B/iter),
+                                      1 SYMV over its lower triangle (4 Np^2 B/iter) */
 };
 
 /* info flags returned by solvers */

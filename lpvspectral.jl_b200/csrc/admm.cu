@@ -70,13 +70,173 @@ __device__ __forceinline__ double2 ldm(const double* p) {
     return STREAM ? __ldcs(reinterpret_cast<const double2*>(p)) : __ldg(reinterpret_cast<const double2*>(p));
 }
 
+// ---- shared pieces of one ADMM iteration ---------------------------------------------------------------------
+
+// element-wise prox + dual update + next rhs for entry i; returns (x-z)^2
+__device__ __forceinline__ double admm_elem_update(const AdmmArgs& a, double* rn, int i, double xi, double gl,
+                                                   double thr0) {
+    double ui = a.u[i];
+    double zi = prox_elem(a.prox, xi + ui, gl, thr0);
+    double di = xi - zi;
+    ui += di;
+    a.z[i] = zi;
+    a.u[i] = ui;
+    rn[i] = next_rhs(a, i, zi, ui);
+    return di * di;
+}
+
+// second phase for the prox operators that need the whole x first (x and v = x+u are in global memory, a grid
+// barrier has been passed).  Returns this thread's contribution to ||x-z||^2.
+__device__ __forceinline__ double admm_phase_nonelem(const AdmmArgs& a, double* rn, int b, int nblocks, int tid,
+                                                     int lane, int w, double gl) {
+    const int Np = a.Np;
+    double d2 = 0.0;
+    if (a.prox == LPVS_PROX_GROUP_L2) {
+        // warp per group: z_g = max(0, 1 - mu*lambda/||v_g||) v_g ; ungrouped entries stay z = 0
+        for (int g = b * ADMM_WARPS + w; g <= a.ngroups; g += nblocks * ADMM_WARPS) {
+            if (g == a.ngroups) {
+                // pseudo group: entries not covered by any group (Q16) -> z = 0
+                const int lo2 = a.goff[a.ngroups], hi2 = a.goff[a.ngroups + 1];
+                for (int m = lo2 + lane; m < hi2; m += 32) {
+                    int i = a.gmem[m];
+                    double xi = __ldcg(a.x + i), ui = a.u[i];
+                    double di = xi;
+                    ui += di;
+                    a.z[i] = 0.0;
+                    a.u[i] = ui;
+                    rn[i] = next_rhs(a, i, 0.0, ui);
+                    d2 += di * di;
+                }
+                continue;
+            }
+            const int lo = a.goff[g], hi = a.goff[g + 1];
+            double ss = 0.0;
+            for (int m = lo + lane; m < hi; m += 32) {
+                double vi = __ldcg(a.v + a.gmem[m]);
+                ss += vi * vi;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            double nrm = sqrt(ss);
+            double scale = nrm > 0.0 ? fmax(0.0, 1.0 - gl / nrm) : 0.0;
+            for (int m = lo + lane; m < hi; m += 32) {
+                int i = a.gmem[m];
+                double vi = __ldcg(a.v + i), xi = __ldcg(a.x + i), ui = a.u[i];
+                double zi = scale * vi;
+                double di = xi - zi;
+                ui += di;
+                a.z[i] = zi;
+                a.u[i] = ui;
+                rn[i] = next_rhs(a, i, zi, ui);
+                d2 += di * di;
+            }
+        }
+    } else if (b == 0) {  // LPVS_PROX_BALL_L0: keep the r largest |v| (ties -> lower index); block 0 only
+        __shared__ unsigned hist[256];
+        __shared__ unsigned long long s_prefix;
+        __shared__ unsigned s_want;
+        __shared__ int s_tie_cut;
+        const unsigned rkeep = (unsigned)a.pparam;
+        if (tid == 0) {
+            s_prefix = 0ull;
+            s_want = rkeep;
+        }
+        __syncthreads();
+        // radix select (MSB first) of the rkeep-th largest key = bits(|v|)
+        for (int pass = 7; pass >= 0 && rkeep > 0 && rkeep < (unsigned)Np; pass--) {
+            for (int k = tid; k < 256; k += ADMM_THREADS) hist[k] = 0;
+            __syncthreads();
+            const unsigned long long hi_mask = pass == 7 ? 0ull : (~0ull << (8 * (pass + 1)));
+            const unsigned long long prefix = s_prefix;
+            for (int i = tid; i < Np; i += ADMM_THREADS) {
+                unsigned long long key = (unsigned long long)__double_as_longlong(fabs(__ldcg(a.v + i)));
+                if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned want = s_want, accn = 0;
+                int d = 255;
+                for (; d > 0; d--) {
+                    if (accn + hist[d] >= want) break;
+                    accn += hist[d];
+                }
+                s_want = want - accn;
+                s_prefix = prefix | ((unsigned long long)d << (8 * pass));
+            }
+            __syncthreads();
+        }
+        const unsigned long long kth = s_prefix;  // key of the r-th largest
+        const unsigned ties_to_take = s_want;     // entries equal to kth that are kept (lowest index first)
+        if (tid == 0) {
+            int cut = -1;
+            if (rkeep > 0 && rkeep < (unsigned)Np) {
+                unsigned seen = 0;
+                for (int i = 0; i < Np && seen < ties_to_take; i++) {
+                    unsigned long long key = (unsigned long long)__double_as_longlong(fabs(__ldcg(a.v + i)));
+                    if (key == kth) {
+                        seen++;
+                        cut = i;
+                    }
+                }
+            }
+            s_tie_cut = cut;
+        }
+        __syncthreads();
+        const int cut = s_tie_cut;
+        for (int i = tid; i < Np; i += ADMM_THREADS) {
+            double vi = __ldcg(a.v + i), xi = __ldcg(a.x + i), ui = a.u[i];
+            unsigned long long key = (unsigned long long)__double_as_longlong(fabs(vi));
+            bool keep;
+            if (rkeep == 0) keep = false;
+            else if (rkeep >= (unsigned)Np) keep = true;
+            else keep = key > kth || (key == kth && i <= cut);
+            double zi = keep ? vi : 0.0;
+            double di = xi - zi;
+            ui += di;
+            a.z[i] = zi;
+            a.u[i] = ui;
+            rn[i] = next_rhs(a, i, zi, ui);
+            d2 += di * di;
+        }
+    }
+    return d2;
+}
+
+// residual partial of this CTA (fixed-order), grid barrier, stop test.  Returns true when ||x-z|| < tol.
+__device__ __forceinline__ bool admm_end_iter(const AdmmArgs& a, cg::grid_group& grid, double d2, long long it,
+                                              int b, int nblocks, int tid, int lane, int w, double* wsum,
+                                              double* s_nxz, double& nxz) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    if (lane == 0) wsum[w] = d2;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int k = 0; k < ADMM_WARPS; k++) s += wsum[k];
+        a.part[(it & 1) * nblocks + b] = s;
+    }
+    grid.sync();
+    if ((it + 1) % a.check_every == 0 || it + 1 == a.max_iters) {
+        if (tid == 0) {
+            double s = 0.0;
+            for (int k = 0; k < nblocks; k++) s += __ldcg(a.part + (it & 1) * nblocks + k);
+            *s_nxz = sqrt(s);
+        }
+        __syncthreads();
+        nxz = *s_nxz;
+        return nxz < a.tol;
+    }
+    return false;
+}
+
+// ---- variant 1: GEMV over the full symmetric M (small problems, M resident in L2) ------------------------------
 // STREAM: M does not fit in L2 -> evict-first loads; otherwise let L2 keep it across iterations
 template <bool STREAM>
 __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const __grid_constant__ AdmmArgs a) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double sm[];
-    double* rs = sm;                      // Np
-    double* red = sm + a.Np;              // [rows_max][ADMM_WARPS]
+    double* rs = sm;          // Np
+    double* red = sm + a.Np;  // [rows_max][ADMM_WARPS]
     __shared__ double wsum[ADMM_WARPS];
     __shared__ double s_nxz;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -158,161 +318,181 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const __grid_constant_
 #pragma unroll
             for (int k = 0; k < ADMM_WARPS; k++) xi += red[tid * ADMM_WARPS + k];
             a.x[i] = xi;
-            double ui = a.u[i];
-            double vi = xi + ui;
-            if (elementwise) {
-                double zi = prox_elem(a.prox, vi, gl, thr0);
-                double di = xi - zi;
-                ui += di;
-                a.z[i] = zi;
-                a.u[i] = ui;
-                rn[i] = next_rhs(a, i, zi, ui);
-                d2 = di * di;
-            } else {
-                a.v[i] = vi;
-            }
+            if (elementwise)
+                d2 = admm_elem_update(a, rn, i, xi, gl, thr0);
+            else
+                a.v[i] = xi + a.u[i];
         }
         if (!elementwise) {
             grid.sync();
-            d2 = 0.0;
-            if (a.prox == LPVS_PROX_GROUP_L2) {
-                // warp per group: z_g = max(0, 1 - mu*lambda/||v_g||) v_g ; ungrouped entries stay z = 0
-                for (int g = b * ADMM_WARPS + w; g <= a.ngroups; g += nblocks * ADMM_WARPS) {
-                    const int lo = a.goff[g], hi = (g < a.ngroups) ? a.goff[g + 1] : a.goff[g];
-                    if (g == a.ngroups) {
-                        // pseudo group: entries not covered by any group (Q16) -> z = 0
-                        const int lo2 = a.goff[a.ngroups], hi2 = a.goff[a.ngroups + 1];
-                        for (int m = lo2 + lane; m < hi2; m += 32) {
-                            int i = a.gmem[m];
-                            double xi = __ldcg(a.x + i), ui = a.u[i];
-                            double di = xi;
-                            ui += di;
-                            a.z[i] = 0.0;
-                            a.u[i] = ui;
-                            rn[i] = next_rhs(a, i, 0.0, ui);
-                            d2 += di * di;
-                        }
-                        continue;
-                    }
-                    double ss = 0.0;
-                    for (int m = lo + lane; m < hi; m += 32) {
-                        double vi = __ldcg(a.v + a.gmem[m]);
-                        ss += vi * vi;
-                    }
+            d2 = admm_phase_nonelem(a, rn, b, nblocks, tid, lane, w, gl);
+        }
+        const bool stop = admm_end_iter(a, grid, d2, it, b, nblocks, tid, lane, w, wsum, &s_nxz, nxz);
+        cur ^= 1;
+        if (stop) {
+            converged = 1;
+            it++;
+            break;
+        }
+    }
+    if (b == 0 && tid == 0) {
+        *a.iters_out = it;
+        *a.res_out = nxz;
+        *a.conv_out = converged;
+        *a.rbuf_out = cur;
+    }
+}
+
+// ---- variant 2: SYMV over the lower triangle only (4*Np^2 bytes per iteration) ---------------------------------
+// Work unit: a segment = up to SEG consecutive 128x128 blocks (I = i0..i1-1) of one block column J of the lower
+// triangle.  Warp w owns rows 8w..8w+7 of every block: 16 independent 16-byte loads per lane per block.
+//   row part:    y_I[8w+r]  += sum_c M[I,J][8w+r, c] * r_J[c]          (warp shuffle reduction, single writer)
+//   column part: y_J[c]     += sum_r M[I,J][r, c] * r_I[r]  (I != J)   (registers across the segment, then one
+//                                                                       cross-warp reduction per segment)
+// Each CTA accumulates into a private y in shared memory and publishes it; the cross-CTA sum (fixed order) is
+// fused with the prox / dual update / next rhs / residual epilogue after one grid barrier.
+constexpr int SEG = 8;
+struct SymvPlan {
+    const int* seg_j;   // block column
+    const int* seg_i0;  // first block row
+    const int* seg_i1;  // one past the last block row
+    const int* cta_seg; // [grid+1] segment ranges per CTA
+    double* ypart;      // [grid][Np]
+};
+
+__global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv(const __grid_constant__ AdmmArgs a,
+                                                               const __grid_constant__ SymvPlan sp) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) double sm[];
+    double* ys = sm;             // Np: CTA-private partial y
+    double* cred = sm + a.Np;    // [ADMM_WARPS][128] column partials of the current segment
+    __shared__ double wsum[ADMM_WARPS];
+    __shared__ double s_nxz;
+    __shared__ double red4[4][128];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nblocks = gridDim.x, b = blockIdx.x;
+    const int Np = a.Np;
+    const bool elementwise = (a.prox == LPVS_PROX_L1 || a.prox == LPVS_PROX_L0);
+    const double gl = a.mu * a.pparam;
+    const double thr0 = sqrt(2.0 * a.mu * a.pparam);
+    // phase-2 row ownership: even split
+    const int base = Np / nblocks, extra = Np % nblocks;
+    const int r0 = b * base + min(b, extra);
+    const int nrows = base + (b < extra ? 1 : 0);
+    const int sg0 = sp.cta_seg[b], sg1 = sp.cta_seg[b + 1];
+
+    int cur = a.rbuf0;
+    long long it = 0;
+    int converged = 0;
+    double nxz = 0.0;
+    for (; it < a.max_iters; it++) {
+        const double* rc = a.r + (long long)cur * Np;
+        double* rn = a.r + (long long)(cur ^ 1) * Np;
+        for (int i = tid; i < Np; i += ADMM_THREADS) ys[i] = 0.0;
+        __syncthreads();
+        // ---- phase 1: this CTA's segments ----
+        for (int sgi = sg0; sgi < sg1; sgi++) {
+            const int J = sp.seg_j[sgi], i0 = sp.seg_i0[sgi], i1 = sp.seg_i1[sgi];
+            // r_J for the lane's four columns: 2*lane, 2*lane+1, 64+2*lane, 64+2*lane+1
+            const double2 rj0 = __ldcg(reinterpret_cast<const double2*>(rc + J * 128 + 2 * lane));
+            const double2 rj1 = __ldcg(reinterpret_cast<const double2*>(rc + J * 128 + 64 + 2 * lane));
+            double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+            for (int I = i0; I < i1; I++) {
+                const double* blk = a.M + ((long long)I * 128 + 8 * w) * Np + (long long)J * 128 + 2 * lane;
+                double2 m0[8], m1[8];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                    double nrm = sqrt(ss);
-                    double scale = nrm > 0.0 ? fmax(0.0, 1.0 - gl / nrm) : 0.0;
-                    for (int m = lo + lane; m < hi; m += 32) {
-                        int i = a.gmem[m];
-                        double vi = __ldcg(a.v + i), xi = __ldcg(a.x + i), ui = a.u[i];
-                        double zi = scale * vi;
-                        double di = xi - zi;
-                        ui += di;
-                        a.z[i] = zi;
-                        a.u[i] = ui;
-                        rn[i] = next_rhs(a, i, zi, ui);
-                        d2 += di * di;
-                    }
+                for (int r = 0; r < 8; r++) {
+                    m0[r] = __ldcs(reinterpret_cast<const double2*>(blk + (long long)r * Np));
+                    m1[r] = __ldcs(reinterpret_cast<const double2*>(blk + (long long)r * Np + 64));
                 }
-            } else {  // LPVS_PROX_BALL_L0: keep the r largest |v| (ties -> lower index); block 0 only
-                if (b == 0) {
-                    __shared__ unsigned hist[256];
-                    __shared__ unsigned long long s_prefix;
-                    __shared__ unsigned s_want;
-                    const unsigned rkeep = (unsigned)a.pparam;
-                    if (tid == 0) {
-                        s_prefix = 0ull;
-                        s_want = rkeep;
-                    }
-                    __syncthreads();
-                    // radix select (MSB first) of the rkeep-th largest key = bits(|v|)
-                    for (int pass = 7; pass >= 0 && rkeep > 0 && rkeep < (unsigned)Np; pass--) {
-                        for (int k = tid; k < 256; k += ADMM_THREADS) hist[k] = 0;
-                        __syncthreads();
-                        const unsigned long long hi_mask = pass == 7 ? 0ull : (~0ull << (8 * (pass + 1)));
-                        const unsigned long long prefix = s_prefix;
-                        for (int i = tid; i < Np; i += ADMM_THREADS) {
-                            unsigned long long key = (unsigned long long)__double_as_longlong(fabs(__ldcg(a.v + i)));
-                            if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255], 1u);
-                        }
-                        __syncthreads();
-                        if (tid == 0) {
-                            unsigned want = s_want, accn = 0;
-                            int d = 255;
-                            for (; d > 0; d--) {
-                                if (accn + hist[d] >= want) break;
-                                accn += hist[d];
-                            }
-                            s_want = want - accn;
-                            s_prefix = prefix | ((unsigned long long)d << (8 * pass));
-                        }
-                        __syncthreads();
-                    }
-                    const unsigned long long kth = s_prefix;  // key of the r-th largest
-                    unsigned ties_to_take = s_want;           // how many entries equal to kth are kept (lowest index)
-                    // serial-by-chunk tie handling: thread 0 walks ties in index order (rare path, Np small)
-                    __shared__ int s_tie_cut;
-                    if (tid == 0) {
-                        int cut = -1;
-                        if (rkeep > 0 && rkeep < (unsigned)Np) {
-                            unsigned seen = 0;
-                            for (int i = 0; i < Np && seen < ties_to_take; i++) {
-                                unsigned long long key =
-                                    (unsigned long long)__double_as_longlong(fabs(__ldcg(a.v + i)));
-                                if (key == kth) {
-                                    seen++;
-                                    cut = i;
-                                }
-                            }
-                        }
-                        s_tie_cut = cut;
-                    }
-                    __syncthreads();
-                    const int cut = s_tie_cut;
-                    for (int i = tid; i < Np; i += ADMM_THREADS) {
-                        double vi = __ldcg(a.v + i), xi = __ldcg(a.x + i), ui = a.u[i];
-                        unsigned long long key = (unsigned long long)__double_as_longlong(fabs(vi));
-                        bool keep;
-                        if (rkeep == 0) keep = false;
-                        else if (rkeep >= (unsigned)Np) keep = true;
-                        else keep = key > kth || (key == kth && i <= cut);
-                        double zi = keep ? vi : 0.0;
-                        double di = xi - zi;
-                        ui += di;
-                        a.z[i] = zi;
-                        a.u[i] = ui;
-                        rn[i] = next_rhs(a, i, zi, ui);
-                        d2 += di * di;
-                    }
+                const bool offdiag = I != J;
+                double rs8[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) rs8[r] = offdiag ? __ldcg(rc + I * 128 + 8 * w + r) : 0.0;
+                double s[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    s[r] = fma(m0[r].x, rj0.x, fma(m0[r].y, rj0.y, fma(m1[r].x, rj1.x, m1[r].y * rj1.y)));
+                    c0 = fma(m0[r].x, rs8[r], c0);
+                    c1 = fma(m0[r].y, rs8[r], c1);
+                    c2 = fma(m1[r].x, rs8[r], c2);
+                    c3 = fma(m1[r].y, rs8[r], c3);
+                }
+                // reduce the 8 row sums over the 32 lanes: 8->4->2->1 values per lane while halving the lane span
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    double keep = (lane & 16) ? s[r + 4] : s[r];
+                    double send = (lane & 16) ? s[r] : s[r + 4];
+                    s[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    double keep = (lane & 8) ? s[r + 2] : s[r];
+                    double send = (lane & 8) ? s[r] : s[r + 2];
+                    s[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+                {
+                    double keep = (lane & 4) ? s[1] : s[0];
+                    double send = (lane & 4) ? s[0] : s[1];
+                    s[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                s[0] += __shfl_xor_sync(0xffffffffu, s[0], 2);
+                s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+                // lanes with (lane & 3) == 0 hold row index ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)
+                if ((lane & 3) == 0) {
+                    int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                    ys[I * 128 + 8 * w + r] += s[0];  // single writer: warp w owns these rows in every block
                 }
             }
-        }
-        // ---- residual partial of this CTA (fixed-order tree) ----
+            // column part of the segment: cross-warp reduction, then into ys[J block]
+            cred[w * 128 + 2 * lane] = c0;
+            cred[w * 128 + 2 * lane + 1] = c1;
+            cred[w * 128 + 64 + 2 * lane] = c2;
+            cred[w * 128 + 64 + 2 * lane + 1] = c3;
+            __syncthreads();
+            if (tid < 128) {
+                double t = 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-        if (lane == 0) wsum[w] = d2;
-        __syncthreads();
-        if (tid == 0) {
-            double s = 0.0;
-            for (int k = 0; k < ADMM_WARPS; k++) s += wsum[k];
-            a.part[(it & 1) * nblocks + b] = s;
-        }
-        grid.sync();
-        cur ^= 1;
-        if ((it + 1) % a.check_every == 0 || it + 1 == a.max_iters) {
-            if (tid == 0) {
-                double s = 0.0;
-                for (int k = 0; k < nblocks; k++) s += __ldcg(a.part + (it & 1) * nblocks + k);
-                s_nxz = sqrt(s);
+                for (int k = 0; k < ADMM_WARPS; k++) t += cred[k * 128 + tid];
+                ys[J * 128 + tid] += t;
             }
             __syncthreads();
-            nxz = s_nxz;
-            if (nxz < a.tol) {
-                converged = 1;
-                it++;
-                break;
+        }
+        double* yp = sp.ypart + (long long)b * Np;
+        for (int i = tid; i < Np; i += ADMM_THREADS) yp[i] = ys[i];
+        grid.sync();
+        // ---- phase 2: x_i = sum over CTAs (fixed order), then the fused epilogue on evenly split rows ----
+        double d2 = 0.0;
+        for (int rb = 0; rb < nrows; rb += 128) {
+            const int rl = rb + (tid & 127), q = tid >> 7;
+            double t = 0.0;
+            if (rl < nrows) {
+                const double* col = sp.ypart + r0 + rl;
+                for (int c = q; c < nblocks; c += 4) t += __ldcg(col + (long long)c * Np);
             }
+            red4[q][tid & 127] = t;
+            __syncthreads();
+            if (tid < 128 && rl < nrows) {
+                const int i = r0 + rl;
+                const double xi = (red4[0][tid] + red4[1][tid]) + (red4[2][tid] + red4[3][tid]);
+                a.x[i] = xi;
+                if (elementwise)
+                    d2 += admm_elem_update(a, rn, i, xi, gl, thr0);
+                else
+                    a.v[i] = xi + a.u[i];
+            }
+            __syncthreads();
+        }
+        if (!elementwise) {
+            grid.sync();
+            d2 = admm_phase_nonelem(a, rn, b, nblocks, tid, lane, w, gl);
+        }
+        const bool stop = admm_end_iter(a, grid, d2, it, b, nblocks, tid, lane, w, wsum, &s_nxz, nxz);
+        cur ^= 1;
+        if (stop) {
+            converged = 1;
+            it++;
+            break;
         }
     }
     if (b == 0 && tid == 0) {
@@ -375,6 +555,11 @@ struct lpvs_admm {
     double* d_res = nullptr;
     int* d_flags = nullptr;
     unsigned long long* sel = nullptr;
+    // SYMV variant (lower triangle only)
+    int symv = 0;
+    int* seg_buf = nullptr;  // seg_j | seg_i0 | seg_i1 | cta_seg
+    int nseg = 0;
+    double* ypart = nullptr;
     int rbuf = 0;
     int grid = 0;
     int64_t iters_total = 0;
@@ -400,12 +585,15 @@ static void admm_release(lpvs_admm* h) {
     cudaFree(h->d_res);
     cudaFree(h->d_flags);
     cudaFree(h->sel);
+    cudaFree(h->seg_buf);
+    cudaFree(h->ypart);
     if (h->e0) cudaEventDestroy(h->e0);
     if (h->e1) cudaEventDestroy(h->e1);
     delete h;
 }
 
 static size_t admm_smem(int Np, int rows_max) { return sizeof(double) * ((size_t)Np + (size_t)rows_max * ADMM_WARPS); }
+static size_t admm_smem_symv(int Np) { return sizeof(double) * ((size_t)Np + (size_t)ADMM_WARPS * 128); }
 
 // Factor (G + I/mu), invert, allocate loop state.  d_G: Np x Np lower tiles (consumed), d_q: Np.
 int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q, const double* d_x0) {
@@ -465,6 +653,47 @@ int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q
     LPVS_CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&maxb, k_admm<true>, ADMM_THREADS, smem));
     if (maxb < 1) return fail(c, LPVS_E_UNSUPPORTED, "ADMM kernel does not fit on an SM");
     h->grid = grid;
+    // variant: SYMV over the lower triangle when M cannot live in L2 (or when forced), else GEMV over full M
+    const bool big = 8.0 * Np * (double)Np > 96.0 * 1024 * 1024;
+    h->symv = c->admm_symv < 0 ? (big && Np <= 24576) : (c->admm_symv != 0);
+    if (h->symv) {
+        size_t sm2 = admm_smem_symv(Np);
+        if (sm2 > 220 * 1024) return fail(c, LPVS_E_UNSUPPORTED, "ADMM SYMV variant: Np=%d too large", Np);
+        LPVS_CU(c, cudaFuncSetAttribute(k_admm_symv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        h->grid = grid = c->sms;
+        // blocks of the lower triangle in block-column-major order, split evenly over the CTAs, then cut into
+        // segments (same block column, <= SEG blocks)
+        const long long T = (long long)nb * (nb + 1) / 2;
+        std::vector<int> sj, si0, si1, cta(grid + 1, 0);
+        std::vector<int> colstart(nb + 1, 0);
+        for (int J = 0; J < nb; J++) colstart[J + 1] = colstart[J] + (nb - J);
+        int J = 0;
+        for (int cta_i = 0; cta_i < grid; cta_i++) {
+            long long t0 = T * cta_i / grid, t1 = T * (cta_i + 1) / grid;
+            cta[cta_i] = (int)sj.size();
+            long long t = t0;
+            while (t < t1) {
+                while (colstart[J + 1] <= t) J++;
+                int I = J + (int)(t - colstart[J]);
+                long long run = std::min<long long>(std::min<long long>(t1 - t, colstart[J + 1] - t), SEG);
+                sj.push_back(J);
+                si0.push_back(I);
+                si1.push_back(I + (int)run);
+                t += run;
+            }
+        }
+        cta[grid] = (int)sj.size();
+        h->nseg = (int)sj.size();
+        std::vector<int> all;
+        all.insert(all.end(), sj.begin(), sj.end());
+        all.insert(all.end(), si0.begin(), si0.end());
+        all.insert(all.end(), si1.begin(), si1.end());
+        all.insert(all.end(), cta.begin(), cta.end());
+        LPVS_CU(c, cudaMalloc(&h->seg_buf, sizeof(int) * all.size()));
+        LPVS_CU(c, cudaMemcpyAsync(h->seg_buf, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice, c->st));
+        LPVS_CU(c, cudaStreamSynchronize(c->st));
+        LPVS_CU(c, cudaMalloc(&h->ypart, sizeof(double) * (size_t)grid * Np));
+    }
     LPVS_CU(c, cudaMalloc(&h->part, sizeof(double) * 2 * grid));
     LPVS_CU(c, cudaMalloc(&h->d_iters, sizeof(long long)));
     LPVS_CU(c, cudaMalloc(&h->d_res, sizeof(double)));
@@ -523,13 +752,25 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
     a.conv_out = h->d_flags;
     a.rbuf_out = h->d_flags + 1;
     a.sel_key = h->sel;
-    int rows_max = (Np + h->grid - 1) / h->grid;
-    size_t smem = admm_smem(Np, rows_max + 1);
-    void* args[] = {&a};
     LPVS_CU(c, cudaEventRecord(h->e0, c->st));
-    const bool stream = 8.0 * Np * (double)Np > 96.0 * 1024 * 1024;  // M larger than what L2 can keep
-    void* kfn = stream ? (void*)k_admm<true> : (void*)k_admm<false>;
-    LPVS_CU(c, cudaLaunchCooperativeKernel(kfn, dim3(h->grid), dim3(ADMM_THREADS), args, smem, c->st));
+    if (h->symv) {
+        SymvPlan sp{};
+        sp.seg_j = h->seg_buf;
+        sp.seg_i0 = h->seg_buf + h->nseg;
+        sp.seg_i1 = h->seg_buf + 2 * h->nseg;
+        sp.cta_seg = h->seg_buf + 3 * h->nseg;
+        sp.ypart = h->ypart;
+        void* args[] = {&a, &sp};
+        LPVS_CU(c, cudaLaunchCooperativeKernel((void*)k_admm_symv, dim3(h->grid), dim3(ADMM_THREADS), args,
+                                               admm_smem_symv(Np), c->st));
+    } else {
+        int rows_max = (Np + h->grid - 1) / h->grid;
+        size_t smem = admm_smem(Np, rows_max + 1);
+        void* args[] = {&a};
+        const bool stream = 8.0 * Np * (double)Np > 96.0 * 1024 * 1024;  // M larger than what L2 can keep
+        void* kfn = stream ? (void*)k_admm<true> : (void*)k_admm<false>;
+        LPVS_CU(c, cudaLaunchCooperativeKernel(kfn, dim3(h->grid), dim3(ADMM_THREADS), args, smem, c->st));
+    }
     LPVS_CU(c, cudaEventRecord(h->e1, c->st));
     c->launches++;
     long long its = 0;
@@ -612,7 +853,11 @@ int lpvs_admm_result(lpvs_admm* h, double* out) {
 int lpvs_admm_last_timing(const lpvs_admm* h, double* ms, double* bytes_per_iter) {
     if (!h) return LPVS_E_BAD_ARG;
     if (ms) *ms = h->last_ms;
-    if (bytes_per_iter) *bytes_per_iter = 8.0 * (double)h->Np * (double)h->Np;
+    if (bytes_per_iter) {
+        // algorithmic bytes of the variant actually run: full M (GEMV) or the lower-triangle blocks (SYMV)
+        double nb = h->Np / 128.0;
+        *bytes_per_iter = h->symv ? nb * (nb + 1.0) / 2.0 * 128.0 * 128.0 * 8.0 : 8.0 * (double)h->Np * (double)h->Np;
+    }
     return LPVS_OK;
 }
 

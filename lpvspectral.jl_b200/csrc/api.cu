@@ -414,6 +414,7 @@ int lpvs_set_option(lpvs_ctx* c, int key, double value) {
         case LPVS_OPT_WINDOW_BATCH: c->window_batch = (int)value; break;
         case LPVS_OPT_JITTER: c->jitter = (int)value; break;
         case LPVS_OPT_ADMM_CHECK_EVERY: c->admm_check_every = std::max(1, (int)value); break;
+        case LPVS_OPT_ADMM_SYMV: c->admm_symv = (int)value; break;
         default: return fail(c, LPVS_E_BAD_ARG, "unknown option %d", key);
     }
     return LPVS_OK;
@@ -538,8 +539,24 @@ int ls_solve_dev(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const do
     if (!d_G || !d_B || !d_md) return fail(c, LPVS_E_NOMEM, "out of device memory (G)");
     int rc;
     if (info) *info = 0;
+    double* d_keep = nullptr;  // pristine copy of G, b for the jitter retry (no second Gram pass)
     for (int attempt = 0; attempt < 2; attempt++) {
-        if ((rc = gram_single(c, pl, d_t, d_y, d_u, d_W, N, nrhs, d_G, d_B))) return rc;
+        if (attempt == 0) {
+            if ((rc = gram_single(c, pl, d_t, d_y, d_u, d_W, N, nrhs, d_G, d_B))) return rc;
+            if (allow_jitter) {
+                d_keep = ws<double>(c, BUF_YINV, (size_t)Np * Np + 2 * Np);
+                if (d_keep) {
+                    LPVS_CU(c, cudaMemcpyAsync(d_keep, d_G, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, c->st));
+                    LPVS_CU(c, cudaMemcpyAsync(d_keep + Np * Np, d_B, sizeof(double) * 2 * Np, cudaMemcpyDeviceToDevice,
+                                               c->st));
+                }
+            }
+        } else if (d_keep) {
+            LPVS_CU(c, cudaMemcpyAsync(d_G, d_keep, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, c->st));
+            LPVS_CU(c, cudaMemcpyAsync(d_B, d_keep + Np * Np, sizeof(double) * 2 * Np, cudaMemcpyDeviceToDevice, c->st));
+        } else {
+            if ((rc = gram_single(c, pl, d_t, d_y, d_u, d_W, N, nrhs, d_G, d_B))) return rc;
+        }
         double maxdiag = 0.0;
         if (attempt == 0 && allow_jitter) {
             launch_max_diag(d_G, Np * Np, pl.Np, pl.Nf, pl.zero_first, d_md, 1, c->st);

@@ -1,6 +1,9 @@
 // Blocked FP64 Cholesky, triangular inverse and SPD inverse on 128x128 tiles.  See chol.cuh.
 #include "chol.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace lpvs {
 
 namespace {
@@ -116,10 +119,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ C
     const int prob = blockIdx.x;
     double* Gd = a.G + (long long)prob * a.strideG + ((long long)k * TB) * a.Np + (long long)k * TB;
 
-    // load the lower triangle of the diagonal block
-    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
-        int r = idx >> 7, c = idx & 127;
-        S[r * LDS + c] = (c <= r) ? Gd[(long long)r * a.Np + c] : 0.0;
+    // load the lower triangle of the diagonal block: 16-byte loads, 8 in flight per thread
+    for (int base = 0; base < TB * TB / 2; base += NTHREADS * 8) {
+        double2 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            int idx = base + q * NTHREADS + tid;  // double2 index
+            int r = idx >> 6, c = (idx & 63) * 2;
+            v[q] = (c <= r) ? __ldcg(reinterpret_cast<const double2*>(Gd + (long long)r * a.Np + c))
+                            : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            int idx = base + q * NTHREADS + tid;
+            int r = idx >> 6, c = (idx & 63) * 2;
+            S[r * LDS + c] = v[q].x;
+            S[r * LDS + c + 1] = (c + 1 <= r) ? v[q].y : 0.0;
+        }
     }
     __syncthreads();
 
@@ -448,6 +464,123 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trsv(const __grid_constant__ Ch
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// multi-CTA blocked TRSV for ONE large problem (cooperative launch, grid = nb CTAs, CTA i owns row block i).
+// Forward:  y_k = Linv_k r_k, publish, then every CTA i > k does r_i -= L[i,k] y_k.   One grid barrier per block.
+// Backward: x_k = Linv_k' r_k, publish, then every CTA i < k does r_i -= L[k,i]' x_k.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) k_trsv_big(const __grid_constant__ CholArgs a, double* b, int nrhs) {
+    cg::grid_group grid = cg::this_grid();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x;
+    const long long Np = a.Np;
+    const double* L = a.G;
+    __shared__ double r[2][TB];     // this CTA's running right-hand side block
+    __shared__ double yk[2][TB];    // the published solution block of the current step
+    __shared__ double part[2][2][TB];
+    for (int q = tid; q < 2 * TB; q += NTHREADS) {
+        int rh = q >> 7, c = q & 127;
+        r[rh][c] = rh < nrhs ? b[(long long)rh * Np + i * TB + c] : 0.0;
+    }
+    __syncthreads();
+    // ---- forward ----
+    for (int k = 0; k < a.nb; k++) {
+        if (i == k) {
+            const double* Li = a.Linv + (long long)k * TB * TB;
+            for (int rr = warp; rr < TB; rr += 8) {
+                double s0 = 0.0, s1 = 0.0;
+                for (int c = lane; c <= rr; c += 32) {
+                    double l = Li[rr * TB + c];
+                    s0 = fma(l, r[0][c], s0);
+                    s1 = fma(l, r[1][c], s1);
+                }
+                s0 = warp_sum(s0);
+                s1 = warp_sum(s1);
+                if (lane == 0) {
+                    b[k * TB + rr] = s0;
+                    if (nrhs > 1) b[Np + k * TB + rr] = s1;
+                }
+            }
+        }
+        grid.sync();
+        if (i > k) {
+            for (int q = tid; q < 2 * TB; q += NTHREADS) {
+                int rh = q >> 7, c = q & 127;
+                yk[rh][c] = rh < nrhs ? __ldcg(b + (long long)rh * Np + k * TB + c) : 0.0;
+            }
+            __syncthreads();
+            const double* T = L + (long long)i * TB * Np + (long long)k * TB;
+            for (int rr = warp; rr < TB; rr += 8) {
+                const double* row = T + (long long)rr * Np;
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    double l = row[lane + 32 * q];
+                    s0 = fma(l, yk[0][lane + 32 * q], s0);
+                    s1 = fma(l, yk[1][lane + 32 * q], s1);
+                }
+                s0 = warp_sum(s0);
+                s1 = warp_sum(s1);
+                if (lane == 0) {
+                    r[0][rr] -= s0;
+                    r[1][rr] -= s1;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // r of CTA i is now stale; reload y_i as the backward right-hand side
+    grid.sync();
+    for (int q = tid; q < 2 * TB; q += NTHREADS) {
+        int rh = q >> 7, c = q & 127;
+        r[rh][c] = rh < nrhs ? __ldcg(b + (long long)rh * Np + i * TB + c) : 0.0;
+    }
+    __syncthreads();
+    // ---- backward ----
+    const int c = tid & 127, h = tid >> 7;
+    for (int k = a.nb - 1; k >= 0; k--) {
+        if (i == k) {
+            const double* Li = a.Linv + (long long)k * TB * TB;
+            double s0 = 0.0, s1 = 0.0;
+            for (int m = c + h; m < TB; m += 2) {
+                double l = Li[m * TB + c];
+                s0 = fma(l, r[0][m], s0);
+                s1 = fma(l, r[1][m], s1);
+            }
+            part[0][h][c] = s0;
+            part[1][h][c] = s1;
+            __syncthreads();
+            if (h == 0) {
+                b[k * TB + c] = part[0][0][c] + part[0][1][c];
+                if (nrhs > 1) b[Np + k * TB + c] = part[1][0][c] + part[1][1][c];
+            }
+        }
+        grid.sync();
+        if (i < k) {
+            for (int q = tid; q < 2 * TB; q += NTHREADS) {
+                int rh = q >> 7, cc = q & 127;
+                yk[rh][cc] = rh < nrhs ? __ldcg(b + (long long)rh * Np + k * TB + cc) : 0.0;
+            }
+            __syncthreads();
+            const double* T = L + (long long)k * TB * Np + (long long)i * TB;  // L[k, i], used transposed
+            double s0 = 0.0, s1 = 0.0;
+            for (int m = h; m < TB; m += 2) {
+                double l = T[(long long)m * Np + c];
+                s0 = fma(l, yk[0][m], s0);
+                s1 = fma(l, yk[1][m], s1);
+            }
+            part[0][h][c] = s0;
+            part[1][h][c] = s1;
+            __syncthreads();
+            if (h == 0) {
+                r[0][c] -= part[0][0][c] + part[0][1][c];
+                r[1][c] -= part[1][0][c] + part[1][1][c];
+            }
+            __syncthreads();
+        }
+    }
+}
+
 bool attrs_done = false;
 void set_attrs() {
     if (attrs_done) return;
@@ -511,6 +644,18 @@ void launch_symmetrize(double* G, long long strideG, int Np, int nproblems, cuda
 }
 
 void launch_trsv(const CholArgs& a, double* B, long long strideB, int nrhs, int nproblems, cudaStream_t st) {
+    if (nproblems == 1 && a.nb >= 8) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (a.nb <= sms) {  // all row blocks co-resident: cooperative multi-CTA substitution
+            CholArgs aa = a;
+            void* args[] = {(void*)&aa, (void*)&B, (void*)&nrhs};
+            if (cudaLaunchCooperativeKernel((void*)k_trsv_big, dim3(a.nb), dim3(NTHREADS), args, 0, st) == cudaSuccess)
+                return;
+            cudaGetLastError();
+        }
+    }
     k_trsv<<<nproblems, NTHREADS, 0, st>>>(a, B, strideB, nrhs);
 }
 

@@ -36,6 +36,7 @@ struct lpvs_ctx {
     int window_batch = 0;
     int jitter = 1;
     int admm_check_every = 1;
+    int admm_symv = -1;  // -1 auto, 0 GEMV over full M, 1 SYMV over the lower triangle
     lpvs::DevBuf buf[lpvs::BUF_COUNT];
     int64_t launches = 0;
     // Gram kernel timing of the last API call

@@ -201,11 +201,21 @@ __global__ void __launch_bounds__(NTHREADS) k_gram_rhs(const __grid_constant__ G
     for (int r = 0; r < 2; r++)
 #pragma unroll
         for (int j = 0; j < GRP; j++) sc[r][j] = ss[r][j] = 0.0;
-    for (int c = 0; c < nchunks; c++) {
-        Pref p = load_pref<MODE, true>(a, c, s_begin, lane, w, I, I);
+    auto load_y = [&](const Pref& p, double& y0, double& y1) {
         long long s = p.si + a.tbl_base;
-        double y0 = a.y ? a.y[s] * p.wt : 0.0;
-        double y1 = (a.nrhs > 1 && a.u) ? a.u[s] * p.wt : 0.0;
+        y0 = a.y ? a.y[s] * p.wt : 0.0;
+        y1 = (a.nrhs > 1 && a.u) ? a.u[s] * p.wt : 0.0;
+    };
+    Pref pn = load_pref<MODE, true>(a, 0, s_begin, lane, w, I, I);
+    double yn0, yn1;
+    load_y(pn, yn0, yn1);
+    for (int c = 0; c < nchunks; c++) {
+        const Pref p = pn;
+        const double y0 = yn0, y1 = yn1;
+        if (c + 1 < nchunks) {  // prefetch the next chunk while this one is consumed
+            pn = load_pref<MODE, true>(a, c + 1, s_begin, lane, w, I, I);
+            load_y(pn, yn0, yn1);
+        }
         double2 z = p.aI;
 #pragma unroll
         for (int j = 0; j < GRP; j++) {

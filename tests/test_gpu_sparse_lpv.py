@@ -144,3 +144,40 @@ def test_sparse_lpv_group_lasso(ctx):
     # active frequencies are the true ones (2,10,20 Hz -> indices 1,5,10 of w)
     active = set((np.flatnonzero(lp.psd(se) > 0) + 1).tolist())
     assert {1, 5, 10} <= active
+
+
+@pytest.mark.parametrize("prox", ["l1", "ball", "group"])
+def test_symv_variant_matches_gemv_variant(ctx, prox):
+    """LPVS_OPT_ADMM_SYMV=1 (lower-triangle x-update, 4 Np^2 B/iter) vs =0 (full GEMV): same iterates to rounding,
+    same support and iteration count, both equal to the oracle."""
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+
+    out = {}
+    for mode in (0, 1):
+        ctx.set_option(L.OPT_ADMM_SYMV, mode)
+        try:
+            if prox == "group":
+                Y, V, X = o.generate_lpv_signal(500, seed=0)
+                w = 2 * np.pi * np.arange(2, 26, 2)
+                se, info = lp.ls_sparse_spectral_lpv(Y, X, V, w, 50, lam=5.0, iters=2000, tol=1e-8, ctx=ctx,
+                                                     return_info=True)
+            else:
+                t, y = sparse_signal(1500, 11)
+                f = np.arange(0, 700) * 0.05
+                pg = lp.NormL1(0.5) if prox == "l1" else lp.IndBallL0(6)
+                x, _, info = lp.ls_sparse_spectral(y, t, f, proxg=pg, iters=1500, tol=1e-9, ctx=ctx,
+                                                   return_info=True)
+        finally:
+            ctx.set_option(L.OPT_ADMM_SYMV, -1)
+        out[mode] = info
+    assert out[0]["iters"] == out[1]["iters"]
+    assert support(out[0]["z"]) == support(out[1]["z"])
+    assert rel(out[1]["z"], out[0]["z"]) <= 1e-10
+    if prox == "l1":
+        t, y = sparse_signal(1500, 11)
+        f = np.arange(0, 700) * 0.05
+        xr, _, ri = o.ls_sparse_spectral(y, t, f, proxg=o.NormL1(0.5), iters=1500, tol=1e-9, mode="gram",
+                                         return_info=True, printerval=10 ** 9)
+        assert ri["iters"] == out[1]["iters"] and support(ri["z"]) == support(out[1]["z"])
+        assert rel(out[1]["z"], ri["z"]) <= 1e-9
