@@ -10,6 +10,8 @@
 // advances with the per-sample rotation e^{-i 2 pi df t}: 4 FP64 ops per (cos,-sin) pair instead of ~35.
 #include "gram.cuh"
 
+#include <stdlib.h>
+
 namespace lpvs {
 
 namespace {
@@ -21,6 +23,7 @@ struct Pref {
     double tt;          // direct: sample position
     long long si;       // table sample index
     double wt, yv;
+    bool valid;  // the weight is zeroed for invalid samples at the point of USE (no stall on the prefetch)
 };
 
 template <int MODE, bool DIAG>
@@ -33,9 +36,9 @@ __device__ __forceinline__ Pref load_pref(const GramArgs& a, int c, long long s_
     if (!valid) s = min(s_begin + (long long)a.n, a.s_end) - 1;
     int idc = (int)(s - s_begin);
     p.si = s - a.tbl_base;
-    double wt = 1.0;
-    if (a.W) wt = a.W[a.w_abs ? s : (long long)idc];
-    p.wt = valid ? wt : 0.0;
+    p.wt = 1.0;
+    if (a.W) p.wt = a.W[a.w_abs ? s : (long long)idc];
+    p.valid = valid;
     p.yv = 0.0;
     if (MODE == GRAM_CHAIN) {
         p.aI = a.anc[(long long)(I * (FB / GRP) + w) * a.tbl_ns + p.si];
@@ -79,23 +82,28 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     const int rowc = (w * GRP) * LDT + lane;       // smem offset of the real-part row for j = 0
     const int rows = (FB + w * GRP) * LDT + lane;  // second-part row
 
-    // synthesise element j (of 8) of a chunk into stage buffer `st`
+    // masking is only needed when this warp's 8-column group is not entirely valid (warp-uniform)
+    const bool maskI = ccI0 + GRP > a.ncc, maskJ = ccJ0 + GRP > a.ncc;
+    // synthesise element j (of 8) of a chunk into stage buffer `st`.  CHAIN, off-diagonal: zJ is pre-scaled by the
+    // sample weight (rotation is linear), so the J tile needs no per-element multiply.
     auto synth_step = [&](const Pref& p, double2& zI, double2& zJ, int j, double* st) {
         double2 vI, vJ;
         if (MODE == GRAM_CHAIN) {
             vI = zI;
-            vJ = DIAG ? zI : zJ;
+            vJ = DIAG ? make_double2(zI.x * p.wt, zI.y * p.wt) : zJ;
         } else {
-            vI = (ccI0 + j < a.ncc) ? synth_elem<MODE>(a, p, ccI0 + j) : make_double2(0.0, 0.0);
-            vJ = DIAG ? vI : ((ccJ0 + j < a.ncc) ? synth_elem<MODE>(a, p, ccJ0 + j) : make_double2(0.0, 0.0));
+            vI = synth_elem<MODE>(a, p, min(ccI0 + j, a.ncc - 1));
+            vJ = DIAG ? vI : synth_elem<MODE>(a, p, min(ccJ0 + j, a.ncc - 1));
+            vJ = make_double2(vJ.x * p.wt, vJ.y * p.wt);
         }
-        bool okI = ccI0 + j < a.ncc, okJ = ccJ0 + j < a.ncc;
+        if (maskI && ccI0 + j >= a.ncc) vI = make_double2(0.0, 0.0);
+        if ((DIAG ? maskI : maskJ) && (DIAG ? ccI0 : ccJ0) + j >= a.ncc) vJ = make_double2(0.0, 0.0);
         double* sI = st;
         double* sJ = st + TILE_D;
-        sI[rowc + j * LDT] = okI ? vI.x : 0.0;
-        sI[rows + j * LDT] = okI ? vI.y : 0.0;
-        sJ[rowc + j * LDT] = okJ ? vJ.x * p.wt : 0.0;
-        sJ[rows + j * LDT] = okJ ? vJ.y * p.wt : 0.0;
+        sI[rowc + j * LDT] = vI.x;
+        sI[rows + j * LDT] = vI.y;
+        sJ[rowc + j * LDT] = vJ.x;
+        sJ[rows + j * LDT] = vJ.y;
         if (MODE == GRAM_CHAIN) {
             double nx = zI.x * p.d.x - zI.y * p.d.y;
             double ny = zI.x * p.d.y + zI.y * p.d.x;
@@ -107,11 +115,14 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
             }
         }
     };
+    auto chain_start_J = [&](const Pref& p) { return make_double2(p.aJ.x * p.wt, p.aJ.y * p.wt); };
 
     // prologue: chunk 0 into stage 0
+    auto resolve = [](Pref& p) { p.wt = p.valid ? p.wt : 0.0; };
     Pref p1 = load_pref<MODE, DIAG>(a, 0, s_begin, lane, w, I, J);
+    resolve(p1);
     {
-        double2 zI = p1.aI, zJ = p1.aJ;
+        double2 zI = p1.aI, zJ = chain_start_J(p1);
 #pragma unroll
         for (int j = 0; j < GRP; j++) synth_step(p1, zI, zJ, j, smem);
     }
@@ -128,7 +139,8 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
         const bool have_next = (c + 1 < nchunks);
         Pref p2 = p1;
         if (c + 2 < nchunks) p2 = load_pref<MODE, DIAG>(a, c + 2, s_begin, lane, w, I, J);
-        double2 zI = p1.aI, zJ = p1.aJ;
+        if (c > 0 || nchunks > 1) resolve(p1);  // p1 was loaded one iteration ago: no stall
+        double2 zI = p1.aI, zJ = chain_start_J(p1);
         const double* pa = cur + fragA;
         const double* pb = cur + TILE_D + fragB;
 #pragma unroll
@@ -188,6 +200,207 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// 16-warp variant: 4 warps per SMSP so the DMMA pipe always has a ready warp (a lone warp sustains only ~90 % of
+// the pipe, tools/fp64_probe.cu).  Warp grid 4(M) x 4(N), warp tile 32x32 (32 accumulators / thread, <= 128 regs).
+// Synthesis: warps 0-7 build the I tile (group = warp), warps 8-15 the weighted J tile: ONE chain per thread.
+// Diagonal tiles: three 64x64 sub-blocks, each split 4x4 into 16x16 warp tiles (12 DMMAs per k4-step, not 16).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int NT16 = 512;
+
+struct Pref16 {
+    double2 a, d;
+    double tt;
+    long long si;
+    double wt;
+    bool valid;
+};
+
+template <int MODE>
+__device__ __forceinline__ Pref16 load_pref16(const GramArgs& a, int c, long long s_begin, int lane, int grp,
+                                              int blk) {
+    Pref16 p{};
+    int idx = c * KC + lane;
+    bool valid = idx < a.n && s_begin + idx < a.s_end;
+    long long s = s_begin + idx;
+    if (!valid) s = min(s_begin + (long long)a.n, a.s_end) - 1;
+    int idc = (int)(s - s_begin);
+    p.si = s - a.tbl_base;
+    p.wt = 1.0;
+    if (a.W) p.wt = a.W[a.w_abs ? s : (long long)idc];
+    p.valid = valid;
+    if (MODE == GRAM_CHAIN) {
+        p.a = a.anc[(long long)(blk * (FB / GRP) + grp) * a.tbl_ns + p.si];
+        p.d = a.del[p.si];
+    } else if (MODE == GRAM_DIRECT) {
+        p.tt = a.t[s];
+    }
+    return p;
+}
+
+template <int MODE>
+__device__ __forceinline__ double2 synth_elem16(const GramArgs& a, const Pref16& p, int cc) {
+    if (MODE == GRAM_DIRECT) {
+        return cis_reference(a.f[cc], p.tt);
+    } else {
+        int fi = cc % a.lpv_nf, ki = cc / a.lpv_nf;
+        double2 e = a.E[(long long)fi * a.tbl_ns + p.si];
+        double k = a.Kt[(long long)ki * a.tbl_ns + p.si];
+        return make_double2(e.x * k, e.y * k);
+    }
+}
+
+template <int MODE, bool DIAG>
+__device__ __forceinline__ void gram_tile16(const GramArgs& a, int I, int J, int prob, double* smem) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wm = w & 3, wn = w >> 2;
+    const long long s_begin = a.start0 + (long long)prob * a.hop;
+    const int nchunks = (a.n + KC - 1) / KC;
+
+    double acc[4][4][2];  // off-diagonal [i][j][e]; diagonal: [sb(3)][i*2+j (4)][e]
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // synthesis role: warps 0-7 -> I tile, warps 8-15 -> J tile (pre-weighted); diagonal: warps 0-7 write both
+    const bool synI = w < 8;
+    const bool syn_active = DIAG ? synI : true;
+    const int grp = w & 7;
+    const int blk = synI ? I : J;
+    const int cc0 = blk * FB + grp * GRP;
+    const bool mask = cc0 + GRP > a.ncc;
+    const int rowc = (grp * GRP) * LDT + lane;
+    const int rows = (FB + grp * GRP) * LDT + lane;
+
+    auto chain_start = [&](const Pref16& p) {
+        return (DIAG || synI) ? p.a : make_double2(p.a.x * p.wt, p.a.y * p.wt);
+    };
+    auto synth_step = [&](const Pref16& p, double2& z, int j, double* st) {
+        double2 v;
+        if (MODE == GRAM_CHAIN) {
+            v = z;
+        } else {
+            v = synth_elem16<MODE>(a, p, min(cc0 + j, a.ncc - 1));
+            if (!DIAG && !synI) v = make_double2(v.x * p.wt, v.y * p.wt);
+        }
+        if (mask && cc0 + j >= a.ncc) v = make_double2(0.0, 0.0);
+        if (DIAG) {
+            st[rowc + j * LDT] = v.x;
+            st[rows + j * LDT] = v.y;
+            st[TILE_D + rowc + j * LDT] = v.x * p.wt;
+            st[TILE_D + rows + j * LDT] = v.y * p.wt;
+        } else {
+            double* dst = st + (synI ? 0 : TILE_D);
+            dst[rowc + j * LDT] = v.x;
+            dst[rows + j * LDT] = v.y;
+        }
+        if (MODE == GRAM_CHAIN) {
+            double nx = z.x * p.d.x - z.y * p.d.y;
+            double ny = z.x * p.d.y + z.y * p.d.x;
+            z = make_double2(nx, ny);
+        }
+    };
+
+    Pref16 p1{};
+    if (syn_active) {
+        p1 = load_pref16<MODE>(a, 0, s_begin, lane, grp, blk);
+        p1.wt = p1.valid ? p1.wt : 0.0;
+        double2 z = chain_start(p1);
+#pragma unroll
+        for (int j = 0; j < GRP; j++) synth_step(p1, z, j, smem);
+        if (nchunks > 1) p1 = load_pref16<MODE>(a, 1, s_begin, lane, grp, blk);
+    }
+    __syncthreads();
+
+    const int fragA = DIAG ? (16 * wm + (lane >> 2)) * LDT + (lane & 3) : (32 * wm + (lane >> 2)) * LDT + (lane & 3);
+    const int fragB = DIAG ? (16 * wn + (lane >> 2)) * LDT + (lane & 3) : (32 * wn + (lane >> 2)) * LDT + (lane & 3);
+
+    for (int c = 0; c < nchunks; c++) {
+        double* cur = smem + (c & 1) * STAGE_D;
+        double* nxt = smem + ((c & 1) ^ 1) * STAGE_D;
+        const bool do_syn = syn_active && (c + 1 < nchunks);
+        Pref16 p2 = p1;
+        if (syn_active && c + 2 < nchunks) p2 = load_pref16<MODE>(a, c + 2, s_begin, lane, grp, blk);
+        p1.wt = p1.valid ? p1.wt : 0.0;
+        double2 z = chain_start(p1);
+        const double* pa = cur + fragA;
+        const double* pb = cur + TILE_D + fragB;
+#pragma unroll
+        for (int kk = 0; kk < KC / 4; kk++) {
+            if (do_syn) synth_step(p1, z, kk, nxt);
+            if (!DIAG) {
+                double fa[4], fb[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) fa[i] = pa[i * 8 * LDT + 4 * kk];
+#pragma unroll
+                for (int j = 0; j < 4; j++) fb[j] = pb[j * 8 * LDT + 4 * kk];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            } else {
+                double fa[4], fb[4];  // [half*2 + r]: rows/cols {0,8} of the 16-wide warp tile in half 0 / half 1
+#pragma unroll
+                for (int i = 0; i < 4; i++) fa[i] = pa[((i >> 1) * 64 + (i & 1) * 8) * LDT + 4 * kk];
+#pragma unroll
+                for (int j = 0; j < 4; j++) fb[j] = pb[((j >> 1) * 64 + (j & 1) * 8) * LDT + 4 * kk];
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        dmma884(acc[0][i * 2 + j][0], acc[0][i * 2 + j][1], fa[i], fb[j]);          // (0,0)
+                        dmma884(acc[1][i * 2 + j][0], acc[1][i * 2 + j][1], fa[2 + i], fb[j]);      // (1,0)
+                        dmma884(acc[2][i * 2 + j][0], acc[2][i * 2 + j][1], fa[2 + i], fb[2 + j]);  // (1,1)
+                    }
+            }
+        }
+        p1 = p2;
+        __syncthreads();
+    }
+
+    const int Np = a.nblk * TB;
+    double* Gp = a.G + (long long)prob * a.strideG;
+    if (!DIAG) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int row = I * TB + 32 * wm + 8 * i + (lane >> 2);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int col = J * TB + 32 * wn + 8 * j + 2 * (lane & 3);
+                double2 v = make_double2(acc[i][j][0] * a.gscale, acc[i][j][1] * a.gscale);
+                *reinterpret_cast<double2*>(Gp + (long long)row * Np + col) = v;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int sb = 0; sb < 3; sb++) {
+            const int sr = sb > 0, sc = sb > 1;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                int row = I * TB + 64 * sr + 16 * wm + 8 * i + (lane >> 2);
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    int col = I * TB + 64 * sc + 16 * wn + 8 * j + 2 * (lane & 3);
+                    double2 v = make_double2(acc[sb][i * 2 + j][0] * a.gscale, acc[sb][i * 2 + j][1] * a.gscale);
+                    *reinterpret_cast<double2*>(Gp + (long long)row * Np + col) = v;
+                }
+            }
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NT16, 1) k_gram16(const __grid_constant__ GramArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    int I, J;
+    tile_ij(blockIdx.x, I, J);
+    if (I == J)
+        gram_tile16<MODE, true>(a, I, J, blockIdx.y, smem);
+    else
+        gram_tile16<MODE, false>(a, I, J, blockIdx.y, smem);
+}
+
 // b = A' diag(W) [y u]: one CTA per (64-frequency block, problem); warp = chain group, lane = sample.
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS) k_gram_rhs(const __grid_constant__ GramArgs a) {
@@ -201,17 +414,18 @@ __global__ void __launch_bounds__(NTHREADS) k_gram_rhs(const __grid_constant__ G
     for (int r = 0; r < 2; r++)
 #pragma unroll
         for (int j = 0; j < GRP; j++) sc[r][j] = ss[r][j] = 0.0;
-    auto load_y = [&](const Pref& p, double& y0, double& y1) {
+    auto load_y = [&](const Pref& p, double& y0, double& y1) {  // raw loads; weights applied at use
         long long s = p.si + a.tbl_base;
-        y0 = a.y ? a.y[s] * p.wt : 0.0;
-        y1 = (a.nrhs > 1 && a.u) ? a.u[s] * p.wt : 0.0;
+        y0 = a.y ? a.y[s] : 0.0;
+        y1 = (a.nrhs > 1 && a.u) ? a.u[s] : 0.0;
     };
     Pref pn = load_pref<MODE, true>(a, 0, s_begin, lane, w, I, I);
     double yn0, yn1;
     load_y(pn, yn0, yn1);
     for (int c = 0; c < nchunks; c++) {
         const Pref p = pn;
-        const double y0 = yn0, y1 = yn1;
+        const double wte = p.valid ? p.wt : 0.0;
+        const double y0 = yn0 * wte, y1 = yn1 * wte;
         if (c + 1 < nchunks) {  // prefetch the next chunk while this one is consumed
             pn = load_pref<MODE, true>(a, c + 1, s_begin, lane, w, I, I);
             load_y(pn, yn0, yn1);
@@ -309,6 +523,8 @@ __global__ void k_lpv_tables(const double* __restrict__ X, const double* __restr
 
 }  // namespace
 
+static int g_gram_warps = 8;  // LPVS_GRAM_WARPS=16 selects the 16-warp kernel (A/B: 82.6 ms vs 81.2 ms at cfg2, so 8 is the default)
+
 size_t gram_smem_bytes() { return 2 * STAGE_D * sizeof(double); }
 
 void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
@@ -318,6 +534,10 @@ void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
         cudaFuncSetAttribute(k_gram<GRAM_CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_gram<GRAM_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_gram<GRAM_LPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_gram16<GRAM_CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_gram16<GRAM_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_gram16<GRAM_LPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (const char* e = getenv("LPVS_GRAM_WARPS")) g_gram_warps = atoi(e) == 16 ? 16 : 8;
         attr_done = true;
     }
     int ntiles = a.nblk * (a.nblk + 1) / 2;
@@ -331,7 +551,16 @@ void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
         dim3 grid(ntiles, np);
         dim3 grid_rhs(a.nblk, np);
         const bool rhs = a.B && a.nrhs > 0 && a.y;
-        if (mode == GRAM_CHAIN) {
+        if (g_gram_warps == 16) {
+            if (mode == GRAM_CHAIN) k_gram16<GRAM_CHAIN><<<grid, NT16, smem, st>>>(b);
+            else if (mode == GRAM_DIRECT) k_gram16<GRAM_DIRECT><<<grid, NT16, smem, st>>>(b);
+            else k_gram16<GRAM_LPV><<<grid, NT16, smem, st>>>(b);
+            if (rhs) {
+                if (mode == GRAM_CHAIN) k_gram_rhs<GRAM_CHAIN><<<grid_rhs, NTHREADS, 0, st>>>(b);
+                else if (mode == GRAM_DIRECT) k_gram_rhs<GRAM_DIRECT><<<grid_rhs, NTHREADS, 0, st>>>(b);
+                else k_gram_rhs<GRAM_LPV><<<grid_rhs, NTHREADS, 0, st>>>(b);
+            }
+        } else if (mode == GRAM_CHAIN) {
             k_gram<GRAM_CHAIN><<<grid, NTHREADS, smem, st>>>(b);
             if (rhs) k_gram_rhs<GRAM_CHAIN><<<grid_rhs, NTHREADS, 0, st>>>(b);
         } else if (mode == GRAM_DIRECT) {
