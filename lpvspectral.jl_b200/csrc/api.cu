@@ -315,7 +315,7 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
 }
 
 int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, double* d_B, int nrhs, double ridge,
-                 int nproblems, int* info_host) {
+                 int nproblems, int* info_host, const double* d_maxdiag, double tol_scale) {
     const int nb = Np / TB;
     CholArgs ca{};
     ca.G = d_G;
@@ -327,6 +327,8 @@ int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, doub
     ca.info = ws<int>(c, BUF_INFO, (size_t)nproblems);
     ca.Np = Np;
     ca.nb = nb;
+    ca.maxdiag = d_maxdiag;
+    ca.tol_scale = tol_scale;
     if (!ca.Linv || !ca.info) return fail(c, LPVS_E_NOMEM, "out of device memory (factor workspace)");
     LPVS_CU(c, cudaMemsetAsync(ca.info, 0, sizeof(int) * nproblems, c->st));
     launch_diag_prepare(d_G, ca.strideG, Np, ncc, zero_first, nullptr, ridge, nproblems, c->st);
@@ -563,7 +565,12 @@ int ls_solve_dev(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const do
             c->launches++;
         }
         int pinfo = 0;
-        if ((rc = factor_solve(c, pl.Nf, pl.zero_first, pl.Np, d_G, d_B, nrhs, ridge, 1, &pinfo))) return rc;
+        // with the jitter policy on, the first attempt also rejects numerically-zero pivots
+        // (<= Nreg*eps*max diag G): a tiny positive pivot would otherwise let null-space garbage through
+        const bool ranktest = attempt == 0 && allow_jitter;
+        if ((rc = factor_solve(c, pl.Nf, pl.zero_first, pl.Np, d_G, d_B, nrhs, ridge, 1, &pinfo,
+                               ranktest ? d_md : nullptr, (double)pl.Nreg * 2.220446049250313e-16)))
+            return rc;
         if (attempt == 0 && allow_jitter)
             LPVS_CU(c, cudaMemcpyAsync(&maxdiag, d_md, sizeof(double), cudaMemcpyDeviceToHost, c->st));
         LPVS_CU(c, cudaStreamSynchronize(c->st));

@@ -65,7 +65,7 @@ constexpr int POTF2_SMEM_D = 128 * LDS + POTF2_TMP + (TB / PB) * PB * LDP;
 // reciprocals are the diagonal of the inverse.  Kept at 16x16 so the unrolled code stays I-cache resident
 // (a 32x32 version was 9.4K straight-line instructions and ran at instruction-fetch speed, ncu potf2_r01).
 __device__ __forceinline__ void warp_potf2_inv(double* D, int ldd, double* Di, int ldi, int lane, int* info,
-                                               int pivot_base) {
+                                               int pivot_base, double tol) {
     const unsigned full = 0xffffffffu;
     const int row = lane & (PB - 1);
     double d[PB], rinv[PB];
@@ -74,7 +74,7 @@ __device__ __forceinline__ void warp_potf2_inv(double* D, int ldd, double* Di, i
 #pragma unroll
     for (int c = 0; c < PB; c++) {
         double piv = __shfl_sync(full, d[c], c);
-        if (!(piv > 0.0) || !isfinite(piv)) {
+        if (!(piv > tol) || !isfinite(piv)) {
             if (lane == 0) atomicCAS(info, 0, pivot_base + c + 1);
             piv = (fabs(piv) > 0.0 && isfinite(piv)) ? fabs(piv) : 1.0;
         }
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ C
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int prob = blockIdx.x;
     double* Gd = a.G + (long long)prob * a.strideG + ((long long)k * TB) * a.Np + (long long)k * TB;
+    const double tol = a.maxdiag ? a.maxdiag[prob] * a.tol_scale : 0.0;
 
     // load the lower triangle of the diagonal block: 16-byte loads, 8 in flight per thread
     for (int base = 0; base < TB * TB / 2; base += NTHREADS * 8) {
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ C
     for (int p = 0; p < TB / PB; p++) {
         const int j0 = p * PB;
         double* Di = Dinv + p * PB * LDP;
-        if (warp == 0) warp_potf2_inv(S + j0 * LDS + j0, LDS, Di, LDP, lane, &a.info[prob], k * TB + j0);
+        if (warp == 0) warp_potf2_inv(S + j0 * LDS + j0, LDS, Di, LDP, lane, &a.info[prob], k * TB + j0, tol);
         __syncthreads();
         const int rem = TB - j0 - PB;
         if (rem > 0) {

@@ -24,6 +24,9 @@ struct CholArgs {
     double* Linv;  // per problem nb blocks of 128x128 (ld 128)
     long long strideLinv;
     int* info;  // per problem: 0 ok, else 1-based failing pivot (internal index)
+    // optional numerical-rank test: a pivot <= maxdiag[prob] * tol_scale counts as breakdown (null = only <= 0)
+    const double* maxdiag;
+    double tol_scale;
     int Np, nb;
 };
 

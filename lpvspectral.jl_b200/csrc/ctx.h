@@ -102,7 +102,8 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
 
 // factor + solve one problem in place: d_G -> L, d_B -> x (internal layout); returns pivot info in *info_host
 int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, double* d_B, int nrhs, double ridge,
-                 int nproblems, int* info_host /* nproblems or null */);
+                 int nproblems, int* info_host /* nproblems or null */, const double* d_maxdiag = nullptr,
+                 double tol_scale = 0.0);
 
 // shared helpers (api.cu)
 int upload(lpvs_ctx* c, int slot, const double* h, int64_t n, double** d);

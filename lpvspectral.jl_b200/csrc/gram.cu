@@ -17,6 +17,7 @@ namespace lpvs {
 namespace {
 
 constexpr int STAGE_D = 2 * TILE_D;  // I tile, J tile (J = weighted copy)
+constexpr int NSTAGE = 3;             // smem ring of the 8-warp kernel (per-stage mbarriers, no __syncthreads)
 
 struct Pref {
     double2 aI, aJ, d;  // chain: anchors + step rotation
@@ -119,6 +120,16 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
 
     // prologue: chunk 0 into stage 0
     auto resolve = [](Pref& p) { p.wt = p.valid ? p.wt : 0.0; };
+    // 3-stage ring: full[s] completes when all 8 warps have stored their part of the chunk living in stage s.
+    // A stage is rewritten two chunks after it was last read; passing full[] of the chunk in between proves every
+    // warp has left that read, so no "empty" barrier is needed.
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_D);
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < NSTAGE; q++) mbar_init(&full[q], NTHREADS / 32);
+    }
+    __syncthreads();
+    // prologue: chunk 0 into stage 0
     Pref p1 = load_pref<MODE, DIAG>(a, 0, s_begin, lane, w, I, J);
     resolve(p1);
     {
@@ -126,26 +137,38 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
 #pragma unroll
         for (int j = 0; j < GRP; j++) synth_step(p1, zI, zJ, j, smem);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full[0]);
     if (nchunks > 1) p1 = load_pref<MODE, DIAG>(a, 1, s_begin, lane, w, I, J);
-    __syncthreads();
+    mbar_wait(&full[0], 0);
 
     // fragment bases: off-diagonal 32(M) x 64(N) warp tile; diagonal 16 x 32 per 64x64 sub-block
     const int fragA = DIAG ? (16 * wm + (lane >> 2)) * LDT + (lane & 3) : (32 * wm + (lane >> 2)) * LDT + (lane & 3);
     const int fragB = DIAG ? (32 * wn + (lane >> 2)) * LDT + (lane & 3) : (64 * wn + (lane >> 2)) * LDT + (lane & 3);
 
+    int st_cur = 0;
     for (int c = 0; c < nchunks; c++) {
-        double* cur = smem + (c & 1) * STAGE_D;
-        double* nxt = smem + ((c & 1) ^ 1) * STAGE_D;
+        const int st_nxt = st_cur == NSTAGE - 1 ? 0 : st_cur + 1;
+        double* cur = smem + st_cur * STAGE_D;
+        double* nxt = smem + st_nxt * STAGE_D;
         const bool have_next = (c + 1 < nchunks);
         Pref p2 = p1;
         if (c + 2 < nchunks) p2 = load_pref<MODE, DIAG>(a, c + 2, s_begin, lane, w, I, J);
-        if (c > 0 || nchunks > 1) resolve(p1);  // p1 was loaded one iteration ago: no stall
+        resolve(p1);  // p1 was loaded one iteration ago: no stall
         double2 zI = p1.aI, zJ = chain_start_J(p1);
         const double* pa = cur + fragA;
         const double* pb = cur + TILE_D + fragB;
 #pragma unroll
         for (int kk = 0; kk < KC / 4; kk++) {
-            if (have_next) synth_step(p1, zI, zJ, kk, nxt);
+            if (have_next) {
+                if (kk < GRP / 2) {  // the next chunk is synthesised in the first half of this one ...
+                    synth_step(p1, zI, zJ, 2 * kk, nxt);
+                    synth_step(p1, zI, zJ, 2 * kk + 1, nxt);
+                } else if (kk == GRP / 2) {  // ... and published half a chunk before anyone needs it
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[st_nxt]);
+                }
+            }
             if (!DIAG) {
                 mma_step(pa, pb, kk, acc);
             } else {
@@ -165,7 +188,8 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
             }
         }
         p1 = p2;
-        __syncthreads();
+        if (have_next) mbar_wait(&full[st_nxt], ((c + 1) / NSTAGE) & 1);
+        st_cur = st_nxt;
     }
 
     // epilogue
@@ -525,7 +549,7 @@ __global__ void k_lpv_tables(const double* __restrict__ X, const double* __restr
 
 static int g_gram_warps = 8;  // LPVS_GRAM_WARPS=16 selects the 16-warp kernel (A/B: 82.6 ms vs 81.2 ms at cfg2, so 8 is the default)
 
-size_t gram_smem_bytes() { return 2 * STAGE_D * sizeof(double); }
+size_t gram_smem_bytes() { return NSTAGE * STAGE_D * sizeof(double) + 64; }
 
 void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
     static bool attr_done = false;
