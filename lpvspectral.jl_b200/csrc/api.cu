@@ -712,7 +712,7 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
         gram_timer_begin(c);
         launch_gram(pl.mode, g, nw, c->st);
         gram_timer_end(c, (double)nw * n * pl.Nreg * (pl.Nreg + 1.0), 1);
-        c->launches++;
+        c->launches += 2;  // k_gram + k_gram_rhs
         // always the weighted estimator: ridge lambda (src/lsfft.jl:121 -> :77)
         if ((rc = factor_solve(c, pl.Nf, pl.zero_first, pl.Np, d_G, d_B, nrhs, lambda, nw, hinfo.data()))) return rc;
         k_window_accum<<<(Nf + 127) / 128, 128, 0, c->st>>>(kind, d_B, 2 * Np, pl.Np, nw, Nf, pl.zero_first, d_sums);

@@ -17,6 +17,9 @@ namespace lpvs {
 namespace {
 
 constexpr int STAGE_D = 2 * TILE_D;  // I tile, J tile (J = weighted copy)
+#ifndef SYNTH_BURST
+#define SYNTH_BURST 1
+#endif
 constexpr int NSTAGE = 3;             // smem ring of the 8-warp kernel (per-stage mbarriers, no __syncthreads)
 
 struct Pref {
@@ -146,6 +149,7 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     const int fragA = DIAG ? (16 * wm + (lane >> 2)) * LDT + (lane & 3) : (32 * wm + (lane >> 2)) * LDT + (lane & 3);
     const int fragB = DIAG ? (32 * wn + (lane >> 2)) * LDT + (lane & 3) : (64 * wn + (lane >> 2)) * LDT + (lane & 3);
 
+    const int burst_kk = 0;  // staggering the bursts of an SMSP's two warps (0 / 4) measured no better (78.0 vs 77.7 ms)
     int st_cur = 0;
     for (int c = 0; c < nchunks; c++) {
         const int st_nxt = st_cur == NSTAGE - 1 ? 0 : st_cur + 1;
@@ -161,7 +165,16 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
 #pragma unroll
         for (int kk = 0; kk < KC / 4; kk++) {
             if (have_next) {
-                if (kk < GRP / 2) {  // the next chunk is synthesised in the first half of this one ...
+                if (SYNTH_BURST) {
+                    // whole next chunk in one burst: fewer DMMA<->DFMA interleave points (79.1 -> 77.7 ms)
+                    if (kk == burst_kk) {
+#pragma unroll
+                        for (int j = 0; j < GRP; j++) synth_step(p1, zI, zJ, j, nxt);
+                    } else if (kk == burst_kk + 1) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full[st_nxt]);
+                    }
+                } else if (kk < GRP / 2) {  // the next chunk is synthesised in the first half of this one ...
                     synth_step(p1, zI, zJ, 2 * kk, nxt);
                     synth_step(p1, zI, zJ, 2 * kk + 1, nxt);
                 } else if (kk == GRP / 2) {  // ... and published half a chunk before anyone needs it

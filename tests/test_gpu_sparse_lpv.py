@@ -181,3 +181,19 @@ def test_symv_variant_matches_gemv_variant(ctx, prox):
                                          return_info=True, printerval=10 ** 9)
         assert ri["iters"] == out[1]["iters"] and support(ri["z"]) == support(out[1]["z"])
         assert rel(out[1]["z"], ri["z"]) <= 1e-9
+
+
+def test_windowed_sparse_estimator(ctx):
+    """ls_windowpsd(estimator=ls_sparse_spectral, ...) (test/test_lasso.jl:36 shape: nw=2, f=1:0.5:22, mu=1e-4):
+    one weighted (Quadratic, Q13) ADMM solve per window."""
+    import lpvspectral_jl_b200 as lp
+
+    Y, V, X = o.generate_lpv_signal(500, seed=2)
+    f = np.arange(1.0, 22.01, 0.5)
+    kw = dict(lam=0.2, tol=1e-10, iters=4000, mu=1e-4)
+    S, _ = lp.ls_windowpsd(Y, X, f, nw=2, estimator=lp.ls_sparse_spectral, ctx=ctx, **kw)
+    est = lambda yi, ti, fr, W, **k: o.ls_sparse_spectral(yi, ti, fr, W, mode="gram", printerval=10 ** 9, **k)
+    Sr, _ = o.ls_windowpsd(Y, X, f, nw=2, estimator=est, **kw)
+    assert np.linalg.norm(S - Sr) <= 1e-9 * np.linalg.norm(Sr)
+    with pytest.raises(ValueError):
+        lp.ls_windowpsd(Y, X, f, nw=2, estimator=lambda *a, **k: None, ctx=ctx)

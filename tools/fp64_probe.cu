@@ -98,6 +98,68 @@ __global__ void k_mixed32(double* out, int iters, double a0, double b0) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// The real warp tile: 32 accumulators (4 A-fragments x 8 B-fragments), operands from registers ...
+__global__ void k_dmma_tile_reg(double* out, int iters, double a0, double b0) {
+    double c[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) c[i][j][0] = c[i][j][1] = 0.0;
+    double a[4], b[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = a0 + i + threadIdx.x * 1e-9;
+#pragma unroll
+    for (int j = 0; j < 8; j++) b[j] = b0 + j * 0.5;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) s += c[i][j][0] + c[i][j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ... and from shared memory with the kernel's conflict-free [row][k] stride-36 layout (12 LDS.64 per 32 DMMA)
+__global__ void k_dmma_tile_lds(double* out, int iters, double a0, double b0) {
+    __shared__ double sA[128 * 36];  // one tile serves as both operands (48 KB static limit)
+    const double* sB = sA;
+    for (int i = threadIdx.x; i < 128 * 36; i += blockDim.x) sA[i] = a0 + b0 * i * 1e-6;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wm = w & 3, wn = (w >> 2) & 1;
+    const double* pa = sA + (32 * wm + (lane >> 2)) * 36 + (lane & 3);
+    const double* pb = sB + (64 * wn + (lane >> 2)) * 36 + (lane & 3);
+    double c[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) c[i][j][0] = c[i][j][1] = 0.0;
+    for (int it = 0; it < iters; it += 8) {
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+            double a[4], b[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = pa[i * 8 * 36 + 4 * kk];
+#pragma unroll
+            for (int j = 0; j < 8; j++) b[j] = pb[j * 8 * 36 + 4 * kk];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) s += c[i][j][0] + c[i][j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 static float time_ms(F launch, int reps) {
     cudaEvent_t e0, e1;
@@ -149,6 +211,19 @@ int main(int argc, char** argv) {
         float ms_s64 = time_ms([&] { k_mixed32<8, 64><<<blocks, threads>>>(out, iters, 1.0000001, 0.999999); }, 5);
         printf(", \"mix_ms\": {\"dmma8\": %.4f, \"dmma8+dfma8\": %.4f, \"dmma8+dfma16\": %.4f, \"dmma8+dfma32\": %.4f, \"dfma8\": %.4f, \"dfma32\": %.4f, \"dmma8+ffma32\": %.4f, \"dmma8+ffma64\": %.4f}",
                ms_m, ms_x8, ms_x16, ms_x32, ms_f8, ms_f32, ms_s32, ms_s64);
+    }
+    {   // the real 32-accumulator warp tile, 8 warps per SM (256 threads, 1 CTA/SM)
+        int threads = 256, blocks = sms;
+        int it2 = 8192;
+        float ms_r = time_ms([&] { k_dmma_tile_reg<<<blocks, threads>>>(out, it2, 1.0000001, 0.999999); }, 5);
+        float ms_l = time_ms([&] { k_dmma_tile_lds<<<blocks, threads>>>(out, it2, 1.0000001, 0.999999); }, 5);
+        double flop = (double)blocks * (threads / 32) * it2 * 32 * 512.0;
+        printf(", \"tile32_reg_tflops\": %.3f, \"tile32_lds_tflops\": %.3f", flop / ms_r * 1e-9, flop / ms_l * 1e-9);
+        threads = 512; blocks = sms;
+        ms_r = time_ms([&] { k_dmma_tile_reg<<<blocks, threads>>>(out, it2, 1.0000001, 0.999999); }, 5);
+        ms_l = time_ms([&] { k_dmma_tile_lds<<<blocks, threads>>>(out, it2, 1.0000001, 0.999999); }, 5);
+        flop = (double)blocks * (threads / 32) * it2 * 32 * 512.0;
+        printf(", \"tile32_reg_tflops_16w\": %.3f, \"tile32_lds_tflops_16w\": %.3f", flop / ms_r * 1e-9, flop / ms_l * 1e-9);
     }
     printf("}\n");
     return 0;
