@@ -99,6 +99,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            return float(json.load(fh)[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def fp64_peak():
     try:
         with open(FP64_PEAK_FILE) as fh:
@@ -167,7 +176,8 @@ def admm_leg(ctx, lp, L, C, rank, world, allsum, allmax, barrier, iters=2000):
             "iters_per_s_per_gpu_min": its_min, "scaling": "replicas only", "setup_s": setup_s,
             "gram_tflops": gfl / gms / 1e9,
             "roofline": {"bound": "hbm", "achieved": bpi * its_min / 1e9, "peak": hbm, "unit": "GB/s",
-                         "frac": bpi * its_min / 1e9 / hbm, "traffic": None, "kernel": "k_admm_symv",
+                         "frac": bpi * its_min / 1e9 / hbm, "traffic": ncu_traffic("k_admm_symv"),
+                         "traffic_unit": "bytes per iteration (one launch = many iterations)", "kernel": "k_admm_symv",
                          "bytes_per_iter": bpi,
                          "note": "algorithmic bytes = lower-triangle 128x128 blocks of (G+I/mu)^-1 actually streamed"}}
 
@@ -291,13 +301,13 @@ def main():
         return float(tt.item())
 
     # ---- resident leg ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # sampled through warm-up + timed region (same workload), 100 ms period
     for _ in range(args.warmup):
         step_resident()
-    sampler = ClockSampler(local)
     launches0 = ctx.launches
     barrier()
-    if rank == 0:
-        sampler.start()
     wall0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -357,7 +367,7 @@ def main():
                     "api": "lpvs_ls_window_sums (host pointers, pinned)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "k_gram<GRAM_CHAIN>",
+                         "frac": achieved / peak, "traffic": ncu_traffic("k_gram"), "kernel": "k_gram<GRAM_CHAIN>",
                          "flops_per_window": float(n) * nreg * (nreg + 1), "windows_per_launch": K,
                          "gram_ms_per_step": gram_ms / args.steps, "gram_share_of_step": gram_ms / call_ms,
                          "peak_source": peak_src},
