@@ -122,6 +122,13 @@ __global__ void k_reduce_parts(double* __restrict__ out, const double* __restric
     out[i] = s;
 }
 
+__global__ void k_check_finite(const double* __restrict__ v, long long n, int* flag) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        bad |= !isfinite(v[i]);
+    if (bad) atomicOr(flag, 1);
+}
+
 // internal x ([nrhs][Np]) -> interleaved complex [nrhs][Nf]   (fourier2complex, src/utilities.jl:62-73)
 __global__ void k_x_to_complex(const double* __restrict__ X, int Np, int Nf, int zero_first, int nrhs,
                                double* __restrict__ out) {
@@ -349,7 +356,20 @@ int upload(lpvs_ctx* c, int slot, const double* h, int64_t n, double** d) {
     double* p = ws<double>(c, slot, (size_t)n);
     if (!p) return fail(c, LPVS_E_NOMEM, "out of device memory (input upload, %lld doubles)", (long long)n);
     LPVS_CU(c, cudaMemcpyAsync(p, h, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+    if (c->d_nonfinite && n > 0) {
+        int blocks = (int)std::min<long long>((n + 255) / 256, 1184);
+        k_check_finite<<<blocks, 256, 0, c->st>>>(p, n, c->d_nonfinite);
+        c->launches++;
+    }
     *d = p;
+    return LPVS_OK;
+}
+
+int inputs_finite(lpvs_ctx* c) {
+    int h = 0;
+    if (c->d_nonfinite) LPVS_CU(c, cudaMemcpyAsync(&h, c->d_nonfinite, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    if (h) return fail(c, LPVS_E_NONFINITE, "non-finite value (NaN/Inf) in an input array");
     return LPVS_OK;
 }
 
@@ -389,6 +409,7 @@ int lpvs_init(int device, lpvs_ctx** out) {
     c->st = c->own_st;
     cudaEventCreate(&c->ev_call0);
     cudaEventCreate(&c->ev_call1);
+    if (cudaMalloc(&c->d_nonfinite, sizeof(int)) != cudaSuccess) c->d_nonfinite = nullptr;
     *out = c;
     return LPVS_OK;
 }
@@ -400,6 +421,7 @@ void lpvs_destroy(lpvs_ctx* c) {
     for (auto& b : c->buf)
         if (b.p) cudaFree(b.p);
     for (auto e : c->ev) cudaEventDestroy(e);
+    cudaFree(c->d_nonfinite);
     cudaEventDestroy(c->ev_call0);
     cudaEventDestroy(c->ev_call1);
     cudaStreamDestroy(c->own_st);
@@ -630,13 +652,16 @@ int lpvs_ls_spectral(lpvs_ctx* c, const double* y, const double* t, int64_t N, c
     // ridge: lambda^2 unweighted (src/utilities.jl:58), lambda weighted (src/lsfft.jl:77)
     double ridge = W ? lambda : lambda * lambda;
     double* d_x;
-    if ((rc = ls_solve_dev(c, pl, d_t, d_y, nullptr, d_W, N, 1, ridge, !W && c->jitter, &d_x, info))) return rc;
+    if ((rc = ls_solve_dev(c, pl, d_t, d_y, nullptr, d_W, N, 1, ridge, !W && c->jitter, &d_x, info))) {
+        if (inputs_finite(c) == LPVS_E_NONFINITE) return LPVS_E_NONFINITE;  // the more specific diagnosis
+        return rc;
+    }
     double* d_out = ws<double>(c, BUF_X, (size_t)2 * Nf);
     if (!d_out) return fail(c, LPVS_E_NOMEM, "out of device memory (x)");
     k_x_to_complex<<<(Nf + 127) / 128, 128, 0, c->st>>>(d_x, pl.Np, Nf, pl.zero_first, 1, d_out);
     c->launches++;
     LPVS_CU(c, cudaMemcpyAsync(x, d_out, sizeof(double) * 2 * Nf, cudaMemcpyDeviceToHost, c->st));
-    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    if ((rc = inputs_finite(c))) return rc;
     gram_timer_resolve(c);
     return LPVS_OK;
 }
@@ -763,8 +788,14 @@ int lpvs_ls_window_sums(lpvs_ctx* c, int kind, const double* y, const double* u,
         k_end -= k_begin;
         k_begin = 0;
     }
-    return lpvs_ls_window_sums_dev(c, kind, d_y, d_u, d_t, N, f, Nf, W, n, noverlap, lambda, k_begin, k_end, sums,
-                                   info);
+    int rc2 = lpvs_ls_window_sums_dev(c, kind, d_y, d_u, d_t, N, f, Nf, W, n, noverlap, lambda, k_begin, k_end, sums,
+                                      info);
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        int rcf = inputs_finite(c);
+        if (rcf) return rcf;
+    }
+    return rc2;
 }
 
 int lpvs_ls_window_finalize(int kind, const double* sums, int Nf, int64_t K, double* out) {

@@ -47,6 +47,7 @@ struct lpvs_ctx {
     double gram_flops = 0.0;
     cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
     int call_depth = 0;
+    int* d_nonfinite = nullptr;  // set by the upload-time scan of host inputs
 };
 
 namespace lpvs {
@@ -57,7 +58,10 @@ int fail(lpvs_ctx* c, int code, const char* fmt, ...);
 struct CallTimer {
     lpvs_ctx* c;
     explicit CallTimer(lpvs_ctx* ctx) : c(ctx) {
-        if (c && c->call_depth++ == 0) cudaEventRecord(c->ev_call0, c->st);
+        if (c && c->call_depth++ == 0) {
+            cudaEventRecord(c->ev_call0, c->st);
+            if (c->d_nonfinite) cudaMemsetAsync(c->d_nonfinite, 0, sizeof(int), c->st);
+        }
     }
     ~CallTimer() {
         if (c && --c->call_depth == 0) cudaEventRecord(c->ev_call1, c->st);
@@ -106,6 +110,8 @@ int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, doub
                  double tol_scale = 0.0);
 
 // shared helpers (api.cu)
+// reads the upload-time non-finite flag (synchronises the stream); LPVS_E_NONFINITE if any host input had NaN/Inf
+int inputs_finite(lpvs_ctx* c);
 int upload(lpvs_ctx* c, int slot, const double* h, int64_t n, double** d);
 void fill_basis_args(const FourierPlan& pl, GramArgs& g);
 // ridge LS on device arrays; on return *d_x points at the internal-layout solution ([nrhs][Np], BUF_B)

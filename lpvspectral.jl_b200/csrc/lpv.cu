@@ -279,7 +279,7 @@ int lpvs_ls_spectral_lpv(lpvs_ctx* c, const double* Y, const double* X, const do
         c->launches++;
         LPVS_CU(c, cudaMemcpyAsync(Sigma, d_e, sizeof(double) * nref * nref, cudaMemcpyDeviceToHost, c->st));
     }
-    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    if ((rc = inputs_finite(c))) return rc;
     gram_timer_resolve(c);
     return LPVS_OK;
 }
@@ -340,7 +340,7 @@ int lpvs_admm_create_fourier(lpvs_ctx* c, const double* y, const double* t, int6
     }
     lpvs_admm* h = admm_new(c);
     admm_set_problem(h, 0, pl.Np, pl.Nf, pl.zero_first, pl.Nreg, pl.Nf, prox_kind, prox_param, mu, W ? 1 : 0, 0, 0);
-    if ((rc = admm_finish_create(c, h, d_G, d_B, d_x0))) {
+    if ((rc = admm_finish_create(c, h, d_G, d_B, d_x0)) || (rc = inputs_finite(c))) {
         admm_delete(h);
         return rc;
     }
@@ -403,7 +403,8 @@ int lpvs_admm_create_lpv(lpvs_ctx* c, const double* y, const double* X, const do
     goff[Nf + 1] = (int)gmem.size();
     lpvs_admm* h = admm_new(c);
     admm_set_problem(h, 1, pl.Np, ncc, 0, len, ncc, LPVS_PROX_GROUP_L2, lambda, mu, 0, Nf, pl.Nvv);
-    if ((rc = admm_set_groups(c, h, goff, gmem)) || (rc = admm_finish_create(c, h, d_G, d_B, nullptr))) {
+    if ((rc = admm_set_groups(c, h, goff, gmem)) || (rc = admm_finish_create(c, h, d_G, d_B, nullptr)) ||
+        (rc = inputs_finite(c))) {
         admm_delete(h);
         return rc;
     }

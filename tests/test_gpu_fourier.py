@@ -186,3 +186,24 @@ def test_ragged_and_tiny_inputs(ctx):
     Sr, _ = o.ls_windowpsd(y, t, f, nw=3, noverlap=7)
     assert rel(S, Sr) <= TOL
     assert lp.window_count(10, 20, 0) == 0
+
+
+def test_nonfinite_inputs_are_reported(ctx):
+    """LPVS_E_NONFINITE: NaN/Inf in a host input array is detected on the device at upload time."""
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+
+    t, y = signal(512, 30)
+    f = np.arange(1, 20) * 0.5
+    yb = y.copy()
+    yb[100] = np.nan
+    with pytest.raises(lp.LpvsError) as ei:
+        lp.ls_spectral(yb, t, f, ctx=ctx)
+    assert ei.value.code == L.E_NONFINITE
+    tb = t.copy()
+    tb[7] = np.inf
+    with pytest.raises(lp.LpvsError) as ei:
+        lp.ls_windowpsd(y, tb, f, nw=4, ctx=ctx)
+    assert ei.value.code == L.E_NONFINITE
+    x, _ = lp.ls_spectral(y, t, f, ctx=ctx)  # the context stays usable
+    assert np.all(np.isfinite(x))
