@@ -34,7 +34,7 @@ enum lpvs_status {
     LPVS_E_NONFINITE = -3,
     LPVS_E_CUDA = -4,
     LPVS_E_NCCL = -5,
-    LPVS_E_UNSUPPORTED = -6, /* e.g. sparse LPV with coulomb=true */
+    LPVS_E_UNSUPPORTED = -6, /* device older than sm_100, or a problem too large for the resident ADMM vector */
     LPVS_E_NOMEM = -7
 };
 

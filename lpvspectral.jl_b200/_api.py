@@ -502,7 +502,7 @@ def ls_sparse_spectral_lpv(y, X, V, w, Nv, *, coulomb=False, normalize=True, ite
     solver = ADMM(ctx, h)
     try:
         solver.run(iters=iters, tol=tol, printerval=printerval, cb=cb, verbose=verbose)
-        params = solver.result(len(wv) * int(Nv))
+        params = solver.result(len(wv) * int(Nv) * (2 if coulomb else 1))  # Nf * Nvv complex parameters
         info = dict(iters=solver.iters, residual=solver.residual, converged=solver.converged, timing=solver.timing())
         if return_info:
             xr, zr = solver.get()

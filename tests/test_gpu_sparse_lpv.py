@@ -197,3 +197,22 @@ def test_windowed_sparse_estimator(ctx):
     assert np.linalg.norm(S - Sr) <= 1e-9 * np.linalg.norm(Sr)
     with pytest.raises(ValueError):
         lp.ls_windowpsd(Y, X, f, nw=2, estimator=lambda *a, **k: None, ctx=ctx)
+
+
+def test_sparse_lpv_coulomb_quirk(ctx):
+    """coulomb=true: the vector has 4*Nf*Nv entries but the reference's groups (src/lasso.jl:46-54) still have 2Nv
+    entries and cover only the first half; uncovered entries of z stay 0.  Reproduced, not fixed."""
+    import lpvspectral_jl_b200 as lp
+
+    Y, V, X = o.generate_lpv_signal(400, seed=5)
+    V = V - 0.5
+    w = 2 * np.pi * np.arange(2, 14, 2)
+    kw = dict(iters=1500, tol=1e-8, mu=0.05)
+    se, info = lp.ls_sparse_spectral_lpv(Y, X, V, w, 8, lam=2.0, coulomb=True, ctx=ctx, return_info=True, **kw)
+    sr, ri = o.ls_sparse_spectral_lpv(Y, X, V, w, 8, lam=2.0, coulomb=True, mode="gram", return_info=True,
+                                      printerval=10 ** 9, **kw)
+    assert len(se.x) == len(sr.x) == len(w) * 16
+    assert info["iters"] == ri["iters"]
+    assert support(info["z"]) == support(ri["z"])
+    assert rel(info["z"], ri["z"]) <= 1e-9
+    assert np.all(ri["z"][len(ri["z"]) // 2:] == 0) and np.all(info["z"][len(info["z"]) // 2:] == 0)
