@@ -1,0 +1,127 @@
+"""Direct ctypes calls into entry points the Python mirror does not route through: the one-shot sparse functions,
+a caller-supplied ADMM start vector, and the lpvs_dev_* helpers a CUDA-less host (the Julia shim) would use to keep
+inputs resident.  (-m gpu)"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import lpvs_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def sig(N, seed):
+    rng = np.random.default_rng(seed)
+    t = np.sort(10 * rng.random(N))
+    y = np.sin(2 * np.pi * 3 * t) + 0.6 * np.cos(2 * np.pi * 8.5 * t) + 0.1 * rng.standard_normal(N)
+    return t, y
+
+
+def test_one_shot_sparse_functions(ctx):
+    from lpvspectral_jl_b200 import _lib as L
+
+    t, y = sig(700, 1)
+    f = np.arange(0, 120) * 0.1
+    x = np.empty(len(f), dtype=np.complex128)
+    its, res = C.c_int64(0), C.c_double(0)
+    ctx.check(ctx.lib.lpvs_ls_sparse_spectral(ctx.h, vp(y), vp(t), len(y), vp(f), len(f), None, L.PROX_L1, 0.3, 0.05,
+                                              0, 0.0, 2000, 1e-9, vp(x), C.byref(its), C.byref(res)))
+    xr, _, ri = o.ls_sparse_spectral(y, t, f, lam=0.3, iters=2000, tol=1e-9, mode="gram", return_info=True,
+                                     printerval=10 ** 9)
+    assert its.value == ri["iters"] and rel(x, xr) <= 1e-9 and res.value < 1e-9
+
+    Y, V, X = o.generate_lpv_signal(300, seed=7)
+    w = 2 * np.pi * np.arange(2, 12, 2)
+    p = np.empty(len(w) * 6, dtype=np.complex128)
+    ctx.check(ctx.lib.lpvs_ls_sparse_spectral_lpv(ctx.h, vp(Y), vp(X), vp(V), len(Y), vp(w), len(w), 6, 0, 1, 1.5, 0.05,
+                                                  800, 1e-8, vp(p), C.byref(its), C.byref(res)))
+    sr, ri = o.ls_sparse_spectral_lpv(Y, X, V, w, 6, lam=1.5, iters=800, tol=1e-8, mode="gram", return_info=True,
+                                      printerval=10 ** 9)
+    assert its.value == ri["iters"] and rel(p, sr.x) <= 1e-9
+
+
+def test_admm_with_caller_start_vector(ctx):
+    from lpvspectral_jl_b200 import _lib as L
+    import lpvspectral_jl_b200 as lp
+
+    t, y = sig(500, 2)
+    f = np.arange(0, 80) * 0.15  # zero frequency first -> Nreg = 159
+    nreg = 2 * len(f) - 1
+    x0 = 0.1 * np.random.default_rng(0).standard_normal(nreg)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.lpvs_admm_create_fourier(ctx.h, vp(y), vp(t), len(y), vp(f), len(f), None, L.PROX_L1, 0.2, 0.05,
+                                               vp(x0), 0, 0.0, C.byref(h)))
+    s = lp.ADMM(ctx, h)
+    assert s.size == nreg
+    xg, zg = s.get()
+    assert np.array_equal(xg, x0) and np.array_equal(zg, x0)  # z = copy(x) (src/lasso.jl:146)
+    s.step(300, 0.0)
+    xg, zg = s.get()
+    s.free()
+    A, _ = o.get_fourier_regressor(t, f)
+    pf = o.QuadProx(A.T @ A, A.T @ y, "ls", "gram")
+    xr, zr, _, _ = o.admm(x0, pf, o.NormL1(0.2), iters=300, tol=0.0, mu=0.05, printerval=10 ** 9)
+    assert rel(zg, zr) <= 1e-9 and rel(xg, xr) <= 1e-9
+
+
+def test_resident_inputs_via_lpvs_dev_helpers(ctx):
+    """What a host without CUDA bindings does: lpvs_dev_alloc/upload once, then many *_dev calls."""
+    from lpvspectral_jl_b200 import _lib as L
+    import lpvspectral_jl_b200 as lp
+
+    t, y = sig(8192, 3)
+    n, nf = 1024, 32
+    f = np.arange(nf) * 2.0 / (t[n] - t[0])
+    W = lp.hanning(n)
+    dy, dt = C.c_void_p(), C.c_void_p()
+    ctx.check(ctx.lib.lpvs_dev_alloc(ctx.h, y.nbytes, C.byref(dy)))
+    ctx.check(ctx.lib.lpvs_dev_alloc(ctx.h, t.nbytes, C.byref(dt)))
+    ctx.check(ctx.lib.lpvs_dev_upload(ctx.h, dy, vp(y), y.nbytes))
+    ctx.check(ctx.lib.lpvs_dev_upload(ctx.h, dt, vp(t), t.nbytes))
+    back = np.empty_like(y)
+    ctx.check(ctx.lib.lpvs_dev_download(ctx.h, vp(back), dy, y.nbytes))
+    assert np.array_equal(back, y)
+    K = lp.window_count(len(y), n, -1)
+    sums = np.zeros(nf)
+    info = C.c_int(0)
+    ctx.check(ctx.lib.lpvs_ls_window_sums_dev(ctx.h, L.WIN_PSD, dy, None, dt, len(y), vp(f), nf, vp(W), n, n >> 1,
+                                              1e-10, 0, K, vp(sums), C.byref(info)))
+    S = lp.window_finalize(L.WIN_PSD, sums, nf, K)
+    Sr, _ = lp.ls_windowpsd(y, t, f, nw=len(y) // n, window_func=lp.hanning, ctx=ctx)
+    assert np.array_equal(S, Sr)
+    ms = ctx.last_call_ms()
+    assert ms > 0 and ctx.launches > 0
+    ctx.check(ctx.lib.lpvs_dev_free(ctx.h, dy))
+    ctx.check(ctx.lib.lpvs_dev_free(ctx.h, dt))
+
+
+def test_bad_arguments_return_codes(ctx):
+    from lpvspectral_jl_b200 import _lib as L
+
+    t, y = sig(64, 4)
+    f = np.array([1.0, 2.0])
+    x = np.empty(2, dtype=np.complex128)
+    info = C.c_int(0)
+    assert ctx.lib.lpvs_ls_spectral(ctx.h, None, vp(t), 64, vp(f), 2, None, 1e-10, vp(x), C.byref(info)) == L.E_BAD_ARG
+    assert ctx.lib.lpvs_ls_spectral(None, vp(y), vp(t), 64, vp(f), 2, None, 1e-10, vp(x), C.byref(info)) == L.E_BAD_ARG
+    sums = np.zeros(2)
+    W = np.ones(16)
+    rc = ctx.lib.lpvs_ls_window_sums(ctx.h, 7, vp(y), None, vp(t), 64, vp(f), 2, vp(W), 16, 8, 1e-10, 0, 1, vp(sums),
+                                     C.byref(info))
+    assert rc == L.E_BAD_ARG
+    rc = ctx.lib.lpvs_ls_window_sums(ctx.h, L.WIN_PSD, vp(y), None, vp(t), 64, vp(f), 2, vp(W), 16, 8, 1e-10, 0, 99,
+                                     vp(sums), C.byref(info))
+    assert rc == L.E_BAD_ARG and b"window range" in ctx.lib.lpvs_last_error(ctx.h)
+    h = C.c_void_p()
+    rc = ctx.lib.lpvs_admm_create_fourier(ctx.h, vp(y), vp(t), 64, vp(f), 2, None, L.PROX_L1, 0.1, 0.0, None, 0, 0.0,
+                                          C.byref(h))
+    assert rc == L.E_BAD_ARG  # mu must be in (0, 1]
