@@ -33,7 +33,7 @@ enum lpvs_status {
     LPVS_E_NOT_SPD = -2,     /* Cholesky breakdown; *info = 1-based failing pivot */
     LPVS_E_NONFINITE = -3,
     LPVS_E_CUDA = -4,
-    LPVS_E_NCCL = -5,
+    LPVS_E_NCCL = -5,        /* reserved: collectives live in the host (torch.distributed / NCCL), not in liblpvs */
     LPVS_E_UNSUPPORTED = -6, /* device older than sm_100, or a problem too large for the resident ADMM vector */
     LPVS_E_NOMEM = -7
 };

@@ -582,12 +582,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trsv_big(const __grid_constant_
     }
 }
 
-bool attrs_done = false;
+bool attrs_done[64] = {};  // per device
 void set_attrs() {
-    if (attrs_done) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attrs_done[dev & 63]) return;
     cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(POTF2_SMEM_D * sizeof(double)));
     cudaFuncSetAttribute(k_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * TILE_D * sizeof(double)));
-    attrs_done = true;
+    attrs_done[dev & 63] = true;
 }
 
 }  // namespace

@@ -26,7 +26,7 @@ struct Pref {
     double2 aI, aJ, d;  // chain: anchors + step rotation
     double tt;          // direct: sample position
     long long si;       // table sample index
-    double wt, yv;
+    double wt;
     bool valid;  // the weight is zeroed for invalid samples at the point of USE (no stall on the prefetch)
 };
 
@@ -43,7 +43,6 @@ __device__ __forceinline__ Pref load_pref(const GramArgs& a, int c, long long s_
     p.wt = 1.0;
     if (a.W) p.wt = a.W[a.w_abs ? s : (long long)idc];
     p.valid = valid;
-    p.yv = 0.0;
     if (MODE == GRAM_CHAIN) {
         p.aI = a.anc[(long long)(I * (FB / GRP) + w) * a.tbl_ns + p.si];
         if (!DIAG) p.aJ = a.anc[(long long)(J * (FB / GRP) + w) * a.tbl_ns + p.si];
@@ -565,9 +564,11 @@ static int g_gram_warps = 8;  // LPVS_GRAM_WARPS=16 selects the 16-warp kernel (
 size_t gram_smem_bytes() { return NSTAGE * STAGE_D * sizeof(double) + 64; }
 
 void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
-    static bool attr_done = false;
+    static bool attr_done[64] = {};  // per device: function attributes belong to the device's context
+    int dev = 0;
+    cudaGetDevice(&dev);
     size_t smem = gram_smem_bytes();
-    if (!attr_done) {
+    if (!attr_done[dev & 63]) {
         cudaFuncSetAttribute(k_gram<GRAM_CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_gram<GRAM_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_gram<GRAM_LPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -575,7 +576,7 @@ void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
         cudaFuncSetAttribute(k_gram16<GRAM_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_gram16<GRAM_LPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (const char* e = getenv("LPVS_GRAM_WARPS")) g_gram_warps = atoi(e) == 16 ? 16 : 8;
-        attr_done = true;
+        attr_done[dev & 63] = true;
     }
     int ntiles = a.nblk * (a.nblk + 1) / 2;
     // gridDim.y is limited to 65535: launch in slabs
