@@ -236,207 +236,6 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// 16-warp variant: 4 warps per SMSP so the DMMA pipe always has a ready warp (a lone warp sustains only ~90 % of
-// the pipe, tools/fp64_probe.cu).  Warp grid 4(M) x 4(N), warp tile 32x32 (32 accumulators / thread, <= 128 regs).
-// Synthesis: warps 0-7 build the I tile (group = warp), warps 8-15 the weighted J tile: ONE chain per thread.
-// Diagonal tiles: three 64x64 sub-blocks, each split 4x4 into 16x16 warp tiles (12 DMMAs per k4-step, not 16).
-// ------------------------------------------------------------------------------------------------------------
-constexpr int NT16 = 512;
-
-struct Pref16 {
-    double2 a, d;
-    double tt;
-    long long si;
-    double wt;
-    bool valid;
-};
-
-template <int MODE>
-__device__ __forceinline__ Pref16 load_pref16(const GramArgs& a, int c, long long s_begin, int lane, int grp,
-                                              int blk) {
-    Pref16 p{};
-    int idx = c * KC + lane;
-    bool valid = idx < a.n && s_begin + idx < a.s_end;
-    long long s = s_begin + idx;
-    if (!valid) s = min(s_begin + (long long)a.n, a.s_end) - 1;
-    int idc = (int)(s - s_begin);
-    p.si = s - a.tbl_base;
-    p.wt = 1.0;
-    if (a.W) p.wt = a.W[a.w_abs ? s : (long long)idc];
-    p.valid = valid;
-    if (MODE == GRAM_CHAIN) {
-        p.a = a.anc[(long long)(blk * (FB / GRP) + grp) * a.tbl_ns + p.si];
-        p.d = a.del[p.si];
-    } else if (MODE == GRAM_DIRECT) {
-        p.tt = a.t[s];
-    }
-    return p;
-}
-
-template <int MODE>
-__device__ __forceinline__ double2 synth_elem16(const GramArgs& a, const Pref16& p, int cc) {
-    if (MODE == GRAM_DIRECT) {
-        return cis_reference(a.f[cc], p.tt);
-    } else {
-        int fi = cc % a.lpv_nf, ki = cc / a.lpv_nf;
-        double2 e = a.E[(long long)fi * a.tbl_ns + p.si];
-        double k = a.Kt[(long long)ki * a.tbl_ns + p.si];
-        return make_double2(e.x * k, e.y * k);
-    }
-}
-
-template <int MODE, bool DIAG>
-__device__ __forceinline__ void gram_tile16(const GramArgs& a, int I, int J, int prob, double* smem) {
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int wm = w & 3, wn = w >> 2;
-    const long long s_begin = a.start0 + (long long)prob * a.hop;
-    const int nchunks = (a.n + KC - 1) / KC;
-
-    double acc[4][4][2];  // off-diagonal [i][j][e]; diagonal: [sb(3)][i*2+j (4)][e]
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    // synthesis role: warps 0-7 -> I tile, warps 8-15 -> J tile (pre-weighted); diagonal: warps 0-7 write both
-    const bool synI = w < 8;
-    const bool syn_active = DIAG ? synI : true;
-    const int grp = w & 7;
-    const int blk = synI ? I : J;
-    const int cc0 = blk * FB + grp * GRP;
-    const bool mask = cc0 + GRP > a.ncc;
-    const int rowc = (grp * GRP) * LDT + lane;
-    const int rows = (FB + grp * GRP) * LDT + lane;
-
-    auto chain_start = [&](const Pref16& p) {
-        return (DIAG || synI) ? p.a : make_double2(p.a.x * p.wt, p.a.y * p.wt);
-    };
-    auto synth_step = [&](const Pref16& p, double2& z, int j, double* st) {
-        double2 v;
-        if (MODE == GRAM_CHAIN) {
-            v = z;
-        } else {
-            v = synth_elem16<MODE>(a, p, min(cc0 + j, a.ncc - 1));
-            if (!DIAG && !synI) v = make_double2(v.x * p.wt, v.y * p.wt);
-        }
-        if (mask && cc0 + j >= a.ncc) v = make_double2(0.0, 0.0);
-        if (DIAG) {
-            st[rowc + j * LDT] = v.x;
-            st[rows + j * LDT] = v.y;
-            st[TILE_D + rowc + j * LDT] = v.x * p.wt;
-            st[TILE_D + rows + j * LDT] = v.y * p.wt;
-        } else {
-            double* dst = st + (synI ? 0 : TILE_D);
-            dst[rowc + j * LDT] = v.x;
-            dst[rows + j * LDT] = v.y;
-        }
-        if (MODE == GRAM_CHAIN) {
-            double nx = z.x * p.d.x - z.y * p.d.y;
-            double ny = z.x * p.d.y + z.y * p.d.x;
-            z = make_double2(nx, ny);
-        }
-    };
-
-    Pref16 p1{};
-    if (syn_active) {
-        p1 = load_pref16<MODE>(a, 0, s_begin, lane, grp, blk);
-        p1.wt = p1.valid ? p1.wt : 0.0;
-        double2 z = chain_start(p1);
-#pragma unroll
-        for (int j = 0; j < GRP; j++) synth_step(p1, z, j, smem);
-        if (nchunks > 1) p1 = load_pref16<MODE>(a, 1, s_begin, lane, grp, blk);
-    }
-    __syncthreads();
-
-    const int fragA = DIAG ? (16 * wm + (lane >> 2)) * LDT + (lane & 3) : (32 * wm + (lane >> 2)) * LDT + (lane & 3);
-    const int fragB = DIAG ? (16 * wn + (lane >> 2)) * LDT + (lane & 3) : (32 * wn + (lane >> 2)) * LDT + (lane & 3);
-
-    for (int c = 0; c < nchunks; c++) {
-        double* cur = smem + (c & 1) * STAGE_D;
-        double* nxt = smem + ((c & 1) ^ 1) * STAGE_D;
-        const bool do_syn = syn_active && (c + 1 < nchunks);
-        Pref16 p2 = p1;
-        if (syn_active && c + 2 < nchunks) p2 = load_pref16<MODE>(a, c + 2, s_begin, lane, grp, blk);
-        p1.wt = p1.valid ? p1.wt : 0.0;
-        double2 z = chain_start(p1);
-        const double* pa = cur + fragA;
-        const double* pb = cur + TILE_D + fragB;
-#pragma unroll
-        for (int kk = 0; kk < KC / 4; kk++) {
-            if (do_syn) synth_step(p1, z, kk, nxt);
-            if (!DIAG) {
-                double fa[4], fb[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) fa[i] = pa[i * 8 * LDT + 4 * kk];
-#pragma unroll
-                for (int j = 0; j < 4; j++) fb[j] = pb[j * 8 * LDT + 4 * kk];
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-            } else {
-                double fa[4], fb[4];  // [half*2 + r]: rows/cols {0,8} of the 16-wide warp tile in half 0 / half 1
-#pragma unroll
-                for (int i = 0; i < 4; i++) fa[i] = pa[((i >> 1) * 64 + (i & 1) * 8) * LDT + 4 * kk];
-#pragma unroll
-                for (int j = 0; j < 4; j++) fb[j] = pb[((j >> 1) * 64 + (j & 1) * 8) * LDT + 4 * kk];
-#pragma unroll
-                for (int i = 0; i < 2; i++)
-#pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        dmma884(acc[0][i * 2 + j][0], acc[0][i * 2 + j][1], fa[i], fb[j]);          // (0,0)
-                        dmma884(acc[1][i * 2 + j][0], acc[1][i * 2 + j][1], fa[2 + i], fb[j]);      // (1,0)
-                        dmma884(acc[2][i * 2 + j][0], acc[2][i * 2 + j][1], fa[2 + i], fb[2 + j]);  // (1,1)
-                    }
-            }
-        }
-        p1 = p2;
-        __syncthreads();
-    }
-
-    const int Np = a.nblk * TB;
-    double* Gp = a.G + (long long)prob * a.strideG;
-    if (!DIAG) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            int row = I * TB + 32 * wm + 8 * i + (lane >> 2);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int col = J * TB + 32 * wn + 8 * j + 2 * (lane & 3);
-                double2 v = make_double2(acc[i][j][0] * a.gscale, acc[i][j][1] * a.gscale);
-                *reinterpret_cast<double2*>(Gp + (long long)row * Np + col) = v;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int sb = 0; sb < 3; sb++) {
-            const int sr = sb > 0, sc = sb > 1;
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                int row = I * TB + 64 * sr + 16 * wm + 8 * i + (lane >> 2);
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    int col = I * TB + 64 * sc + 16 * wn + 8 * j + 2 * (lane & 3);
-                    double2 v = make_double2(acc[sb][i * 2 + j][0] * a.gscale, acc[sb][i * 2 + j][1] * a.gscale);
-                    *reinterpret_cast<double2*>(Gp + (long long)row * Np + col) = v;
-                }
-            }
-        }
-    }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(NT16, 1) k_gram16(const __grid_constant__ GramArgs a) {
-    extern __shared__ __align__(16) double smem[];
-    int I, J;
-    tile_ij(blockIdx.x, I, J);
-    if (I == J)
-        gram_tile16<MODE, true>(a, I, J, blockIdx.y, smem);
-    else
-        gram_tile16<MODE, false>(a, I, J, blockIdx.y, smem);
-}
-
 // b = A' diag(W) [y u]: one CTA per (64-frequency block, problem); warp = chain group, lane = sample.
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS) k_gram_rhs(const __grid_constant__ GramArgs a) {
@@ -559,8 +358,6 @@ __global__ void k_lpv_tables(const double* __restrict__ X, const double* __restr
 
 }  // namespace
 
-static int g_gram_warps = 8;  // LPVS_GRAM_WARPS=16 selects the 16-warp kernel (A/B: 82.6 ms vs 81.2 ms at cfg2, so 8 is the default)
-
 size_t gram_smem_bytes() { return NSTAGE * STAGE_D * sizeof(double) + 64; }
 
 void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
@@ -572,10 +369,6 @@ void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
         cudaFuncSetAttribute(k_gram<GRAM_CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_gram<GRAM_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_gram<GRAM_LPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_gram16<GRAM_CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_gram16<GRAM_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_gram16<GRAM_LPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (const char* e = getenv("LPVS_GRAM_WARPS")) g_gram_warps = atoi(e) == 16 ? 16 : 8;
         attr_done[dev & 63] = true;
     }
     int ntiles = a.nblk * (a.nblk + 1) / 2;
@@ -589,16 +382,7 @@ void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
         dim3 grid(ntiles, np);
         dim3 grid_rhs(a.nblk, np);
         const bool rhs = a.B && a.nrhs > 0 && a.y;
-        if (g_gram_warps == 16) {
-            if (mode == GRAM_CHAIN) k_gram16<GRAM_CHAIN><<<grid, NT16, smem, st>>>(b);
-            else if (mode == GRAM_DIRECT) k_gram16<GRAM_DIRECT><<<grid, NT16, smem, st>>>(b);
-            else k_gram16<GRAM_LPV><<<grid, NT16, smem, st>>>(b);
-            if (rhs) {
-                if (mode == GRAM_CHAIN) k_gram_rhs<GRAM_CHAIN><<<grid_rhs, NTHREADS, 0, st>>>(b);
-                else if (mode == GRAM_DIRECT) k_gram_rhs<GRAM_DIRECT><<<grid_rhs, NTHREADS, 0, st>>>(b);
-                else k_gram_rhs<GRAM_LPV><<<grid_rhs, NTHREADS, 0, st>>>(b);
-            }
-        } else if (mode == GRAM_CHAIN) {
+        if (mode == GRAM_CHAIN) {
             k_gram<GRAM_CHAIN><<<grid, NTHREADS, smem, st>>>(b);
             if (rhs) k_gram_rhs<GRAM_CHAIN><<<grid_rhs, NTHREADS, 0, st>>>(b);
         } else if (mode == GRAM_DIRECT) {
