@@ -253,7 +253,12 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
     int nseg = (int)((N + seg_cap - 1) / seg_cap);
     if (nseg < 1) nseg = 1;
     long long seg_len = (N + nseg - 1) / nseg;
-    int split_per_seg = std::max(1, nsplit / nseg);
+    // segments run one after the other, so EACH must be split enough to fill the machine on its own
+    int split_per_seg = nseg == 1 ? nsplit : 1;
+    if (nseg > 1 && ntiles < 4 * c->sms) {
+        long long want = (4LL * c->sms + ntiles - 1) / ntiles;
+        split_per_seg = (int)std::min(want, std::max<long long>(1, seg_len / 2048));
+    }
     const bool direct_out = (nseg == 1 && split_per_seg == 1);
     double* parts = nullptr;
     const long long part_stride = Np * Np + 2 * Np;
