@@ -61,7 +61,7 @@ enum lpvs_option {
 int lpvs_version(void);
 int lpvs_device_count(void);
 int lpvs_init(int device, lpvs_ctx** ctx);
-void lpvs_destroy(lpvs_ctx* ctx);
+void lpvs_destroy(lpvs_ctx* ctx); /* also frees ADMM handles of this context that were not freed; they become invalid */
 const char* lpvs_last_error(const lpvs_ctx* ctx);
 int lpvs_set_option(lpvs_ctx* ctx, int key, double value);
 /* enqueue all work of this context on the caller's CUDA stream (cudaStream_t as void*; NULL = the context's own

@@ -437,7 +437,8 @@ class ADMM:
 
     def free(self):
         if self.h:
-            self.ctx.lib.lpvs_admm_free(self.h)
+            if getattr(self.ctx, "h", None):  # a closed context has already released its handles
+                self.ctx.lib.lpvs_admm_free(self.h)
             self.h = None
 
     def __del__(self):

@@ -592,6 +592,8 @@ namespace lpvs {
 
 static void admm_release(lpvs_admm* h) {
     if (!h) return;
+    auto& live = h->ctx->live_admm;
+    live.erase(std::remove(live.begin(), live.end(), h), live.end());
     cudaSetDevice(h->ctx->device);
     cudaStreamSynchronize(h->ctx->st);
     cudaFree(h->M);
@@ -901,7 +903,11 @@ namespace lpvs {
 lpvs_admm* admm_new(lpvs_ctx* c) {
     lpvs_admm* h = new lpvs_admm();
     h->ctx = c;
+    c->live_admm.push_back(h);
     return h;
+}
+void admm_release_all(lpvs_ctx* c) {
+    while (!c->live_admm.empty()) admm_release(c->live_admm.back());
 }
 void admm_delete(lpvs_admm* h) { admm_release(h); }
 void admm_set_problem(lpvs_admm* h, int kind, int Np, int ncc, int zero_first, int nref, int half, int prox,

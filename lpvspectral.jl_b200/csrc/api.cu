@@ -422,6 +422,7 @@ int lpvs_init(int device, lpvs_ctx** out) {
 void lpvs_destroy(lpvs_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    admm_release_all(c);
     cudaStreamSynchronize(c->st);
     for (auto& b : c->buf)
         if (b.p) cudaFree(b.p);

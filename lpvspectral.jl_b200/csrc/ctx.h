@@ -48,6 +48,7 @@ struct lpvs_ctx {
     cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
     int call_depth = 0;
     int* d_nonfinite = nullptr;  // set by the upload-time scan of host inputs
+    std::vector<lpvs_admm*> live_admm;  // handles created on this context and not yet freed
 };
 
 namespace lpvs {
@@ -140,6 +141,7 @@ int lpv_gram(lpvs_ctx* c, const LpvPlan& pl, const double* d_y, double* d_G, dou
 
 // ADMM plumbing (admm.cu)
 lpvs_admm* admm_new(lpvs_ctx* c);
+void admm_release_all(lpvs_ctx* c);  // lpvs_destroy: free handles the caller leaked
 void admm_delete(lpvs_admm* h);
 void admm_set_problem(lpvs_admm* h, int kind, int Np, int ncc, int zero_first, int nref, int half, int prox,
                       double pparam, double mu, int quad, int lpv_nf, int lpv_nvv);
