@@ -10,6 +10,8 @@
 // need the whole x first: they run as a second, tiny phase after a barrier.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -47,7 +49,14 @@ struct AdmmArgs {
     double* res_out;
     int* conv_out;
     int* rbuf_out;
+    // diagnostics (LPVS_ADMM_TRACE=<file>): clock64 stamps, [TRACE_ITERS][grid][8], of iterations trace_it0..
+    long long* trace;
+    long long trace_it0;
 };
+constexpr int TRACE_ITERS = 4;
+#define ADMM_TR(slot)                                                                            \
+    if (a.trace && tid == 0 && it >= a.trace_it0 && it < a.trace_it0 + TRACE_ITERS)             \
+        a.trace[((it - a.trace_it0) * gridDim.x + blockIdx.x) * 8 + (slot)] = clock64();
 
 __device__ __forceinline__ double prox_elem(int kind, double v, double gl, double thr0) {
     if (kind == LPVS_PROX_L1) {  // sign(v) max(|v| - mu*lambda, 0)
@@ -91,7 +100,7 @@ __device__ __forceinline__ double admm_phase_nonelem(const AdmmArgs& a, double* 
     double d2 = 0.0;
     if (a.prox == LPVS_PROX_GROUP_L2) {
         // warp per group: z_g = max(0, 1 - mu*lambda/||v_g||) v_g ; ungrouped entries stay z = 0
-        for (int g = b * ADMM_WARPS + w; g <= a.ngroups; g += nblocks * ADMM_WARPS) {
+        for (int g = w * nblocks + b; g <= a.ngroups; g += nblocks * ADMM_WARPS) {  // spread over the CTAs first
             if (g == a.ngroups) {
                 // pseudo group: entries not covered by any group (Q16) -> z = 0
                 const int lo2 = a.goff[a.ngroups], hi2 = a.goff[a.ngroups + 1];
@@ -215,10 +224,12 @@ __device__ __forceinline__ bool admm_end_iter(const AdmmArgs& a, cg::grid_group&
     }
     grid.sync();
     if ((it + 1) % a.check_every == 0 || it + 1 == a.max_iters) {
-        if (tid == 0) {
+        if (w == 0) {  // fixed-order parallel sum: identical in every CTA and every run
             double s = 0.0;
-            for (int k = 0; k < nblocks; k++) s += __ldcg(a.part + (it & 1) * nblocks + k);
-            *s_nxz = sqrt(s);
+            for (int k = lane; k < nblocks; k += 32) s += __ldcg(a.part + (it & 1) * nblocks + k);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) *s_nxz = sqrt(s);
         }
         __syncthreads();
         nxz = *s_nxz;
@@ -370,8 +381,28 @@ struct SymvPlan {
     const int* seg_i1;  // one past the last block row
     const int* cta_seg; // [grid+1] segment ranges per CTA
     const int* cta_persist;  // [grid] number of leading blocks of each CTA kept L2-resident (evict_last)
-    double* ypart;      // [grid][Np]
+    // sparse exchange of the CTA-private partial y: a CTA publishes only the 128-blocks its segments touch
+    const int* cta_slot;  // [grid+1] slot range of each CTA
+    const int* slot_blk;  // [nslots] which 128-block of y the slot holds
+    const int* red_ptr;   // [nb+1] contributors of each 128-block ...
+    const int* red_slot;  // ... as slot indices, ordered by CTA (fixed summation order)
+    // phase-2 work items of the group prox (ADMM order: groups are contiguous row ranges)
+    const int* cta_item;   // [grid+1]
+    const int* item_lo;    // first row
+    const int* item_hi;    // one past the last row
+    const int* item_kind;  // 0 = group (block soft threshold), 1 = rows outside every group (z = 0, Q16)
+    double* ypart;         // [nslots][128]
 };
+
+// x_i = sum of the published partials of row i; the four q-lanes of a row split the contributor list
+__device__ __forceinline__ double symv_row_sum(const SymvPlan& sp, int i, int q) {
+    const int R = i >> 7, c = i & 127;
+    const int k1 = __ldg(sp.red_ptr + R + 1);
+    double t = 0.0;
+    for (int k = __ldg(sp.red_ptr + R) + q; k < k1; k += 4)
+        t += __ldcg(sp.ypart + (long long)__ldg(sp.red_slot + k) * 128 + c);
+    return t;
+}
 
 __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv(const __grid_constant__ AdmmArgs a,
                                                                const __grid_constant__ SymvPlan sp) {
@@ -379,6 +410,8 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv(const __grid_cons
     extern __shared__ __align__(16) double sm[];
     double* ys = sm;             // Np: CTA-private partial y
     double* cred = sm + a.Np;    // [ADMM_WARPS][128] column partials of the current segment
+    double* xs = cred + ADMM_WARPS * 128;  // [Np] x of the current group item (group prox only)
+    __shared__ double gsum[ADMM_WARPS];
     __shared__ double wsum[ADMM_WARPS];
     __shared__ double s_nxz;
     __shared__ double red4[4][128];
@@ -393,6 +426,8 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv(const __grid_cons
     const int r0 = b * base + min(b, extra);
     const int nrows = base + (b < extra ? 1 : 0);
     const int sg0 = sp.cta_seg[b], sg1 = sp.cta_seg[b + 1];
+    const int slot0 = sp.cta_slot[b], slot1 = sp.cta_slot[b + 1];
+    const int item0 = sp.cta_item[b], item1 = sp.cta_item[b + 1];
     // M is re-read every iteration: a fixed prefix of this CTA's blocks is loaded evict_last so that ~88 MB of M
     // stays in the 126 MB L2 across iterations; the rest streams evict_first
     const int my_persist = sp.cta_persist[b];
@@ -405,7 +440,12 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv(const __grid_cons
     for (; it < a.max_iters; it++) {
         const double* rc = a.r + (long long)cur * Np;
         double* rn = a.r + (long long)(cur ^ 1) * Np;
-        for (int i = tid; i < Np; i += ADMM_THREADS) ys[i] = 0.0;
+        ADMM_TR(0)
+        for (int sl = slot0 + w; sl < slot1; sl += ADMM_WARPS) {
+            const int blk = __ldg(sp.slot_blk + sl);
+#pragma unroll
+            for (int k = 0; k < 4; k++) ys[blk * 128 + lane + 32 * k] = 0.0;
+        }
         __syncthreads();
         // ---- phase 1: this CTA's segments ----
         int bcount = 0;
@@ -477,36 +517,86 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv(const __grid_cons
             }
             __syncthreads();
         }
-        double* yp = sp.ypart + (long long)b * Np;
-        for (int i = tid; i < Np; i += ADMM_THREADS) yp[i] = ys[i];
+        ADMM_TR(1)
+        for (int sl = slot0 + w; sl < slot1; sl += ADMM_WARPS) {
+            const int blk = __ldg(sp.slot_blk + sl);
+            double* yp = sp.ypart + (long long)sl * 128;
+#pragma unroll
+            for (int k = 0; k < 4; k++) yp[lane + 32 * k] = ys[blk * 128 + lane + 32 * k];
+        }
+        ADMM_TR(2)
         grid.sync();
-        // ---- phase 2: x_i = sum over CTAs (fixed order), then the fused epilogue on evenly split rows ----
+        ADMM_TR(3)
+        // ---- phase 2: x_i = sum of the published partials (fixed order), then the fused epilogue ----
         double d2 = 0.0;
-        for (int rb = 0; rb < nrows; rb += 128) {
-            const int rl = rb + (tid & 127), q = tid >> 7;
-            double t = 0.0;
-            if (rl < nrows) {
-                const double* col = sp.ypart + r0 + rl;
-                for (int c = q; c < nblocks; c += 4) t += __ldcg(col + (long long)c * Np);
+        if (a.prox != LPVS_PROX_GROUP_L2) {  // evenly split rows
+            for (int rb = 0; rb < nrows; rb += 128) {
+                const int rl = rb + (tid & 127), q = tid >> 7;
+                red4[q][tid & 127] = rl < nrows ? symv_row_sum(sp, r0 + rl, q) : 0.0;
+                __syncthreads();
+                if (tid < 128 && rl < nrows) {
+                    const int i = r0 + rl;
+                    const double xi = (red4[0][tid] + red4[1][tid]) + (red4[2][tid] + red4[3][tid]);
+                    a.x[i] = xi;
+                    if (elementwise)
+                        d2 += admm_elem_update(a, rn, i, xi, gl, thr0);
+                    else
+                        a.v[i] = xi + a.u[i];
+                }
+                __syncthreads();
             }
-            red4[q][tid & 127] = t;
-            __syncthreads();
-            if (tid < 128 && rl < nrows) {
-                const int i = r0 + rl;
-                const double xi = (red4[0][tid] + red4[1][tid]) + (red4[2][tid] + red4[3][tid]);
-                a.x[i] = xi;
-                if (elementwise)
-                    d2 += admm_elem_update(a, rn, i, xi, gl, thr0);
-                else
-                    a.v[i] = xi + a.u[i];
+        } else {
+            // whole groups per CTA: x, v = x+u, ||v_g||, block soft threshold, dual update -- no second barrier.
+            // ys was published before the barrier and is free: it holds v of the current item.
+            for (int itx = item0; itx < item1; itx++) {
+                const int lo = __ldg(sp.item_lo + itx), hi = __ldg(sp.item_hi + itx), kind = __ldg(sp.item_kind + itx);
+                for (int rb = lo; rb < hi; rb += 128) {
+                    const int i = rb + (tid & 127), q = tid >> 7;
+                    red4[q][tid & 127] = i < hi ? symv_row_sum(sp, i, q) : 0.0;
+                    __syncthreads();
+                    if (tid < 128 && i < hi) {
+                        const double xi = (red4[0][tid] + red4[1][tid]) + (red4[2][tid] + red4[3][tid]);
+                        a.x[i] = xi;
+                        xs[i - lo] = xi;
+                        ys[i - lo] = xi + a.u[i];
+                    }
+                    __syncthreads();
+                }
+                double scale = 0.0;
+                if (kind == 0) {
+                    double ss = 0.0;
+                    for (int m = tid; m < hi - lo; m += ADMM_THREADS) ss = fma(ys[m], ys[m], ss);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                    if (lane == 0) gsum[w] = ss;
+                    __syncthreads();
+                    double tot = 0.0;
+#pragma unroll
+                    for (int k = 0; k < ADMM_WARPS; k++) tot += gsum[k];
+                    const double nrm = sqrt(tot);
+                    scale = nrm > 0.0 ? fmax(0.0, 1.0 - gl / nrm) : 0.0;
+                }
+                for (int m = tid; m < hi - lo; m += ADMM_THREADS) {
+                    const int i = lo + m;
+                    const double xi = xs[m], zi = scale * ys[m];
+                    double ui = a.u[i];
+                    const double di = xi - zi;
+                    ui += di;
+                    a.z[i] = zi;
+                    a.u[i] = ui;
+                    rn[i] = next_rhs(a, i, zi, ui);
+                    d2 += di * di;
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
-        if (!elementwise) {
-            grid.sync();
-            d2 = admm_phase_nonelem(a, rn, b, nblocks, tid, lane, w, gl);
-        }
+        ADMM_TR(4)
+        if (a.prox == LPVS_PROX_BALL_L0) grid.sync();
+        ADMM_TR(5)
+        if (a.prox == LPVS_PROX_BALL_L0) d2 = admm_phase_nonelem(a, rn, b, nblocks, tid, lane, w, gl);
+        ADMM_TR(6)
         const bool stop = admm_end_iter(a, grid, d2, it, b, nblocks, tid, lane, w, wsum, &s_nxz, nxz);
+        ADMM_TR(7)
         cur ^= 1;
         if (stop) {
             converged = 1;
@@ -536,7 +626,7 @@ __global__ void k_admm_init(const double* __restrict__ q, const double* __restri
 
 // internal vector -> reference order (Fourier: cos block then -sin block; LPV: column-major [Re|Im] un-permuted)
 __global__ void k_gather_vec(const double* __restrict__ xin, int nref, int half, int zero_first,
-                             double* __restrict__ out) {
+                             const int* __restrict__ pos, double* __restrict__ out) {
     // reference index j: j < half -> real part of complex column j; else imaginary part of column j-half+zero_first
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nref) return;
@@ -548,7 +638,20 @@ __global__ void k_gather_vec(const double* __restrict__ xin, int nref, int half,
         cc = j - half + zero_first;
         part = 1;
     }
-    out[j] = xin[(cc >> 6) * 128 + part * 64 + (cc & 63)];
+    const int idx = (cc >> 6) * 128 + part * 64 + (cc & 63);
+    out[j] = xin[pos ? pos[idx] : idx];
+}
+
+// ADMM order: Mp[p][q] = M[order[p]][order[q]] (M symmetric), vp[p] = v[order[p]]
+__global__ void k_permute_sym(const double* __restrict__ M, double* __restrict__ Mp, const int* __restrict__ order,
+                              int Np) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (q < Np) Mp[(long long)p * Np + q] = M[(long long)order[p] * Np + order[q]];
+}
+__global__ void k_permute_vec(const double* __restrict__ v, double* __restrict__ vp, const int* __restrict__ order,
+                              int Np) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < Np) vp[p] = v[order[p]];
 }
 
 }  // namespace lpvs
@@ -575,8 +678,15 @@ struct lpvs_admm {
     int* d_flags = nullptr;
     // SYMV variant (lower triangle only)
     int symv = 0;
-    int* seg_buf = nullptr;  // seg_j | seg_i0 | seg_i1 | cta_seg
+    int* seg_buf = nullptr;  // all SymvPlan index tables, one allocation
     int nseg = 0;
+    size_t off_cta_seg = 0, off_persist = 0, off_cta_slot = 0, off_slot_blk = 0, off_red_ptr = 0, off_red_slot = 0,
+           off_cta_item = 0, off_item_lo = 0, off_item_hi = 0, off_item_kind = 0;
+    int max_item = 0;  // longest phase-2 item (rows) of the group prox
+    // ADMM order (group prox): position p of the loop vectors holds internal index order[p]; pos is the inverse
+    std::vector<int> h_order, h_goff;
+    int* d_order = nullptr;
+    int* d_pos = nullptr;
     double* ypart = nullptr;
     int rbuf = 0;
     int grid = 0;
@@ -606,13 +716,65 @@ static void admm_release(lpvs_admm* h) {
     cudaFree(h->d_flags);
     cudaFree(h->seg_buf);
     cudaFree(h->ypart);
+    cudaFree(h->d_order);
+    cudaFree(h->d_pos);
     if (h->e0) cudaEventDestroy(h->e0);
     if (h->e1) cudaEventDestroy(h->e1);
     delete h;
 }
 
 static size_t admm_smem(int Np, int rows_max) { return sizeof(double) * ((size_t)Np + (size_t)rows_max * ADMM_WARPS); }
-static size_t admm_smem_symv(int Np) { return sizeof(double) * ((size_t)Np + (size_t)ADMM_WARPS * 128); }
+static size_t admm_smem_symv(int Np, int max_item) {
+    return sizeof(double) * ((size_t)Np + (size_t)ADMM_WARPS * 128 + (size_t)max_item);
+}
+
+// Phase-2 work items of the group prox: whole groups (ADMM order), the rows outside every group in 128-row pieces;
+// longest first onto the least loaded CTA.  Returns the longest item.
+struct GroupItems {
+    std::vector<int> cta_item, lo, hi, kind;
+    int max_item = 0;
+};
+static GroupItems build_group_items(const lpvs_admm* h, int grid) {
+    GroupItems gi;
+    gi.cta_item.assign((size_t)grid + 1, 0);
+    if (h->prox != LPVS_PROX_GROUP_L2) return gi;
+    std::vector<int> ilo, ihi, ikind;
+    const int ng = h->ngroups;
+    for (int g = 0; g < ng; g++)
+        if (h->h_goff[g + 1] > h->h_goff[g]) {
+            ilo.push_back(h->h_goff[g]);
+            ihi.push_back(h->h_goff[g + 1]);
+            ikind.push_back(0);
+        }
+    for (int r = h->h_goff[ng]; r < h->h_goff[ng + 1]; r += 128) {
+        ilo.push_back(r);
+        ihi.push_back(std::min(r + 128, h->h_goff[ng + 1]));
+        ikind.push_back(1);
+    }
+    std::vector<int> idx(ilo.size());
+    for (size_t k = 0; k < idx.size(); k++) idx[k] = (int)k;
+    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return ihi[x] - ilo[x] > ihi[y] - ilo[y]; });
+    std::vector<long long> load((size_t)grid, 0);
+    std::vector<std::vector<int>> per((size_t)grid);
+    for (int k : idx) {
+        int best = 0;
+        for (int b2 = 1; b2 < grid; b2++)
+            if (load[b2] < load[best]) best = b2;
+        per[best].push_back(k);
+        load[best] += ihi[k] - ilo[k] + 32;  // + a fixed per-item cost
+        gi.max_item = std::max(gi.max_item, ihi[k] - ilo[k]);
+    }
+    for (int b2 = 0; b2 < grid; b2++) {
+        gi.cta_item[b2] = (int)gi.lo.size();
+        for (int k : per[b2]) {
+            gi.lo.push_back(ilo[k]);
+            gi.hi.push_back(ihi[k]);
+            gi.kind.push_back(ikind[k]);
+        }
+    }
+    gi.cta_item[grid] = (int)gi.lo.size();
+    return gi;
+}
 
 // Factor (G + I/mu), invert, allocate loop state.  d_G: Np x Np lower tiles (consumed), d_q: Np.
 int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q, const double* d_x0) {
@@ -654,13 +816,38 @@ int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q
         return fail(c, LPVS_E_NOT_SPD, "Cholesky breakdown of (G + I/mu) at internal pivot %d", pinfo);
     }
     c->launches += potri(ca, 1, c->st);
-    e = cudaStreamSynchronize(c->st);
-    cudaFree(Y);
-    if (e != cudaSuccess) return fail(c, LPVS_E_CUDA, "inverse failed: %s", cudaGetErrorString(e));
-    // loop state
-    if (cudaMalloc(&h->vecs, sizeof(double) * 7 * Np) != cudaSuccess) return fail(c, LPVS_E_NOMEM, "out of memory");
+    if (cudaMalloc(&h->vecs, sizeof(double) * 7 * Np) != cudaSuccess) {
+        cudaStreamSynchronize(c->st);
+        cudaFree(Y);
+        return fail(c, LPVS_E_NOMEM, "out of memory");
+    }
     double* q = h->vecs;
-    LPVS_CU(c, cudaMemcpyAsync(q, d_q, sizeof(double) * Np, cudaMemcpyDeviceToDevice, c->st));
+    const bool permuted = !h->h_order.empty();
+    if (permuted) {
+        // group prox: bring M and q into ADMM order (groups contiguous); the inverse workspace becomes M
+        bool ok = cudaMalloc(&h->d_order, sizeof(int) * Np) == cudaSuccess &&
+                  cudaMalloc(&h->d_pos, sizeof(int) * Np) == cudaSuccess;
+        if (!ok) {
+            cudaStreamSynchronize(c->st);
+            cudaFree(Y);
+            return fail(c, LPVS_E_NOMEM, "out of memory");
+        }
+        std::vector<int> pos((size_t)Np);
+        for (int p = 0; p < Np; p++) pos[h->h_order[p]] = p;
+        cudaMemcpyAsync(h->d_order, h->h_order.data(), sizeof(int) * Np, cudaMemcpyHostToDevice, c->st);
+        cudaMemcpyAsync(h->d_pos, pos.data(), sizeof(int) * Np, cudaMemcpyHostToDevice, c->st);
+        k_permute_sym<<<dim3((Np + 255) / 256, Np), 256, 0, c->st>>>(d_G, Y, h->d_order, Np);
+        k_permute_vec<<<(Np + 255) / 256, 256, 0, c->st>>>(d_q, q, h->d_order, Np);
+        c->launches += 2;
+        e = cudaStreamSynchronize(c->st);
+        h->M = Y;
+        cudaFree(d_G);
+    } else {
+        cudaMemcpyAsync(q, d_q, sizeof(double) * Np, cudaMemcpyDeviceToDevice, c->st);
+        e = cudaStreamSynchronize(c->st);
+        cudaFree(Y);
+    }
+    if (e != cudaSuccess) return fail(c, LPVS_E_CUDA, "inverse failed: %s", cudaGetErrorString(e));
     // cooperative grid: one CTA per SM, never more CTAs than rows/2
     int maxb = 0;
     int grid = std::min(c->sms, std::max(1, Np / 8));
@@ -675,9 +862,18 @@ int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q
     // variant: SYMV over the lower triangle when M cannot live in L2 (or when forced), else GEMV over full M
     const bool big = 8.0 * Np * (double)Np > 96.0 * 1024 * 1024;
     h->symv = c->admm_symv < 0 ? (big && Np <= 24576) : (c->admm_symv != 0);
+    GroupItems gitems;
     if (h->symv) {
-        size_t sm2 = admm_smem_symv(Np);
-        if (sm2 > 220 * 1024) return fail(c, LPVS_E_UNSUPPORTED, "ADMM SYMV variant: Np=%d too large", Np);
+        gitems = build_group_items(h, c->sms);
+        h->max_item = gitems.max_item;
+        size_t sm2 = admm_smem_symv(Np, h->max_item);
+        if (sm2 > 220 * 1024) {
+            if (c->admm_symv > 0) return fail(c, LPVS_E_UNSUPPORTED, "ADMM SYMV variant: Np=%d too large", Np);
+            h->symv = 0;  // the GEMV variant only needs the resident rhs
+        }
+    }
+    if (h->symv) {
+        size_t sm2 = admm_smem_symv(Np, h->max_item);
         LPVS_CU(c, cudaFuncSetAttribute(k_admm_symv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
         h->grid = grid = c->sms;
         // blocks of the lower triangle in block-column-major order, split evenly over the CTAs, then cut into
@@ -713,16 +909,57 @@ int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q
                 persist[cta_i] = (int)(frac * (double)nblk);
             }
         }
+        // sparse exchange: slots = the 128-blocks of y each CTA touches (block column J and block rows I of its
+        // segments); contributor lists per block, ordered by CTA
+        std::vector<int> cta_slot(grid + 1, 0), slot_blk;
+        std::vector<std::vector<int>> contrib((size_t)nb);
+        {
+            std::vector<int> seen((size_t)nb, -1);
+            for (int cta_i = 0; cta_i < grid; cta_i++) {
+                cta_slot[cta_i] = (int)slot_blk.size();
+                auto touch = [&](int blk) {
+                    if (seen[blk] == cta_i) return;
+                    seen[blk] = cta_i;
+                    contrib[blk].push_back((int)slot_blk.size());
+                    slot_blk.push_back(blk);
+                };
+                for (int sgi = cta[cta_i]; sgi < cta[cta_i + 1]; sgi++) {
+                    touch(sj[sgi]);
+                    for (int I = si0[sgi]; I < si1[sgi]; I++) touch(I);
+                }
+            }
+            cta_slot[grid] = (int)slot_blk.size();
+        }
+        std::vector<int> red_ptr(nb + 1, 0), red_slot;
+        for (int R = 0; R < nb; R++) {
+            red_ptr[R] = (int)red_slot.size();
+            red_slot.insert(red_slot.end(), contrib[R].begin(), contrib[R].end());
+        }
+        red_ptr[nb] = (int)red_slot.size();
         std::vector<int> all;
-        all.insert(all.end(), sj.begin(), sj.end());
-        all.insert(all.end(), si0.begin(), si0.end());
-        all.insert(all.end(), si1.begin(), si1.end());
-        all.insert(all.end(), cta.begin(), cta.end());
-        all.insert(all.end(), persist.begin(), persist.end());
+        auto put = [&](const std::vector<int>& v) {
+            size_t off = all.size();
+            all.insert(all.end(), v.begin(), v.end());
+            return off;
+        };
+        put(sj);
+        put(si0);
+        put(si1);
+        h->off_cta_seg = put(cta);
+        h->off_persist = put(persist);
+        h->off_cta_slot = put(cta_slot);
+        h->off_slot_blk = put(slot_blk);
+        h->off_red_ptr = put(red_ptr);
+        h->off_red_slot = put(red_slot);
+        h->off_cta_item = put(gitems.cta_item);
+        h->off_item_lo = put(gitems.lo);
+        h->off_item_hi = put(gitems.hi);
+        h->off_item_kind = put(gitems.kind);
+        all.push_back(0);
         LPVS_CU(c, cudaMalloc(&h->seg_buf, sizeof(int) * all.size()));
         LPVS_CU(c, cudaMemcpyAsync(h->seg_buf, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice, c->st));
         LPVS_CU(c, cudaStreamSynchronize(c->st));
-        LPVS_CU(c, cudaMalloc(&h->ypart, sizeof(double) * (size_t)grid * Np));
+        LPVS_CU(c, cudaMalloc(&h->ypart, sizeof(double) * (size_t)slot_blk.size() * 128));
     }
     LPVS_CU(c, cudaMalloc(&h->part, sizeof(double) * 2 * grid));
     LPVS_CU(c, cudaMalloc(&h->d_iters, sizeof(long long)));
@@ -730,6 +967,7 @@ int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q
     LPVS_CU(c, cudaMalloc(&h->d_flags, sizeof(int) * 2));
     LPVS_CU(c, cudaEventCreate(&h->e0));
     LPVS_CU(c, cudaEventCreate(&h->e1));
+    if (permuted && d_x0) return fail(c, LPVS_E_UNSUPPORTED, "start vector with a group prox");
     k_admm_init<<<(Np + 255) / 256, 256, 0, c->st>>>(q, d_x0, Np, h->mu, h->quad, h->vecs + Np, h->vecs + 2 * Np,
                                                     h->vecs + 3 * Np, h->vecs + 5 * Np);
     c->launches++;
@@ -780,18 +1018,34 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
     a.res_out = h->d_res;
     a.conv_out = h->d_flags;
     a.rbuf_out = h->d_flags + 1;
+    long long* d_trace = nullptr;
+    const char* trace_path = getenv("LPVS_ADMM_TRACE");
+    if (trace_path && *trace_path && max_iters > 16) {
+        LPVS_CU(c, cudaMalloc(&d_trace, sizeof(long long) * TRACE_ITERS * h->grid * 8));
+        LPVS_CU(c, cudaMemsetAsync(d_trace, 0, sizeof(long long) * TRACE_ITERS * h->grid * 8, c->st));
+        a.trace = d_trace;
+        a.trace_it0 = max_iters / 2;
+    }
     LPVS_CU(c, cudaEventRecord(h->e0, c->st));
     if (h->symv) {
         SymvPlan sp{};
         sp.seg_j = h->seg_buf;
         sp.seg_i0 = h->seg_buf + h->nseg;
         sp.seg_i1 = h->seg_buf + 2 * h->nseg;
-        sp.cta_seg = h->seg_buf + 3 * h->nseg;
-        sp.cta_persist = h->seg_buf + 3 * h->nseg + h->grid + 1;
+        sp.cta_seg = h->seg_buf + h->off_cta_seg;
+        sp.cta_persist = h->seg_buf + h->off_persist;
+        sp.cta_slot = h->seg_buf + h->off_cta_slot;
+        sp.slot_blk = h->seg_buf + h->off_slot_blk;
+        sp.red_ptr = h->seg_buf + h->off_red_ptr;
+        sp.red_slot = h->seg_buf + h->off_red_slot;
+        sp.cta_item = h->seg_buf + h->off_cta_item;
+        sp.item_lo = h->seg_buf + h->off_item_lo;
+        sp.item_hi = h->seg_buf + h->off_item_hi;
+        sp.item_kind = h->seg_buf + h->off_item_kind;
         sp.ypart = h->ypart;
         void* args[] = {&a, &sp};
         LPVS_CU(c, cudaLaunchCooperativeKernel((void*)k_admm_symv, dim3(h->grid), dim3(ADMM_THREADS), args,
-                                               admm_smem_symv(Np), c->st));
+                                               admm_smem_symv(Np, h->max_item), c->st));
     } else {
         int rows_max = (Np + h->grid - 1) / h->grid;
         size_t smem = admm_smem(Np, rows_max + 1);
@@ -809,6 +1063,17 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
     LPVS_CU(c, cudaMemcpyAsync(&res, h->d_res, sizeof(double), cudaMemcpyDeviceToHost, c->st));
     LPVS_CU(c, cudaMemcpyAsync(flags, h->d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->st));
     LPVS_CU(c, cudaStreamSynchronize(c->st));
+    if (d_trace) {
+        std::vector<long long> tr((size_t)TRACE_ITERS * h->grid * 8);
+        cudaMemcpy(tr.data(), d_trace, sizeof(long long) * tr.size(), cudaMemcpyDeviceToHost);
+        cudaFree(d_trace);
+        if (FILE* fp = fopen(trace_path, "wb")) {
+            int hdr[2] = {TRACE_ITERS, h->grid};
+            fwrite(hdr, sizeof(int), 2, fp);
+            fwrite(tr.data(), sizeof(long long), tr.size(), fp);
+            fclose(fp);
+        }
+    }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->e0, h->e1);
     h->last_ms = ms;
@@ -833,9 +1098,10 @@ int lpvs_admm_get(lpvs_admm* h, double* x, double* z) {
     double* tmp = ws<double>(c, BUF_X, (size_t)2 * h->nref);
     if (!tmp) return fail(c, LPVS_E_NOMEM, "out of device memory");
     const int Np = h->Np;
-    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(h->vecs + Np, h->nref, h->half, h->zero_first, tmp);
+    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(h->vecs + Np, h->nref, h->half, h->zero_first, h->d_pos,
+                                                           tmp);
     k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(h->vecs + 2 * Np, h->nref, h->half, h->zero_first,
-                                                           tmp + h->nref);
+                                                           h->d_pos, tmp + h->nref);
     c->launches += 2;
     if (x) LPVS_CU(c, cudaMemcpyAsync(x, tmp, sizeof(double) * h->nref, cudaMemcpyDeviceToHost, c->st));
     if (z) LPVS_CU(c, cudaMemcpyAsync(z, tmp + h->nref, sizeof(double) * h->nref, cudaMemcpyDeviceToHost, c->st));
@@ -866,7 +1132,8 @@ int lpvs_admm_result(lpvs_admm* h, double* out) {
     const int Np = h->Np, ncx = h->half;
     double* tmp = ws<double>(c, BUF_X, (size_t)2 * h->nref + 2);
     if (!tmp) return fail(c, LPVS_E_NOMEM, "out of device memory");
-    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(h->vecs + 2 * Np, h->nref, h->half, h->zero_first, tmp);
+    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(h->vecs + 2 * Np, h->nref, h->half, h->zero_first, h->d_pos,
+                                                           tmp);
     c->launches++;
     std::vector<double> z((size_t)h->nref);
     LPVS_CU(c, cudaMemcpyAsync(z.data(), tmp, sizeof(double) * h->nref, cudaMemcpyDeviceToHost, c->st));
@@ -926,12 +1193,19 @@ void admm_set_problem(lpvs_admm* h, int kind, int Np, int ncc, int zero_first, i
     h->lpv_nvv = lpv_nvv;
 }
 int admm_set_groups(lpvs_ctx* c, lpvs_admm* h, const std::vector<int>& goff, const std::vector<int>& gmem) {
+    // gmem lists the internal index of every member, group after group, then the entries outside every group:
+    // that IS the ADMM order.  The loop vectors and M are permuted into it (admm_finish_create), so on the device
+    // the groups are the contiguous ranges goff[g]..goff[g+1] and the member table is the identity.
     h->ngroups = (int)goff.size() - 2;
+    if ((int)gmem.size() != h->Np) return fail(c, LPVS_E_BAD_ARG, "group table does not cover the vector");
+    h->h_order = gmem;
+    h->h_goff = goff;
+    std::vector<int> ident(gmem.size());
+    for (size_t k = 0; k < ident.size(); k++) ident[k] = (int)k;
     LPVS_CU(c, cudaMalloc(&h->goff, sizeof(int) * goff.size()));
-    LPVS_CU(c, cudaMalloc(&h->gmem, sizeof(int) * std::max<size_t>(1, gmem.size())));
+    LPVS_CU(c, cudaMalloc(&h->gmem, sizeof(int) * std::max<size_t>(1, ident.size())));
     LPVS_CU(c, cudaMemcpyAsync(h->goff, goff.data(), sizeof(int) * goff.size(), cudaMemcpyHostToDevice, c->st));
-    if (!gmem.empty())
-        LPVS_CU(c, cudaMemcpyAsync(h->gmem, gmem.data(), sizeof(int) * gmem.size(), cudaMemcpyHostToDevice, c->st));
+    LPVS_CU(c, cudaMemcpyAsync(h->gmem, ident.data(), sizeof(int) * ident.size(), cudaMemcpyHostToDevice, c->st));
     LPVS_CU(c, cudaStreamSynchronize(c->st));
     return LPVS_OK;
 }
