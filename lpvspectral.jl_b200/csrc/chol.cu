@@ -53,142 +53,237 @@ __device__ __forceinline__ void smem_gemm(double* C, int ldc, const double* A, i
 
 constexpr int LDS = 132;  // 128x128 block stride (== 4 mod 16)
 constexpr int PB = 16;    // inner panel width
-constexpr int LDP = 20;   // stride of 16-wide panels
-constexpr int LDH = 68;   // stride of the 64x64 temp
+constexpr int LDP = 20;   // stride of the 16x16 inverses
+constexpr int LDH = 68;   // stride of the 64-row temp of the inverse phase
 
-// smem layout of k_potf2: S[128*LDS] | tmp[max(112*LDP, 64*LDH)] | dinv[8][16*LDP]
-constexpr int POTF2_TMP = (112 * LDP > 64 * LDH) ? 112 * LDP : 64 * LDH;
-constexpr int POTF2_SMEM_D = 128 * LDS + POTF2_TMP + (TB / PB) * PB * LDP;
+// smem layout of k_potf2: S[128*LDS] | T[64*LDH] | dinv[8][16*LDP] | LT[16*16] | colbuf[2*16]
+constexpr int POTF2_SMEM_D = 128 * LDS + 64 * LDH + (TB / PB) * PB * LDP + PB * PB + 2 * PB;
 
-// One warp factorises a 16x16 SPD block held in registers (lane = row, lanes 16..31 idle) with shuffles, then
-// inverts the triangle (lane = column).  No divisions on the critical path: one rsqrt per column, and the same
-// reciprocals are the diagonal of the inverse.  Kept at 16x16 so the unrolled code stays I-cache resident
-// (a 32x32 version was 9.4K straight-line instructions and ran at instruction-fetch speed, ncu potf2_r01).
-__device__ __forceinline__ void warp_potf2_inv(double* D, int ldd, double* Di, int ldi, int lane, int* info,
-                                               int pivot_base, double tol) {
+// One warp, one 8-row tile row of C, up to NT adjacent 8x8 tiles (NT*2 independent DMMA chains):
+//   C[8 x 8nt] (+)= alpha * A[8 x k0..k1) * op(B),  op(B)[k][n] = BT ? B[n*ldb + k] : B[k*ldb + n]
+// A -> first row of the tile row, B -> first column of the first tile, C -> first element; k0, k1 multiples of 4.
+template <bool BT, int NT>
+__device__ __forceinline__ void warp_mma_row(double* C, int ldc, const double* A, int lda, const double* B, int ldb,
+                                             int k0, int k1, int nt, double alpha, bool accumulate, int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    double c[NT][2][2];
+#pragma unroll
+    for (int j = 0; j < NT; j++) c[j][0][0] = c[j][0][1] = c[j][1][0] = c[j][1][1] = 0.0;
+    const double* pa = A + r * lda + q;
+    const double* pb = BT ? (B + r * ldb + q) : (B + q * ldb + r);
+    int k = k0;
+    for (; k + 8 <= k1; k += 8) {
+        const double a0 = pa[k], a1 = pa[k + 4];
+#pragma unroll
+        for (int j = 0; j < NT; j++)
+            if (j < nt) {
+                const double b0 = BT ? pb[8 * j * ldb + k] : pb[k * ldb + 8 * j];
+                const double b1 = BT ? pb[8 * j * ldb + k + 4] : pb[(k + 4) * ldb + 8 * j];
+                dmma884(c[j][0][0], c[j][0][1], a0, b0);
+                dmma884(c[j][1][0], c[j][1][1], a1, b1);
+            }
+    }
+    if (k < k1) {
+        const double a0 = pa[k];
+#pragma unroll
+        for (int j = 0; j < NT; j++)
+            if (j < nt) {
+                const double b0 = BT ? pb[8 * j * ldb + k] : pb[k * ldb + 8 * j];
+                dmma884(c[j][0][0], c[j][0][1], a0, b0);
+            }
+    }
+    __syncwarp();  // in-place use (C aliases A): every lane has its operands before anyone stores
+#pragma unroll
+    for (int j = 0; j < NT; j++)
+        if (j < nt) {
+            double2* pc = reinterpret_cast<double2*>(C + r * ldc + 8 * j + 2 * q);
+            double2 v = make_double2(alpha * (c[j][0][0] + c[j][1][0]), alpha * (c[j][0][1] + c[j][1][1]));
+            if (accumulate) {
+                const double2 o = *pc;
+                v.x += o.x;
+                v.y += o.y;
+            }
+            *pc = v;
+        }
+}
+
+// One warp factorises a 16x16 SPD block (lane & 15 = row) and inverts the factor (lane & 15 = column).
+// The critical path per column is pivot -> rsqrt -> two multiplies -> one FMA: the column is broadcast UNSCALED
+// through shared memory (double-buffered, one __syncwarp per column) while the pivot travels by shuffle, and the
+// scaling by rsqrt(pivot) is applied to the multiplier instead of to the column (an LDL'-style update).
+// Measured (tools/potf2_probe.cu): the previous all-shuffle version spent 15.9 K cycles per panel here.
+__device__ __forceinline__ void warp_potf2_inv(double* D, int ldd, double* Di, int ldi, double* LT, double* colbuf,
+                                               int lane, int* info, int pivot_base, double tol) {
     const unsigned full = 0xffffffffu;
     const int row = lane & (PB - 1);
-    double d[PB], rinv[PB];
+    double d[PB], rs[PB];
 #pragma unroll
     for (int c = 0; c < PB; c++) d[c] = (c <= row) ? D[row * ldd + c] : 0.0;
 #pragma unroll
     for (int c = 0; c < PB; c++) {
+        double* cb = colbuf + (c & 1) * PB;
+        if (lane < PB) cb[row] = d[c];
         double piv = __shfl_sync(full, d[c], c);
         if (!(piv > tol) || !isfinite(piv)) {
             if (lane == 0) atomicCAS(info, 0, pivot_base + c + 1);
             piv = (fabs(piv) > 0.0 && isfinite(piv)) ? fabs(piv) : 1.0;
         }
         const double ri = rsqrt(piv);
-        rinv[c] = ri;
-        d[c] = (row == c) ? piv * ri : d[c] * ri;
+        rs[c] = ri;
+        const double l = (row == c) ? piv * ri : d[c] * ri;  // L[row][c]
+        const double w = l * ri;                             // a[row][c] / pivot
+        d[c] = l;
+        __syncwarp();
 #pragma unroll
-        for (int c2 = c + 1; c2 < PB; c2++) {
-            double l2 = __shfl_sync(full, d[c], c2);
-            if (row >= c2) d[c2] = fma(-d[c], l2, d[c2]);
+        for (int kk = (c + 1) / 2; kk < PB / 2; kk++) {
+            const double2 v = reinterpret_cast<const double2*>(cb)[kk];
+            if (2 * kk > c) d[2 * kk] = fma(-w, v.x, d[2 * kk]);
+            d[2 * kk + 1] = fma(-w, v.y, d[2 * kk + 1]);
         }
     }
-    // inverse, lane = column: x[m] final once all s[m] updates from columns < m are in
+    // L back to the block (rows) and transposed to LT (LT[c][row] = L[row][c]) for the broadcast reads below
+    if (lane < PB) {
+#pragma unroll
+        for (int c = 0; c < PB; c++) {
+            if (c <= row) D[row * ldd + c] = d[c];
+            LT[c * PB + row] = (c <= row) ? d[c] : 0.0;
+        }
+    }
+    __syncwarp();
+    // inverse, lane & 15 = column j: x[m] = -rs[m] * sum_{k<m} L[m][k] x[k]; the sums are kept running so that one
+    // FMA and one multiply separate consecutive x[m]
     double sacc[PB], x[PB];
 #pragma unroll
     for (int i = 0; i < PB; i++) sacc[i] = 0.0;
 #pragma unroll
     for (int m = 0; m < PB; m++) {
-        const double xm = (m == row) ? rinv[m] : ((m > row) ? -sacc[m] * rinv[m] : 0.0);
+        const double xm = (m == row) ? rs[m] : ((m > row) ? -sacc[m] * rs[m] : 0.0);
         x[m] = xm;
 #pragma unroll
-        for (int i = m + 1; i < PB; i++) {
-            double lim = __shfl_sync(full, d[m], i);
-            sacc[i] = fma(lim, xm, sacc[i]);
+        for (int kk = (m + 1) / 2; kk < PB / 2; kk++) {
+            const double2 v = reinterpret_cast<const double2*>(LT + m * PB)[kk];  // L[2kk][m], L[2kk+1][m]
+            if (2 * kk > m) sacc[2 * kk] = fma(v.x, xm, sacc[2 * kk]);
+            sacc[2 * kk + 1] = fma(v.y, xm, sacc[2 * kk + 1]);
         }
     }
     if (lane < PB) {
 #pragma unroll
-        for (int c = 0; c < PB; c++) {
-            if (c <= row) D[row * ldd + c] = d[c];
-            Di[c * ldi + row] = x[c];
-        }
+        for (int c = 0; c < PB; c++) Di[c * ldi + row] = x[c];
     }
 }
 
+#ifdef LPVS_POTF2_TRACE  // tools/potf2_probe.cu: clock stamps of CTA 0
+__device__ long long* g_potf2_trace;
+#define POTF2_TR(slot) if (blockIdx.x == 0 && threadIdx.x == 0) g_potf2_trace[slot] = clock64();
+#else
+#define POTF2_TR(slot)
+#endif
+
+// 128x128 diagonal block: L_kk (in place in G) and its inverse (Linv), one CTA per problem.
 __global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ CholArgs a, int k) {
     extern __shared__ __align__(16) double sm[];
     double* S = sm;
     double* T = sm + 128 * LDS;
-    double* Dinv = T + POTF2_TMP;
+    double* Dinv = T + 64 * LDH;
+    double* LT = Dinv + (TB / PB) * PB * LDP;
+    double* colbuf = LT + PB * PB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int prob = blockIdx.x;
     double* Gd = a.G + (long long)prob * a.strideG + ((long long)k * TB) * a.Np + (long long)k * TB;
     const double tol = a.maxdiag ? a.maxdiag[prob] * a.tol_scale : 0.0;
+    POTF2_TR(0)
 
-    // load the lower triangle of the diagonal block: 16-byte loads, 8 in flight per thread
-    for (int base = 0; base < TB * TB / 2; base += NTHREADS * 8) {
-        double2 v[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            int idx = base + q * NTHREADS + tid;  // double2 index
-            int r = idx >> 6, c = (idx & 63) * 2;
-            v[q] = (c <= r) ? __ldcg(reinterpret_cast<const double2*>(Gd + (long long)r * a.Np + c))
-                            : make_double2(0.0, 0.0);
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            int idx = base + q * NTHREADS + tid;
-            int r = idx >> 6, c = (idx & 63) * 2;
-            S[r * LDS + c] = v[q].x;
-            S[r * LDS + c + 1] = (c + 1 <= r) ? v[q].y : 0.0;
-        }
+    // lower triangle of the diagonal block: all 16-byte pieces in flight at once (cp.async); zeros above
+    for (int idx = tid; idx < TB * TB / 2; idx += NTHREADS) {
+        const int r = idx >> 6, c = (idx & 63) * 2;
+        if (c <= r)
+            cp_async16(S + r * LDS + c, Gd + (long long)r * a.Np + c);
+        else
+            *reinterpret_cast<double2*>(S + r * LDS + c) = make_double2(0.0, 0.0);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
+    POTF2_TR(1)
 
     for (int p = 0; p < TB / PB; p++) {
         const int j0 = p * PB;
         double* Di = Dinv + p * PB * LDP;
-        if (warp == 0) warp_potf2_inv(S + j0 * LDS + j0, LDS, Di, LDP, lane, &a.info[prob], k * TB + j0, tol);
+        if (warp == 0)
+            warp_potf2_inv(S + j0 * LDS + j0, LDS, Di, LDP, LT, colbuf, lane, &a.info[prob], k * TB + j0, tol);
         __syncthreads();
-        const int rem = TB - j0 - PB;
-        if (rem > 0) {
-            // panel: T = P * Dinv'   (P = S[j0+16.., j0..j0+16))
-            smem_gemm<true>(T, LDP, S + (j0 + PB) * LDS + j0, LDS, Di, LDP, rem, PB, PB, 1.0, 0.0, false);
+        POTF2_TR(2 + 2 * p)
+        const int nt = (TB - j0 - PB) >> 3;  // 8-row tiles below the panel's diagonal block
+        if (nt > 0) {
+            double* P = S + (j0 + PB) * LDS + j0;  // panel below the diagonal block
+            // P <- P * Dinv' in place (a warp owns whole tile rows)
+            for (int ti = warp; ti < nt; ti += NTHREADS / 32)
+                warp_mma_row<true, 2>(P + 8 * ti * LDS, LDS, P + 8 * ti * LDS, LDS, Di, LDP, 0, PB, 2, 1.0, false, lane);
             __syncthreads();
-            for (int idx = tid; idx < rem * PB; idx += NTHREADS) {
-                int r = idx >> 4, c = idx & 15;
-                S[(j0 + PB + r) * LDS + j0 + c] = T[r * LDP + c];
-            }
-            // trailing update (lower tiles): S22 -= T T'
-            smem_gemm<true>(S + (j0 + PB) * LDS + j0 + PB, LDS, T, LDP, T, LDP, rem, rem, PB, -1.0, 1.0, true);
+            // trailing update of the lower tiles: S22 -= P P', units of (tile row, up to 4 tiles) round-robin
+            double* S22 = S + (j0 + PB) * LDS + j0 + PB;
+            int cnt = 0;
+            for (int ti = nt - 1; ti >= 0; ti--)
+                for (int g = 0; g <= ti; g += 4) {
+                    if ((cnt++ & 7) == warp)
+                        warp_mma_row<true, 4>(S22 + 8 * ti * LDS + 8 * g, LDS, P + 8 * ti * LDS, LDS, P + 8 * g * LDS,
+                                              LDS, 0, PB, min(4, ti + 1 - g), -1.0, true, lane);
+                }
             __syncthreads();
         }
+        POTF2_TR(3 + 2 * p)
     }
 
     // write L_kk back (strictly-upper part of the block zeroed)
-    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
-        int r = idx >> 7, c = idx & 127;
-        Gd[(long long)r * a.Np + c] = (c <= r) ? S[r * LDS + c] : 0.0;
+    for (int idx = tid; idx < TB * TB / 2; idx += NTHREADS) {
+        const int r = idx >> 6, c = (idx & 63) * 2;
+        double2 v = *reinterpret_cast<const double2*>(S + r * LDS + c);
+        if (c > r) v.x = 0.0;
+        if (c + 1 > r) v.y = 0.0;
+        *reinterpret_cast<double2*>(Gd + (long long)r * a.Np + c) = v;
     }
     __syncthreads();
+    POTF2_TR(18)
 
-    // in-place inverse: diagonal 16x16 blocks first, then recursive doubling X21 = -X22 (L21 X11)
+    // in-place inverse: diagonal 16x16 blocks first, then recursive doubling X21 = -X22 (L21 X11), all pairs of a
+    // level at once, zero blocks of the triangular factors skipped
     for (int idx = tid; idx < (TB / PB) * PB * PB; idx += NTHREADS) {
         int p = idx >> 8, r = (idx >> 4) & 15, c = idx & 15;
         S[(p * PB + r) * LDS + p * PB + c] = (c <= r) ? Dinv[p * PB * LDP + r * LDP + c] : 0.0;
     }
     __syncthreads();
     for (int h = PB; h < TB; h <<= 1) {
-        for (int o = 0; o < TB; o += 2 * h) {
-            double* X11 = S + o * LDS + o;
-            double* X22 = S + (o + h) * LDS + o + h;
-            double* L21 = S + (o + h) * LDS + o;
-            smem_gemm<false>(T, LDH, L21, LDS, X11, LDS, h, h, h, 1.0, 0.0, false);
-            __syncthreads();
-            smem_gemm<false>(L21, LDS, X22, LDS, T, LDH, h, h, h, -1.0, 0.0, false);
-            __syncthreads();
+        const int ht = h >> 3;                 // tiles per side of a sub-block
+        const int ng = (ht + 3) >> 2;          // tile groups per tile row
+        const int npair = TB / (2 * h);
+        const int nunits = npair * ht * ng;
+        // T_pair = L21 * X11  (X11 lower triangular: k >= first column of the group)
+        for (int u = warp; u < nunits; u += NTHREADS / 32) {
+            const int pr = u / (ht * ng), rem = u - pr * ht * ng, ti = rem / ng, g = (rem - ti * ng) * 4;
+            const int o = pr * 2 * h;
+            warp_mma_row<false, 4>(T + (pr * h + 8 * ti) * LDH + 8 * g, LDH, S + (o + h + 8 * ti) * LDS + o, LDS,
+                                   S + o * LDS + o + 8 * g, LDS, 8 * g, h, min(4, ht - g), 1.0, false, lane);
         }
+        __syncthreads();
+        // X21 = -X22 * T_pair  (X22 lower triangular: k <= last row of the tile row)
+        for (int u = warp; u < nunits; u += NTHREADS / 32) {
+            const int pr = u / (ht * ng), rem = u - pr * ht * ng, ti = rem / ng, g = (rem - ti * ng) * 4;
+            const int o = pr * 2 * h;
+            warp_mma_row<false, 4>(S + (o + h + 8 * ti) * LDS + o + 8 * g, LDS, S + (o + h + 8 * ti) * LDS + o + h, LDS,
+                                   T + pr * h * LDH + 8 * g, LDH, 0, 8 * (ti + 1), min(4, ht - g), -1.0, false, lane);
+        }
+        __syncthreads();
     }
+    POTF2_TR(19)
     double* Li = a.Linv + (long long)prob * a.strideLinv + (long long)k * TB * TB;
-    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
-        int r = idx >> 7, c = idx & 127;
-        Li[idx] = (c <= r) ? S[r * LDS + c] : 0.0;
+    for (int idx = tid; idx < TB * TB / 2; idx += NTHREADS) {
+        const int r = idx >> 6, c = (idx & 63) * 2;
+        double2 v = *reinterpret_cast<const double2*>(S + r * LDS + c);
+        if (c > r) v.x = 0.0;
+        if (c + 1 > r) v.y = 0.0;
+        *reinterpret_cast<double2*>(Li + r * TB + c) = v;
     }
+    POTF2_TR(20)
 }
 
 // ------------------------------------------------------------------------------------------------------------
