@@ -118,6 +118,17 @@ int lpvs_ls_window(lpvs_ctx* ctx, int kind, const double* y, const double* u, co
                    const double* f, int Nf, const double* W, int n, int noverlap, double lambda, double* out,
                    int64_t* K, int* info);
 
+/* ---- windowed estimators with estimator = ls_sparse_spectral (src/lsfft.jl:121,150-151,184-185 -> the weighted
+ * method src/lasso.jl:105-126; exercised by test/test_lasso.jl:36) ----
+ * Every window is an independent ADMM problem on Quadratic(A'WA, A'Wy) (sign quirk Q13 kept), x0 = 0 (init=false),
+ * run on the device to its own stop test ||x-z||_2 < tol (or `iters`); sums as lpvs_ls_window_sums, to be finished with
+ * lpvs_ls_window_finalize.  iters_done / residuals (may be NULL): one entry per window and channel,
+ * [(k_end-k_begin)][nrhs], nrhs = 1 (PSD) or 2 -- what the reference prints when a window stops (src/lasso.jl:164). */
+int lpvs_ls_window_sparse_sums(lpvs_ctx* ctx, int kind, const double* y, const double* u, const double* t, int64_t N,
+                               const double* f, int Nf, const double* W, int n, int noverlap, int prox_kind,
+                               double prox_param, double mu, int64_t iters, double tol, int64_t k_begin,
+                               int64_t k_end, double* sums, int64_t* iters_done, double* residuals, int* info);
+
 /* ---- ls_spectral_lpv (src/lsfft.jl:239-259; basis src/utilities.jl:23-36, src/lsfft.jl:195-207) ----
  * params: Nf*Nvv complex (Nvv = coulomb ? 2Nv : Nv), column order f + k*Nf.
  * Sigma (may be NULL): (2 Nf Nvv)^2 doubles = var(e) * inv(Ar'Ar + lambda I).  fva: fraction of variance explained. */

@@ -241,7 +241,42 @@ def _windowed(kind, y, u, t, freqs, nw, noverlap, window_func, estimator, ctx, k
         return out, freqs
     if estimator is not ls_sparse_spectral:
         raise ValueError("estimator must be ls_spectral or ls_sparse_spectral (no host-side fallback)")
-    # estimator = ls_sparse_spectral: one device ADMM solve per window (src/lsfft.jl:121, test/test_lasso.jl:36)
+    # estimator = ls_sparse_spectral (src/lsfft.jl:121, test/test_lasso.jl:36)
+    kws = dict(kw)
+    verbose = bool(kws.get("verbose", False))
+    batched = not kws.get("init", False) and kws.get("cb") is None and not (
+        verbose and kws.get("printerval", 100) < kws.get("iters", 10000))
+    if batched:
+        # all windows in one device pass: batched Gram / Cholesky / inverse, one CTA per window runs its ADMM
+        lam = _lam(kws, 1.0)
+        for key in ("init", "cb", "verbose"):
+            kws.pop(key, None)
+        kws.pop("printerval", None)
+        iters, tol = int(kws.pop("iters", 10000)), float(kws.pop("tol", 1e-5))
+        mu_kw = kws.pop("μ", kws.pop("mu", None))
+        mu = 0.05 if mu_kw is None else float(mu_kw)
+        proxg = kws.pop("proxg", None)
+        if kws:
+            raise TypeError(f"unexpected keyword arguments {sorted(kws)}")
+        if not (0 <= mu <= 1):
+            raise AssertionError("μ should be ≤ 1")  # src/lasso.jl:143
+        pk, pp = _prox_desc(proxg if proxg is not None else NormL1(lam))
+        nrhs = 1 if kind == L.WIN_PSD else 2
+        sums = np.zeros({L.WIN_PSD: 1, L.WIN_CSD: 2, L.WIN_COHERE: 4}[kind] * len(fv))
+        its = np.zeros(max(K, 1) * nrhs, dtype=np.int64)
+        res = np.zeros(max(K, 1) * nrhs)
+        info = C.c_int(0)
+        if K > 0:
+            ctx.check(ctx.lib.lpvs_ls_window_sparse_sums(ctx.h, kind, _ptr(yv), _ptr(uv), _ptr(tv), len(yv), _ptr(fv),
+                                                         len(fv), _ptr(Wv), n, int(noverlap), pk, pp, mu, iters, tol,
+                                                         0, K, _ptr(sums), _ptr(its), _ptr(res), C.byref(info)))
+        if verbose:  # the line the reference prints when a window stops (src/lasso.jl:164-166)
+            for k in range(K * nrhs):
+                if res[k] < tol:
+                    print("%d ||x-z||₂ %.10f" % (its[k], res[k]))
+        ctx.last_window_iters = its[:K * nrhs].reshape(K, nrhs)
+        return window_finalize(kind, sums, len(fv), K), freqs
+    # init / callbacks / periodic prints: one device ADMM solve per window through the single-problem entry point
     hop = n - noverlap
     Nf = len(fv)
     Syy, Suu = np.zeros(Nf), np.zeros(Nf)

@@ -48,6 +48,9 @@ _PROTOS = {
                                       C.c_double, C.c_int64, C.c_int64, _vp, _ip]),
     "lpvs_ls_window_sums_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int,
                                           C.c_int, C.c_double, C.c_int64, C.c_int64, _vp, _ip]),
+    "lpvs_ls_window_sparse_sums": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int,
+                                             C.c_int, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_double,
+                                             C.c_int64, C.c_int64, _vp, _vp, _vp, _ip]),
     "lpvs_ls_window_finalize": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int64, _vp]),
     "lpvs_ls_window": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int, C.c_int,
                                  C.c_double, _vp, _i64p, _ip]),

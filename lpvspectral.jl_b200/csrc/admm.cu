@@ -612,6 +612,210 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv(const __grid_cons
     }
 }
 
+// ---- variant 3: one CTA per window, many windows per launch (ls_windowpsd/csd/cohere with estimator =
+// ls_sparse_spectral, src/lsfft.jl:121 -> src/lasso.jl:105-126).  The windows are independent ADMM problems with
+// their own stop test; both channels of a window share M = (A'WA + I/mu)^-1, so one pass over M serves two
+// right-hand sides.  No grid barrier: everything a window needs lives in its CTA.
+struct AdmmBatchArgs {
+    const double* M;      // [nw] Np x Np full symmetric
+    long long strideM;
+    double* vecs;         // [nw][nrhs][7 Np]: q, x, z, u, v, r0, r1
+    int Np, nrhs;
+    double mu;
+    int quad, prox;
+    double pparam;
+    long long max_iters;
+    double tol;
+    long long* iters_out;  // [nw][nrhs]
+    double* res_out;       // [nw][nrhs]
+};
+
+__global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_batch(const __grid_constant__ AdmmBatchArgs ba) {
+    extern __shared__ __align__(16) double sm[];
+    const int Np = ba.Np, nrhs = ba.nrhs;
+    double* rs = sm;            // [2][Np] current right-hand sides
+    double* xs = sm + 2 * Np;   // [2][Np] x of this iteration
+    __shared__ double wsum[2][ADMM_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wdx = blockIdx.x;
+    const double* M = ba.M + (long long)wdx * ba.strideM;
+    AdmmArgs ch[2];
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        double* v = ba.vecs + ((long long)wdx * nrhs + (c < nrhs ? c : 0)) * 7 * Np;
+        ch[c] = AdmmArgs{};
+        ch[c].Np = Np;
+        ch[c].q = v;
+        ch[c].x = v + Np;
+        ch[c].z = v + 2 * Np;
+        ch[c].u = v + 3 * Np;
+        ch[c].v = v + 4 * Np;
+        ch[c].r = v + 5 * Np;
+        ch[c].mu = ba.mu;
+        ch[c].quad = ba.quad;
+        ch[c].prox = ba.prox;
+        ch[c].pparam = ba.pparam;
+    }
+    const bool elementwise = (ba.prox == LPVS_PROX_L1 || ba.prox == LPVS_PROX_L0);
+    const double gl = ba.mu * ba.pparam;
+    const double thr0 = sqrt(2.0 * ba.mu * ba.pparam);
+    bool active[2] = {true, nrhs > 1};
+    long long its[2] = {0, 0};
+    double nxz[2] = {0.0, 0.0};
+    int cur = 0;
+    for (long long it = 0; it < ba.max_iters && (active[0] || active[1]); it++) {
+        for (int i = tid; i < Np; i += ADMM_THREADS) {
+            rs[i] = __ldcg(ch[0].r + (long long)cur * Np + i);
+            rs[Np + i] = active[1] ? __ldcg(ch[1].r + (long long)cur * Np + i) : 0.0;
+        }
+        __syncthreads();
+        // x = M r for both channels: two rows per pass, lanes across the columns
+        for (int rr = 2 * w; rr < Np; rr += 2 * ADMM_WARPS) {
+            const double* m0 = M + (long long)rr * Np + 2 * lane;
+            const double* m1 = m0 + Np;
+            double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+            for (int c = 0; c < Np; c += 256) {
+                double2 a[4], b[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const bool in = c + 64 * k < Np;
+                    a[k] = in ? __ldg(reinterpret_cast<const double2*>(m0 + c + 64 * k)) : make_double2(0.0, 0.0);
+                    b[k] = in ? __ldg(reinterpret_cast<const double2*>(m1 + c + 64 * k)) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (c + 64 * k < Np) {
+                        const double2 v0 = *reinterpret_cast<const double2*>(rs + c + 64 * k + 2 * lane);
+                        const double2 v1 = *reinterpret_cast<const double2*>(rs + Np + c + 64 * k + 2 * lane);
+                        s00 = fma(a[k].x, v0.x, s00); s00 = fma(a[k].y, v0.y, s00);
+                        s10 = fma(b[k].x, v0.x, s10); s10 = fma(b[k].y, v0.y, s10);
+                        s01 = fma(a[k].x, v1.x, s01); s01 = fma(a[k].y, v1.y, s01);
+                        s11 = fma(b[k].x, v1.x, s11); s11 = fma(b[k].y, v1.y, s11);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s00 += __shfl_xor_sync(0xffffffffu, s00, o);
+                s10 += __shfl_xor_sync(0xffffffffu, s10, o);
+                s01 += __shfl_xor_sync(0xffffffffu, s01, o);
+                s11 += __shfl_xor_sync(0xffffffffu, s11, o);
+            }
+            if (lane == 0) {
+                xs[rr] = s00;
+                xs[rr + 1] = s10;
+                xs[Np + rr] = s01;
+                xs[Np + rr + 1] = s11;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            if (!active[c]) continue;  // block-uniform
+            double* rn = ch[c].r + (long long)(cur ^ 1) * Np;
+            double d2 = 0.0;
+            for (int i = tid; i < Np; i += ADMM_THREADS) {
+                const double xi = xs[c * Np + i];
+                ch[c].x[i] = xi;
+                if (elementwise)
+                    d2 += admm_elem_update(ch[c], rn, i, xi, gl, thr0);
+                else
+                    ch[c].v[i] = xi + ch[c].u[i];
+            }
+            if (!elementwise) {
+                __syncthreads();
+                d2 = admm_phase_nonelem(ch[c], rn, 0, 1, tid, lane, w, gl);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+            if (lane == 0) wsum[c][w] = d2;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            if (!active[c]) continue;
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < ADMM_WARPS; k++) s += wsum[c][k];
+            nxz[c] = sqrt(s);
+            its[c] = it + 1;
+            if (nxz[c] < ba.tol) active[c] = false;
+        }
+        cur ^= 1;
+    }
+    if (tid == 0) {
+        for (int c = 0; c < nrhs; c++) {
+            ba.iters_out[(long long)wdx * nrhs + c] = its[c];
+            ba.res_out[(long long)wdx * nrhs + c] = nxz[c];
+        }
+    }
+}
+
+// z = copy(x) = x0 (zeros), u = 0, r = rhs(z, u) for every (window, channel); q comes from B[window][channel][Np]
+__global__ void k_admm_batch_init(const double* __restrict__ B, int Np, int nrhs, double mu, int quad, double* vecs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np) return;
+    const long long wc = blockIdx.y;  // window * nrhs + channel
+    const long long wdx = wc / nrhs, c = wc - wdx * nrhs;
+    const double q = B[(wdx * 2 + c) * Np + i];
+    double* v = vecs + wc * 7 * Np;
+    v[i] = q;
+    v[Np + i] = 0.0;
+    v[2 * Np + i] = 0.0;
+    v[3 * Np + i] = 0.0;
+    v[4 * Np + i] = 0.0;
+    v[5 * Np + i] = quad ? -q : q;
+    v[6 * Np + i] = 0.0;
+}
+
+// z of every (window, channel) back into the [window][2][Np] solution layout of the windowed estimators
+__global__ void k_admm_batch_collect(const double* __restrict__ vecs, int Np, int nrhs, double* __restrict__ B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np) return;
+    const long long wc = blockIdx.y;
+    const long long wdx = wc / nrhs, c = wc - wdx * nrhs;
+    B[(wdx * 2 + c) * Np + i] = vecs[wc * 7 * Np + 2 * Np + i];
+}
+
+// All windows of a batch: M already holds (G + I/mu)^-1 per window, B the weighted right-hand sides A'W[y u].
+// On return B holds z (internal layout) per window and channel.
+int admm_batch_run(lpvs_ctx* c, const double* d_M, double* d_B, int Np, int nrhs, int nw, int prox, double pparam,
+                   double mu, int quad, long long iters, double tol, long long* d_iters, double* d_res) {
+    double* vecs = ws<double>(c, BUF_MISC, (size_t)nw * nrhs * 7 * Np);
+    if (!vecs) return fail(c, LPVS_E_NOMEM, "out of device memory (ADMM state of %d windows)", nw);
+    const size_t smem = sizeof(double) * 4 * (size_t)Np;
+    if (smem > 200 * 1024) return fail(c, LPVS_E_UNSUPPORTED, "windowed sparse estimator: Np=%d too large", Np);
+    LPVS_CU(c, cudaFuncSetAttribute(k_admm_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int w0 = 0; w0 < nw; w0 += 16384) {
+        const int nn = std::min(16384, nw - w0);
+        k_admm_batch_init<<<dim3((Np + 255) / 256, nn * nrhs), 256, 0, c->st>>>(d_B + (long long)w0 * 2 * Np, Np, nrhs, mu,
+                                                                               quad, vecs + (long long)w0 * nrhs * 7 * Np);
+    }
+    AdmmBatchArgs ba{};
+    ba.M = d_M;
+    ba.strideM = (long long)Np * Np;
+    ba.vecs = vecs;
+    ba.Np = Np;
+    ba.nrhs = nrhs;
+    ba.mu = mu;
+    ba.quad = quad;
+    ba.prox = prox;
+    ba.pparam = pparam;
+    ba.max_iters = iters;
+    ba.tol = tol;
+    ba.iters_out = d_iters;
+    ba.res_out = d_res;
+    k_admm_batch<<<nw, ADMM_THREADS, smem, c->st>>>(ba);
+    for (int w0 = 0; w0 < nw; w0 += 16384) {
+        const int nn = std::min(16384, nw - w0);
+        k_admm_batch_collect<<<dim3((Np + 255) / 256, nn * nrhs), 256, 0, c->st>>>(
+            vecs + (long long)w0 * nrhs * 7 * Np, Np, nrhs, d_B + (long long)w0 * 2 * Np);
+    }
+    c->launches += 3;
+    LPVS_CU(c, cudaGetLastError());
+    return LPVS_OK;
+}
+
 __global__ void k_admm_init(const double* __restrict__ q, const double* __restrict__ x0, int Np, double mu,
                             int quad, double* x, double* z, double* u, double* r) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

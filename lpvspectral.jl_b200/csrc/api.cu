@@ -804,6 +804,172 @@ int lpvs_ls_window_sums(lpvs_ctx* c, int kind, const double* y, const double* u,
     return rc2;
 }
 
+// ---- windowed estimators with estimator = ls_sparse_spectral (src/lsfft.jl:121,150-151,184-185 calling the weighted
+// method src/lasso.jl:105-126): every window is an independent ADMM problem on Quadratic(A'WA, A'Wy) (sign quirk Q13
+// kept), x0 = 0.  Batched: Gram of all windows, batched Cholesky + SPD inverse of (A'WA + I/mu), then one CTA per
+// window iterates to its own stop test (k_admm_batch); both channels of csd/cohere share the window's inverse.
+int lpvs_ls_window_sparse_sums(lpvs_ctx* c, int kind, const double* y, const double* u, const double* t, int64_t N,
+                               const double* f, int Nf, const double* W, int n, int noverlap, int prox_kind,
+                               double prox_param, double mu, int64_t iters, double tol, int64_t k_begin,
+                               int64_t k_end, double* sums, int64_t* iters_done, double* residuals, int* info) {
+    if (!c) return LPVS_E_BAD_ARG;
+    CallTimer call_timer(c);
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    if (info) *info = 0;
+    if (kind < 0 || kind > 2) return fail(c, LPVS_E_BAD_ARG, "bad window kind %d", kind);
+    if (!y || !t || !W || !sums || N <= 0 || n <= 0) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
+    if (kind != LPVS_WIN_PSD && !u) return fail(c, LPVS_E_BAD_ARG, "second signal required");
+    if (!(mu > 0.0) || mu > 1.0) return fail(c, LPVS_E_BAD_ARG, "mu should be in (0, 1]");  // src/lasso.jl:143
+    if (prox_kind < LPVS_PROX_L1 || prox_kind > LPVS_PROX_BALL_L0)
+        return fail(c, LPVS_E_BAD_ARG, "prox kind %d not valid for the Fourier problem", prox_kind);
+    if (noverlap < 0) noverlap = n >> 1;  // src/windows.jl:29
+    if (noverlap >= n) return fail(c, LPVS_E_BAD_ARG, "noverlap must be < n");
+    const int64_t K = lpvs_window_count(N, n, noverlap);
+    if (k_begin < 0 || k_end > K || k_begin > k_end) return fail(c, LPVS_E_BAD_ARG, "window range out of bounds");
+    const int nrhs = kind == LPVS_WIN_PSD ? 1 : 2;
+    const int slen = sums_len(kind, Nf);
+    if (k_end == k_begin) {
+        memset(sums, 0, sizeof(double) * slen);
+        return LPVS_OK;
+    }
+    gram_timer_reset(c);
+    FourierPlan pl;
+    int rc = make_fourier_plan(c, f, Nf, &pl);
+    if (rc) return rc;
+    const long long Np = pl.Np, hop = n - noverlap;
+    const int nb = pl.Np / TB;
+    // only this range's samples travel to the device
+    const int64_t so = k_begin * hop, s_end = (k_end - 1) * hop + n;
+    double *d_t, *d_y, *d_u, *d_W;
+    if ((rc = upload(c, BUF_T, t + so, s_end - so, &d_t))) return rc;
+    if ((rc = upload(c, BUF_Y, y + so, s_end - so, &d_y))) return rc;
+    if ((rc = upload(c, BUF_U, u ? u + so : nullptr, s_end - so, &d_u))) return rc;
+    if ((rc = upload(c, BUF_W, W, n, &d_W))) return rc;
+    const int64_t Nloc = s_end - so, nwin = k_end - k_begin;
+    double* d_sums = ws<double>(c, BUF_SUMS, (size_t)slen);
+    if (!d_sums) return fail(c, LPVS_E_NOMEM, "out of device memory");
+    LPVS_CU(c, cudaMemsetAsync(d_sums, 0, sizeof(double) * slen, c->st));
+    // batch: Gram/inverse plus the inverse workspace <= ~6 GiB
+    int64_t batch = c->window_batch > 0 ? c->window_batch : std::max<int64_t>(1, (3LL << 30) / (Np * Np * 8));
+    batch = std::min<int64_t>(batch, nwin);
+    std::vector<int> hinfo((size_t)batch);
+    std::vector<long long> hits((size_t)batch * nrhs);
+    long long* d_its = nullptr;
+    double* d_res = nullptr;
+    LPVS_CU(c, cudaMalloc(&d_its, sizeof(long long) * batch * nrhs));
+    if (cudaMalloc(&d_res, sizeof(double) * batch * nrhs) != cudaSuccess) {
+        cudaFree(d_its);
+        return fail(c, LPVS_E_NOMEM, "out of device memory");
+    }
+    int bad = 0;
+    int64_t bad_window = -1;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(c->st);
+        cudaFree(d_its);
+        cudaFree(d_res);
+    };
+    for (int64_t k0 = 0; k0 < nwin && !bad; k0 += batch) {
+        const int nw = (int)std::min<int64_t>(batch, nwin - k0);
+        const long long s0 = k0 * hop, ns = (long long)(nw - 1) * hop + n;
+        double* d_G = ws<double>(c, BUF_G, (size_t)nw * Np * Np);
+        double* d_Y = ws<double>(c, BUF_YINV, (size_t)nw * Np * Np);
+        double* d_B = ws<double>(c, BUF_B, (size_t)nw * 2 * Np);
+        if (!d_G || !d_Y || !d_B) {
+            cleanup();
+            return fail(c, LPVS_E_NOMEM, "out of device memory (window batch of %d)", nw);
+        }
+        GramArgs g{};
+        fill_basis_args(pl, g);
+        if (pl.mode == GRAM_CHAIN) {
+            double2* anc = ws<double2>(c, BUF_ANC, (size_t)pl.ngroups * ns);
+            double2* del = ws<double2>(c, BUF_DEL, (size_t)ns);
+            if (!anc || !del) {
+                cleanup();
+                return fail(c, LPVS_E_NOMEM, "out of device memory (anchor table)");
+            }
+            launch_anchor_table(d_t, s0, ns, pl.d_f, pl.Nf, pl.ngroups, pl.f0, pl.df, anc, del, c->st);
+            c->launches++;
+            g.anc = anc;
+            g.del = del;
+        }
+        g.t = d_t;
+        g.y = d_y;
+        g.u = nrhs > 1 ? d_u : nullptr;
+        g.W = d_W;
+        g.w_abs = 0;
+        g.start0 = s0;
+        g.hop = hop;
+        g.n = n;
+        g.s_end = Nloc;
+        g.nrhs = nrhs;
+        g.tbl_base = s0;
+        g.tbl_ns = ns;
+        g.G = d_G;
+        g.strideG = Np * Np;
+        g.B = d_B;
+        g.strideB = 2 * Np;
+        gram_timer_begin(c);
+        launch_gram(pl.mode, g, nw, c->st);
+        gram_timer_end(c, (double)nw * n * pl.Nreg * (pl.Nreg + 1.0), 1);
+        c->launches += 2;
+        // M = (A'WA + I/mu)^-1 per window
+        CholArgs ca{};
+        ca.G = d_G;
+        ca.strideG = Np * Np;
+        ca.Y = d_Y;
+        ca.strideY = Np * Np;
+        ca.Linv = ws<double>(c, BUF_LINV, (size_t)nw * nb * TB * TB);
+        ca.strideLinv = (long long)nb * TB * TB;
+        ca.info = ws<int>(c, BUF_INFO, (size_t)nw);
+        ca.Np = pl.Np;
+        ca.nb = nb;
+        if (!ca.Linv || !ca.info) {
+            cleanup();
+            return fail(c, LPVS_E_NOMEM, "out of device memory (factor workspace)");
+        }
+        cudaMemsetAsync(ca.info, 0, sizeof(int) * nw, c->st);
+        launch_diag_prepare(d_G, ca.strideG, pl.Np, pl.Nf, pl.zero_first, nullptr, 1.0 / mu, nw, c->st);
+        c->launches += 1 + potrf(ca, nw, c->sms, c->st);
+        c->launches += potri(ca, nw, c->st);
+        cudaMemcpyAsync(hinfo.data(), ca.info, sizeof(int) * nw, cudaMemcpyDeviceToHost, c->st);
+        if ((rc = admm_batch_run(c, d_G, d_B, pl.Np, nrhs, nw, prox_kind, prox_param, mu, /*quad=*/1, iters, tol, d_its,
+                                 d_res))) {
+            cleanup();
+            return rc;
+        }
+        k_window_accum<<<(Nf + 127) / 128, 128, 0, c->st>>>(kind, d_B, 2 * Np, pl.Np, nw, Nf, pl.zero_first, d_sums);
+        c->launches++;
+        if (iters_done)
+            cudaMemcpyAsync(hits.data(), d_its, sizeof(long long) * nw * nrhs, cudaMemcpyDeviceToHost, c->st);
+        if (residuals)
+            cudaMemcpyAsync(residuals + k0 * nrhs, d_res, sizeof(double) * nw * nrhs, cudaMemcpyDeviceToHost, c->st);
+        cudaError_t e = cudaStreamSynchronize(c->st);
+        if (e != cudaSuccess) {
+            cleanup();
+            return fail(c, LPVS_E_CUDA, "windowed sparse batch failed: %s", cudaGetErrorString(e));
+        }
+        if (iters_done)
+            for (int i = 0; i < nw * nrhs; i++) iters_done[k0 * nrhs + i] = hits[i];
+        for (int i = 0; i < nw && !bad; i++)
+            if (hinfo[i]) {
+                bad = hinfo[i];
+                bad_window = k_begin + k0 + i;
+            }
+    }
+    cleanup();
+    if ((rc = inputs_finite(c))) return rc;
+    if (bad) {
+        if (info) *info = bad;
+        return fail(c, LPVS_E_NOT_SPD, "Cholesky breakdown in window %lld at internal pivot %d", (long long)bad_window,
+                    bad);
+    }
+    LPVS_CU(c, cudaMemcpyAsync(sums, d_sums, sizeof(double) * slen, cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    gram_timer_resolve(c);
+    return LPVS_OK;
+}
+
 int lpvs_ls_window_finalize(int kind, const double* sums, int Nf, int64_t K, double* out) {
     if (!sums || !out || Nf <= 0) return LPVS_E_BAD_ARG;
     if (kind == LPVS_WIN_PSD) {
