@@ -51,6 +51,12 @@ end
 
 vecf(x) = collect(Float64, x)
 nullable(x) = x === nothing ? Ptr{Float64}(C_NULL) : pointer(x)
+# Float32 instantiation of the generic signatures (e.g. src/lasso.jl:85 `AbstractArray{T}`): results carry the signal's
+# eltype.  The device arithmetic is the FP64 path on the up-converted inputs (there are no FP32 kernels), so a Float32
+# caller gets the correctly rounded-to-single FP64 answer.
+like(y, x::AbstractArray{<:Complex}) = eltype(y) === Float32 ? ComplexF32.(x) : x
+like(y, x::AbstractArray{<:Real}) = eltype(y) === Float32 ? Float32.(x) : x
+like(y, x) = x
 
 # ---- ls_spectral (src/lsfft.jl:62-80) ---------------------------------------------------------------------
 function ls_spectral(y, t, f=default_freqs(t); λ=1e-10, verbose=false)
@@ -73,7 +79,7 @@ function _ls_spectral(y, t, f, W, λ)
             ctx(), yv, tv, length(yv), fv, length(fv), nullable(Wv), Float64(λ), x, info))
     end
     info[] == 1 && @warn "Gram matrix numerically rank deficient: solved with a jitter ridge (see DESIGN.md H1)"
-    x, f                                             # the caller's own f object, untouched
+    like(y, x), f                                    # the caller's own f object, untouched
 end
 
 # ---- windowed estimators (src/lsfft.jl:112-193) -----------------------------------------------------------
@@ -97,16 +103,46 @@ function _windowed(kind, y, u, t, freqs, nw, noverlap, window_func, estimator, k
              Cint, Cint, Float64, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cint}),
             ctx(), kind, yv, nullable(uv), tv, length(yv), fv, length(fv), Wv, n, noverlap, Float64(λ), out, K, info))
     end
-    out, freqs
+    like(y, out), freqs
 end
 
-# estimator = ls_sparse_spectral: one device ADMM solve per window (test/test_lasso.jl:36)
+# estimator = ls_sparse_spectral (test/test_lasso.jl:36).  Without init / callback / periodic prints all windows run
+# in ONE device pass (lpvs_ls_window_sparse_sums: batched Gram, Cholesky and inverse, one CTA per window iterates to
+# its own stop test); otherwise one device ADMM solve per window through the single-problem entry point.
 function _windowed_generic(kind, y, u, t, freqs, n, noverlap, window_func, estimator, kwargs)
     estimator === ls_sparse_spectral ||
         throw(ArgumentError("estimator must be ls_spectral or ls_sparse_spectral (no CPU fallback)"))
     noverlap < 0 && (noverlap = n >> 1)
     W = vecf(window_func(n)); hop = n - noverlap
     K = length(y) >= n ? (length(y) - n) ÷ hop + 1 : 0
+    kw = Dict{Symbol,Any}(kwargs)
+    iters = get(kw, :iters, 10000); tol = get(kw, :tol, 1e-5); printerval = get(kw, :printerval, 100)
+    if !get(kw, :init, false) && get(kw, :cb, nothing) === nothing && printerval >= iters
+        λ = get(kw, :λ, 1.0); μ = get(kw, :μ, 0.05)
+        0 ≤ μ ≤ 1 || throw(AssertionError("μ should be ≤ 1"))                   # src/lasso.jl:143
+        pg = get(kw, :proxg, nothing)
+        pk, pp = pg === nothing ? (PROX_L1, Float64(λ)) : proxdesc(pg)                 # Q15
+        yv, tv, fv = vecf(y), vecf(t), vecf(freqs)
+        uv = u === nothing ? nothing : vecf(u)
+        nrhs = kind == WIN_PSD ? 1 : 2
+        sums = zeros((kind == WIN_PSD ? 1 : kind == WIN_CSD ? 2 : 4) * length(fv))
+        its = zeros(Int64, max(K, 1) * nrhs); res = zeros(max(K, 1) * nrhs); info = Ref{Cint}(0)
+        GC.@preserve yv uv tv fv W sums its res begin
+            K > 0 && check(ccall((:lpvs_ls_window_sparse_sums, liblpvs), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Ptr{Float64},
+                 Cint, Cint, Cint, Float64, Float64, Int64, Float64, Int64, Int64, Ptr{Float64}, Ptr{Int64},
+                 Ptr{Float64}, Ptr{Cint}),
+                ctx(), kind, yv, nullable(uv), tv, length(yv), fv, length(fv), W, n, noverlap, pk, Float64(pp),
+                Float64(μ), iters, Float64(tol), 0, K, sums, its, res, info))
+        end
+        for k in 1:K*nrhs                       # the line the reference prints when a window stops (src/lasso.jl:164)
+            res[k] < tol && @printf("%d ||x-z||₂ %.10f\n", its[k], res[k])
+        end
+        out = kind == WIN_CSD ? Vector{ComplexF64}(undef, length(fv)) : Vector{Float64}(undef, length(fv))
+        check(ccall((:lpvs_ls_window_finalize, liblpvs), Cint, (Cint, Ptr{Float64}, Cint, Int64, Ptr{Cvoid}),
+                    kind, sums, length(fv), K, out))
+        return like(y, out), freqs
+    end
     Syy = zeros(length(freqs)); Suu = zeros(length(freqs)); Syu = zeros(ComplexF64, length(freqs))
     for k in 0:K-1
         r = k*hop+1:k*hop+n
@@ -144,7 +180,7 @@ function ls_spectral_lpv(Y::AbstractVector, X::AbstractVector, V::AbstractVector
             ctx(), Yv, Xv, Vv, length(Yv), wv, length(wv), Nv, Float64(λ), coulomb, normalize, params, Σ, fva, info))
     end
     fva[] < 0.9 && @warn("Fraction of variance explained = $(fva[])")       # src/lsfft.jl:256
-    SpectralExt(Y, X, V, wv, Nv, λ, coulomb, normalize, params, Σ)
+    SpectralExt(Y, X, V, wv, Nv, λ, coulomb, normalize, like(Y, params), like(Y, Σ))
 end
 
 # ---- ADMM-backed sparse estimators (src/lasso.jl) ---------------------------------------------------------------
@@ -199,7 +235,7 @@ function ls_sparse_spectral(y::AbstractArray{T}, t, f=default_freqs(t), W=nothin
     finally
         ccall((:lpvs_admm_free, liblpvs), Cvoid, (Ptr{Cvoid},), h[])
     end
-    params, f
+    like(y, params), f
 end
 
 function ls_sparse_spectral_lpv(y::AbstractVector{S}, X::AbstractVector{S}, V::AbstractVector{S}, w, Nv::Integer;
@@ -224,7 +260,7 @@ function ls_sparse_spectral_lpv(y::AbstractVector{S}, X::AbstractVector{S}, V::A
     finally
         ccall((:lpvs_admm_free, liblpvs), Cvoid, (Ptr{Cvoid},), h[])
     end
-    SpectralExt(y, X, V, wv, Nv, λ, coulomb, normalize, params, nothing)
+    SpectralExt(y, X, V, wv, Nv, λ, coulomb, normalize, like(y, params), nothing)
 end
 
 end # module

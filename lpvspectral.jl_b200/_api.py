@@ -36,6 +36,36 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _cast_like(val, single):
+    if not single or not isinstance(val, np.ndarray):
+        return val
+    return val.astype(np.complex64 if np.iscomplexobj(val) else np.float32)
+
+
+def _preserve_eltype(fn):
+    """Float32 instantiation of the generic signatures (e.g. src/lasso.jl:85 `AbstractArray{T}`): a
+    Float32 signal gives Float32 / ComplexF32 results, as the reference's eltype-generic code does.  The arithmetic is
+    still the library's FP64 path on the up-converted inputs (no FP32 kernels), so the result is the correctly
+    rounded-to-single FP64 answer -- at least as accurate as the reference's Float32 arithmetic."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(y, *a, **k):
+        single = isinstance(y, np.ndarray) and y.dtype == np.float32
+        out = fn(y, *a, **k)
+        if not single:
+            return out
+        if isinstance(out, tuple):
+            return (_cast_like(out[0], True),) + out[1:]
+        if isinstance(out, SpectralExt):
+            out.x = _cast_like(out.x, True)
+            out.Σ = _cast_like(out.Σ, True)
+            return out
+        return _cast_like(out, True)
+
+    return wrapper
+
+
 class Context:
     """One liblpvs context = one GPU (one process per GPU)."""
 
@@ -164,6 +194,7 @@ def gram_fourier(t, f, W=None, y=None, ctx: Optional[Context] = None):
     return (G, b) if yv is not None else G
 
 
+@_preserve_eltype
 def ls_spectral(y, t, f=None, W=None, *, verbose=False, ctx: Optional[Context] = None, return_info=False, **kw):
     """ls_spectral(y,t,f=default_freqs(t)[,W]; λ=1e-10) -> (x, f)   (src/lsfft.jl:62-80)."""
     lam = _lam(kw, 1e-10)
@@ -296,18 +327,21 @@ def _windowed(kind, y, u, t, freqs, nw, noverlap, window_func, estimator, ctx, k
     return (Syu.real * Syu.real + Syu.imag * Syu.imag) / (Suu * Syy), freqs
 
 
+@_preserve_eltype
 def ls_windowpsd(y, t, freqs=None, *, nw=8, noverlap=-1, window_func: Callable = rect, estimator=None, ctx=None,
                  **kw):
     """ls_windowpsd (src/lsfft.jl:112-126): S = Σ|x_i|²/K², weighted estimator per window."""
     return _windowed(L.WIN_PSD, y, None, t, freqs, nw, noverlap, window_func, estimator, ctx, kw)
 
 
+@_preserve_eltype
 def ls_windowcsd(y, u, t, freqs=None, *, nw=10, noverlap=-1, window_func: Callable = rect, estimator=None,
                  ctx=None, **kw):
     """ls_windowcsd (src/lsfft.jl:140-156): S = Σ xy·conj(xu)/K."""
     return _windowed(L.WIN_CSD, y, u, t, freqs, nw, noverlap, window_func, estimator, ctx, kw)
 
 
+@_preserve_eltype
 def ls_cohere(y, u, t, freqs=None, *, nw=10, noverlap=-1, estimator=None, ctx=None, **kw):
     """ls_cohere (src/lsfft.jl:176-193): window hard-coded to hanning (Q8)."""
     if "window_func" in kw:
@@ -342,6 +376,7 @@ def psd(se: SpectralExt):
     return s.real * s.real + s.imag * s.imag
 
 
+@_preserve_eltype
 def ls_spectral_lpv(Y, X, V, w, Nv, *, coulomb=False, normalize=True, want_sigma=True, ctx=None, **kw):
     """ls_spectral_lpv(Y,X,V,w,Nv; λ=1e-8, coulomb=false, normalize=true) -> SpectralExt (src/lsfft.jl:239-259)."""
     lam = _lam(kw, 1e-8)
@@ -367,6 +402,7 @@ def ls_spectral_lpv(Y, X, V, w, Nv, *, coulomb=False, normalize=True, want_sigma
     return SpectralExt(Yv, Xv, Vv, wv, int(Nv), lam, bool(coulomb), bool(normalize), params, Sigma, fva.value)
 
 
+@_preserve_eltype
 def ls_windowpsd_lpv(Y, X, V, w, Nv, nw=10, noverlap=0, *, ctx=None, **kw):
     """ls_windowpsd_lpv (src/lsfft.jl:267-277): rect windows, S not normalised."""
     Yv, Xv, Vv, wv = _f64(Y), _f64(X), _f64(V), _f64(w)
@@ -483,6 +519,7 @@ class ADMM:
             pass
 
 
+@_preserve_eltype
 def ls_sparse_spectral(y, t, f=None, W=None, *, init=False, proxg=None, iters=10000, tol=1e-5, printerval=100,
                        cb=None, μ=None, mu=None, verbose=False, ctx=None, return_info=False, **kw):
     """ls_sparse_spectral(y,t,f[,W]; init=false, λ=1, proxg=NormL1(λ), iters, tol, printerval, cb, μ)
@@ -520,6 +557,7 @@ def ls_sparse_spectral(y, t, f=None, W=None, *, init=False, proxg=None, iters=10
     return x, f_in
 
 
+@_preserve_eltype
 def ls_sparse_spectral_lpv(y, X, V, w, Nv, *, coulomb=False, normalize=True, iters=10000, tol=1e-5, printerval=100,
                            cb=None, μ=None, mu=None, verbose=False, ctx=None, return_info=False, **kw):
     """ls_sparse_spectral_lpv(y,X,V,w,Nv; λ=1, coulomb=false, normalize=true, ADMM kwargs) -> SpectralExt

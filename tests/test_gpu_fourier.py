@@ -207,3 +207,26 @@ def test_nonfinite_inputs_are_reported(ctx):
     assert ei.value.code == L.E_NONFINITE
     x, _ = lp.ls_spectral(y, t, f, ctx=ctx)  # the context stays usable
     assert np.all(np.isfinite(x))
+
+
+def test_float32_signatures(ctx):
+    """the reference's signatures are eltype-generic (e.g. src/lasso.jl:85).  A Float32 signal gives
+    Float32 / ComplexF32 results; the arithmetic is the FP64 device path on the up-converted inputs, so the result must
+    equal the FP64 answer for the same (single-precision) inputs rounded to single."""
+    import lpvspectral_jl_b200 as lp
+
+    t, y = signal(2048, 9)
+    t32, y32 = t.astype(np.float32), y.astype(np.float32)
+    f = np.arange(0, 60) * 0.9
+    x32, _ = lp.ls_spectral(y32, t32, f, ctx=ctx)
+    x64, _ = lp.ls_spectral(y32.astype(np.float64), t32.astype(np.float64), f, ctx=ctx)
+    assert x32.dtype == np.complex64 and x64.dtype == np.complex128
+    assert np.array_equal(x32, x64.astype(np.complex64))
+    S32, _ = lp.ls_windowpsd(y32, t32, f, nw=4, window_func=lp.hanning, ctx=ctx)
+    S64, _ = lp.ls_windowpsd(y32.astype(np.float64), t32.astype(np.float64), f, nw=4, window_func=lp.hanning, ctx=ctx)
+    assert S32.dtype == np.float32 and np.array_equal(S32, S64.astype(np.float32))
+    z32, _ = lp.ls_sparse_spectral(y32, t32, f[1:], lam=0.2, iters=300, tol=1e-9, ctx=ctx)
+    assert z32.dtype == np.complex64
+    # and against the oracle run in FP64 on the same single-precision inputs: single-precision agreement
+    xr, _ = o.ls_spectral(y32.astype(np.float64), t32.astype(np.float64), f, mode="literal")
+    assert rel(x32, xr) <= 1e-6

@@ -142,6 +142,35 @@ def cfg4(ctx, args):
     dump("cfg4", res)
 
 
+def cfg2s(ctx, args):
+    """cfg2's record with estimator = ls_sparse_spectral (L1): K windows x `iters` ADMM iterations, batched."""
+    rng = np.random.default_rng(2)
+    NS = args.get("N", 1 << 22)
+    t = np.sort(10 * rng.random(NS))
+    n = 4096
+    fs = 1.0 / np.mean(np.diff(t))
+    f = np.arange(256) * 2 * fs / n
+    y = np.sin(2 * np.pi * f[40] * t) + 0.5 * np.cos(2 * np.pi * f[100] * t + 1) + 0.1 * rng.standard_normal(NS)
+    iters = args.get("iters", 300)
+    K = lp.window_count(NS, n, -1)
+    kw = dict(nw=NS // n, window_func=lp.hanning, estimator=lp.ls_sparse_spectral, lam=0.01, iters=iters, tol=0.0,
+              ctx=ctx)
+    S, _ = lp.ls_windowpsd(y, t, f, **kw)
+    t0 = time.perf_counter()
+    S, _ = lp.ls_windowpsd(y, t, f, **kw)
+    wall = time.perf_counter() - t0
+    Sd, _ = lp.ls_windowpsd(y, t, f, nw=NS // n, window_func=lp.hanning, ctx=ctx)
+    t0 = time.perf_counter()
+    Sd, _ = lp.ls_windowpsd(y, t, f, nw=NS // n, window_func=lp.hanning, ctx=ctx)
+    wall_dense = time.perf_counter() - t0
+    Np = 512
+    res = dict(samples=NS, windows=K, iters=iters, wall_s=wall, wall_dense_s=wall_dense,
+               admm_s=wall - wall_dense, window_iters_per_s=K * iters / max(wall - wall_dense, 1e-9),
+               gbs_full_M=K * iters * 8.0 * Np * Np / max(wall - wall_dense, 1e-9) / 1e9,
+               peak_bins=[int(i) for i in np.argsort(S)[-2:]], dense_peak_bins=[int(i) for i in np.argsort(Sd)[-2:]])
+    dump("cfg2s", res)
+
+
 def cfg5a(ctx, args):
     rng = np.random.default_rng(5)
     NS = args.get("N", 1 << 24)
