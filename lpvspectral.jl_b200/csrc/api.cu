@@ -341,12 +341,18 @@ int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, doub
     ca.nb = nb;
     ca.maxdiag = d_maxdiag;
     ca.tol_scale = tol_scale;
+    const bool fuse_fwd = d_B && nrhs > 0;  // L y = b rides along with the factorisation
+    if (fuse_fwd) {
+        ca.rhs = d_B;
+        ca.strideRhs = 2LL * Np;
+        ca.nrhs = nrhs;
+    }
     if (!ca.Linv || !ca.info) return fail(c, LPVS_E_NOMEM, "out of device memory (factor workspace)");
     LPVS_CU(c, cudaMemsetAsync(ca.info, 0, sizeof(int) * nproblems, c->st));
     launch_diag_prepare(d_G, ca.strideG, Np, ncc, zero_first, nullptr, ridge, nproblems, c->st);
     c->launches += 1 + potrf(ca, nproblems, c->sms, c->st);
     if (d_B && nrhs > 0) {
-        launch_trsv(ca, d_B, 2LL * Np, nrhs, nproblems, c->st);
+        launch_trsv(ca, d_B, 2LL * Np, nrhs, nproblems, c->st, fuse_fwd);
         c->launches++;
     }
     LPVS_CU(c, cudaGetLastError());

@@ -275,6 +275,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ C
         __syncthreads();
     }
     POTF2_TR(19)
+    if (a.rhs) {
+        // fused forward substitution: y_k = Linv_kk r_k (r_k already carries -sum_{j<k} L_kj y_j from the TRSM tiles)
+        double* rk = a.rhs + (long long)prob * a.strideRhs + (long long)k * TB;
+        for (int q = tid; q < 2 * TB; q += NTHREADS) T[q] = (q >> 7) < a.nrhs ? __ldcg(rk + (long long)(q >> 7) * a.Np + (q & 127)) : 0.0;
+        __syncthreads();
+        for (int rr = warp; rr < TB; rr += NTHREADS / 32) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int c = lane + 32 * q;
+                const double l = c <= rr ? S[rr * LDS + c] : 0.0;
+                s0 = fma(l, T[c], s0);
+                s1 = fma(l, T[TB + c], s1);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            }
+            if (lane == 0) {
+                rk[rr] = s0;
+                if (a.nrhs > 1) rk[a.Np + rr] = s1;
+            }
+        }
+    }
     double* Li = a.Linv + (long long)prob * a.strideLinv + (long long)k * TB * TB;
     for (int idx = tid; idx < TB * TB / 2; idx += NTHREADS) {
         const int r = idx >> 6, c = (idx & 63) * 2;
@@ -368,6 +393,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const __grid_constant__ Ch
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    __shared__ double ysm[2][TB];       // y_k of the fused forward substitution (TRSM only)
+    __shared__ double yred[2][2][TB];   // [wn][rhs][row]
+    const bool fwd = mode == GM_TRSM && a.rhs != nullptr;
+    if (fwd) {
+        const double* yk = a.rhs + (long long)prob * a.strideRhs + (long long)k * TB;
+        ysm[tid >> 7][tid & 127] = (tid >> 7) < a.nrhs ? __ldcg(yk + (long long)(tid >> 7) * Np + (tid & 127)) : 0.0;
+    }
     const int nchunks = K / KC;
     double* st0 = sm;
     double* st1 = sm + 2 * TILE_D;
@@ -410,6 +442,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const __grid_constant__ Ch
                 v.y += beta * o.y;
             }
             *pc = v;
+        }
+    }
+    if (fwd) {
+        // r_i -= L_ik y_k for this tile's 128 rows (this CTA is the only writer of r_i in this launch)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int col = 64 * wn + 8 * j + 2 * (lane & 3);
+                p0 = fma(acc[i][j][0], ysm[0][col], fma(acc[i][j][1], ysm[0][col + 1], p0));
+                p1 = fma(acc[i][j][0], ysm[1][col], fma(acc[i][j][1], ysm[1][col + 1], p1));
+            }
+            p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+            p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+            if ((lane & 3) == 0) {
+                const int row = 32 * wm + 8 * i + (lane >> 2);
+                yred[wn][0][row] = p0;
+                yred[wn][1][row] = p1;
+            }
+        }
+        __syncthreads();
+        const int v = tid >> 7, row = tid & 127;
+        if (v < a.nrhs) {
+            double* ri = a.rhs + (long long)prob * a.strideRhs + (long long)v * Np + (long long)(k + 1 + t) * TB + row;
+            *ri -= yred[0][v][row] + yred[1][v][row];
         }
     }
 }
@@ -479,7 +539,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_trsv(const __grid_constant__ CholArgs a, double* Bm,
-                                                      long long strideB, int nrhs) {
+                                                      long long strideB, int nrhs, int fwd_done) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int prob = blockIdx.x;
     const long long Np = a.Np;
@@ -490,7 +550,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trsv(const __grid_constant__ Ch
     __shared__ double part[2][2][TB];
 
     // forward: L y = b
-    for (int kb = 0; kb < a.nb; kb++) {
+    for (int kb = fwd_done ? a.nb : 0; kb < a.nb; kb++) {
         for (int rr = warp; rr < TB; rr += 8) {
             const double* row = L + (long long)(kb * TB + rr) * Np;
             double s0 = 0.0, s1 = 0.0;
@@ -560,12 +620,82 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trsv(const __grid_constant__ Ch
     }
 }
 
+// Backward substitution only (L' x = y), one CTA per problem, for the batched path whose forward substitution was
+// fused into the factorisation.  x lives in shared memory; thread (c, h) walks every TRSV_H-th row of column c of the
+// block column below the diagonal block (coalesced 1 KB row pieces, 8 independent loads in flight per thread).
+constexpr int TRSV_T = 512, TRSV_H = TRSV_T / TB;
+__global__ void __launch_bounds__(TRSV_T, 2) k_trsv_bwd(const __grid_constant__ CholArgs a, double* Bm, long long strideB,
+                                                        int nrhs) {
+    extern __shared__ __align__(16) double xs[];  // [2][Np]
+    __shared__ double part[2][TRSV_H][TB];
+    __shared__ double rbuf[2][TB];
+    const int tid = threadIdx.x, c = tid & 127, h = tid >> 7;
+    const int prob = blockIdx.x;
+    const int Np = a.Np;
+    const double* L = a.G + (long long)prob * a.strideG;
+    const double* Linv = a.Linv + (long long)prob * a.strideLinv;
+    double* b = Bm + (long long)prob * strideB;
+    for (int q = tid; q < 2 * Np; q += TRSV_T) xs[q] = (q / Np) < nrhs ? __ldcg(b + q) : 0.0;
+    __syncthreads();
+    for (int kb = a.nb - 1; kb >= 0; kb--) {
+        double s0 = 0.0, s1 = 0.0;
+        const double* col = L + (long long)kb * TB + c;
+        int r = (kb + 1) * TB + h;
+        for (; r + 7 * TRSV_H < Np; r += 8 * TRSV_H) {
+            double l[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) l[q] = __ldcs(col + (long long)(r + q * TRSV_H) * Np);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                s0 = fma(l[q], xs[r + q * TRSV_H], s0);
+                s1 = fma(l[q], xs[Np + r + q * TRSV_H], s1);
+            }
+        }
+        for (; r < Np; r += TRSV_H) {
+            const double l = __ldcs(col + (long long)r * Np);
+            s0 = fma(l, xs[r], s0);
+            s1 = fma(l, xs[Np + r], s1);
+        }
+        part[0][h][c] = s0;
+        part[1][h][c] = s1;
+        __syncthreads();
+        if (h < 2) {  // h = rhs here
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < TRSV_H; q++) t += part[h][q][c];
+            rbuf[h][c] = xs[h * Np + kb * TB + c] - t;
+        }
+        __syncthreads();
+        // x_k = Linv_kk' rbuf: column c of Linv', rows m >= c
+        const double* Li = Linv + (long long)kb * TB * TB;
+        s0 = 0.0;
+        s1 = 0.0;
+        for (int m = c + h; m < TB; m += TRSV_H) {
+            const double l = Li[m * TB + c];
+            s0 = fma(l, rbuf[0][m], s0);
+            s1 = fma(l, rbuf[1][m], s1);
+        }
+        part[0][h][c] = s0;
+        part[1][h][c] = s1;
+        __syncthreads();
+        if (h < 2) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < TRSV_H; q++) t += part[h][q][c];
+            xs[h * Np + kb * TB + c] = t;
+            if (h < nrhs) b[(long long)h * Np + kb * TB + c] = t;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // multi-CTA blocked TRSV for ONE large problem (cooperative launch, grid = nb CTAs, CTA i owns row block i).
 // Forward:  y_k = Linv_k r_k, publish, then every CTA i > k does r_i -= L[i,k] y_k.   One grid barrier per block.
 // Backward: x_k = Linv_k' r_k, publish, then every CTA i < k does r_i -= L[k,i]' x_k.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1) k_trsv_big(const __grid_constant__ CholArgs a, double* b, int nrhs) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_trsv_big(const __grid_constant__ CholArgs a, double* b, int nrhs,
+                                                          int fwd_done) {
     cg::grid_group grid = cg::this_grid();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = blockIdx.x;
@@ -579,8 +709,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trsv_big(const __grid_constant_
         r[rh][c] = rh < nrhs ? b[(long long)rh * Np + i * TB + c] : 0.0;
     }
     __syncthreads();
-    // ---- forward ----
-    for (int k = 0; k < a.nb; k++) {
+    // ---- forward ---- (skipped when the factorisation already produced y, see CholArgs::rhs)
+    for (int k = fwd_done ? a.nb : 0; k < a.nb; k++) {
         if (i == k) {
             const double* Li = a.Linv + (long long)k * TB * TB;
             for (int rr = warp; rr < TB; rr += 8) {
@@ -741,20 +871,34 @@ void launch_symmetrize(double* G, long long strideG, int Np, int nproblems, cuda
     k_symmetrize<<<grid, 256, 0, st>>>(G, strideG, Np);
 }
 
-void launch_trsv(const CholArgs& a, double* B, long long strideB, int nrhs, int nproblems, cudaStream_t st) {
+void launch_trsv(const CholArgs& a, double* B, long long strideB, int nrhs, int nproblems, cudaStream_t st,
+                 bool fwd_done) {
     if (nproblems == 1 && a.nb >= 8) {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (a.nb <= sms) {  // all row blocks co-resident: cooperative multi-CTA substitution
             CholArgs aa = a;
-            void* args[] = {(void*)&aa, (void*)&B, (void*)&nrhs};
+            int fd = fwd_done ? 1 : 0;
+            void* args[] = {(void*)&aa, (void*)&B, (void*)&nrhs, (void*)&fd};
             if (cudaLaunchCooperativeKernel((void*)k_trsv_big, dim3(a.nb), dim3(NTHREADS), args, 0, st) == cudaSuccess)
                 return;
             cudaGetLastError();
         }
     }
-    k_trsv<<<nproblems, NTHREADS, 0, st>>>(a, B, strideB, nrhs);
+    const size_t xs_bytes = sizeof(double) * 2 * (size_t)a.Np;
+    if (fwd_done && xs_bytes <= 200 * 1024) {
+        static bool attr_done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_done[dev & 63]) {
+            cudaFuncSetAttribute(k_trsv_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_done[dev & 63] = true;
+        }
+        k_trsv_bwd<<<nproblems, TRSV_T, xs_bytes, st>>>(a, B, strideB, nrhs);
+        return;
+    }
+    k_trsv<<<nproblems, NTHREADS, 0, st>>>(a, B, strideB, nrhs, fwd_done ? 1 : 0);
 }
 
 int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st) {

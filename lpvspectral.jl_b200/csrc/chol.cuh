@@ -28,6 +28,11 @@ struct CholArgs {
     const double* maxdiag;
     double tol_scale;
     int Np, nb;
+    // optional right-hand sides [nrhs][Np] per problem: the forward substitution L y = b rides along with the
+    // factorisation (k_potf2 finishes y_k = Linv_kk r_k, the TRSM tiles apply r_i -= L_ik y_k), b is overwritten by y
+    double* rhs;
+    long long strideRhs;
+    int nrhs;
 };
 
 size_t potf2_smem_bytes();
@@ -43,7 +48,9 @@ void launch_init_y(const CholArgs& a, int nproblems, cudaStream_t st);
 // mirror lower tiles of G into the upper triangle
 void launch_symmetrize(double* G, long long strideG, int Np, int nproblems, cudaStream_t st);
 // B[p][r][Np] <- (L L')^{-1} B, nrhs <= 2, one CTA per problem
-void launch_trsv(const CholArgs& a, double* B, long long strideB, int nrhs, int nproblems, cudaStream_t st);
+// fwd_done: B already holds y = L^-1 b (fused forward substitution), only L' x = y remains
+void launch_trsv(const CholArgs& a, double* B, long long strideB, int nrhs, int nproblems, cudaStream_t st,
+                 bool fwd_done = false);
 // max_i G[i][i] over non-dummy i  -> out[prob]
 void launch_max_diag(const double* G, long long strideG, int Np, int ncc, int zero_first, double* out,
                      int nproblems, cudaStream_t st);
