@@ -66,8 +66,12 @@ __device__ __forceinline__ double2 synth_elem(const GramArgs& a, const Pref& p, 
     }
 }
 
-// DIAG tiles (I == J) compute only the three lower 64x64 sub-blocks (0,0), (1,0), (1,1): warp tile 16x32 per
-// sub-block, 24 DMMAs per k4-step instead of 32.
+// DIAG tiles (I == J) compute only the 20 of 32 pieces (16 rows x 32 columns) that touch the lower triangle:
+// piece (r, c) is needed iff r >= 2c.  Pieces are dealt so that every SM sub-partition (warps w and w+4) issues
+// 5 pieces = 40 DMMAs per k4-step instead of 64: warps 0-3 take three pieces of one row strip (rows 4..7, columns
+// 0..2: one A fragment pair, three B fragment quads), warps 4-7 take the remaining pairs {(6,3),(7,3)}, {(2,0),(2,1)},
+// {(3,0),(3,1)}, {(0,0),(1,0)} which share either the A or the B fragments.  (Computing the three lower 64x64
+// sub-blocks instead costs 48 per sub-partition: measured 77.8 ms vs this layout on cfg2, see profiles/.)
 template <int MODE, bool DIAG>
 __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int prob, double* smem) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -75,7 +79,7 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     const long long s_begin = a.start0 + (long long)prob * a.hop;
     const int nchunks = (a.n + KC - 1) / KC;
 
-    double acc[4][8][2];   // off-diagonal: [i][j][e]; diagonal: viewed as [sb(3)][i(2)][j(4)][e(2)] = 48 used
+    double acc[4][8][2];   // off-diagonal: [i][j][e]; diagonal: viewed as [piece(3)][i(2)*4+j(4)][e(2)] = 48 used
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -144,9 +148,28 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     if (nchunks > 1) p1 = load_pref<MODE, DIAG>(a, 1, s_begin, lane, w, I, J);
     mbar_wait(&full[0], 0);
 
-    // fragment bases: off-diagonal 32(M) x 64(N) warp tile; diagonal 16 x 32 per 64x64 sub-block
-    const int fragA = DIAG ? (16 * wm + (lane >> 2)) * LDT + (lane & 3) : (32 * wm + (lane >> 2)) * LDT + (lane & 3);
-    const int fragB = DIAG ? (32 * wn + (lane >> 2)) * LDT + (lane & 3) : (64 * wn + (lane >> 2)) * LDT + (lane & 3);
+    // fragment bases: off-diagonal 32(M) x 64(N) warp tile; diagonal: per-piece offsets added below
+    const int fragA = DIAG ? (lane >> 2) * LDT + (lane & 3) : (32 * wm + (lane >> 2)) * LDT + (lane & 3);
+    const int fragB = DIAG ? (lane >> 2) * LDT + (lane & 3) : (64 * wn + (lane >> 2)) * LDT + (lane & 3);
+    // diagonal tile: this warp's pieces (16-row strip pr, 32-column strip pc); the third piece of warps 0-3 shares
+    // the A fragments of the first
+    int pr0, pr1, pc0, pc1, pc2 = 2;
+    if (w < 4) {
+        pr0 = pr1 = 4 + w;
+        pc0 = 0;
+        pc1 = 1;
+    } else if (w == 4) {
+        pr0 = 6; pr1 = 7; pc0 = pc1 = 3;
+    } else if (w == 7) {
+        pr0 = 0; pr1 = 1; pc0 = pc1 = 0;
+    } else {
+        pr0 = pr1 = w - 3;  // 2, 3
+        pc0 = 0;
+        pc1 = 1;
+    }
+    const bool three = w < 4, sameA = pr0 == pr1, sameB = pc0 == pc1;
+    const int offA0 = 16 * pr0 * LDT, offA1 = 16 * pr1 * LDT;
+    const int offB0 = 32 * pc0 * LDT, offB1 = 32 * pc1 * LDT, offB2 = 32 * pc2 * LDT;
 
     const int burst_kk = 0;  // staggering the bursts of an SMSP's two warps (0 / 4) measured no better (78.0 vs 77.7 ms)
     int st_cur = 0;
@@ -184,19 +207,39 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
             if (!DIAG) {
                 mma_step(pa, pb, kk, acc);
             } else {
-                double fa[4], fb[8];  // fa: rows {0,8} of half 0 then half 1; fb: cols {0,8,16,24} of half 0 then half 1
+                double fa0[2], fa1[2], fb[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) fa[i] = pa[((i >> 1) * 64 + (i & 1) * 8) * LDT + 4 * kk];
+                for (int i = 0; i < 2; i++) fa0[i] = pa[offA0 + 8 * i * LDT + 4 * kk];
 #pragma unroll
-                for (int j = 0; j < 8; j++) fb[j] = pb[((j >> 2) * 64 + (j & 3) * 8) * LDT + 4 * kk];
+                for (int j = 0; j < 4; j++) fb[j] = pb[offB0 + 8 * j * LDT + 4 * kk];
+                if (sameA) {
+                    fa1[0] = fa0[0];
+                    fa1[1] = fa0[1];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 2; i++) fa1[i] = pa[offA1 + 8 * i * LDT + 4 * kk];
+                }
 #pragma unroll
                 for (int i = 0; i < 2; i++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        dmma884(acc[0][i * 4 + j][0], acc[0][i * 4 + j][1], fa[i], fb[j]);          // (0,0)
-                        dmma884(acc[1][i * 4 + j][0], acc[1][i * 4 + j][1], fa[2 + i], fb[j]);      // (1,0)
-                        dmma884(acc[2][i * 4 + j][0], acc[2][i * 4 + j][1], fa[2 + i], fb[4 + j]);  // (1,1)
-                    }
+                    for (int j = 0; j < 4; j++) dmma884(acc[0][i * 4 + j][0], acc[0][i * 4 + j][1], fa0[i], fb[j]);
+                if (!sameB) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) fb[j] = pb[offB1 + 8 * j * LDT + 4 * kk];
+                }
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) dmma884(acc[1][i * 4 + j][0], acc[1][i * 4 + j][1], fa1[i], fb[j]);
+                if (three) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) fb[j] = pb[offB2 + 8 * j * LDT + 4 * kk];
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            dmma884(acc[2][i * 4 + j][0], acc[2][i * 4 + j][1], fa0[i], fb[j]);
+                }
             }
         }
         p1 = p2;
@@ -220,15 +263,16 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
         }
     } else {
 #pragma unroll
-        for (int sb = 0; sb < 3; sb++) {
-            const int sr = sb > 0, sc = sb > 1;
+        for (int pz = 0; pz < 3; pz++) {
+            if (pz == 2 && !three) break;
+            const int pr = pz == 1 ? pr1 : pr0, pc = pz == 0 ? pc0 : (pz == 1 ? pc1 : pc2);
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-                int row = I * TB + 64 * sr + 16 * wm + 8 * i + (lane >> 2);
+                int row = I * TB + 16 * pr + 8 * i + (lane >> 2);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    int col = I * TB + 64 * sc + 32 * wn + 8 * j + 2 * (lane & 3);
-                    double2 v = make_double2(acc[sb][i * 4 + j][0] * a.gscale, acc[sb][i * 4 + j][1] * a.gscale);
+                    int col = I * TB + 32 * pc + 8 * j + 2 * (lane & 3);
+                    double2 v = make_double2(acc[pz][i * 4 + j][0] * a.gscale, acc[pz][i * 4 + j][1] * a.gscale);
                     *reinterpret_cast<double2*>(Gp + (long long)row * Np + col) = v;
                 }
             }
