@@ -21,7 +21,7 @@ __all__ = [
     "Context", "default_context", "default_freqs", "check_freq", "rect", "hanning", "hamming", "window_count",
     "ls_spectral", "ls_windowpsd", "ls_windowcsd", "ls_cohere", "ls_spectral_lpv", "ls_sparse_spectral",
     "ls_sparse_spectral_lpv", "ls_windowpsd_lpv", "gram_fourier", "SpectralExt", "psd", "NormL1", "NormL0",
-    "IndBallL0", "ADMM", "LpvsError", "NotPositiveDefinite", "window_sums", "window_finalize",
+    "IndBallL0", "ADMM", "LpvsError", "NotPositiveDefinite", "window_sums", "window_sparse_sums", "window_finalize",
 ]
 
 LpvsError = L.LpvsError
@@ -233,6 +233,29 @@ def window_sums(kind, y, u, t, freqs, W, n, noverlap, lam, k_begin, k_end, ctx: 
     ctx.check(ctx.lib.lpvs_ls_window_sums(ctx.h, kind, _ptr(yv), _ptr(uv), _ptr(tv), len(yv), _ptr(fv), len(fv),
                                           _ptr(Wv), int(n), int(noverlap), float(lam), int(k_begin), int(k_end),
                                           _ptr(sums), C.byref(info)))
+    return sums
+
+
+def window_sparse_sums(kind, y, u, t, freqs, W, n, noverlap, proxg, mu, iters, tol, k_begin, k_end,
+                       ctx: Optional[Context] = None, return_info=False):
+    """Raw cross-window sums of the windowed estimators with estimator = ls_sparse_spectral for windows
+    [k_begin,k_end): every window an independent device ADMM (lpvs_ls_window_sparse_sums) -- the sharding unit."""
+    ctx = ctx or default_context()
+    yv, tv, fv, Wv = _f64(y), _f64(t), _f64(freqs), _f64(W)
+    uv = None if u is None else _f64(u)
+    pk, pp = _prox_desc(proxg)
+    nrhs = 1 if kind == L.WIN_PSD else 2
+    sums = np.zeros({L.WIN_PSD: 1, L.WIN_CSD: 2, L.WIN_COHERE: 4}[kind] * len(fv))
+    nk = max(int(k_end) - int(k_begin), 1)
+    its = np.zeros(nk * nrhs, dtype=np.int64)
+    res = np.zeros(nk * nrhs)
+    info = C.c_int(0)
+    ctx.check(ctx.lib.lpvs_ls_window_sparse_sums(ctx.h, kind, _ptr(yv), _ptr(uv), _ptr(tv), len(yv), _ptr(fv), len(fv),
+                                                 _ptr(Wv), int(n), int(noverlap), pk, pp, float(mu), int(iters),
+                                                 float(tol), int(k_begin), int(k_end), _ptr(sums), _ptr(its),
+                                                 _ptr(res), C.byref(info)))
+    if return_info:
+        return sums, its.reshape(nk, nrhs), res.reshape(nk, nrhs)
     return sums
 
 

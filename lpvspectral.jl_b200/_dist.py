@@ -21,7 +21,7 @@ import numpy as np
 from . import _api as A
 from . import _lib as L
 
-__all__ = ["shard_range", "ls_window_sharded", "ls_spectral_rowsharded"]
+__all__ = ["shard_range", "ls_window_sharded", "ls_window_sparse_sharded", "ls_spectral_rowsharded"]
 
 
 def shard_range(K: int, rank: int, world: int):
@@ -69,6 +69,17 @@ def ls_window_sharded(kind, y, u, t, freqs, *, n, noverlap=-1, W, lam=1e-10, ctx
     sums = sums_fn(kind, y, u, t, freqs, W, n, noverlap, lam, k0, k1) if k1 > k0 else np.zeros(slen)
     sums = _allreduce_sum_np(np.asarray(sums, dtype=np.float64), group, reduce_device)
     return A.window_finalize(kind, sums, nf, K), K
+
+
+def ls_window_sparse_sharded(kind, y, u, t, freqs, *, n, noverlap=-1, W, proxg, mu=0.05, iters=10000, tol=1e-5,
+                             ctx: Optional[A.Context] = None, group=None, reduce_device=None):
+    """Windowed estimators with estimator = ls_sparse_spectral, windows sharded across ranks: every window is an
+    independent ADMM problem, so as for the dense estimators there is no data-path collective -- one all-reduce of
+    the Nf-long accumulators at the end."""
+    fn = lambda k, yy, uu, tt, ff, WW, nn, nov, _lam, k0, k1: A.window_sparse_sums(  # noqa: E731
+        k, yy, uu, tt, ff, WW, nn, nov, proxg, mu, iters, tol, k0, k1, ctx=ctx)
+    return ls_window_sharded(kind, y, u, t, freqs, n=n, noverlap=noverlap, W=W, ctx=ctx, group=group, sums_fn=fn,
+                             reduce_device=reduce_device)
 
 
 def ls_spectral_rowsharded(y, t, f, W=None, *, u=None, lam=1e-10, ctx: Optional[A.Context] = None, group=None):

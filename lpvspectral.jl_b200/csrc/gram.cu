@@ -298,16 +298,26 @@ __global__ void __launch_bounds__(NTHREADS) k_gram_rhs(const __grid_constant__ G
         y0 = a.y ? a.y[s] : 0.0;
         y1 = (a.nrhs > 1 && a.u) ? a.u[s] : 0.0;
     };
+    // two chunks of operands in flight per thread (the kernel is DRAM-latency bound: it streams the anchor table once)
     Pref pn = load_pref<MODE, true>(a, 0, s_begin, lane, w, I, I);
     double yn0, yn1;
     load_y(pn, yn0, yn1);
+    Pref pm = pn;
+    double ym0 = yn0, ym1 = yn1;
+    if (nchunks > 1) {
+        pm = load_pref<MODE, true>(a, 1, s_begin, lane, w, I, I);
+        load_y(pm, ym0, ym1);
+    }
     for (int c = 0; c < nchunks; c++) {
         const Pref p = pn;
         const double wte = p.valid ? p.wt : 0.0;
         const double y0 = yn0 * wte, y1 = yn1 * wte;
-        if (c + 1 < nchunks) {  // prefetch the next chunk while this one is consumed
-            pn = load_pref<MODE, true>(a, c + 1, s_begin, lane, w, I, I);
-            load_y(pn, yn0, yn1);
+        pn = pm;
+        yn0 = ym0;
+        yn1 = ym1;
+        if (c + 2 < nchunks) {
+            pm = load_pref<MODE, true>(a, c + 2, s_begin, lane, w, I, I);
+            load_y(pm, ym0, ym1);
         }
         double2 z = p.aI;
 #pragma unroll

@@ -239,6 +239,45 @@ def test_windowed_sparse_batched(ctx, kind, prox):
     assert np.linalg.norm(S[ok] - Sr[ok]) <= 1e-8 * np.linalg.norm(Sr[ok])
 
 
+def test_windowed_sparse_ranges_and_batches(ctx):
+    """Window ranges (the multi-GPU sharding unit) and small device batches of the batched sparse path add up to the
+    one-pass result; per-window iteration counts are independent of how the windows were grouped."""
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+
+    t, y = sparse_signal(3000, 4)
+    u = np.roll(y, 7)
+    f = np.arange(1, 50) * 0.4
+    n, nov = 300, 150
+    W = lp.hanning(n)
+    K = lp.window_count(len(y), n, nov)
+    args = (L.WIN_COHERE, y, u, t, f, W, n, nov, lp.NormL1(0.05), 0.05, 800, 1e-9)
+    full, its, res = lp.window_sparse_sums(*args, 0, K, ctx=ctx, return_info=True)
+    parts, its_parts = np.zeros_like(full), []
+    for k0, k1 in [(0, 5), (5, 6), (6, 6), (6, K)]:
+        s, i, _ = lp.window_sparse_sums(*args, k0, k1, ctx=ctx, return_info=True)
+        parts += s
+        if k1 > k0:
+            its_parts.append(i)
+    assert np.array_equal(np.concatenate(its_parts), its)
+    assert np.allclose(parts, full, rtol=1e-13, atol=0)
+    ctx.set_option(L.OPT_WINDOW_BATCH, 4)
+    try:
+        small, its2, _ = lp.window_sparse_sums(*args, 0, K, ctx=ctx, return_info=True)
+    finally:
+        ctx.set_option(L.OPT_WINDOW_BATCH, 0)
+    assert np.array_equal(its2, its) and np.allclose(small, full, rtol=1e-13, atol=0)
+    # single-rank sharded wrapper == the estimator
+    from lpvspectral_jl_b200 import _dist as D
+
+    C1, K1 = D.ls_window_sparse_sharded(L.WIN_COHERE, y, u, t, f, n=n, noverlap=nov, W=W, proxg=lp.NormL1(0.05),
+                                        iters=800, tol=1e-9, ctx=ctx)
+    C2, _ = lp.ls_cohere(y, u, t, f, nw=len(y) // n, noverlap=nov, estimator=lp.ls_sparse_spectral,
+                         proxg=lp.NormL1(0.05), iters=800, tol=1e-9, ctx=ctx)
+    ok = np.isfinite(C2)
+    assert K1 == K and np.array_equal(C1[ok], C2[ok])
+
+
 def test_sparse_lpv_coulomb_quirk(ctx):
     """coulomb=true: the vector has 4*Nf*Nv entries but the reference's groups (src/lasso.jl:46-54) still have 2Nv
     entries and cover only the first half; uncovered entries of z stay 0.  Reproduced, not fixed."""
