@@ -27,10 +27,11 @@ struct Pref {
     double tt;          // direct: sample position
     long long si;       // table sample index
     double wt;
+    double yv;   // rhs sample (diagonal tiles with the fused single right-hand side)
     bool valid;  // the weight is zeroed for invalid samples at the point of USE (no stall on the prefetch)
 };
 
-template <int MODE, bool DIAG>
+template <int MODE, bool DIAG, bool RHS = false>
 __device__ __forceinline__ Pref load_pref(const GramArgs& a, int c, long long s_begin, int lane, int w, int I,
                                           int J) {
     Pref p{};
@@ -43,6 +44,7 @@ __device__ __forceinline__ Pref load_pref(const GramArgs& a, int c, long long s_
     p.wt = 1.0;
     if (a.W) p.wt = a.W[a.w_abs ? s : (long long)idc];
     p.valid = valid;
+    if (RHS) p.yv = a.y[s];
     if (MODE == GRAM_CHAIN) {
         p.aI = a.anc[(long long)(I * (FB / GRP) + w) * a.tbl_ns + p.si];
         if (!DIAG) p.aJ = a.anc[(long long)(J * (FB / GRP) + w) * a.tbl_ns + p.si];
@@ -72,7 +74,10 @@ __device__ __forceinline__ double2 synth_elem(const GramArgs& a, const Pref& p, 
 // 0..2: one A fragment pair, three B fragment quads), warps 4-7 take the remaining pairs {(6,3),(7,3)}, {(2,0),(2,1)},
 // {(3,0),(3,1)}, {(0,0),(1,0)} which share either the A or the B fragments.  (Computing the three lower 64x64
 // sub-blocks instead costs 48 per sub-partition: measured 77.8 ms vs this layout on cfg2, see profiles/.)
-template <int MODE, bool DIAG>
+// RHS (diagonal tiles only, nrhs == 1): b_I = A_I' W y is accumulated by the threads that synthesise A_I anyway --
+// 2 FMAs per synthesised element in the 16 accumulator registers the diagonal layout leaves free -- instead of a second
+// pass over the anchor table (k_gram_rhs: 2.2 ms of a 85 ms step on cfg2).
+template <int MODE, bool DIAG, bool RHS = false>
 __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int prob, double* smem) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int wm = w & 3, wn = w >> 2;
@@ -93,6 +98,9 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     const bool maskI = ccI0 + GRP > a.ncc, maskJ = ccJ0 + GRP > a.ncc;
     // synthesise element j (of 8) of a chunk into stage buffer `st`.  CHAIN, off-diagonal: zJ is pre-scaled by the
     // sample weight (rotation is linear), so the J tile needs no per-element multiply.
+    double rc[RHS ? GRP : 1], rs[RHS ? GRP : 1];
+#pragma unroll
+    for (int j = 0; j < (RHS ? GRP : 1); j++) rc[j] = rs[j] = 0.0;
     auto synth_step = [&](const Pref& p, double2& zI, double2& zJ, int j, double* st) {
         double2 vI, vJ;
         if (MODE == GRAM_CHAIN) {
@@ -105,6 +113,10 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
         }
         if (maskI && ccI0 + j >= a.ncc) vI = make_double2(0.0, 0.0);
         if ((DIAG ? maskI : maskJ) && (DIAG ? ccI0 : ccJ0) + j >= a.ncc) vJ = make_double2(0.0, 0.0);
+        if (RHS) {  // p.yv already carries the (validity-resolved) weight
+            rc[j] = fma(vI.x, p.yv, rc[j]);
+            rs[j] = fma(vI.y, p.yv, rs[j]);
+        }
         double* sI = st;
         double* sJ = st + TILE_D;
         sI[rowc + j * LDT] = vI.x;
@@ -125,7 +137,10 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     auto chain_start_J = [&](const Pref& p) { return make_double2(p.aJ.x * p.wt, p.aJ.y * p.wt); };
 
     // prologue: chunk 0 into stage 0
-    auto resolve = [](Pref& p) { p.wt = p.valid ? p.wt : 0.0; };
+    auto resolve = [](Pref& p) {
+        p.wt = p.valid ? p.wt : 0.0;
+        if (RHS) p.yv *= p.wt;
+    };
     // 3-stage ring: full[s] completes when all 8 warps have stored their part of the chunk living in stage s.
     // A stage is rewritten two chunks after it was last read; passing full[] of the chunk in between proves every
     // warp has left that read, so no "empty" barrier is needed.
@@ -136,7 +151,7 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     }
     __syncthreads();
     // prologue: chunk 0 into stage 0
-    Pref p1 = load_pref<MODE, DIAG>(a, 0, s_begin, lane, w, I, J);
+    Pref p1 = load_pref<MODE, DIAG, RHS>(a, 0, s_begin, lane, w, I, J);
     resolve(p1);
     {
         double2 zI = p1.aI, zJ = chain_start_J(p1);
@@ -145,7 +160,7 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&full[0]);
-    if (nchunks > 1) p1 = load_pref<MODE, DIAG>(a, 1, s_begin, lane, w, I, J);
+    if (nchunks > 1) p1 = load_pref<MODE, DIAG, RHS>(a, 1, s_begin, lane, w, I, J);
     mbar_wait(&full[0], 0);
 
     // fragment bases: off-diagonal 32(M) x 64(N) warp tile; diagonal: per-piece offsets added below
@@ -179,7 +194,7 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
         double* nxt = smem + st_nxt * STAGE_D;
         const bool have_next = (c + 1 < nchunks);
         Pref p2 = p1;
-        if (c + 2 < nchunks) p2 = load_pref<MODE, DIAG>(a, c + 2, s_begin, lane, w, I, J);
+        if (c + 2 < nchunks) p2 = load_pref<MODE, DIAG, RHS>(a, c + 2, s_begin, lane, w, I, J);
         resolve(p1);  // p1 was loaded one iteration ago: no stall
         double2 zI = p1.aI, zJ = chain_start_J(p1);
         const double* pa = cur + fragA;
@@ -250,6 +265,23 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     // epilogue
     const int Np = a.nblk * TB;
     double* Gp = a.G + (long long)prob * a.strideG;
+    if (RHS) {
+        double* Bp = a.B + (long long)prob * a.strideB;
+#pragma unroll
+        for (int j = 0; j < GRP; j++) {
+            double vc = rc[j], vs = rs[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                vc += __shfl_xor_sync(0xffffffffu, vc, o);
+                vs += __shfl_xor_sync(0xffffffffu, vs, o);
+            }
+            if (lane == 0) {
+                const bool ok = ccI0 + j < a.ncc;
+                Bp[I * TB + w * GRP + j] = ok ? vc * a.bscale : 0.0;
+                Bp[I * TB + FB + w * GRP + j] = ok ? vs * a.bscale : 0.0;
+            }
+        }
+    }
     if (!DIAG) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -360,10 +392,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gram(const __grid_constant__ Gr
     extern __shared__ __align__(16) double smem[];
     int I, J;
     tile_ij(blockIdx.x, I, J);
-    if (I == J)
-        gram_tile<MODE, true>(a, I, J, blockIdx.y, smem);
-    else
+    if (I == J) {
+        if (a.fuse_rhs)
+            gram_tile<MODE, true, true>(a, I, J, blockIdx.y, smem);
+        else
+            gram_tile<MODE, true, false>(a, I, J, blockIdx.y, smem);
+    } else {
         gram_tile<MODE, false>(a, I, J, blockIdx.y, smem);
+    }
 }
 
 __global__ void k_anchor_table(const double* __restrict__ t, long long s0, long long ns,
@@ -435,7 +471,9 @@ void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
         if (a.B) b.B = a.B + (long long)p0 * a.strideB;
         dim3 grid(ntiles, np);
         dim3 grid_rhs(a.nblk, np);
-        const bool rhs = a.B && a.nrhs > 0 && a.y;
+        // a single right-hand side rides along in the diagonal tiles; two need the separate pass
+        b.fuse_rhs = (a.B && a.nrhs == 1 && a.y) ? 1 : 0;
+        const bool rhs = a.B && a.nrhs > 0 && a.y && !b.fuse_rhs;
         if (mode == GRAM_CHAIN) {
             k_gram<GRAM_CHAIN><<<grid, NTHREADS, smem, st>>>(b);
             if (rhs) k_gram_rhs<GRAM_CHAIN><<<grid_rhs, NTHREADS, 0, st>>>(b);

@@ -27,6 +27,7 @@ struct GramArgs {
     int ncc;  // valid complex columns (Nf, or Nf*Nvv for LPV)
     int nblk; // Np / 128
     int nrhs;
+    int fuse_rhs;  // set by launch_gram: b for nrhs == 1 is accumulated inside the diagonal tiles
     // GRAM_CHAIN tables, indexed [g * tbl_ns + (s - tbl_base)]
     const double2* anc;
     const double2* del;
