@@ -709,6 +709,8 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
     const long long Np = pl.Np, hop = n - noverlap;
     // batch: keep the per-batch Gram workspace <= ~6 GiB
     int64_t batch = c->window_batch > 0 ? c->window_batch : std::max<int64_t>(1, (6LL << 30) / (Np * Np * 8));
+    // whole waves: the one-CTA-per-window launches (k_potf2, the last TRSM / SYRK steps) then fill every SM
+    if (c->window_batch <= 0 && batch > c->sms) batch -= batch % c->sms;
     batch = std::min<int64_t>(batch, std::max<int64_t>(1, k_end - k_begin));
     std::vector<int> hinfo((size_t)batch);
     int bad = 0;
