@@ -12,6 +12,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace lpvs {
 
 namespace {
@@ -96,12 +98,13 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
 
     // masking is only needed when this warp's 8-column group is not entirely valid (warp-uniform)
     const bool maskI = ccI0 + GRP > a.ncc, maskJ = ccJ0 + GRP > a.ncc;
+    const bool any_mask = maskI || (!DIAG && maskJ);
     // synthesise element j (of 8) of a chunk into stage buffer `st`.  CHAIN, off-diagonal: zJ is pre-scaled by the
     // sample weight (rotation is linear), so the J tile needs no per-element multiply.
     double rc[RHS ? GRP : 1], rs[RHS ? GRP : 1];
 #pragma unroll
     for (int j = 0; j < (RHS ? GRP : 1); j++) rc[j] = rs[j] = 0.0;
-    auto synth_step = [&](const Pref& p, double2& zI, double2& zJ, int j, double* st) {
+    auto synth_step = [&](auto masked, const Pref& p, double2& zI, double2& zJ, int j, double* st) {
         double2 vI, vJ;
         if (MODE == GRAM_CHAIN) {
             vI = zI;
@@ -111,8 +114,10 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
             vJ = DIAG ? vI : synth_elem<MODE>(a, p, min(ccJ0 + j, a.ncc - 1));
             vJ = make_double2(vJ.x * p.wt, vJ.y * p.wt);
         }
-        if (maskI && ccI0 + j >= a.ncc) vI = make_double2(0.0, 0.0);
-        if ((DIAG ? maskI : maskJ) && (DIAG ? ccI0 : ccJ0) + j >= a.ncc) vJ = make_double2(0.0, 0.0);
+        if constexpr (decltype(masked)::value) {  // only the last (partial) 8-column group of a basis needs this
+            if (maskI && ccI0 + j >= a.ncc) vI = make_double2(0.0, 0.0);
+            if ((DIAG ? maskI : maskJ) && (DIAG ? ccI0 : ccJ0) + j >= a.ncc) vJ = make_double2(0.0, 0.0);
+        }
         if (RHS) {  // p.yv already carries the (validity-resolved) weight
             rc[j] = fma(vI.x, p.yv, rc[j]);
             rs[j] = fma(vI.y, p.yv, rs[j]);
@@ -156,7 +161,7 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     {
         double2 zI = p1.aI, zJ = chain_start_J(p1);
 #pragma unroll
-        for (int j = 0; j < GRP; j++) synth_step(p1, zI, zJ, j, smem);
+        for (int j = 0; j < GRP; j++) synth_step(std::true_type{}, p1, zI, zJ, j, smem);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&full[0]);
@@ -205,15 +210,20 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
                 if (SYNTH_BURST) {
                     // whole next chunk in one burst: fewer DMMA<->DFMA interleave points (79.1 -> 77.7 ms)
                     if (kk == burst_kk) {
+                        if (any_mask) {  // warp-uniform: the masked variant costs 128 selects per chunk
 #pragma unroll
-                        for (int j = 0; j < GRP; j++) synth_step(p1, zI, zJ, j, nxt);
+                            for (int j = 0; j < GRP; j++) synth_step(std::true_type{}, p1, zI, zJ, j, nxt);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < GRP; j++) synth_step(std::false_type{}, p1, zI, zJ, j, nxt);
+                        }
                     } else if (kk == burst_kk + 1) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&full[st_nxt]);
                     }
                 } else if (kk < GRP / 2) {  // the next chunk is synthesised in the first half of this one ...
-                    synth_step(p1, zI, zJ, 2 * kk, nxt);
-                    synth_step(p1, zI, zJ, 2 * kk + 1, nxt);
+                    synth_step(std::true_type{}, p1, zI, zJ, 2 * kk, nxt);
+                    synth_step(std::true_type{}, p1, zI, zJ, 2 * kk + 1, nxt);
                 } else if (kk == GRP / 2) {  // ... and published half a chunk before anyone needs it
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&full[st_nxt]);
