@@ -11,7 +11,7 @@ NCU="ncu --clock-control none"
 python bench.py --steps 2 --warmup 1 --cpu-windows 2 > $OUT/plain_$TAG.json 2> $OUT/plain_$TAG.err || { echo "plain bench failed"; exit 1; }
 $NCU --metrics gpu__time_duration.sum -c 600 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --cpu-windows 2 > $OUT/ncu_launches_$TAG.log 2>&1
-$NCU --set full --import-source on -k "regex:^k_gram$" -s 10 -c 1 -o $OUT/gram_$TAG -f \
+$NCU --set full --import-source on -k "regex:^k_gram$" -s 2 -c 1 -o $OUT/gram_$TAG -f \
     python bench.py --steps 2 --warmup 1 --cpu-windows 2 --no-admm > $OUT/ncu_gram_$TAG.log 2>&1
 python tools/admm_run.py 200 cfg3 > $OUT/plain_admm3_$TAG.log 2>&1 || { echo "plain admm cfg3 failed"; exit 1; }
 $NCU --set full --import-source on -k regex:k_admm_symv -c 1 -o $OUT/admm3_$TAG -f \
