@@ -125,3 +125,38 @@ def test_bad_arguments_return_codes(ctx):
     rc = ctx.lib.lpvs_admm_create_fourier(ctx.h, vp(y), vp(t), 64, vp(f), 2, None, L.PROX_L1, 0.1, 0.0, None, 0, 0.0,
                                           C.byref(h))
     assert rc == L.E_BAD_ARG  # mu must be in (0, 1]
+    # windowed sparse entry point: same validation sites
+    sp = lambda kind, u, prox, mu, k1: ctx.lib.lpvs_ls_window_sparse_sums(  # noqa: E731
+        ctx.h, kind, vp(y), u, vp(t), 64, vp(f), 2, vp(W), 16, 8, prox, 0.1, mu, 10, 1e-6, 0, k1, vp(sums), None, None,
+        C.byref(info))
+    assert sp(L.WIN_PSD, None, L.PROX_GROUP_L2, 0.05, 1) == L.E_BAD_ARG      # group prox is LPV only
+    assert sp(L.WIN_PSD, None, L.PROX_L1, 1.5, 1) == L.E_BAD_ARG             # mu in (0, 1]
+    assert sp(L.WIN_CSD, None, L.PROX_L1, 0.05, 1) == L.E_BAD_ARG            # second signal required
+    assert sp(L.WIN_PSD, None, L.PROX_L1, 0.05, 99) == L.E_BAD_ARG           # window range
+    assert sp(L.WIN_PSD, None, L.PROX_L1, 0.05, 1) == L.OK
+
+
+def test_windowed_sparse_direct_call_outputs(ctx):
+    """lpvs_ls_window_sparse_sums through ctypes: per-window iteration counts / residuals come back per channel, a
+    zero-iteration budget leaves z = x0 = 0 (sums exactly zero), and tol = inf stops every window after one iteration."""
+    from lpvspectral_jl_b200 import _lib as L
+
+    t, y = sig(1200, 9)
+    u = np.roll(y, 3).copy()
+    f = np.arange(1, 20) * 0.6
+    n, nov = 200, 100
+    W = np.hanning(n)
+    K = int(ctx.lib.lpvs_window_count(len(y), n, nov))
+    sums = np.ones(4 * len(f))
+    its = np.full(2 * K, -1, dtype=np.int64)
+    res = np.full(2 * K, -1.0)
+    info = C.c_int(0)
+    call = lambda iters, tol: ctx.lib.lpvs_ls_window_sparse_sums(  # noqa: E731
+        ctx.h, L.WIN_COHERE, vp(y), vp(u), vp(t), len(y), vp(f), len(f), vp(W), n, nov, L.PROX_L1, 0.05, 0.05, iters,
+        tol, 0, K, vp(sums), vp(its), vp(res), C.byref(info))
+    assert call(0, 1e-9) == L.OK
+    assert np.all(sums == 0.0) and np.all(its == 0)
+    assert call(50, np.inf) == L.OK
+    assert np.all(its == 1) and np.all(res >= 0.0) and np.any(sums != 0.0)
+    assert call(300, 1e-7) == L.OK
+    assert its.min() >= 2 and its.max() <= 300 and np.all(res[its < 300] < 1e-7)
