@@ -119,3 +119,31 @@ def test_cfg4_group_lasso_full_size_variants_agree(ctx):
     assert rel(out[1][1]["z"], out[0][1]["z"]) <= 1e-10
     p = lp.psd(out[1][0])
     assert set((np.argsort(-p)[:3] + 1).tolist()) == {5, 25, 50}  # 2, 10, 20 Hz on the 0.4 Hz grid
+
+
+def test_cfg2_windowed_sparse_full_size_properties(ctx):
+    """cfg2's record through the batched windowed-sparse path (2047 device ADMM problems in one pass):
+    every window stops on its own test, only the planted tones survive the L1 threshold, and single windows of the
+    batched kernel (one CTA per window) reproduce the single-problem solver (cooperative multi-CTA kernel) -- two
+    independent x-update kernels -- including the iteration count, at the first, a middle and the last window."""
+    import bench
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+
+    t, y, f, n = bench.make_cfg2()
+    kw = dict(iters=3000, tol=1e-9)
+    S1, _ = lp.ls_windowpsd(y, t, f, nw=1024, window_func=lp.hanning, estimator=lp.ls_sparse_spectral,
+                            proxg=lp.NormL1(2.0), ctx=ctx, **kw)
+    its = ctx.last_window_iters
+    assert its.shape == (2047, 1) and 2 <= its.min() and its.max() < 3000
+    assert set(np.flatnonzero(S1).tolist()) == {40, 100}  # only the two planted tones survive the threshold
+    W = lp.hanning(n)
+    hop = n >> 1
+    for k in (0, 1023, 2046):
+        sl = slice(k * hop, k * hop + n)
+        x, _, info = lp.ls_sparse_spectral(y[sl], t[sl], f, W, proxg=lp.NormL1(2.0), ctx=ctx, return_info=True,
+                                           printerval=10 ** 9, **kw)
+        s, i, _ = lp.window_sparse_sums(L.WIN_PSD, y, None, t, f, W, n, hop, lp.NormL1(2.0), 0.05, 3000, 1e-9, k, k + 1,
+                                        ctx=ctx, return_info=True)
+        assert int(i[0, 0]) == info["iters"] == int(its[k, 0])
+        assert rel(s, x.real ** 2 + x.imag ** 2) <= 1e-10
