@@ -41,7 +41,8 @@ struct GramArgs {
     int lpv_nf;
     // output
     double gscale, bscale;
-    double* G;  // per problem Np x Np row-major, lower tiles written (full 128x128 tiles on the diagonal)
+    double* G;  // per problem Np x Np row-major: lower 128x128 tiles; of a diagonal tile only the 16x32 pieces that touch
+                // the lower triangle are written -- entries above the diagonal are unspecified, no consumer reads them
     long long strideG;
     double* B;  // per problem [2][Np]
     long long strideB;
