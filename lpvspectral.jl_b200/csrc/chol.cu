@@ -206,29 +206,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ C
     __syncthreads();
     POTF2_TR(1)
 
+    // Left-looking over 16-column panels with look-ahead: while warp 0 runs the serial 16x16 factor + inverse of panel p
+    // (5.7 K cycles, tools/potf2_probe.cu), warps 1-7 already apply the finished columns [0, 16p) to panel p+1, so after
+    // the panel's TRSM only its own rank-16 contribution to panel p+1 is left.  Every tile is read-modify-written a few
+    // times with long DMMA chains instead of once per panel with chains of 4.
     for (int p = 0; p < TB / PB; p++) {
         const int j0 = p * PB;
         double* Di = Dinv + p * PB * LDP;
-        if (warp == 0)
+        const int nt = (TB - j0 - PB) >> 3;  // 8-row tiles below the panel's diagonal block
+        if (warp == 0) {
             warp_potf2_inv(S + j0 * LDS + j0, LDS, Di, LDP, LT, colbuf, lane, &a.info[prob], k * TB + j0, tol);
+        } else if (nt > 0 && j0 > 0) {
+            // panel p+1 (columns j0+16 .. j0+31, rows >= j0+16) -= L[rows, 0:j0) * L[j0+16 .. j0+31, 0:j0)'
+            const double* Brow = S + (j0 + PB) * LDS;
+            for (int ti = warp - 1; ti < nt; ti += NTHREADS / 32 - 1)
+                warp_mma_row<true, 2>(S + (j0 + PB + 8 * ti) * LDS + j0 + PB, LDS, S + (j0 + PB + 8 * ti) * LDS, LDS, Brow,
+                                      LDS, 0, j0, 2, -1.0, true, lane);
+        }
         __syncthreads();
         POTF2_TR(2 + 2 * p)
-        const int nt = (TB - j0 - PB) >> 3;  // 8-row tiles below the panel's diagonal block
         if (nt > 0) {
             double* P = S + (j0 + PB) * LDS + j0;  // panel below the diagonal block
             // P <- P * Dinv' in place (a warp owns whole tile rows)
             for (int ti = warp; ti < nt; ti += NTHREADS / 32)
                 warp_mma_row<true, 2>(P + 8 * ti * LDS, LDS, P + 8 * ti * LDS, LDS, Di, LDP, 0, PB, 2, 1.0, false, lane);
             __syncthreads();
-            // trailing update of the lower tiles: S22 -= P P', units of (tile row, up to 4 tiles) round-robin
-            double* S22 = S + (j0 + PB) * LDS + j0 + PB;
-            int cnt = 0;
-            for (int ti = nt - 1; ti >= 0; ti--)
-                for (int g = 0; g <= ti; g += 4) {
-                    if ((cnt++ & 7) == warp)
-                        warp_mma_row<true, 4>(S22 + 8 * ti * LDS + 8 * g, LDS, P + 8 * ti * LDS, LDS, P + 8 * g * LDS,
-                                              LDS, 0, PB, min(4, ti + 1 - g), -1.0, true, lane);
-                }
+            // panel p+1 -= P P[0:16]'  (this panel's own contribution)
+            for (int ti = warp; ti < nt; ti += NTHREADS / 32)
+                warp_mma_row<true, 2>(S + (j0 + PB + 8 * ti) * LDS + j0 + PB, LDS, P + 8 * ti * LDS, LDS, P, LDS, 0, PB, 2,
+                                      -1.0, true, lane);
             __syncthreads();
         }
         POTF2_TR(3 + 2 * p)
