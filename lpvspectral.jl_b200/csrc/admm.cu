@@ -1007,7 +1007,7 @@ int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q
     }
     cudaMemsetAsync(ca.info, 0, sizeof(int), c->st);
     launch_diag_prepare(d_G, NN, Np, h->ncc, h->zero_first, nullptr, 1.0 / h->mu, 1, c->st);
-    c->launches += 1 + potrf(ca, 1, c->sms, c->st);
+    c->launches += 1 + potrf(ca, 1, c->sms, c->st, &c->la);
     int pinfo = 0;
     cudaMemcpyAsync(&pinfo, ca.info, sizeof(int), cudaMemcpyDeviceToHost, c->st);
     cudaError_t e = cudaStreamSynchronize(c->st);

@@ -350,7 +350,7 @@ int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, doub
     if (!ca.Linv || !ca.info) return fail(c, LPVS_E_NOMEM, "out of device memory (factor workspace)");
     LPVS_CU(c, cudaMemsetAsync(ca.info, 0, sizeof(int) * nproblems, c->st));
     launch_diag_prepare(d_G, ca.strideG, Np, ncc, zero_first, nullptr, ridge, nproblems, c->st);
-    c->launches += 1 + potrf(ca, nproblems, c->sms, c->st);
+    c->launches += 1 + potrf(ca, nproblems, c->sms, c->st, &c->la);
     if (d_B && nrhs > 0) {
         launch_trsv(ca, d_B, 2LL * Np, nrhs, nproblems, c->st, fuse_fwd);
         c->launches++;
@@ -418,6 +418,9 @@ int lpvs_init(int device, lpvs_ctx** out) {
         return LPVS_E_CUDA;
     }
     c->st = c->own_st;
+    cudaStreamCreateWithFlags(&c->la.aux, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->la.e_trsm, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->la.e_rest, cudaEventDisableTiming);
     cudaEventCreate(&c->ev_call0);
     cudaEventCreate(&c->ev_call1);
     if (cudaMalloc(&c->d_nonfinite, sizeof(int)) != cudaSuccess) c->d_nonfinite = nullptr;
@@ -437,6 +440,9 @@ void lpvs_destroy(lpvs_ctx* c) {
     cudaEventDestroy(c->ev_call0);
     cudaEventDestroy(c->ev_call1);
     cudaStreamDestroy(c->own_st);
+    if (c->la.aux) cudaStreamDestroy(c->la.aux);
+    if (c->la.e_trsm) cudaEventDestroy(c->la.e_trsm);
+    if (c->la.e_rest) cudaEventDestroy(c->la.e_rest);
     delete c;
 }
 

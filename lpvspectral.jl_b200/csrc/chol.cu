@@ -362,6 +362,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const __grid_constant__ Ch
             C = G + (long long)i * TB * Np + (long long)j * TB;
             K = TB; alpha = -1.0; beta = 1.0;
         } break;
+        case GM_SYRK_COL: {
+            int i = k + 1 + t, j = k + 1;
+            A = G + (long long)i * TB * Np + (long long)k * TB; lda = Np;
+            B = G + (long long)j * TB * Np + (long long)k * TB; ldb = Np;
+            C = G + (long long)i * TB * Np + (long long)j * TB;
+            K = TB; alpha = -1.0; beta = 1.0;
+        } break;
+        case GM_SYRK_REST: {
+            int ii, jj;
+            tile_ij(t, ii, jj);
+            int i = k + 2 + ii, j = k + 2 + jj;
+            A = G + (long long)i * TB * Np + (long long)k * TB; lda = Np;
+            B = G + (long long)j * TB * Np + (long long)k * TB; ldb = Np;
+            C = G + (long long)i * TB * Np + (long long)j * TB;
+            K = TB; alpha = -1.0; beta = 1.0;
+        } break;
         case GM_SYRK_LEFT: {
             int i = k + t;
             A = G + (long long)i * TB * Np; lda = Np;
@@ -907,10 +923,32 @@ void launch_trsv(const CholArgs& a, double* B, long long strideB, int nrhs, int 
     k_trsv<<<nproblems, NTHREADS, 0, st>>>(a, B, strideB, nrhs, fwd_done ? 1 : 0);
 }
 
-int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st) {
+int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st, const Lookahead* la) {
     int launches = 0;
     const int nb = a.nb;
     const bool left = (long long)nproblems * nb >= 2LL * sms;
+    if (!left && la && nb >= 4) {
+        // right-looking with look-ahead: main stream = potf2 / TRSM / next-panel update, aux = the rest of the update
+        launch_potf2(a, 0, nproblems, st);
+        launches++;
+        for (int k = 0; k + 1 < nb; k++) {
+            const int m = nb - k - 1;
+            launch_gemm(GM_TRSM, a, k, m, nproblems, st);
+            cudaEventRecord(la->e_trsm, st);
+            if (k > 0) cudaStreamWaitEvent(st, la->e_rest, 0);  // block column k+1 carries the updates up to k-1
+            launch_gemm(GM_SYRK_COL, a, k, m, nproblems, st);
+            launch_potf2(a, k + 1, nproblems, st);
+            launches += 3;
+            if (m > 1) {
+                cudaStreamWaitEvent(la->aux, la->e_trsm, 0);
+                launch_gemm(GM_SYRK_REST, a, k, (m - 1) * m / 2, nproblems, la->aux);
+                launches++;
+            }
+            cudaEventRecord(la->e_rest, la->aux);
+        }
+        cudaStreamWaitEvent(st, la->e_rest, 0);
+        return launches;
+    }
     for (int k = 0; k < nb; k++) {
         if (left && k > 0) {
             launch_gemm(GM_SYRK_LEFT, a, k, nb - k, nproblems, st);

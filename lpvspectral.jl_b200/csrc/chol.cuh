@@ -13,7 +13,16 @@ enum GemmMode {
     GM_SYRK_LEFT = 2,  // A_ik -= sum_{j<k} A_ij A_kj'                  (i >= k)
     GM_TRTRI_A = 3,    // Y_ki  = Y[k, k:i) * L[i, k:i)'                (k < i)
     GM_TRTRI_B = 4,    // Y_ki <- -Y_ki * Linv_ii'
-    GM_LAUUM = 5       // M_ab  = Y[a, a:nb) * Y[b, a:nb)'              (a >= b), M written into G
+    GM_LAUUM = 5,      // M_ab  = Y[a, a:nb) * Y[b, a:nb)'              (a >= b), M written into G
+    GM_SYRK_COL = 6,   // GM_SYRK_RIGHT restricted to block column k+1  (the next panel: look-ahead)
+    GM_SYRK_REST = 7   // GM_SYRK_RIGHT for block columns >= k+2
+};
+
+// Look-ahead for ONE large problem (right-looking): the trailing update of columns >= k+2 runs on `aux` while the next
+// diagonal block is factorised on the main stream.  Null = plain in-order factorisation.
+struct Lookahead {
+    cudaStream_t aux;
+    cudaEvent_t e_trsm, e_rest;
 };
 
 struct CholArgs {
@@ -56,7 +65,7 @@ void launch_max_diag(const double* G, long long strideG, int Np, int ncc, int ze
                      int nproblems, cudaStream_t st);
 
 // full factorisation driver (left-looking when batched, right-looking for few large problems); returns launches
-int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st);
+int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st, const Lookahead* la = nullptr);
 // after potrf: M = (L L')^{-1} written (full symmetric) into G; uses Y. returns launches
 int potri(const CholArgs& a, int nproblems, cudaStream_t st);
 

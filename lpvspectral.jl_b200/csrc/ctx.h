@@ -30,6 +30,7 @@ struct lpvs_ctx {
     int sms = 148;
     cudaStream_t st = nullptr;      // stream in use
     cudaStream_t own_st = nullptr;  // the context's own stream
+    lpvs::Lookahead la{};           // aux stream + events of the look-ahead factorisation (single large problems)
     std::string err;
     std::mutex mu;
     int phase_mode = LPVS_PHASE_AUTO;

@@ -266,7 +266,7 @@ int lpvs_ls_spectral_lpv(lpvs_ctx* c, const double* Y, const double* X, const do
         ca.nb = pl.nblk;
         LPVS_CU(c, cudaMemsetAsync(ca.info, 0, sizeof(int), c->st));
         launch_diag_prepare(d_G2, NN, pl.Np, pl.ncc, 0, nullptr, lambda, 1, c->st);
-        c->launches += 1 + potrf(ca, 1, c->sms, c->st);
+        c->launches += 1 + potrf(ca, 1, c->sms, c->st, &c->la);
         LPVS_CU(c, cudaMemcpyAsync(&pinfo, ca.info, sizeof(int), cudaMemcpyDeviceToHost, c->st));
         LPVS_CU(c, cudaStreamSynchronize(c->st));
         if (pinfo) {
