@@ -657,6 +657,7 @@ __global__ void __launch_bounds__(TRSV_T, 2) k_trsv_bwd(const __grid_constant__ 
     const double* L = a.G + (long long)prob * a.strideG;
     const double* Linv = a.Linv + (long long)prob * a.strideLinv;
     double* b = Bm + (long long)prob * strideB;
+    if (__ldcg(a.info + prob) != 0) return;  // broken factorisation: nothing to solve
     for (int q = tid; q < 2 * Np; q += TRSV_T) xs[q] = (q / Np) < nrhs ? __ldcg(b + q) : 0.0;
     __syncthreads();
     for (int kb = a.nb - 1; kb >= 0; kb--) {
@@ -723,6 +724,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trsv_big(const __grid_constant_
     const int i = blockIdx.x;
     const long long Np = a.Np;
     const double* L = a.G;
+    if (__ldcg(a.info) != 0) return;  // broken factorisation (set before this launch): every CTA leaves, the host retries
     __shared__ double r[2][TB];     // this CTA's running right-hand side block
     __shared__ double yk[2][TB];    // the published solution block of the current step
     __shared__ double part[2][2][TB];
