@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "ctx.h"
@@ -1110,7 +1111,9 @@ int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q
             const double frac = std::min(1.0, keep_bytes / ((double)T * blk_bytes));
             for (int cta_i = 0; cta_i < grid; cta_i++) {
                 long long nblk = T * (cta_i + 1) / grid - T * cta_i / grid;
-                persist[cta_i] = (int)(frac * (double)nblk);
+                // rounded, not truncated: a CTA that owns one block more keeps one block more in L2, so the number
+                // of blocks STREAMED from HBM -- what phase 1 waits for -- is the same for every CTA
+                persist[cta_i] = (int)std::lround(frac * (double)nblk);
             }
         }
         // sparse exchange: slots = the 128-blocks of y each CTA touches (block column J and block rows I of its
