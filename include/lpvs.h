@@ -31,7 +31,7 @@ enum lpvs_status {
     LPVS_OK = 0,
     LPVS_E_BAD_ARG = -1,     /* reference: ArgumentError / @assert sites (src/lsfft.jl:22, src/windows.jl:31,96, src/lasso.jl:143) */
     LPVS_E_NOT_SPD = -2,     /* Cholesky breakdown; *info = 1-based failing pivot */
-    LPVS_E_NONFINITE = -3,
+    LPVS_E_NONFINITE = -3,   /* NaN/Inf in an input array, or a 0/0 LPV basis normalisation (coulomb with V == 0; the reference returns NaNs) */
     LPVS_E_CUDA = -4,
     LPVS_E_NCCL = -5,        /* reserved: collectives live in the host (torch.distributed / NCCL), not in liblpvs */
     LPVS_E_UNSUPPORTED = -6, /* device older than sm_100, or a problem too large for the resident ADMM vector */

@@ -380,6 +380,10 @@ int inputs_finite(lpvs_ctx* c) {
     int h = 0;
     if (c->d_nonfinite) LPVS_CU(c, cudaMemcpyAsync(&h, c->d_nonfinite, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     LPVS_CU(c, cudaStreamSynchronize(c->st));
+    if (h & 2)
+        return fail(c, LPVS_E_NONFINITE,
+                    "LPV basis normalisation is 0/0 for some sample: with coulomb=true a scheduling value whose sign "
+                    "matches no centre (V == 0) activates no basis function (the reference returns NaNs here)");
     if (h) return fail(c, LPVS_E_NONFINITE, "non-finite value (NaN/Inf) in an input array");
     return LPVS_OK;
 }

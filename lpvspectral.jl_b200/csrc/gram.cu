@@ -431,7 +431,7 @@ __global__ void k_anchor_table(const double* __restrict__ t, long long s0, long 
 __global__ void k_lpv_tables(const double* __restrict__ X, const double* __restrict__ V, long long N,
                              const double* __restrict__ w, int Nf, int Nvv, const double* __restrict__ centers,
                              double gamma, int coulomb, int normalize, double2* __restrict__ E,
-                             double* __restrict__ Kt) {
+                             double* __restrict__ Kt, int* __restrict__ nonfinite) {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
     double x = X[s], v = V[s];
@@ -453,6 +453,9 @@ __global__ void k_lpv_tables(const double* __restrict__ X, const double* __restr
     }
     if (normalize) {
         for (int k = 0; k < Nvv; k++) Kt[(long long)k * N + s] /= sum;
+        // coulomb masks every basis function when sign(v) matches no centre (v == 0): 0/0, as in the reference
+        // (src/lsfft.jl:199-207), which then returns NaNs; reported as LPVS_E_NONFINITE instead
+        if (nonfinite && !(sum > 0.0 && isfinite(sum))) atomicOr(nonfinite, 2);
     }
 }
 
@@ -505,9 +508,9 @@ void launch_anchor_table(const double* t, long long s0, long long ns, const doub
 
 void launch_lpv_tables(const double* X, const double* V, long long N, const double* w, int Nf, int Nvv,
                        const double* centers, double gamma, int coulomb, int normalize, double2* E, double* Kt,
-                       cudaStream_t st) {
+                       int* nonfinite, cudaStream_t st) {
     k_lpv_tables<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(X, V, N, w, Nf, Nvv, centers, gamma, coulomb,
-                                                              normalize, E, Kt);
+                                                              normalize, E, Kt, nonfinite);
 }
 
 }  // namespace lpvs

@@ -58,6 +58,6 @@ void launch_anchor_table(const double* t, long long s0, long long ns, const doub
 // LPV factor tables: E[fi][s] = (cos, -sin)(w_fi * X_s) (reference rounding), Kt[ki][s] = RBF activations
 void launch_lpv_tables(const double* X, const double* V, long long N, const double* w, int Nf, int Nvv,
                        const double* centers, double gamma, int coulomb, int normalize, double2* E, double* Kt,
-                       cudaStream_t st);
+                       int* nonfinite /* device flag, bit 2 set on a 0/0 normalisation; nullable */, cudaStream_t st);
 
 }  // namespace lpvs

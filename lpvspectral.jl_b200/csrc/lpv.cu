@@ -138,7 +138,7 @@ int lpv_prepare(lpvs_ctx* c, const double* X, const double* V, int64_t N, const 
     double2* E = ws<double2>(c, BUF_E, (size_t)Nf * N);
     double* K = ws<double>(c, BUF_K, (size_t)pl->Nvv * N);
     if (!E || !K) return fail(c, LPVS_E_NOMEM, "out of device memory (LPV tables)");
-    launch_lpv_tables(d_X, d_V, N, d_w, Nf, pl->Nvv, d_cen, gamma, coulomb, normalize, E, K, c->st);
+    launch_lpv_tables(d_X, d_V, N, d_w, Nf, pl->Nvv, d_cen, gamma, coulomb, normalize, E, K, c->d_nonfinite, c->st);
     c->launches++;
     pl->d_E = E;
     pl->d_K = K;
@@ -233,6 +233,7 @@ int lpvs_ls_spectral_lpv(lpvs_ctx* c, const double* Y, const double* X, const do
     if (Sigma) LPVS_CU(c, cudaMemcpyAsync(d_G + NN, d_G, sizeof(double) * NN, cudaMemcpyDeviceToDevice, c->st));
     int pinfo = 0;
     if ((rc = factor_solve(c, pl.ncc, 0, pl.Np, d_G, d_B, 1, lambda * lambda, 1, &pinfo))) return rc;
+    if ((rc = inputs_finite(c))) return rc;  // NaN inputs / 0/0 basis normalisation: the cause, not "not SPD"
     LPVS_CU(c, cudaStreamSynchronize(c->st));
     if (pinfo) {
         if (info) *info = pinfo;
@@ -406,7 +407,8 @@ int lpvs_admm_create_lpv(lpvs_ctx* c, const double* y, const double* X, const do
     if ((rc = admm_set_groups(c, h, goff, gmem)) || (rc = admm_finish_create(c, h, d_G, d_B, nullptr)) ||
         (rc = inputs_finite(c))) {
         admm_delete(h);
-        return rc;
+        const int rcf = inputs_finite(c);  // a NaN basis breaks the factorisation first: report the cause
+        return rcf ? rcf : rc;
     }
     gram_timer_resolve(c);
     *out = h;

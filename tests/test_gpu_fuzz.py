@@ -70,3 +70,89 @@ def test_random_windowed(ctx, seed):
         S, _ = lp.ls_cohere(y, u, t, f, nw=nw, noverlap=nov, ctx=ctx)
         Sr, _ = o.ls_cohere(y, u, t, f, nw=nw, noverlap=nov, mode="gram")
     assert rel(S, Sr) <= 1e-8, (N, n, Nf, nov, kind)
+
+
+def support(z):
+    return set(np.flatnonzero(np.asarray(z) != 0).tolist())
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("symv", [0, 1])
+def test_random_sparse_lpv(ctx, seed, symv):
+    """Group lasso over random (Nf, Nv): group sizes from 4 to 60, vectors with and without tile padding, both x-update
+    kernels (GEMV over the full inverse / SYMV over its lower triangle with the ADMM-order permutation and whole groups
+    per CTA), coulomb on odd seeds (uncovered entries)."""
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+
+    rng = np.random.default_rng(500 + seed)
+    N = int(rng.integers(300, 900))
+    Nf = int(rng.integers(2, 14))
+    Nv = int(rng.integers(2, 31))
+    coul = bool(seed % 2)
+    Y, V, X = o.generate_lpv_signal(N, seed=seed)
+    if coul:
+        V = V - 0.5 + 1e-3  # no sample exactly at 0 (see test_coulomb_zero_sample_is_reported)
+    w = 2 * np.pi * np.sort(rng.choice(np.arange(1, 30), size=Nf, replace=False)).astype(float)
+    kw = dict(iters=600, tol=1e-8, mu=0.05)
+    lam = float(rng.choice([0.5, 2.0, 5.0]))
+    ctx.set_option(L.OPT_ADMM_SYMV, symv)
+    try:
+        se, info = lp.ls_sparse_spectral_lpv(Y, X, V, w, Nv, lam=lam, coulomb=coul, ctx=ctx, return_info=True, **kw)
+    finally:
+        ctx.set_option(L.OPT_ADMM_SYMV, -1)
+    sr, ri = o.ls_sparse_spectral_lpv(Y, X, V, w, Nv, lam=lam, coulomb=coul, mode="gram", return_info=True,
+                                      printerval=10 ** 9, **kw)
+    assert info["iters"] == ri["iters"], (N, Nf, Nv, coul, lam)
+    assert support(info["z"]) == support(ri["z"])
+    assert rel(info["z"], ri["z"]) <= 1e-8 if np.linalg.norm(ri["z"]) > 0 else np.all(info["z"] == 0)
+    assert rel(info["x"], ri["x"]) <= 1e-8
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_sparse_fourier(ctx, seed):
+    """ls_sparse_spectral over random shapes and every Fourier prox operator, weighted (Quadratic, sign quirk) on odd
+    seeds: identical iteration count and support, iterates to 1e-8."""
+    import lpvspectral_jl_b200 as lp
+
+    rng, N, Nf, t, f, y = _case(200 + seed)
+    N = min(N, 900)
+    t, y = t[:N], y[:N]
+    Nf = min(Nf, 150)
+    f = f[:Nf]
+    W = 0.3 + rng.random(N) if seed % 2 else None
+    pg, pgo = [(lp.NormL1(0.3), o.NormL1(0.3)), (lp.NormL0(0.05), o.NormL0(0.05)),
+               (lp.IndBallL0(5), o.IndBallL0(5))][seed % 3]
+    kw = dict(iters=500, tol=1e-9, mu=0.05)
+    x, _, info = lp.ls_sparse_spectral(y, t, f, W, proxg=pg, ctx=ctx, return_info=True, **kw)
+    xr, _, ri = o.ls_sparse_spectral(y, t, f, W, proxg=pgo, mode="gram", return_info=True, printerval=10 ** 9, **kw)
+    assert info["iters"] == ri["iters"], (N, Nf, seed)
+    assert support(info["z"]) == support(ri["z"])
+    assert rel(info["z"], ri["z"]) <= 1e-8
+
+
+def test_coulomb_zero_sample_is_reported(ctx):
+    """coulomb=true masks every basis function for a scheduling value whose sign matches no centre (V == 0), so the
+    reference's normalisation K/sum(K) is 0/0 and it returns NaNs (src/lsfft.jl:199-207).  The library reports the cause
+    (LPVS_E_NONFINITE) instead of a misleading factorisation failure; found by the random-shape tests."""
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+
+    Y, V, X = o.generate_lpv_signal(401, seed=1)
+    V = V - 0.5
+    assert np.any(V == 0.0)
+    w = 2 * np.pi * np.array([2.0, 10.0])
+    with pytest.raises(lp.LpvsError) as e1:
+        lp.ls_sparse_spectral_lpv(Y, X, V, w, 6, lam=1.0, coulomb=True, iters=50, ctx=ctx)
+    assert e1.value.code == L.E_NONFINITE and "0/0" in str(e1.value)
+    with pytest.raises(lp.LpvsError) as e2:
+        lp.ls_spectral_lpv(Y, X, V, w, 6, lam=0.05, coulomb=True, ctx=ctx)
+    assert e2.value.code == L.E_NONFINITE
+    # the oracle (like the reference) just propagates NaN
+    sr = o.ls_spectral_lpv(Y, X, V, w, 6, lam=0.05, coulomb=True, mode="gram")
+    assert not np.all(np.isfinite(sr.x))
+    # and without the offending sample everything is fine
+    keep = V != 0.0
+    se = lp.ls_spectral_lpv(Y[keep], X[keep], V[keep], w, 6, lam=0.05, coulomb=True, ctx=ctx)
+    so = o.ls_spectral_lpv(Y[keep], X[keep], V[keep], w, 6, lam=0.05, coulomb=True, mode="gram")
+    assert rel(se.x, so.x) <= 1e-9
