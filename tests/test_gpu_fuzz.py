@@ -156,3 +156,31 @@ def test_coulomb_zero_sample_is_reported(ctx):
     se = lp.ls_spectral_lpv(Y[keep], X[keep], V[keep], w, 6, lam=0.05, coulomb=True, ctx=ctx)
     so = o.ls_spectral_lpv(Y[keep], X[keep], V[keep], w, 6, lam=0.05, coulomb=True, mode="gram")
     assert rel(se.x, so.x) <= 1e-9
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_ls_spectral_lpv(ctx, seed):
+    """Dense LPV estimator over random (N, Nf, Nv), all four coulomb / normalize combinations: parameters, covariance
+    and fraction of variance explained vs the oracle."""
+    import warnings
+
+    import lpvspectral_jl_b200 as lp
+
+    rng = np.random.default_rng(900 + seed)
+    N = int(rng.integers(200, 1500))
+    Nf = int(rng.integers(1, 12))
+    Nv = int(rng.integers(2, 25))
+    coul, norm = bool(seed & 1), bool(seed & 2)
+    Y, V, X = o.generate_lpv_signal(N, seed=seed)
+    if coul:
+        V = V - 0.5 + 1e-3
+    w = 2 * np.pi * np.sort(rng.choice(np.arange(1, 25), size=Nf, replace=False)).astype(float)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        se = lp.ls_spectral_lpv(Y, X, V, w, Nv, lam=0.05, coulomb=coul, normalize=norm, ctx=ctx)
+        so = o.ls_spectral_lpv(Y, X, V, w, Nv, lam=0.05, coulomb=coul, normalize=norm, mode="gram")
+    assert se.x.shape == so.x.shape
+    assert rel(se.x, so.x) <= 1e-8, (N, Nf, Nv, coul, norm)
+    assert rel(se.Σ, so.Sigma) <= 1e-8
+    assert abs(se.fva - so.fva) <= 1e-9
+    assert rel(lp.psd(se), o.psd(so)) <= 1e-8
