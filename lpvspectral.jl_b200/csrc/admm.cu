@@ -375,6 +375,57 @@ __device__ __forceinline__ double2 ld_hint(const double* p, unsigned long long p
     return v;
 }
 
+// One 128x128 block of M, this warp's 8 rows (blk -> row 8w, the lane's columns 2*lane, 2*lane+1, 64+2*lane, 65+2*lane):
+// row part M[rows, cols] * r_J reduced over the lanes (returned value is valid in lanes with (lane & 3) == 0, for row
+// ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1) of the 8), column part M[rows, cols]' * r_I accumulated into c0..c3.
+// 16 independent 16-byte loads per lane.
+template <bool HINT>
+__device__ __forceinline__ double symv_block(const double* blk, long long Np, unsigned long long pol,
+                                             const double (&rs8)[8], double2 rj0, double2 rj1, double& c0, double& c1,
+                                             double& c2, double& c3, int lane) {
+    double2 m0[8], m1[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        if (HINT) {
+            m0[r] = ld_hint(blk + (long long)r * Np, pol);
+            m1[r] = ld_hint(blk + (long long)r * Np + 64, pol);
+        } else {
+            m0[r] = __ldg(reinterpret_cast<const double2*>(blk + (long long)r * Np));
+            m1[r] = __ldg(reinterpret_cast<const double2*>(blk + (long long)r * Np + 64));
+        }
+    }
+    double s[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        s[r] = fma(m0[r].x, rj0.x, fma(m0[r].y, rj0.y, fma(m1[r].x, rj1.x, m1[r].y * rj1.y)));
+        c0 = fma(m0[r].x, rs8[r], c0);
+        c1 = fma(m0[r].y, rs8[r], c1);
+        c2 = fma(m1[r].x, rs8[r], c2);
+        c3 = fma(m1[r].y, rs8[r], c3);
+    }
+    // reduce the 8 row sums over the 32 lanes: 8->4->2->1 values per lane while halving the lane span
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        double keep = (lane & 16) ? s[r + 4] : s[r];
+        double send = (lane & 16) ? s[r] : s[r + 4];
+        s[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        double keep = (lane & 8) ? s[r + 2] : s[r];
+        double send = (lane & 8) ? s[r] : s[r + 2];
+        s[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        double keep = (lane & 4) ? s[1] : s[0];
+        double send = (lane & 4) ? s[0] : s[1];
+        s[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 2);
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+    return s[0];
+}
+
 constexpr int SEG = 8;
 struct SymvPlan {
     const int* seg_j;   // block column
@@ -459,49 +510,15 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv(const __grid_cons
             for (int I = i0; I < i1; I++) {
                 const double* blk = a.M + ((long long)I * 128 + 8 * w) * Np + (long long)J * 128 + 2 * lane;
                 const unsigned long long pol = (bcount++ < my_persist) ? pol_keep : pol_stream;
-                double2 m0[8], m1[8];
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    m0[r] = ld_hint(blk + (long long)r * Np, pol);
-                    m1[r] = ld_hint(blk + (long long)r * Np + 64, pol);
-                }
                 const bool offdiag = I != J;
                 double rs8[8];
 #pragma unroll
                 for (int r = 0; r < 8; r++) rs8[r] = offdiag ? __ldcg(rc + I * 128 + 8 * w + r) : 0.0;
-                double s[8];
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    s[r] = fma(m0[r].x, rj0.x, fma(m0[r].y, rj0.y, fma(m1[r].x, rj1.x, m1[r].y * rj1.y)));
-                    c0 = fma(m0[r].x, rs8[r], c0);
-                    c1 = fma(m0[r].y, rs8[r], c1);
-                    c2 = fma(m1[r].x, rs8[r], c2);
-                    c3 = fma(m1[r].y, rs8[r], c3);
-                }
-                // reduce the 8 row sums over the 32 lanes: 8->4->2->1 values per lane while halving the lane span
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    double keep = (lane & 16) ? s[r + 4] : s[r];
-                    double send = (lane & 16) ? s[r] : s[r + 4];
-                    s[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                }
-#pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    double keep = (lane & 8) ? s[r + 2] : s[r];
-                    double send = (lane & 8) ? s[r] : s[r + 2];
-                    s[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                }
-                {
-                    double keep = (lane & 4) ? s[1] : s[0];
-                    double send = (lane & 4) ? s[0] : s[1];
-                    s[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                }
-                s[0] += __shfl_xor_sync(0xffffffffu, s[0], 2);
-                s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+                const double srow = symv_block<true>(blk, Np, pol, rs8, rj0, rj1, c0, c1, c2, c3, lane);
                 // lanes with (lane & 3) == 0 hold row index ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)
                 if ((lane & 3) == 0) {
                     int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                    ys[I * 128 + 8 * w + r] += s[0];  // single writer: warp w owns these rows in every block
+                    ys[I * 128 + 8 * w + r] += srow;  // single writer: warp w owns these rows in every block
                 }
             }
             // column part of the segment: cross-warp reduction, then into ys[J block]
@@ -752,6 +769,105 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_batch(const __grid_con
     }
 }
 
+// Single-channel variant (PSD, the reference's own windowed-sparse use, test/test_lasso.jl:36): SYMV over the lower
+// triangle of the window's inverse -- half the bytes of the GEMV above.  Warp w owns rows 8w..8w+7 of every 128x128
+// block; a block column is one segment (column partials stay in registers down the column, one cross-warp reduction per
+// column); everything else as k_admm_batch.
+__global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_batch_symv(const __grid_constant__ AdmmBatchArgs ba) {
+    extern __shared__ __align__(16) double sm[];
+    const int Np = ba.Np, nb = Np >> 7;
+    double* rs = sm;                    // [Np] current right-hand side
+    double* ys = sm + Np;               // [Np] y = M r
+    double* cred = sm + 2 * Np;         // [ADMM_WARPS][128]
+    __shared__ double wsum[ADMM_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wdx = blockIdx.x;
+    const double* M = ba.M + (long long)wdx * ba.strideM;
+    double* v = ba.vecs + (long long)wdx * 7 * Np;
+    AdmmArgs ch{};
+    ch.Np = Np;
+    ch.q = v;
+    ch.x = v + Np;
+    ch.z = v + 2 * Np;
+    ch.u = v + 3 * Np;
+    ch.v = v + 4 * Np;
+    ch.r = v + 5 * Np;
+    ch.mu = ba.mu;
+    ch.quad = ba.quad;
+    ch.prox = ba.prox;
+    ch.pparam = ba.pparam;
+    const bool elementwise = (ba.prox == LPVS_PROX_L1 || ba.prox == LPVS_PROX_L0);
+    const double gl = ba.mu * ba.pparam;
+    const double thr0 = sqrt(2.0 * ba.mu * ba.pparam);
+    long long its = 0;
+    double nxz = 0.0;
+    int cur = 0;
+    for (long long it = 0; it < ba.max_iters; it++) {
+        for (int i = tid; i < Np; i += ADMM_THREADS) {
+            rs[i] = __ldcg(ch.r + (long long)cur * Np + i);
+            ys[i] = 0.0;
+        }
+        __syncthreads();
+        for (int J = 0; J < nb; J++) {
+            const double2 rj0 = *reinterpret_cast<const double2*>(rs + J * 128 + 2 * lane);
+            const double2 rj1 = *reinterpret_cast<const double2*>(rs + J * 128 + 64 + 2 * lane);
+            double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+            for (int I = J; I < nb; I++) {
+                const double* blk = M + ((long long)I * 128 + 8 * w) * Np + (long long)J * 128 + 2 * lane;
+                double rs8[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) rs8[r] = I != J ? rs[I * 128 + 8 * w + r] : 0.0;
+                const double srow = symv_block<false>(blk, Np, 0ull, rs8, rj0, rj1, c0, c1, c2, c3, lane);
+                if ((lane & 3) == 0) {
+                    const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                    ys[I * 128 + 8 * w + r] += srow;  // single writer: warp w owns these rows in every block
+                }
+            }
+            cred[w * 128 + 2 * lane] = c0;
+            cred[w * 128 + 2 * lane + 1] = c1;
+            cred[w * 128 + 64 + 2 * lane] = c2;
+            cred[w * 128 + 64 + 2 * lane + 1] = c3;
+            __syncthreads();
+            if (tid < 128) {
+                double t = 0.0;
+#pragma unroll
+                for (int k = 0; k < ADMM_WARPS; k++) t += cred[k * 128 + tid];
+                ys[J * 128 + tid] += t;
+            }
+            __syncthreads();
+        }
+        double* rn = ch.r + (long long)(cur ^ 1) * Np;
+        double d2 = 0.0;
+        for (int i = tid; i < Np; i += ADMM_THREADS) {
+            const double xi = ys[i];
+            ch.x[i] = xi;
+            if (elementwise)
+                d2 += admm_elem_update(ch, rn, i, xi, gl, thr0);
+            else
+                ch.v[i] = xi + ch.u[i];
+        }
+        if (!elementwise) {
+            __syncthreads();
+            d2 = admm_phase_nonelem(ch, rn, 0, 1, tid, lane, w, gl);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        if (lane == 0) wsum[w] = d2;
+        __syncthreads();
+        double sres = 0.0;
+#pragma unroll
+        for (int k = 0; k < ADMM_WARPS; k++) sres += wsum[k];
+        nxz = sqrt(sres);
+        its = it + 1;
+        cur ^= 1;
+        if (nxz < ba.tol) break;
+    }
+    if (tid == 0) {
+        ba.iters_out[wdx] = its;
+        ba.res_out[wdx] = nxz;
+    }
+}
+
 // z = copy(x) = x0 (zeros), u = 0, r = rhs(z, u) for every (window, channel); q comes from B[window][channel][Np]
 __global__ void k_admm_batch_init(const double* __restrict__ B, int Np, int nrhs, double mu, int quad, double* vecs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -806,7 +922,14 @@ int admm_batch_run(lpvs_ctx* c, const double* d_M, double* d_B, int Np, int nrhs
     ba.tol = tol;
     ba.iters_out = d_iters;
     ba.res_out = d_res;
-    k_admm_batch<<<nw, ADMM_THREADS, smem, c->st>>>(ba);
+    const size_t smem_symv = sizeof(double) * (2 * (size_t)Np + (size_t)ADMM_WARPS * 128);
+    if (nrhs == 1 && c->admm_symv != 0 && smem_symv <= 200 * 1024) {
+        // one channel: SYMV over the lower triangle of the window's inverse (4 Np^2 B per window-iteration)
+        LPVS_CU(c, cudaFuncSetAttribute(k_admm_batch_symv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_symv));
+        k_admm_batch_symv<<<nw, ADMM_THREADS, smem_symv, c->st>>>(ba);
+    } else {
+        k_admm_batch<<<nw, ADMM_THREADS, smem, c->st>>>(ba);
+    }
     for (int w0 = 0; w0 < nw; w0 += 16384) {
         const int nn = std::min(16384, nw - w0);
         k_admm_batch_collect<<<dim3((Np + 255) / 256, nn * nrhs), 256, 0, c->st>>>(

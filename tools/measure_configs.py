@@ -166,7 +166,8 @@ def cfg2s(ctx, args):
     Np = 512
     res = dict(samples=NS, windows=K, iters=iters, wall_s=wall, wall_dense_s=wall_dense,
                admm_s=wall - wall_dense, window_iters_per_s=K * iters / max(wall - wall_dense, 1e-9),
-               gbs_full_M=K * iters * 8.0 * Np * Np / max(wall - wall_dense, 1e-9) / 1e9,
+               # PSD (one channel) streams the lower 128x128 blocks of each window's inverse: nb(nb+1)/2 * 128 KB
+               gbs_lower_M=K * iters * 10 * 131072.0 / max(wall - wall_dense, 1e-9) / 1e9,
                peak_bins=[int(i) for i in np.argsort(S)[-2:]], dense_peak_bins=[int(i) for i in np.argsort(Sd)[-2:]])
     dump("cfg2s", res)
 
