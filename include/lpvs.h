@@ -151,6 +151,19 @@ int lpvs_admm_create_lpv(lpvs_ctx* ctx, const double* y, const double* X, const 
                          lpvs_admm** h);
 int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_done, double* residual,
                   int* converged);
+/* ---- ONE problem sharded over the GPUs of a node (third row): one process per GPU, every rank creates the
+ * SAME problem, then
+ *   lpvs_admm_shard_begin(h, rank, world)   re-plans the loop for this rank's share of the inverse and allocates the
+ *                                           exchange region;
+ *   lpvs_admm_shard_handle(h, buf64)        exports the region (CUDA IPC, 64 bytes) -- the host all-gathers these;
+ *   lpvs_admm_shard_connect(h, handles)     maps the peers' regions (world x 64 bytes, rank order).
+ * After a host barrier, lpvs_admm_run (same max_iters / tol on every rank) iterates with device-initiated peer stores
+ * over NVLink: reduce-scatter of the partial products, all-gather of the new right-hand side, two flag exchanges per
+ * iteration, no host or NCCL call inside the loop.  NormL1 / NormL0 only.  lpvs_admm_get / _result are valid on every
+ * rank after a host barrier that follows the run. */
+int lpvs_admm_shard_begin(lpvs_admm* h, int rank, int world);
+int lpvs_admm_shard_handle(lpvs_admm* h, void* handle64);
+int lpvs_admm_shard_connect(lpvs_admm* h, const void* handles);
 int lpvs_admm_size(const lpvs_admm* h); /* length of x / z in reference order */
 int lpvs_admm_get(lpvs_admm* h, double* x, double* z);
 /* fourier2complex(z) (Nf complex) or LPV params (Nf*Nv complex, un-permuted as src/lasso.jl:67-68) */

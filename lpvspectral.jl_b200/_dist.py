@@ -21,7 +21,7 @@ import numpy as np
 from . import _api as A
 from . import _lib as L
 
-__all__ = ["shard_range", "ls_window_sharded", "ls_window_sparse_sharded", "ls_spectral_rowsharded"]
+__all__ = ["shard_range", "ls_window_sharded", "ls_window_sparse_sharded", "ls_spectral_rowsharded", "admm_shard"]
 
 
 def shard_range(K: int, rank: int, world: int):
@@ -118,3 +118,26 @@ def ls_spectral_rowsharded(y, t, f, W=None, *, u=None, lam=1e-10, ctx: Optional[
     ctx.check(ctx.lib.lpvs_solve_packed_dev(ctx.h, p(packed), A._ptr(fv), len(fv), nrhs, ridge, A._ptr(x),
                                             C.byref(info)))
     return x[0] if nrhs == 1 else x
+
+
+def admm_shard(solver: "A.ADMM", group=None):
+    """Shard ONE ADMM problem over the ranks of a node (every rank must have created the same problem; NormL1 / NormL0).
+
+    The loop then runs as a persistent kernel per GPU that exchanges partial products and the new right-hand side with
+    device-initiated peer stores over NVLink (lpvs_admm_shard_*); torch.distributed only carries the 64-byte CUDA IPC
+    handles and the barriers around the runs.  Call ``dist.barrier()`` after ``solver.step/run`` before reading results."""
+    import torch.distributed as dist
+
+    rank, world = _world(group)
+    if world < 2:
+        return solver
+    ctx = solver.ctx
+    ctx.check(ctx.lib.lpvs_admm_shard_begin(solver.h, rank, world))
+    buf = C.create_string_buffer(64)
+    ctx.check(ctx.lib.lpvs_admm_shard_handle(solver.h, C.cast(buf, C.c_void_p)))
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(buf.raw), group=group)
+    blob = C.create_string_buffer(b"".join(handles), 64 * world)
+    ctx.check(ctx.lib.lpvs_admm_shard_connect(solver.h, C.cast(blob, C.c_void_p)))
+    dist.barrier(group=group)
+    return solver

@@ -61,6 +61,9 @@ _PROTOS = {
     "lpvs_admm_create_lpv": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_double, C.c_double, C.POINTER(_vp)]),
     "lpvs_admm_run": (C.c_int, [_vp, C.c_int64, C.c_double, _i64p, _dp, _ip]),
+    "lpvs_admm_shard_begin": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "lpvs_admm_shard_handle": (C.c_int, [_vp, _vp]),
+    "lpvs_admm_shard_connect": (C.c_int, [_vp, _vp]),
     "lpvs_admm_size": (C.c_int, [_vp]),
     "lpvs_admm_get": (C.c_int, [_vp, _vp, _vp]),
     "lpvs_admm_result": (C.c_int, [_vp, _vp]),

@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <cmath>
@@ -940,6 +941,263 @@ int admm_batch_run(lpvs_ctx* c, const double* d_M, double* d_B, int Np, int nrhs
     return LPVS_OK;
 }
 
+// ---- variant 4: ONE problem sharded over the GPUs of a node (one process per GPU, peer memory over NVLink) --------
+// Rank r streams a contiguous share of the lower-triangle blocks of M (phase 1 as k_admm_symv); the partial products
+// are reduce-scattered to the rank that owns each 128-row block (P2P stores into its receive slots), the owner applies
+// prox / dual update and all-gathers the new right-hand side into every rank's copy (P2P stores again).  Two flag
+// exchanges per iteration (release/acquire at system scope); no host involvement, no NCCL inside the loop.
+// Element-wise prox operators only (L1, L0).
+constexpr int SHARD_MAXP = 8;
+struct ShardArgs {
+    int rank, world;
+    int rb[SHARD_MAXP + 1];        // 128-row block ranges owned by the ranks
+    double* base[SHARD_MAXP];      // exchange region of every rank (own = local), layout below
+    long long off_recv, off_rhs, off_resid, off_flagA, off_flagB, off_abort;  // in doubles
+    int rows_max;                  // max rows owned by a rank
+    long long it_base;             // iterations done before this launch (flags are absolute iteration counters)
+    long long spin_limit;          // clock64 budget of one flag wait
+};
+
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+    asm volatile("st.global.release.sys.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+    long long v;
+    asm volatile("ld.global.acquire.sys.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Abort protocol (a peer that never shows up must not hang the GPU): every flag wait is bounded by a clock budget and
+// never decides anything by itself -- a timeout is only recorded (abort word [1]).  Thread 0 of CTA 0 folds the
+// recorded timeouts and the word peers write on their own failure ([0]) into the decision word [2] right BEFORE each
+// grid barrier, and every CTA reads [2] right AFTER it, so all CTAs of a rank leave the loop at the same barrier.
+__device__ __forceinline__ void shard_wait(const ShardArgs& sh, long long off_flag, long long target, int tid) {
+    if (tid < sh.world) {
+        const long long* f = reinterpret_cast<const long long*>(sh.base[sh.rank] + off_flag) + tid;
+        long long* ab = reinterpret_cast<long long*>(sh.base[sh.rank] + sh.off_abort);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < target) {
+            if (clock64() - t0 > sh.spin_limit || ld_acquire_sys(ab) != 0) {
+                atomicExch(reinterpret_cast<unsigned long long*>(ab + 1), 1ull);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void shard_fold_abort(const ShardArgs& sh, int b, int tid) {
+    if (b == 0 && tid == 0) {
+        long long* ab = reinterpret_cast<long long*>(sh.base[sh.rank] + sh.off_abort);
+        if (ld_acquire_sys(ab) != 0 || ld_acquire_sys(ab + 1) != 0) atomicExch(reinterpret_cast<unsigned long long*>(ab + 2), 1ull);
+        __threadfence();
+    }
+}
+__device__ __forceinline__ bool shard_aborted(const ShardArgs& sh) {
+    const long long* ab = reinterpret_cast<const long long*>(sh.base[sh.rank] + sh.off_abort);
+    return __ldcg(ab + 2) != 0;
+}
+
+__global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv_sharded(const __grid_constant__ AdmmArgs a,
+                                                                       const __grid_constant__ SymvPlan sp,
+                                                                       const __grid_constant__ ShardArgs sh) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) double sm[];
+    double* ys = sm;
+    double* cred = sm + a.Np;
+    __shared__ double wsum[ADMM_WARPS];
+    __shared__ double red4[4][128];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nblocks = gridDim.x, b = blockIdx.x;
+    const int Np = a.Np, P = sh.world, me = sh.rank;
+    const double gl = a.mu * a.pparam;
+    const double thr0 = sqrt(2.0 * a.mu * a.pparam);
+    const int sg0 = sp.cta_seg[b], sg1 = sp.cta_seg[b + 1];
+    const int slot0 = sp.cta_slot[b], slot1 = sp.cta_slot[b + 1];
+    const int my_persist = sp.cta_persist[b];
+    const unsigned long long pol_keep = l2_policy(true), pol_stream = l2_policy(false);
+    // phase 2a: all Np rows split evenly over this rank's CTAs; phase 2b: the rows this rank owns, split evenly
+    const int baseA = Np / nblocks, extraA = Np % nblocks;
+    const int a0 = b * baseA + min(b, extraA), an = baseA + (b < extraA ? 1 : 0);
+    const int own0 = sh.rb[me] * 128, ownn = (sh.rb[me + 1] - sh.rb[me]) * 128;
+    const int baseB = ownn / nblocks, extraB = ownn % nblocks;
+    const int b0 = own0 + b * baseB + min(b, extraB), bn = baseB + (b < extraB ? 1 : 0);
+    double* mine = sh.base[me];
+    int cur = a.rbuf0;
+    long long it = 0;
+    int converged = 0, failed = 0;
+    double nxz = 0.0;
+    for (; it < a.max_iters; it++) {
+        const long long tick = sh.it_base + it + 1;
+        const double* rc = mine + sh.off_rhs + (long long)cur * Np;
+        for (int sl = slot0 + w; sl < slot1; sl += ADMM_WARPS) {
+            const int blk = __ldg(sp.slot_blk + sl);
+#pragma unroll
+            for (int k = 0; k < 4; k++) ys[blk * 128 + lane + 32 * k] = 0.0;
+        }
+        __syncthreads();
+        // ---- phase 1: this CTA's segments of this rank's share of the triangle ----
+        int bcount = 0;
+        for (int sgi = sg0; sgi < sg1; sgi++) {
+            const int J = sp.seg_j[sgi], i0 = sp.seg_i0[sgi], i1 = sp.seg_i1[sgi];
+            const double2 rj0 = __ldcg(reinterpret_cast<const double2*>(rc + J * 128 + 2 * lane));
+            const double2 rj1 = __ldcg(reinterpret_cast<const double2*>(rc + J * 128 + 64 + 2 * lane));
+            double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+            for (int I = i0; I < i1; I++) {
+                const double* blk = a.M + ((long long)I * 128 + 8 * w) * Np + (long long)J * 128 + 2 * lane;
+                const unsigned long long pol = (bcount++ < my_persist) ? pol_keep : pol_stream;
+                const bool offdiag = I != J;
+                double rs8[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) rs8[r] = offdiag ? __ldcg(rc + I * 128 + 8 * w + r) : 0.0;
+                const double srow = symv_block<true>(blk, Np, pol, rs8, rj0, rj1, c0, c1, c2, c3, lane);
+                if ((lane & 3) == 0) {
+                    int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                    ys[I * 128 + 8 * w + r] += srow;
+                }
+            }
+            cred[w * 128 + 2 * lane] = c0;
+            cred[w * 128 + 2 * lane + 1] = c1;
+            cred[w * 128 + 64 + 2 * lane] = c2;
+            cred[w * 128 + 64 + 2 * lane + 1] = c3;
+            __syncthreads();
+            if (tid < 128) {
+                double t = 0.0;
+#pragma unroll
+                for (int k = 0; k < ADMM_WARPS; k++) t += cred[k * 128 + tid];
+                ys[J * 128 + tid] += t;
+            }
+            __syncthreads();
+        }
+        for (int sl = slot0 + w; sl < slot1; sl += ADMM_WARPS) {
+            const int blk = __ldg(sp.slot_blk + sl);
+            double* yp = sp.ypart + (long long)sl * 128;
+#pragma unroll
+            for (int k = 0; k < 4; k++) yp[lane + 32 * k] = ys[blk * 128 + lane + 32 * k];
+        }
+        shard_fold_abort(sh, b, tid);
+        grid.sync();
+        if (shard_aborted(sh)) {
+            failed = 1;
+            break;
+        }
+        // ---- phase 2a: this rank's partial of every row -> the owner's receive slot [me] (reduce-scatter) ----
+        for (int rb0 = 0; rb0 < an; rb0 += 128) {
+            const int rl = rb0 + (tid & 127), q = tid >> 7;
+            red4[q][tid & 127] = rl < an ? symv_row_sum(sp, a0 + rl, q) : 0.0;
+            __syncthreads();
+            if (tid < 128 && rl < an) {
+                const int i = a0 + rl;
+                const double yi = (red4[0][tid] + red4[1][tid]) + (red4[2][tid] + red4[3][tid]);
+                const int blk = i >> 7;
+                int owner = 0;
+                while (blk >= sh.rb[owner + 1]) owner++;
+                double* dst = sh.base[owner] + sh.off_recv + (long long)me * sh.rows_max + (i - sh.rb[owner] * 128);
+                *dst = yi;  // peer (or local) store over NVLink
+            }
+            __syncthreads();
+        }
+        __threadfence_system();
+        shard_fold_abort(sh, b, tid);
+        grid.sync();
+        if (shard_aborted(sh)) {
+            failed = 1;
+            break;
+        }
+        if (b == 0 && tid < P)
+            st_release_sys(reinterpret_cast<long long*>(sh.base[tid] + sh.off_flagA) + me, tick);
+        shard_wait(sh, sh.off_flagA, tick, tid);
+        // ---- phase 2b: owned rows: x = sum over ranks (fixed order), prox, dual update, new rhs -> every rank ----
+        const int nxt = cur ^ 1;
+        double d2 = 0.0;
+        for (int r = tid; r < bn; r += ADMM_THREADS) {
+            const int i = b0 + r;
+            const double* rv = mine + sh.off_recv + (i - own0);
+            double xi = 0.0;
+            for (int s = 0; s < P; s++) xi += __ldcg(rv + (long long)s * sh.rows_max);
+            a.x[i] = xi;
+            double ui = a.u[i];
+            const double zi = prox_elem(a.prox, xi + ui, gl, thr0);
+            const double di = xi - zi;
+            ui += di;
+            a.z[i] = zi;
+            a.u[i] = ui;
+            const double rn = next_rhs(a, i, zi, ui);
+            for (int s = 0; s < P; s++) sh.base[s][sh.off_rhs + (long long)nxt * Np + i] = rn;
+            d2 += di * di;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        if (lane == 0) wsum[w] = d2;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int k = 0; k < ADMM_WARPS; k++) s += wsum[k];
+            a.part[(it & 1) * nblocks + b] = s;
+        }
+        __threadfence_system();
+        shard_fold_abort(sh, b, tid);
+        grid.sync();
+        if (shard_aborted(sh)) {
+            failed = 1;
+            break;
+        }
+        if (b == 0) {
+            if (w == 0) {  // this rank's residual partial, fixed order, to every rank; then the flag
+                double s = 0.0;
+                for (int k = lane; k < nblocks; k += 32) s += __ldcg(a.part + (it & 1) * nblocks + k);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane < P) {
+                    sh.base[lane][sh.off_resid + (it & 1) * SHARD_MAXP + me] = s;
+                    __threadfence_system();
+                    st_release_sys(reinterpret_cast<long long*>(sh.base[lane] + sh.off_flagB) + me, tick);
+                }
+            }
+        }
+        shard_wait(sh, sh.off_flagB, tick, tid);
+        {
+            double s = 0.0;
+            for (int k = 0; k < P; k++) s += __ldcg(mine + sh.off_resid + (it & 1) * SHARD_MAXP + k);
+            nxz = sqrt(s);
+        }
+        cur = nxt;
+        if ((it + 1) % a.check_every == 0 || it + 1 == a.max_iters) {
+            if (nxz < a.tol) {
+                converged = 1;
+                it++;
+                break;
+            }
+        }
+    }
+    if (!failed) {  // a timeout in the very last wait has no later barrier to surface at
+        shard_fold_abort(sh, b, tid);
+        grid.sync();
+        if (shard_aborted(sh)) failed = 1;
+    }
+    if (failed && b == 0 && tid < P)  // tell the peers to stop spinning
+        st_release_sys(reinterpret_cast<long long*>(sh.base[tid] + sh.off_abort), 1);
+    if (b == 0 && tid == 0) {
+        *a.iters_out = it;
+        *a.res_out = nxz;
+        *a.conv_out = failed ? -1 : converged;
+        *a.rbuf_out = cur;
+    }
+}
+
+// owner -> everyone: final x, z, u rows (so that every rank can answer lpvs_admm_get) -- peer stores, host-synchronised
+__global__ void k_shard_broadcast(double* x, double* z, double* u, int row0, int nrows, int Np, ShardArgs sh,
+                                  long long off_xzu) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int g = row0 + i;
+    for (int s = 0; s < sh.world; s++) {
+        double* dst = sh.base[s] + off_xzu;
+        dst[g] = x[g];
+        dst[Np + g] = z[g];
+        dst[2 * Np + g] = u[g];
+    }
+}
+
 __global__ void k_admm_init(const double* __restrict__ q, const double* __restrict__ x0, int Np, double mu,
                             int quad, double* x, double* z, double* u, double* r) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1015,6 +1273,13 @@ struct lpvs_admm {
     std::vector<int> h_order, h_goff;
     int* d_order = nullptr;
     int* d_pos = nullptr;
+    // one problem sharded over several GPUs (k_admm_symv_sharded): exchange region + the peers' mappings of theirs
+    int shard_rank = 0, shard_world = 1, shard_connected = 0;
+    double* xchg = nullptr;
+    double* peer_base[8] = {};
+    int shard_rb[9] = {};
+    long long off_recv = 0, off_rhs = 0, off_resid = 0, off_flagA = 0, off_flagB = 0, off_abort = 0, off_xzu = 0;
+    int shard_rows_max = 0;
     double* ypart = nullptr;
     int rbuf = 0;
     int grid = 0;
@@ -1046,6 +1311,9 @@ static void admm_release(lpvs_admm* h) {
     cudaFree(h->ypart);
     cudaFree(h->d_order);
     cudaFree(h->d_pos);
+    for (int sidx = 0; sidx < h->shard_world; sidx++)
+        if (sidx != h->shard_rank && h->peer_base[sidx]) cudaIpcCloseMemHandle(h->peer_base[sidx]);
+    cudaFree(h->xchg);
     if (h->e0) cudaEventDestroy(h->e0);
     if (h->e1) cudaEventDestroy(h->e1);
     delete h;
@@ -1102,6 +1370,108 @@ static GroupItems build_group_items(const lpvs_admm* h, int grid) {
     }
     gi.cta_item[grid] = (int)gi.lo.size();
     return gi;
+}
+
+// SYMV plan for the blocks [tb, te) of the lower triangle (block-column-major order; the whole triangle on one GPU, a
+// contiguous share of it when one problem is sharded over several): segments per CTA, L2-resident counts, the sparse
+// partial-y exchange tables and the group items.  Replaces any previous plan of the handle.
+static int build_symv_plan(lpvs_ctx* c, lpvs_admm* h, const GroupItems& gitems, long long tb, long long te) {
+    const int Np = h->Np, nb = Np / TB;
+    const int grid = c->sms;
+    const long long Tr = te - tb;
+    cudaFree(h->seg_buf);
+    cudaFree(h->ypart);
+    h->seg_buf = nullptr;
+    h->ypart = nullptr;
+    {
+        // blocks of the lower triangle in block-column-major order, split evenly over the CTAs, then cut into
+        // segments (same block column, <= SEG blocks)
+        const long long T = (long long)nb * (nb + 1) / 2;
+        std::vector<int> sj, si0, si1, cta(grid + 1, 0);
+        std::vector<int> colstart(nb + 1, 0);
+        for (int J = 0; J < nb; J++) colstart[J + 1] = colstart[J] + (nb - J);
+        int J = 0;
+        for (int cta_i = 0; cta_i < grid; cta_i++) {
+            long long t0 = tb + Tr * cta_i / grid, t1 = tb + Tr * (cta_i + 1) / grid;
+            cta[cta_i] = (int)sj.size();
+            long long t = t0;
+            while (t < t1) {
+                while (colstart[J + 1] <= t) J++;
+                int I = J + (int)(t - colstart[J]);
+                long long run = std::min<long long>(std::min<long long>(t1 - t, colstart[J + 1] - t), SEG);
+                sj.push_back(J);
+                si0.push_back(I);
+                si1.push_back(I + (int)run);
+                t += run;
+            }
+        }
+        cta[grid] = (int)sj.size();
+        h->nseg = (int)sj.size();
+        // L2-resident share: 88 MB of blocks spread evenly over the CTAs
+        std::vector<int> persist(grid, 0);
+        {
+            const double keep_bytes = 88.0 * 1024 * 1024, blk_bytes = 128.0 * 128.0 * 8.0;
+            const double frac = std::min(1.0, keep_bytes / ((double)Tr * blk_bytes));
+            for (int cta_i = 0; cta_i < grid; cta_i++) {
+                long long nblk = Tr * (cta_i + 1) / grid - Tr * cta_i / grid;
+                // rounded, not truncated: a CTA that owns one block more keeps one block more in L2, so the number
+                // of blocks STREAMED from HBM -- what phase 1 waits for -- is the same for every CTA
+                persist[cta_i] = (int)std::lround(frac * (double)nblk);
+            }
+        }
+        // sparse exchange: slots = the 128-blocks of y each CTA touches (block column J and block rows I of its
+        // segments); contributor lists per block, ordered by CTA
+        std::vector<int> cta_slot(grid + 1, 0), slot_blk;
+        std::vector<std::vector<int>> contrib((size_t)nb);
+        {
+            std::vector<int> seen((size_t)nb, -1);
+            for (int cta_i = 0; cta_i < grid; cta_i++) {
+                cta_slot[cta_i] = (int)slot_blk.size();
+                auto touch = [&](int blk) {
+                    if (seen[blk] == cta_i) return;
+                    seen[blk] = cta_i;
+                    contrib[blk].push_back((int)slot_blk.size());
+                    slot_blk.push_back(blk);
+                };
+                for (int sgi = cta[cta_i]; sgi < cta[cta_i + 1]; sgi++) {
+                    touch(sj[sgi]);
+                    for (int I = si0[sgi]; I < si1[sgi]; I++) touch(I);
+                }
+            }
+            cta_slot[grid] = (int)slot_blk.size();
+        }
+        std::vector<int> red_ptr(nb + 1, 0), red_slot;
+        for (int R = 0; R < nb; R++) {
+            red_ptr[R] = (int)red_slot.size();
+            red_slot.insert(red_slot.end(), contrib[R].begin(), contrib[R].end());
+        }
+        red_ptr[nb] = (int)red_slot.size();
+        std::vector<int> all;
+        auto put = [&](const std::vector<int>& v) {
+            size_t off = all.size();
+            all.insert(all.end(), v.begin(), v.end());
+            return off;
+        };
+        put(sj);
+        put(si0);
+        put(si1);
+        h->off_cta_seg = put(cta);
+        h->off_persist = put(persist);
+        h->off_cta_slot = put(cta_slot);
+        h->off_slot_blk = put(slot_blk);
+        h->off_red_ptr = put(red_ptr);
+        h->off_red_slot = put(red_slot);
+        h->off_cta_item = put(gitems.cta_item);
+        h->off_item_lo = put(gitems.lo);
+        h->off_item_hi = put(gitems.hi);
+        h->off_item_kind = put(gitems.kind);
+        all.push_back(0);
+        LPVS_CU(c, cudaMalloc(&h->seg_buf, sizeof(int) * all.size()));
+        LPVS_CU(c, cudaMemcpyAsync(h->seg_buf, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice, c->st));
+        LPVS_CU(c, cudaStreamSynchronize(c->st));
+        LPVS_CU(c, cudaMalloc(&h->ypart, sizeof(double) * (size_t)slot_blk.size() * 128));
+        }
+    return LPVS_OK;
 }
 
 // Factor (G + I/mu), invert, allocate loop state.  d_G: Np x Np lower tiles (consumed), d_q: Np.
@@ -1204,92 +1574,8 @@ int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q
         size_t sm2 = admm_smem_symv(Np, h->max_item);
         LPVS_CU(c, cudaFuncSetAttribute(k_admm_symv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
         h->grid = grid = c->sms;
-        // blocks of the lower triangle in block-column-major order, split evenly over the CTAs, then cut into
-        // segments (same block column, <= SEG blocks)
-        const long long T = (long long)nb * (nb + 1) / 2;
-        std::vector<int> sj, si0, si1, cta(grid + 1, 0);
-        std::vector<int> colstart(nb + 1, 0);
-        for (int J = 0; J < nb; J++) colstart[J + 1] = colstart[J] + (nb - J);
-        int J = 0;
-        for (int cta_i = 0; cta_i < grid; cta_i++) {
-            long long t0 = T * cta_i / grid, t1 = T * (cta_i + 1) / grid;
-            cta[cta_i] = (int)sj.size();
-            long long t = t0;
-            while (t < t1) {
-                while (colstart[J + 1] <= t) J++;
-                int I = J + (int)(t - colstart[J]);
-                long long run = std::min<long long>(std::min<long long>(t1 - t, colstart[J + 1] - t), SEG);
-                sj.push_back(J);
-                si0.push_back(I);
-                si1.push_back(I + (int)run);
-                t += run;
-            }
-        }
-        cta[grid] = (int)sj.size();
-        h->nseg = (int)sj.size();
-        // L2-resident share: 88 MB of blocks spread evenly over the CTAs
-        std::vector<int> persist(grid, 0);
-        {
-            const double keep_bytes = 88.0 * 1024 * 1024, blk_bytes = 128.0 * 128.0 * 8.0;
-            const double frac = std::min(1.0, keep_bytes / ((double)T * blk_bytes));
-            for (int cta_i = 0; cta_i < grid; cta_i++) {
-                long long nblk = T * (cta_i + 1) / grid - T * cta_i / grid;
-                // rounded, not truncated: a CTA that owns one block more keeps one block more in L2, so the number
-                // of blocks STREAMED from HBM -- what phase 1 waits for -- is the same for every CTA
-                persist[cta_i] = (int)std::lround(frac * (double)nblk);
-            }
-        }
-        // sparse exchange: slots = the 128-blocks of y each CTA touches (block column J and block rows I of its
-        // segments); contributor lists per block, ordered by CTA
-        std::vector<int> cta_slot(grid + 1, 0), slot_blk;
-        std::vector<std::vector<int>> contrib((size_t)nb);
-        {
-            std::vector<int> seen((size_t)nb, -1);
-            for (int cta_i = 0; cta_i < grid; cta_i++) {
-                cta_slot[cta_i] = (int)slot_blk.size();
-                auto touch = [&](int blk) {
-                    if (seen[blk] == cta_i) return;
-                    seen[blk] = cta_i;
-                    contrib[blk].push_back((int)slot_blk.size());
-                    slot_blk.push_back(blk);
-                };
-                for (int sgi = cta[cta_i]; sgi < cta[cta_i + 1]; sgi++) {
-                    touch(sj[sgi]);
-                    for (int I = si0[sgi]; I < si1[sgi]; I++) touch(I);
-                }
-            }
-            cta_slot[grid] = (int)slot_blk.size();
-        }
-        std::vector<int> red_ptr(nb + 1, 0), red_slot;
-        for (int R = 0; R < nb; R++) {
-            red_ptr[R] = (int)red_slot.size();
-            red_slot.insert(red_slot.end(), contrib[R].begin(), contrib[R].end());
-        }
-        red_ptr[nb] = (int)red_slot.size();
-        std::vector<int> all;
-        auto put = [&](const std::vector<int>& v) {
-            size_t off = all.size();
-            all.insert(all.end(), v.begin(), v.end());
-            return off;
-        };
-        put(sj);
-        put(si0);
-        put(si1);
-        h->off_cta_seg = put(cta);
-        h->off_persist = put(persist);
-        h->off_cta_slot = put(cta_slot);
-        h->off_slot_blk = put(slot_blk);
-        h->off_red_ptr = put(red_ptr);
-        h->off_red_slot = put(red_slot);
-        h->off_cta_item = put(gitems.cta_item);
-        h->off_item_lo = put(gitems.lo);
-        h->off_item_hi = put(gitems.hi);
-        h->off_item_kind = put(gitems.kind);
-        all.push_back(0);
-        LPVS_CU(c, cudaMalloc(&h->seg_buf, sizeof(int) * all.size()));
-        LPVS_CU(c, cudaMemcpyAsync(h->seg_buf, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice, c->st));
-        LPVS_CU(c, cudaStreamSynchronize(c->st));
-        LPVS_CU(c, cudaMalloc(&h->ypart, sizeof(double) * (size_t)slot_blk.size() * 128));
+        int rcp = build_symv_plan(c, h, gitems, 0, (long long)nb * (nb + 1) / 2);
+        if (rcp) return rcp;
     }
     LPVS_CU(c, cudaMalloc(&h->part, sizeof(double) * 2 * grid));
     LPVS_CU(c, cudaMalloc(&h->d_iters, sizeof(long long)));
@@ -1357,7 +1643,45 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
         a.trace_it0 = max_iters / 2;
     }
     LPVS_CU(c, cudaEventRecord(h->e0, c->st));
-    if (h->symv) {
+    if (h->shard_world > 1) {
+        if (!h->shard_connected) return fail(c, LPVS_E_BAD_ARG, "sharded ADMM handle is not connected to its peers");
+        SymvPlan sp{};
+        sp.seg_j = h->seg_buf;
+        sp.seg_i0 = h->seg_buf + h->nseg;
+        sp.seg_i1 = h->seg_buf + 2 * h->nseg;
+        sp.cta_seg = h->seg_buf + h->off_cta_seg;
+        sp.cta_persist = h->seg_buf + h->off_persist;
+        sp.cta_slot = h->seg_buf + h->off_cta_slot;
+        sp.slot_blk = h->seg_buf + h->off_slot_blk;
+        sp.red_ptr = h->seg_buf + h->off_red_ptr;
+        sp.red_slot = h->seg_buf + h->off_red_slot;
+        sp.cta_item = h->seg_buf + h->off_cta_item;
+        sp.item_lo = h->seg_buf + h->off_item_lo;
+        sp.item_hi = h->seg_buf + h->off_item_hi;
+        sp.item_kind = h->seg_buf + h->off_item_kind;
+        sp.ypart = h->ypart;
+        ShardArgs sh{};
+        sh.rank = h->shard_rank;
+        sh.world = h->shard_world;
+        for (int k = 0; k <= h->shard_world; k++) sh.rb[k] = h->shard_rb[k];
+        for (int k = 0; k < h->shard_world; k++) sh.base[k] = h->peer_base[k];
+        sh.off_recv = h->off_recv;
+        sh.off_rhs = h->off_rhs;
+        sh.off_resid = h->off_resid;
+        sh.off_flagA = h->off_flagA;
+        sh.off_flagB = h->off_flagB;
+        sh.off_abort = h->off_abort;
+        sh.rows_max = h->shard_rows_max;
+        sh.it_base = h->iters_total;
+        sh.spin_limit = 6000000000LL;  // ~3 s of SM clocks: a peer that is this late is gone
+        void* args[] = {&a, &sp, &sh};
+        LPVS_CU(c, cudaLaunchCooperativeKernel((void*)k_admm_symv_sharded, dim3(h->grid), dim3(ADMM_THREADS), args,
+                                               admm_smem_symv(Np, 0), c->st));
+        const int own0 = h->shard_rb[h->shard_rank] * 128;
+        const int ownn = (h->shard_rb[h->shard_rank + 1] - h->shard_rb[h->shard_rank]) * 128;
+        k_shard_broadcast<<<(ownn + 255) / 256, 256, 0, c->st>>>(a.x, a.z, a.u, own0, ownn, Np, sh, h->off_xzu);
+        c->launches++;
+    } else if (h->symv) {
         SymvPlan sp{};
         sp.seg_j = h->seg_buf;
         sp.seg_i0 = h->seg_buf + h->nseg;
@@ -1410,11 +1734,95 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
     h->last_iters = its;
     h->iters_total += its;
     h->residual = res;
+    if (flags[0] < 0)
+        return fail(c, LPVS_E_CUDA, "sharded ADMM: a peer GPU did not answer within the spin budget (loop aborted)");
     h->converged = flags[0];
     h->rbuf = flags[1];
     if (iters_done) *iters_done = its;
     if (residual) *residual = res;
     if (converged) *converged = flags[0];
+    return LPVS_OK;
+}
+
+int lpvs_admm_shard_begin(lpvs_admm* h, int rank, int world) {
+    if (!h) return LPVS_E_BAD_ARG;
+    lpvs_ctx* c = h->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    const int Np = h->Np, nb = Np / TB;
+    if (world < 2 || world > SHARD_MAXP || rank < 0 || rank >= world)
+        return fail(c, LPVS_E_BAD_ARG, "sharded ADMM: world must be 2..%d and 0 <= rank < world", SHARD_MAXP);
+    if (h->prox != LPVS_PROX_L1 && h->prox != LPVS_PROX_L0)
+        return fail(c, LPVS_E_UNSUPPORTED, "sharded ADMM supports the element-wise prox operators (NormL1, NormL0)");
+    if (!h->h_order.empty() || nb < world || h->shard_world > 1 || h->iters_total > 0)
+        return fail(c, LPVS_E_UNSUPPORTED, "sharded ADMM: needs a fresh Fourier problem with at least `world` 128-blocks");
+    if (admm_smem_symv(Np, 0) > 220 * 1024) return fail(c, LPVS_E_UNSUPPORTED, "sharded ADMM: Np=%d too large", Np);
+    LPVS_CU(c, cudaFuncSetAttribute(k_admm_symv_sharded, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)admm_smem_symv(Np, 0)));
+    // this rank's contiguous share of the lower-triangle blocks, and the 128-row blocks every rank owns
+    const long long T = (long long)nb * (nb + 1) / 2;
+    h->symv = 1;
+    h->grid = c->sms;
+    h->max_item = 0;
+    GroupItems none;
+    none.cta_item.assign((size_t)c->sms + 1, 0);
+    int rc = build_symv_plan(c, h, none, T * rank / world, T * (rank + 1) / world);
+    if (rc) return rc;
+    cudaFree(h->part);
+    h->part = nullptr;
+    LPVS_CU(c, cudaMalloc(&h->part, sizeof(double) * 2 * h->grid));
+    h->shard_rows_max = 0;
+    for (int k = 0; k <= world; k++) h->shard_rb[k] = (int)((long long)nb * k / world);
+    for (int k = 0; k < world; k++) h->shard_rows_max = std::max(h->shard_rows_max, (h->shard_rb[k + 1] - h->shard_rb[k]) * 128);
+    long long off = 0;
+    h->off_recv = off;   off += (long long)world * h->shard_rows_max;
+    h->off_rhs = off;    off += 2LL * Np;
+    h->off_resid = off;  off += 2LL * SHARD_MAXP;
+    h->off_flagA = off;  off += SHARD_MAXP;
+    h->off_flagB = off;  off += SHARD_MAXP;
+    h->off_abort = off;  off += 4;
+    h->off_xzu = off;    off += 3LL * Np;
+    LPVS_CU(c, cudaMalloc(&h->xchg, sizeof(double) * off));
+    LPVS_CU(c, cudaMemsetAsync(h->xchg, 0, sizeof(double) * off, c->st));
+    // the current right-hand side (rhs of iteration 0) moves into the exchange region, buffer 0
+    LPVS_CU(c, cudaMemcpyAsync(h->xchg + h->off_rhs, h->vecs + 5 * Np + (long long)h->rbuf * Np, sizeof(double) * Np,
+                               cudaMemcpyDeviceToDevice, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    h->rbuf = 0;
+    h->shard_rank = rank;
+    h->shard_world = world;
+    h->shard_connected = 0;
+    for (int k = 0; k < SHARD_MAXP; k++) h->peer_base[k] = nullptr;
+    h->peer_base[rank] = h->xchg;
+    return LPVS_OK;
+}
+
+int lpvs_admm_shard_handle(lpvs_admm* h, void* handle64) {
+    if (!h || !handle64 || h->shard_world < 2) return LPVS_E_BAD_ARG;
+    lpvs_ctx* c = h->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t mh;
+    LPVS_CU(c, cudaIpcGetMemHandle(&mh, h->xchg));
+    memcpy(handle64, &mh, 64);
+    return LPVS_OK;
+}
+
+int lpvs_admm_shard_connect(lpvs_admm* h, const void* handles) {
+    if (!h || !handles || h->shard_world < 2) return LPVS_E_BAD_ARG;
+    lpvs_ctx* c = h->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    for (int k = 0; k < h->shard_world; k++) {
+        if (k == h->shard_rank) continue;
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, (const char*)handles + 64 * k, 64);
+        void* p = nullptr;
+        LPVS_CU(c, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_base[k] = (double*)p;
+    }
+    h->shard_connected = 1;
     return LPVS_OK;
 }
 
@@ -1428,10 +1836,12 @@ int lpvs_admm_get(lpvs_admm* h, double* x, double* z) {
     double* tmp = ws<double>(c, BUF_X, (size_t)2 * h->nref);
     if (!tmp) return fail(c, LPVS_E_NOMEM, "out of device memory");
     const int Np = h->Np;
-    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(h->vecs + Np, h->nref, h->half, h->zero_first, h->d_pos,
-                                                           tmp);
-    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(h->vecs + 2 * Np, h->nref, h->half, h->zero_first,
-                                                           h->d_pos, tmp + h->nref);
+    // sharded handles: every owner broadcast its rows of x, z, u into each rank's exchange region after the run
+    const double* xsrc = h->shard_world > 1 ? h->xchg + h->off_xzu : h->vecs + Np;
+    const double* zsrc = h->shard_world > 1 ? h->xchg + h->off_xzu + Np : h->vecs + 2 * Np;
+    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(xsrc, h->nref, h->half, h->zero_first, h->d_pos, tmp);
+    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(zsrc, h->nref, h->half, h->zero_first, h->d_pos,
+                                                           tmp + h->nref);
     c->launches += 2;
     if (x) LPVS_CU(c, cudaMemcpyAsync(x, tmp, sizeof(double) * h->nref, cudaMemcpyDeviceToHost, c->st));
     if (z) LPVS_CU(c, cudaMemcpyAsync(z, tmp + h->nref, sizeof(double) * h->nref, cudaMemcpyDeviceToHost, c->st));
@@ -1462,8 +1872,8 @@ int lpvs_admm_result(lpvs_admm* h, double* out) {
     const int Np = h->Np, ncx = h->half;
     double* tmp = ws<double>(c, BUF_X, (size_t)2 * h->nref + 2);
     if (!tmp) return fail(c, LPVS_E_NOMEM, "out of device memory");
-    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(h->vecs + 2 * Np, h->nref, h->half, h->zero_first, h->d_pos,
-                                                           tmp);
+    k_gather_vec<<<(h->nref + 255) / 256, 256, 0, c->st>>>(
+        h->shard_world > 1 ? h->xchg + h->off_xzu + Np : h->vecs + 2 * Np, h->nref, h->half, h->zero_first, h->d_pos, tmp);
     c->launches++;
     std::vector<double> z((size_t)h->nref);
     LPVS_CU(c, cudaMemcpyAsync(z.data(), tmp, sizeof(double) * h->nref, cudaMemcpyDeviceToHost, c->st));
