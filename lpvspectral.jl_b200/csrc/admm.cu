@@ -1029,6 +1029,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv_sharded(const __g
     for (; it < a.max_iters; it++) {
         const long long tick = sh.it_base + it + 1;
         const double* rc = mine + sh.off_rhs + (long long)cur * Np;
+        ADMM_TR(0)
         for (int sl = slot0 + w; sl < slot1; sl += ADMM_WARPS) {
             const int blk = __ldg(sp.slot_blk + sl);
 #pragma unroll
@@ -1074,12 +1075,14 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv_sharded(const __g
 #pragma unroll
             for (int k = 0; k < 4; k++) yp[lane + 32 * k] = ys[blk * 128 + lane + 32 * k];
         }
+        ADMM_TR(1)
         shard_fold_abort(sh, b, tid);
         grid.sync();
         if (shard_aborted(sh)) {
             failed = 1;
             break;
         }
+        ADMM_TR(2)
         // ---- phase 2a: this rank's partial of every row -> the owner's receive slot [me] (reduce-scatter) ----
         for (int rb0 = 0; rb0 < an; rb0 += 128) {
             const int rl = rb0 + (tid & 127), q = tid >> 7;
@@ -1096,7 +1099,9 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv_sharded(const __g
             }
             __syncthreads();
         }
-        __threadfence_system();
+        // no per-thread system fence: the stores above happen-before the grid barrier, and the signalling thread's
+        // release.sys store after it is cumulative over everything that happened before it
+        ADMM_TR(3)
         shard_fold_abort(sh, b, tid);
         grid.sync();
         if (shard_aborted(sh)) {
@@ -1105,7 +1110,9 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv_sharded(const __g
         }
         if (b == 0 && tid < P)
             st_release_sys(reinterpret_cast<long long*>(sh.base[tid] + sh.off_flagA) + me, tick);
+        ADMM_TR(4)
         shard_wait(sh, sh.off_flagA, tick, tid);
+        ADMM_TR(5)
         // ---- phase 2b: owned rows: x = sum over ranks (fixed order), prox, dual update, new rhs -> every rank ----
         const int nxt = cur ^ 1;
         double d2 = 0.0;
@@ -1134,13 +1141,13 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv_sharded(const __g
             for (int k = 0; k < ADMM_WARPS; k++) s += wsum[k];
             a.part[(it & 1) * nblocks + b] = s;
         }
-        __threadfence_system();
         shard_fold_abort(sh, b, tid);
         grid.sync();
         if (shard_aborted(sh)) {
             failed = 1;
             break;
         }
+        ADMM_TR(6)
         if (b == 0) {
             if (w == 0) {  // this rank's residual partial, fixed order, to every rank; then the flag
                 double s = 0.0;
@@ -1149,12 +1156,12 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv_sharded(const __g
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 if (lane < P) {
                     sh.base[lane][sh.off_resid + (it & 1) * SHARD_MAXP + me] = s;
-                    __threadfence_system();
                     st_release_sys(reinterpret_cast<long long*>(sh.base[lane] + sh.off_flagB) + me, tick);
                 }
             }
         }
         shard_wait(sh, sh.off_flagB, tick, tid);
+        ADMM_TR(7)
         {
             double s = 0.0;
             for (int k = 0; k < P; k++) s += __ldcg(mine + sh.off_resid + (it & 1) * SHARD_MAXP + k);
