@@ -160,3 +160,35 @@ def test_windowed_sparse_direct_call_outputs(ctx):
     assert np.all(its == 1) and np.all(res >= 0.0) and np.any(sums != 0.0)
     assert call(300, 1e-7) == L.OK
     assert its.min() >= 2 and its.max() <= 300 and np.all(res[its < 300] < 1e-7)
+
+
+def test_sharded_admm_entry_points_single_gpu(ctx):
+    """lpvs_admm_shard_*: argument validation, handle export, and the guard against running unconnected.  The exchange
+    itself needs >= 2 GPUs (tests/test_gpu_multi.py, tools/admm_shard_check.py)."""
+    from lpvspectral_jl_b200 import _lib as L
+
+    t, y = sig(900, 6)
+    f = np.arange(0, 300) * 0.1
+
+    def create(prox=L.PROX_L1, param=0.2):
+        h = C.c_void_p()
+        ctx.check(ctx.lib.lpvs_admm_create_fourier(ctx.h, vp(y), vp(t), len(y), vp(f), len(f), None, prox, param, 0.05,
+                                                   None, 0, 0.0, C.byref(h)))
+        return h
+
+    h = create()
+    assert ctx.lib.lpvs_admm_shard_begin(h, 0, 1) == L.E_BAD_ARG        # world >= 2
+    assert ctx.lib.lpvs_admm_shard_begin(h, 2, 2) == L.E_BAD_ARG        # rank < world
+    assert ctx.lib.lpvs_admm_shard_begin(h, 0, 8) == L.E_UNSUPPORTED    # 5 row blocks cannot feed 8 ranks
+    buf = C.create_string_buffer(64)
+    assert ctx.lib.lpvs_admm_shard_handle(h, C.cast(buf, C.c_void_p)) == L.E_BAD_ARG  # not sharded yet
+    assert ctx.lib.lpvs_admm_shard_begin(h, 1, 2) == L.OK
+    assert ctx.lib.lpvs_admm_shard_handle(h, C.cast(buf, C.c_void_p)) == L.OK and any(buf.raw)
+    it, res, conv = C.c_int64(0), C.c_double(0.0), C.c_int(0)
+    rc = ctx.lib.lpvs_admm_run(h, 10, 1e-9, C.byref(it), C.byref(res), C.byref(conv))
+    assert rc == L.E_BAD_ARG and b"not connected" in ctx.lib.lpvs_last_error(ctx.h)
+    assert ctx.lib.lpvs_admm_shard_begin(h, 1, 2) == L.E_UNSUPPORTED    # already sharded
+    ctx.lib.lpvs_admm_free(h)
+    h = create(L.PROX_BALL_L0, 5.0)
+    assert ctx.lib.lpvs_admm_shard_begin(h, 0, 2) == L.E_UNSUPPORTED    # element-wise prox operators only
+    ctx.lib.lpvs_admm_free(h)
