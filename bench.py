@@ -172,8 +172,40 @@ def admm_leg(ctx, lp, L, C, rank, world, allsum, allmax, barrier, iters=2000):
             hbm = float(json.load(fh)["hbm_gbs"])
     except Exception:
         pass
+    sharded = None
+    if world > 1 and world <= 8:
+        # the same problem (rank 0's data on every rank) as ONE problem over all GPUs: device-initiated peer stores over
+        # NVLink inside the persistent loop (lpvs_admm_shard_*, DESIGN.md section 5 iii)
+        try:
+            from lpvspectral_jl_b200 import _dist as D
+
+            t0s, y0s, f0s = make_cfg3(seed=3)
+            hs = C.c_void_p()
+            rc = ctx.lib.lpvs_admm_create_fourier(ctx.h, y0s.ctypes.data_as(C.c_void_p),
+                                                  t0s.ctypes.data_as(C.c_void_p), len(y0s),
+                                                  f0s.ctypes.data_as(C.c_void_p), len(f0s), None, L.PROX_L1, 0.1, 0.05,
+                                                  None, 0, 0.0, C.byref(hs))
+            if allmax(1.0 if rc else 0.0) > 0:  # all ranks agree before any collective of the sharded leg
+                if not rc:
+                    ctx.lib.lpvs_admm_free(hs)
+                raise RuntimeError("sharded ADMM: problem creation failed on some rank")
+            ss = D.admm_shard(lp.ADMM(ctx, hs))
+            ss.step(100, 0.0)
+            barrier()
+            ss.step(iters, 0.0)
+            ms_s, _ = ss.timing()
+            barrier()
+            ss.free()
+            ms_max = allmax(ms_s)
+            sharded = {"iters_per_s": iters / (ms_max * 1e-3), "us_per_iter": ms_max / iters * 1e3,
+                       "vs_one_gpu": (iters / (ms_max * 1e-3)) / its_min,
+                       "how": "one problem over all GPUs: reduce-scatter of partial products + all-gather of the rhs by "
+                              "peer stores over NVLink inside the persistent kernel, max over ranks of the device time"}
+        except Exception as e:  # never lose the headline line to the optional leg
+            sharded = {"error": repr(e)[:200]}
     return {"workload": "cfg3_l1_admm", "nreg": 2 * len(f) - 1, "iters": iters, "iters_per_s": total,
-            "iters_per_s_per_gpu_min": its_min, "scaling": "replicas only", "setup_s": setup_s,
+            "iters_per_s_per_gpu_min": its_min, "scaling": "replicas (weak); `sharded` = one problem (strong)",
+            "sharded": sharded, "setup_s": setup_s,
             "gram_tflops": gfl / gms / 1e9,
             "roofline": {"bound": "hbm", "achieved": bpi * its_min / 1e9, "peak": hbm, "unit": "GB/s",
                          "frac": bpi * its_min / 1e9 / hbm, "traffic": ncu_traffic("k_admm_symv"),
