@@ -16,7 +16,7 @@ import LPVSpectral: SpectralExt, default_freqs, check_freq   # host-side pieces 
 import DSP: rect, hanning
 
 export ls_spectral, ls_windowpsd, ls_windowcsd, ls_cohere, ls_sparse_spectral, ls_spectral_lpv,
-       ls_sparse_spectral_lpv
+       ls_sparse_spectral_lpv, ls_windowpsd_lpv
 
 const liblpvs = get(ENV, "LIBLPVS", "liblpvs")
 const WIN_PSD, WIN_CSD, WIN_COHERE = Cint(0), Cint(1), Cint(2)
@@ -183,6 +183,23 @@ function ls_spectral_lpv(Y::AbstractVector, X::AbstractVector, V::AbstractVector
     SpectralExt(Y, X, V, wv, Nv, λ, coulomb, normalize, like(Y, params), like(Y, Σ))
 end
 
+# ---- ls_windowpsd_lpv (src/lsfft.jl:267-277): rect windows (Windows3), S = Σ_windows |Σ_k x[f,k]|², not normalised ----
+function ls_windowpsd_lpv(Y::AbstractVector, X::AbstractVector, V::AbstractVector, w, Nv::Integer, nw::Int=10,
+                          noverlap=0; kwargs...)
+    length(Y) == length(X) == length(V) || throw(AssertionError("y, t and v has to be the same length"))  # src/windows.jl:96
+    n = length(Y) ÷ nw
+    noverlap < 0 && (noverlap = n >> 1)                                     # src/windows.jl:97
+    hop = n - noverlap
+    K = length(Y) >= n ? (length(Y) - n) ÷ hop + 1 : 0
+    S = zeros(length(w))
+    for k in 0:K-1
+        r = k*hop+1:k*hop+n
+        se = ls_spectral_lpv(Y[r], X[r], V[r], w, Nv; kwargs...)
+        S .+= abs2.(vec(sum(reshape(se.x, length(w), :), dims=2)))         # reshape_params, src/utilities.jl:77
+    end
+    S
+end
+
 # ---- ADMM-backed sparse estimators (src/lasso.jl) ---------------------------------------------------------------
 # proxg objects are ProximalOperators types; only their (kind, parameter) crosses the ABI.
 proxdesc(p) = begin
@@ -201,16 +218,19 @@ function run_admm(h, n; iters=10000, tol=1e-5, printerval=100, cb=nothing, μ=no
         check(ccall((:lpvs_admm_run, liblpvs), Cint, (Ptr{Cvoid}, Int64, Float64, Ptr{Int64}, Ptr{Float64}, Ptr{Cint}),
                     h, chunk, Float64(tol), it, res, conv))
         done += it[]
-        if conv[] != 0 || done % printerval == 0
+        if done % printerval == 0                                               # src/lasso.jl:158-163
             @printf("%d ||x-z||₂ %.10f\n", done, res[])
-            if cb !== nothing && done % printerval == 0
+            if cb !== nothing
                 x = Vector{Float64}(undef, n); z = similar(x)
                 check(ccall((:lpvs_admm_get, liblpvs), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h, x, z))
                 cb(x, z)
             end
         end
+        if conv[] != 0                                # :164-168 (a stop on a print iteration prints the line twice)
+            @printf("%d ||x-z||₂ %.10f\n", done, res[])
+            @info("||x-z||₂ ≤ tol")
+        end
     end
-    conv[] != 0 && @info("||x-z||₂ ≤ tol")
 end
 
 function ls_sparse_spectral(y::AbstractArray{T}, t, f=default_freqs(t), W=nothing;

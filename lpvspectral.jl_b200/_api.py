@@ -504,13 +504,14 @@ class ADMM:
         while self.iters < iters and not self.converged:
             chunk = min(printerval - self.iters % printerval, iters - self.iters)
             self.step(chunk, tol)
-            if self.converged or self.iters % printerval == 0:
+            if self.iters % printerval == 0:  # src/lasso.jl:158-163
                 if verbose:
                     print("%d ||x-z||₂ %.10f" % (self.iters, self.residual))
-                if cb is not None and self.iters % printerval == 0:
+                if cb is not None:
                     cb(*self.get())
-        if self.converged and verbose:
-            print("[ Info: ||x-z||₂ ≤ tol")
+            if self.converged and verbose:  # :164-168 (a stop on a print iteration prints the line twice)
+                print("%d ||x-z||₂ %.10f" % (self.iters, self.residual))
+                print("[ Info: ||x-z||₂ ≤ tol")
         return self
 
     def get(self):
