@@ -136,6 +136,16 @@ int lpvs_ls_spectral_lpv(lpvs_ctx* ctx, const double* Y, const double* X, const 
                          const double* w, int Nf, int Nv, double lambda, int coulomb, int normalize,
                          double* params, double* Sigma, double* fva, int* info);
 
+/* ---- ls_windowpsd_lpv (src/lsfft.jl:267-277; Windows3, src/windows.jl:94-104) ----
+ * Rect windows of n samples overlapping by `noverlap` (< 0 means n>>1): window k is the sample range
+ * [k (n-noverlap), +n) of Y, X, V (uploaded once), estimated by ls_spectral_lpv on the window's OWN basis centres.
+ * S: Nf doubles = sum over windows of |sum_k x[f,k]|^2 (not normalised, as the reference).  fva (may be NULL): one
+ * fraction of variance explained per window (the reference warns per window when it is < 0.9); size it with
+ * lpvs_window_count(N, n, noverlap).  *K = number of windows. */
+int lpvs_ls_windowpsd_lpv(lpvs_ctx* ctx, const double* Y, const double* X, const double* V, int64_t N,
+                          const double* w, int Nf, int Nv, int n, int noverlap, double lambda, int coulomb,
+                          int normalize, double* S, double* fva, int64_t* K, int* info);
+
 /* ---- ADMM (src/lasso.jl:136-171) behind ls_sparse_spectral / ls_sparse_spectral_lpv (src/lasso.jl:27-126) ----
  * create: builds the Gram on device, factorises (G + I/mu), keeps everything resident.
  *   W == NULL  -> LeastSquares(A,y):   x-update solves (G + I/mu) x = A'y + (z-u)/mu

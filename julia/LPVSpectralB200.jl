@@ -185,19 +185,24 @@ end
 
 # ---- ls_windowpsd_lpv (src/lsfft.jl:267-277): rect windows (Windows3), S = Σ_windows |Σ_k x[f,k]|², not normalised ----
 function ls_windowpsd_lpv(Y::AbstractVector, X::AbstractVector, V::AbstractVector, w, Nv::Integer, nw::Int=10,
-                          noverlap=0; kwargs...)
+                          noverlap=0; λ=1e-8, coulomb=false, normalize=true)
     length(Y) == length(X) == length(V) || throw(AssertionError("y, t and v has to be the same length"))  # src/windows.jl:96
-    n = length(Y) ÷ nw
-    noverlap < 0 && (noverlap = n >> 1)                                     # src/windows.jl:97
-    hop = n - noverlap
-    K = length(Y) >= n ? (length(Y) - n) ÷ hop + 1 : 0
-    S = zeros(length(w))
-    for k in 0:K-1
-        r = k*hop+1:k*hop+n
-        se = ls_spectral_lpv(Y[r], X[r], V[r], w, Nv; kwargs...)
-        S .+= abs2.(vec(sum(reshape(se.x, length(w), :), dims=2)))         # reshape_params, src/utilities.jl:77
+    Yv, Xv, Vv, wv = vecf(Y), vecf(X), vecf(V), vecf(w[:])
+    n = length(Yv) ÷ nw
+    Kw = ccall((:lpvs_window_count, liblpvs), Int64, (Int64, Cint, Cint), length(Yv), n, noverlap)
+    S = zeros(length(wv)); fva = ones(max(Kw, 1))
+    K = Ref{Int64}(0); info = Ref{Cint}(0)
+    GC.@preserve Yv Xv Vv wv S fva begin
+        check(ccall((:lpvs_ls_windowpsd_lpv, liblpvs), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Cint, Cint, Cint, Float64,
+             Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Cint}),
+            ctx(), Yv, Xv, Vv, length(Yv), wv, length(wv), Nv, n, noverlap, Float64(λ), coulomb, normalize, S, fva, K,
+            info))
     end
-    S
+    for k in 1:K[]
+        fva[k] < 0.9 && @warn("Fraction of variance explained = $(fva[k])")  # src/lsfft.jl:256, once per window
+    end
+    like(Y, S)
 end
 
 # ---- ADMM-backed sparse estimators (src/lasso.jl) ---------------------------------------------------------------

@@ -426,19 +426,30 @@ def ls_spectral_lpv(Y, X, V, w, Nv, *, coulomb=False, normalize=True, want_sigma
 
 
 @_preserve_eltype
-def ls_windowpsd_lpv(Y, X, V, w, Nv, nw=10, noverlap=0, *, ctx=None, **kw):
-    """ls_windowpsd_lpv (src/lsfft.jl:267-277): rect windows, S not normalised."""
+def ls_windowpsd_lpv(Y, X, V, w, Nv, nw=10, noverlap=0, *, coulomb=False, normalize=True, ctx=None, **kw):
+    """ls_windowpsd_lpv(Y,X,V,w,Nv,nw=10,noverlap=0; kwargs...) (src/lsfft.jl:267-277): rect windows (Windows3), one
+    ls_spectral_lpv per window on the window's own basis centres, S = Σ_windows |Σ_k x[f,k]|², not normalised.  The
+    signals go to the device once; windows are sample ranges (lpvs_ls_windowpsd_lpv)."""
+    lam = _lam(kw, 1e-8)
+    if kw:
+        raise TypeError(f"unexpected keyword arguments {sorted(kw)}")
+    ctx = ctx or default_context()
     Yv, Xv, Vv, wv = _f64(Y), _f64(X), _f64(V), _f64(w)
+    if not (len(Yv) == len(Xv) == len(Vv)):
+        raise ValueError("y, t and v has to be the same length")  # src/windows.jl:96
     n = len(Yv) // int(nw)
-    if noverlap < 0:
-        noverlap = n >> 1
-    K = window_count(len(Yv), n, noverlap)
-    hop = n - noverlap
+    Kw = window_count(len(Yv), n, noverlap) if n > 0 else 0
     S = np.zeros(len(wv))
-    for k in range(K):
-        sl = slice(k * hop, k * hop + n)
-        se = ls_spectral_lpv(Yv[sl], Xv[sl], Vv[sl], wv, Nv, want_sigma=False, ctx=ctx, **dict(kw))
-        S += psd(se)
+    fva = np.ones(max(Kw, 1))
+    K, info = C.c_int64(0), C.c_int(0)
+    ctx.check(ctx.lib.lpvs_ls_windowpsd_lpv(ctx.h, _ptr(Yv), _ptr(Xv), _ptr(Vv), len(Yv), _ptr(wv), len(wv), int(Nv),
+                                            int(n), int(noverlap), lam, int(bool(coulomb)), int(bool(normalize)),
+                                            _ptr(S), _ptr(fva), C.byref(K), C.byref(info)))
+    for v in fva[:K.value]:
+        if v < 0.9:  # src/lsfft.jl:256, once per window
+            import warnings
+
+            warnings.warn(f"Fraction of variance explained = {v}")
     return S
 
 

@@ -86,9 +86,9 @@ int device_var(lpvs_ctx* c, const double* d_v, long long N, double* var_out) {
 
 }  // namespace
 
-int lpv_prepare(lpvs_ctx* c, const double* X, const double* V, int64_t N, const double* w, int Nf, int Nv,
-                int coulomb, int normalize, LpvPlan* pl) {
-    if (!X || !V || !w || N <= 1 || Nf <= 0 || Nv <= 0) return fail(c, LPVS_E_BAD_ARG, "bad LPV arguments");
+// tables for samples [0,N) of DEVICE arrays d_X / d_V; V is the same range on the HOST (centres need its min / max)
+int lpv_prepare_dev(lpvs_ctx* c, const double* V, const double* d_X, const double* d_V, int64_t N, const double* d_w,
+                    int Nf, int Nv, int coulomb, int normalize, LpvPlan* pl) {
     pl->Nf = Nf;
     pl->Nv = Nv;
     pl->Nvv = coulomb ? 2 * Nv : Nv;
@@ -129,11 +129,8 @@ int lpv_prepare(lpvs_ctx* c, const double* X, const double* V, int64_t N, const 
         gamma = (double)Nv / fabs(cen[0] - cen[Nv - 1]);
     }
     if (!isfinite(gamma)) return fail(c, LPVS_E_BAD_ARG, "degenerate scheduling signal (all V equal)");
-    double *d_X, *d_V, *d_w, *d_cen;
+    double* d_cen;
     int rc;
-    if ((rc = upload(c, BUF_T, X, N, &d_X))) return rc;
-    if ((rc = upload(c, BUF_V, V, N, &d_V))) return rc;
-    if ((rc = upload(c, BUF_F, w, Nf, &d_w))) return rc;
     if ((rc = upload(c, BUF_CENT, cen.data(), pl->Nvv, &d_cen))) return rc;
     double2* E = ws<double2>(c, BUF_E, (size_t)Nf * N);
     double* K = ws<double>(c, BUF_K, (size_t)pl->Nvv * N);
@@ -143,6 +140,17 @@ int lpv_prepare(lpvs_ctx* c, const double* X, const double* V, int64_t N, const 
     pl->d_E = E;
     pl->d_K = K;
     return LPVS_OK;
+}
+
+int lpv_prepare(lpvs_ctx* c, const double* X, const double* V, int64_t N, const double* w, int Nf, int Nv,
+                int coulomb, int normalize, LpvPlan* pl) {
+    if (!X || !V || !w || N <= 1 || Nf <= 0 || Nv <= 0) return fail(c, LPVS_E_BAD_ARG, "bad LPV arguments");
+    double *d_X, *d_V, *d_w;
+    int rc;
+    if ((rc = upload(c, BUF_T, X, N, &d_X))) return rc;
+    if ((rc = upload(c, BUF_V, V, N, &d_V))) return rc;
+    if ((rc = upload(c, BUF_F, w, Nf, &d_w))) return rc;
+    return lpv_prepare_dev(c, V, d_X, d_V, N, d_w, Nf, Nv, coulomb, normalize, pl);
 }
 
 int lpv_gram(lpvs_ctx* c, const LpvPlan& pl, const double* d_y, double* d_G, double* d_B) {
@@ -204,25 +212,15 @@ int lpv_gram(lpvs_ctx* c, const LpvPlan& pl, const double* d_y, double* d_G, dou
 
 }  // namespace lpvs
 
-using namespace lpvs;
+namespace lpvs {
+namespace {
 
-extern "C" {
-
-int lpvs_ls_spectral_lpv(lpvs_ctx* c, const double* Y, const double* X, const double* V, int64_t N, const double* w,
-                         int Nf, int Nv, double lambda, int coulomb, int normalize, double* params, double* Sigma,
-                         double* fva, int* info) {
-    if (!c) return LPVS_E_BAD_ARG;
-    CallTimer call_timer(c);
-    std::lock_guard<std::mutex> lk(c->mu);
-    cudaSetDevice(c->device);
-    if (info) *info = 0;
-    if (!Y || !params) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
-    gram_timer_reset(c);
-    LpvPlan pl;
-    int rc = lpv_prepare(c, X, V, N, w, Nf, Nv, coulomb, normalize, &pl);
-    if (rc) return rc;
-    double* d_Y;
-    if ((rc = upload(c, BUF_Y, Y, N, &d_Y))) return rc;
+// ls_spectral_lpv on prepared tables and a device-resident Y (src/lsfft.jl:248-257); params / Sigma / fva are host outputs
+int lpv_ls_core(lpvs_ctx* c, const LpvPlan& pl, const double* d_Y, double lambda, double* params, double* Sigma,
+                double* fva, int* info) {
+    const int64_t N = pl.N;
+    const int Nf = pl.Nf;
+    int rc;
     const long long Np = pl.Np, NN = Np * Np;
     const int nref = 2 * pl.ncc;
     // two copies of G: ridge lambda^2 for the solve (src/utilities.jl:52), ridge lambda for Sigma (src/lsfft.jl:254)
@@ -247,12 +245,16 @@ int lpvs_ls_spectral_lpv(lpvs_ctx* c, const double* Y, const double* X, const do
     launch_x_to_complex(c, d_B, pl.Np, pl.ncc, 0, 1, d_out);
     LPVS_CU(c, cudaMemcpyAsync(params, d_out, sizeof(double) * nref, cudaMemcpyDeviceToHost, c->st));
     // residual, variances, fraction of variance explained (src/lsfft.jl:252-256)
-    k_lpv_residual<<<(unsigned)((N + 127) / 128), 128, 0, c->st>>>(pl.d_E, pl.d_K, N, Nf, pl.Nvv, d_B, d_Y, d_e);
-    c->launches++;
     double ve = 0.0, vy = 0.0;
-    if ((rc = device_var(c, d_e, N, &ve))) return rc;
-    if ((rc = device_var(c, d_Y, N, &vy))) return rc;
-    if (fva) *fva = 1.0 - ve / vy;
+    if (fva || Sigma) {
+        k_lpv_residual<<<(unsigned)((N + 127) / 128), 128, 0, c->st>>>(pl.d_E, pl.d_K, N, Nf, pl.Nvv, d_B, d_Y, d_e);
+        c->launches++;
+        if ((rc = device_var(c, d_e, N, &ve))) return rc;
+    }
+    if (fva) {
+        if ((rc = device_var(c, d_Y, N, &vy))) return rc;
+        *fva = 1.0 - ve / vy;
+    }
     if (Sigma) {
         double* d_G2 = d_G + NN;
         CholArgs ca{};
@@ -280,7 +282,81 @@ int lpvs_ls_spectral_lpv(lpvs_ctx* c, const double* Y, const double* X, const do
         c->launches++;
         LPVS_CU(c, cudaMemcpyAsync(Sigma, d_e, sizeof(double) * nref * nref, cudaMemcpyDeviceToHost, c->st));
     }
-    if ((rc = inputs_finite(c))) return rc;
+    return inputs_finite(c);
+}
+
+}  // namespace
+}  // namespace lpvs
+
+using namespace lpvs;
+
+extern "C" {
+
+int lpvs_ls_spectral_lpv(lpvs_ctx* c, const double* Y, const double* X, const double* V, int64_t N, const double* w,
+                         int Nf, int Nv, double lambda, int coulomb, int normalize, double* params, double* Sigma,
+                         double* fva, int* info) {
+    if (!c) return LPVS_E_BAD_ARG;
+    CallTimer call_timer(c);
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    if (info) *info = 0;
+    if (!Y || !params) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
+    gram_timer_reset(c);
+    LpvPlan pl;
+    int rc = lpv_prepare(c, X, V, N, w, Nf, Nv, coulomb, normalize, &pl);
+    if (rc) return rc;
+    double* d_Y;
+    if ((rc = upload(c, BUF_Y, Y, N, &d_Y))) return rc;
+    if ((rc = lpv_ls_core(c, pl, d_Y, lambda, params, Sigma, fva, info))) return rc;
+    gram_timer_resolve(c);
+    return LPVS_OK;
+}
+
+// ls_windowpsd_lpv (src/lsfft.jl:267-277): Y, X, V, w go to the device once; every rect window (Windows3,
+// src/windows.jl:94-104) is a sample range of those arrays with its own basis centres (basis_activation_func is
+// evaluated on the window's V) and runs the dense LPV estimator above.
+int lpvs_ls_windowpsd_lpv(lpvs_ctx* c, const double* Y, const double* X, const double* V, int64_t N, const double* w,
+                          int Nf, int Nv, int n, int noverlap, double lambda, int coulomb, int normalize, double* S,
+                          double* fva, int64_t* K, int* info) {
+    if (!c) return LPVS_E_BAD_ARG;
+    CallTimer call_timer(c);
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    if (info) *info = 0;
+    if (K) *K = 0;
+    if (!Y || !X || !V || !w || !S || N <= 0 || Nf <= 0 || Nv <= 0 || n <= 1)
+        return fail(c, LPVS_E_BAD_ARG, "bad LPV window arguments");
+    if (noverlap < 0) noverlap = n >> 1;  // src/windows.jl:97
+    if (noverlap >= n) return fail(c, LPVS_E_BAD_ARG, "noverlap must be smaller than the window length");
+    const int64_t hop = n - noverlap;
+    const int64_t nwin = N >= n ? (N - n) / hop + 1 : 0;
+    if (K) *K = nwin;
+    for (int f = 0; f < Nf; f++) S[f] = 0.0;
+    if (nwin == 0) return LPVS_OK;
+    gram_timer_reset(c);
+    double *d_Y, *d_X, *d_V, *d_w;
+    int rc;
+    if ((rc = upload(c, BUF_Y, Y, N, &d_Y))) return rc;
+    if ((rc = upload(c, BUF_T, X, N, &d_X))) return rc;
+    if ((rc = upload(c, BUF_V, V, N, &d_V))) return rc;
+    if ((rc = upload(c, BUF_F, w, Nf, &d_w))) return rc;
+    const int nvv = coulomb ? 2 * Nv : Nv;
+    std::vector<double> p((size_t)2 * Nf * nvv);
+    for (int64_t k = 0; k < nwin; k++) {
+        const int64_t off = k * hop;
+        LpvPlan pl;
+        if ((rc = lpv_prepare_dev(c, V + off, d_X + off, d_V + off, n, d_w, Nf, Nv, coulomb, normalize, &pl))) return rc;
+        // the core ends with a stream synchronisation, so p is complete when it returns
+        if ((rc = lpv_ls_core(c, pl, d_Y + off, lambda, p.data(), nullptr, fva ? fva + k : nullptr, info))) return rc;
+        for (int f = 0; f < Nf; f++) {  // abs2(sum(reshape_params(x, Nf), dims=2)), src/lsfft.jl:273-274
+            double re = 0.0, im = 0.0;
+            for (int kk = 0; kk < nvv; kk++) {
+                re += p[2 * ((size_t)f + (size_t)kk * Nf)];
+                im += p[2 * ((size_t)f + (size_t)kk * Nf) + 1];
+            }
+            S[f] += re * re + im * im;
+        }
+    }
     gram_timer_resolve(c);
     return LPVS_OK;
 }

@@ -123,6 +123,22 @@ def test_ls_windowpsd_lpv(ctx):
     S = lp.ls_windowpsd_lpv(Y, X, V, w, 12, nw=4, noverlap=0, lam=0.05, ctx=ctx)
     Sr = o.ls_windowpsd_lpv(Y, X, V, w, 12, nw=4, noverlap=0, lam=0.05)
     assert rel(S, Sr) <= 1e-9
+    # overlapping windows (ragged tail dropped), the reference's default nw, coulomb / un-normalised basis
+    S = lp.ls_windowpsd_lpv(Y[:997], X[:997], V[:997], w, 8, 5, 37, lam=0.05, ctx=ctx)
+    Sr = o.ls_windowpsd_lpv(Y[:997], X[:997], V[:997], w, 8, nw=5, noverlap=37, lam=0.05)
+    assert rel(S, Sr) <= 1e-9
+    S = lp.ls_windowpsd_lpv(Y, X, V - 0.5 + 1e-4, w, 4, nw=4, lam=0.05, coulomb=True, normalize=False, ctx=ctx)
+    Sr = o.ls_windowpsd_lpv(Y, X, V - 0.5 + 1e-4, w, 4, nw=4, lam=0.05, coulomb=True, normalize=False)
+    assert rel(S, Sr) <= 1e-9
+    # the same windows one by one through the single-problem entry point
+    n, hop = 997 // 5, 997 // 5 - 37
+    Sk = np.zeros(len(w))
+    for k in range((997 - n) // hop + 1):
+        sl = slice(k * hop, k * hop + n)
+        Sk += lp.psd(lp.ls_spectral_lpv(Y[sl], X[sl], V[sl], w, 8, lam=0.05, want_sigma=False, ctx=ctx))
+    assert rel(lp.ls_windowpsd_lpv(Y[:997], X[:997], V[:997], w, 8, 5, 37, lam=0.05, ctx=ctx), Sk) <= 1e-13
+    with pytest.raises(ValueError):
+        lp.ls_windowpsd_lpv(Y, X[:-1], V, w, 8, ctx=ctx)
 
 
 def test_sparse_lpv_group_lasso(ctx):
