@@ -1393,7 +1393,6 @@ static int build_symv_plan(lpvs_ctx* c, lpvs_admm* h, const GroupItems& gitems, 
     {
         // blocks of the lower triangle in block-column-major order, split evenly over the CTAs, then cut into
         // segments (same block column, <= SEG blocks)
-        const long long T = (long long)nb * (nb + 1) / 2;
         std::vector<int> sj, si0, si1, cta(grid + 1, 0);
         std::vector<int> colstart(nb + 1, 0);
         for (int J = 0; J < nb; J++) colstart[J + 1] = colstart[J] + (nb - J);
@@ -1607,7 +1606,7 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
                   int* converged) {
     if (!h) return LPVS_E_BAD_ARG;
     lpvs_ctx* c = h->ctx;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lock lk(c->mu);
     cudaSetDevice(c->device);
     if (iters_done) *iters_done = 0;
     if (max_iters <= 0 || h->converged) {
@@ -1754,7 +1753,7 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
 int lpvs_admm_shard_begin(lpvs_admm* h, int rank, int world) {
     if (!h) return LPVS_E_BAD_ARG;
     lpvs_ctx* c = h->ctx;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lock lk(c->mu);
     cudaSetDevice(c->device);
     const int Np = h->Np, nb = Np / TB;
     if (world < 2 || world > SHARD_MAXP || rank < 0 || rank >= world)
@@ -1807,7 +1806,7 @@ int lpvs_admm_shard_begin(lpvs_admm* h, int rank, int world) {
 int lpvs_admm_shard_handle(lpvs_admm* h, void* handle64) {
     if (!h || !handle64 || h->shard_world < 2) return LPVS_E_BAD_ARG;
     lpvs_ctx* c = h->ctx;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lock lk(c->mu);
     cudaSetDevice(c->device);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t mh;
@@ -1819,7 +1818,7 @@ int lpvs_admm_shard_handle(lpvs_admm* h, void* handle64) {
 int lpvs_admm_shard_connect(lpvs_admm* h, const void* handles) {
     if (!h || !handles || h->shard_world < 2) return LPVS_E_BAD_ARG;
     lpvs_ctx* c = h->ctx;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lock lk(c->mu);
     cudaSetDevice(c->device);
     for (int k = 0; k < h->shard_world; k++) {
         if (k == h->shard_rank) continue;
@@ -1838,7 +1837,7 @@ int lpvs_admm_size(const lpvs_admm* h) { return h ? h->nref : 0; }
 int lpvs_admm_get(lpvs_admm* h, double* x, double* z) {
     if (!h) return LPVS_E_BAD_ARG;
     lpvs_ctx* c = h->ctx;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lock lk(c->mu);
     cudaSetDevice(c->device);
     double* tmp = ws<double>(c, BUF_X, (size_t)2 * h->nref);
     if (!tmp) return fail(c, LPVS_E_NOMEM, "out of device memory");
@@ -1873,7 +1872,7 @@ int lpvs_admm_get(lpvs_admm* h, double* x, double* z) {
 int lpvs_admm_result(lpvs_admm* h, double* out) {
     if (!h || !out) return LPVS_E_BAD_ARG;
     lpvs_ctx* c = h->ctx;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lock lk(c->mu);
     cudaSetDevice(c->device);
     // complex column cc -> (z_re, z_im); Fourier zero frequency has no imaginary coefficient
     const int Np = h->Np, ncx = h->half;
@@ -1907,7 +1906,7 @@ int lpvs_admm_last_timing(const lpvs_admm* h, double* ms, double* bytes_per_iter
 void lpvs_admm_free(lpvs_admm* h) {
     if (!h) return;
     lpvs_ctx* c = h->ctx;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lock lk(c->mu);
     admm_release(h);
 }
 

@@ -454,7 +454,7 @@ const char* lpvs_last_error(const lpvs_ctx* c) { return c ? c->err.c_str() : "no
 
 int lpvs_set_option(lpvs_ctx* c, int key, double value) {
     if (!c) return LPVS_E_BAD_ARG;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lock lk(c->mu);
     switch (key) {
         case LPVS_OPT_PHASE_MODE: c->phase_mode = (int)value; break;
         case LPVS_OPT_WINDOW_BATCH: c->window_batch = (int)value; break;
@@ -468,7 +468,7 @@ int lpvs_set_option(lpvs_ctx* c, int key, double value) {
 
 int lpvs_set_stream(lpvs_ctx* c, void* stream) {
     if (!c) return LPVS_E_BAD_ARG;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lock lk(c->mu);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     c->st = stream ? (cudaStream_t)stream : c->own_st;
@@ -539,8 +539,8 @@ int64_t lpvs_window_count(int64_t N, int n, int noverlap) {
 int lpvs_gram_fourier(lpvs_ctx* c, const double* y, const double* t, int64_t N, const double* f, int Nf,
                       const double* W, double* G, double* b) {
     if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
     CallTimer call_timer(c);
-    std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (!t || N <= 0 || !G) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
     gram_timer_reset(c);
@@ -659,8 +659,8 @@ extern "C" {
 int lpvs_ls_spectral(lpvs_ctx* c, const double* y, const double* t, int64_t N, const double* f, int Nf,
                      const double* W, double lambda, double* x, int* info) {
     if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
     CallTimer call_timer(c);
-    std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (!y || !t || !x || N <= 0) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
     gram_timer_reset(c);
@@ -694,8 +694,8 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
                             int64_t N, const double* f, int Nf, const double* W, int n, int noverlap, double lambda,
                             int64_t k_begin, int64_t k_end, double* sums, int* info) {
     if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
     CallTimer call_timer(c);
-    std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (info) *info = 0;
     if (kind < 0 || kind > 2) return fail(c, LPVS_E_BAD_ARG, "bad window kind %d", kind);
@@ -788,38 +788,29 @@ int lpvs_ls_window_sums(lpvs_ctx* c, int kind, const double* y, const double* u,
                         const double* f, int Nf, const double* W, int n, int noverlap, double lambda, int64_t k_begin,
                         int64_t k_end, double* sums, int* info) {
     if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);  // held across upload + compute: the uploaded samples live in the context's workspace
     CallTimer call_timer(c);
     if (!y || !t || N <= 0 || n <= 0) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
     if (noverlap < 0) noverlap = n >> 1;
     if (noverlap >= n) return fail(c, LPVS_E_BAD_ARG, "noverlap must be < n");
+    cudaSetDevice(c->device);
+    // only this rank's sample range travels to the device
+    const int64_t K = lpvs_window_count(N, n, noverlap);
+    if (k_begin < 0 || k_end > K || k_begin > k_end) return fail(c, LPVS_E_BAD_ARG, "window range out of bounds");
+    if (k_end == k_begin) {
+        if (sums) memset(sums, 0, sizeof(double) * sums_len(kind, Nf));
+        return LPVS_OK;
+    }
     double *d_t, *d_y, *d_u;
-    {
-        std::lock_guard<std::mutex> lk(c->mu);
-        cudaSetDevice(c->device);
-        // only this rank's sample range travels to the device
-        const int64_t K = lpvs_window_count(N, n, noverlap);
-        if (k_begin < 0 || k_end > K || k_begin > k_end) return fail(c, LPVS_E_BAD_ARG, "window range out of bounds");
-        int rc;
-        if (k_end == k_begin) {
-            memset(sums, 0, sizeof(double) * sums_len(kind, Nf));
-            return LPVS_OK;
-        }
-        const int64_t hop = n - noverlap, s0 = k_begin * hop, s1 = (k_end - 1) * hop + n;
-        if ((rc = upload(c, BUF_T, t + s0, s1 - s0, &d_t))) return rc;
-        if ((rc = upload(c, BUF_Y, y + s0, s1 - s0, &d_y))) return rc;
-        if ((rc = upload(c, BUF_U, u ? u + s0 : nullptr, s1 - s0, &d_u))) return rc;
-        N = s1 - s0;
-        k_end -= k_begin;
-        k_begin = 0;
-    }
-    int rc2 = lpvs_ls_window_sums_dev(c, kind, d_y, d_u, d_t, N, f, Nf, W, n, noverlap, lambda, k_begin, k_end, sums,
-                                      info);
-    {
-        std::lock_guard<std::mutex> lk(c->mu);
-        int rcf = inputs_finite(c);
-        if (rcf) return rcf;
-    }
-    return rc2;
+    int rc;
+    const int64_t hop = n - noverlap, s0 = k_begin * hop, s1 = (k_end - 1) * hop + n;
+    if ((rc = upload(c, BUF_T, t + s0, s1 - s0, &d_t))) return rc;
+    if ((rc = upload(c, BUF_Y, y + s0, s1 - s0, &d_y))) return rc;
+    if ((rc = upload(c, BUF_U, u ? u + s0 : nullptr, s1 - s0, &d_u))) return rc;
+    int rc2 = lpvs_ls_window_sums_dev(c, kind, d_y, d_u, d_t, s1 - s0, f, Nf, W, n, noverlap, lambda, 0,
+                                      k_end - k_begin, sums, info);
+    int rcf = inputs_finite(c);
+    return rcf ? rcf : rc2;
 }
 
 // ---- windowed estimators with estimator = ls_sparse_spectral (src/lsfft.jl:121,150-151,184-185 calling the weighted
@@ -831,8 +822,8 @@ int lpvs_ls_window_sparse_sums(lpvs_ctx* c, int kind, const double* y, const dou
                                double prox_param, double mu, int64_t iters, double tol, int64_t k_begin,
                                int64_t k_end, double* sums, int64_t* iters_done, double* residuals, int* info) {
     if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
     CallTimer call_timer(c);
-    std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (info) *info = 0;
     if (kind < 0 || kind > 2) return fail(c, LPVS_E_BAD_ARG, "bad window kind %d", kind);

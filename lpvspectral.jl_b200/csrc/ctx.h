@@ -32,7 +32,7 @@ struct lpvs_ctx {
     cudaStream_t own_st = nullptr;  // the context's own stream
     lpvs::Lookahead la{};           // aux stream + events of the look-ahead factorisation (single large problems)
     std::string err;
-    std::mutex mu;
+    std::recursive_mutex mu;  // serialises every call on this context; recursive so composite entry points hold it throughout
     int phase_mode = LPVS_PHASE_AUTO;
     int window_batch = 0;
     int jitter = 1;
@@ -53,6 +53,8 @@ struct lpvs_ctx {
 };
 
 namespace lpvs {
+
+using Lock = std::lock_guard<std::recursive_mutex>;
 
 int fail(lpvs_ctx* c, int code, const char* fmt, ...);
 

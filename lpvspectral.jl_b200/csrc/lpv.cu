@@ -296,8 +296,8 @@ int lpvs_ls_spectral_lpv(lpvs_ctx* c, const double* Y, const double* X, const do
                          int Nf, int Nv, double lambda, int coulomb, int normalize, double* params, double* Sigma,
                          double* fva, int* info) {
     if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
     CallTimer call_timer(c);
-    std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (info) *info = 0;
     if (!Y || !params) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
@@ -319,8 +319,8 @@ int lpvs_ls_windowpsd_lpv(lpvs_ctx* c, const double* Y, const double* X, const d
                           int Nf, int Nv, int n, int noverlap, double lambda, int coulomb, int normalize, double* S,
                           double* fva, int64_t* K, int* info) {
     if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
     CallTimer call_timer(c);
-    std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (info) *info = 0;
     if (K) *K = 0;
@@ -365,8 +365,8 @@ int lpvs_admm_create_fourier(lpvs_ctx* c, const double* y, const double* t, int6
                              const double* W, int prox_kind, double prox_param, double mu, const double* x0, int init,
                              double lambda_init, lpvs_admm** out) {
     if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
     CallTimer call_timer(c);
-    std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (!out) return fail(c, LPVS_E_BAD_ARG, "null handle pointer");
     *out = nullptr;
@@ -429,8 +429,8 @@ int lpvs_admm_create_fourier(lpvs_ctx* c, const double* y, const double* t, int6
 int lpvs_admm_create_lpv(lpvs_ctx* c, const double* y, const double* X, const double* V, int64_t N, const double* w,
                          int Nf, int Nv, int coulomb, int normalize, double lambda, double mu, lpvs_admm** out) {
     if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
     CallTimer call_timer(c);
-    std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (!out) return fail(c, LPVS_E_BAD_ARG, "null handle pointer");
     *out = nullptr;
@@ -494,6 +494,8 @@ int lpvs_admm_create_lpv(lpvs_ctx* c, const double* y, const double* X, const do
 int lpvs_ls_sparse_spectral(lpvs_ctx* c, const double* y, const double* t, int64_t N, const double* f, int Nf,
                             const double* W, int prox_kind, double prox_param, double mu, int init, double lambda_init,
                             int64_t iters, double tol, double* x, int64_t* iters_done, double* residual) {
+    if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);  // create / run / result / free as one serialised unit
     lpvs_admm* h = nullptr;
     int rc = lpvs_admm_create_fourier(c, y, t, N, f, Nf, W, prox_kind, prox_param, mu, nullptr, init, lambda_init, &h);
     if (rc) return rc;
@@ -507,6 +509,8 @@ int lpvs_ls_sparse_spectral(lpvs_ctx* c, const double* y, const double* t, int64
 int lpvs_ls_sparse_spectral_lpv(lpvs_ctx* c, const double* y, const double* X, const double* V, int64_t N,
                                 const double* w, int Nf, int Nv, int coulomb, int normalize, double lambda, double mu,
                                 int64_t iters, double tol, double* params, int64_t* iters_done, double* residual) {
+    if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);  // create / run / result / free as one serialised unit
     lpvs_admm* h = nullptr;
     int rc = lpvs_admm_create_lpv(c, y, X, V, N, w, Nf, Nv, coulomb, normalize, lambda, mu, &h);
     if (rc) return rc;
@@ -527,8 +531,8 @@ int64_t lpvs_packed_size(int Nf) {
 int lpvs_gram_partial_dev(lpvs_ctx* c, const double* d_y, const double* d_u, const double* d_t, const double* d_W,
                           int64_t N, const double* f, int Nf, double* d_packed) {
     if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
     CallTimer call_timer(c);
-    std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (!d_t || !d_packed || N <= 0) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
     gram_timer_reset(c);
@@ -547,8 +551,8 @@ int lpvs_gram_partial_dev(lpvs_ctx* c, const double* d_y, const double* d_u, con
 int lpvs_solve_packed_dev(lpvs_ctx* c, double* d_packed, const double* f, int Nf, int nrhs, double ridge, double* x,
                           int* info) {
     if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
     CallTimer call_timer(c);
-    std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     if (info) *info = 0;
     if (!d_packed || !x || nrhs < 1 || nrhs > 2) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
