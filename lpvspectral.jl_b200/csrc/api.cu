@@ -310,9 +310,8 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
             g.strideB = part_stride;
         }
         gram_timer_begin(c);
-        launch_gram(pl.mode, g, nprob, c->st);
+        c->launches += launch_gram(pl.mode, g, nprob, c->st);
         gram_timer_end(c, (double)ns * pl.Nreg * (pl.Nreg + 1.0), 1);
-        c->launches++;
         if (!direct_out) {
             k_reduce_parts<<<(unsigned)((Np * Np + 255) / 256), 256, 0, c->st>>>(d_G, parts, Np * Np, part_stride,
                                                                                  nprob, sgi > 0);
@@ -759,9 +758,8 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
         g.B = d_B;
         g.strideB = 2 * Np;
         gram_timer_begin(c);
-        launch_gram(pl.mode, g, nw, c->st);
+        c->launches += launch_gram(pl.mode, g, nw, c->st);  // k_gram (+ k_gram_rhs when there are two channels)
         gram_timer_end(c, (double)nw * n * pl.Nreg * (pl.Nreg + 1.0), 1);
-        c->launches += 2;  // k_gram + k_gram_rhs
         // always the weighted estimator: ridge lambda (src/lsfft.jl:121 -> :77)
         if ((rc = factor_solve(c, pl.Nf, pl.zero_first, pl.Np, d_G, d_B, nrhs, lambda, nw, hinfo.data()))) return rc;
         k_window_accum<<<(Nf + 127) / 128, 128, 0, c->st>>>(kind, d_B, 2 * Np, pl.Np, nw, Nf, pl.zero_first, d_sums);
@@ -919,9 +917,8 @@ int lpvs_ls_window_sparse_sums(lpvs_ctx* c, int kind, const double* y, const dou
         g.B = d_B;
         g.strideB = 2 * Np;
         gram_timer_begin(c);
-        launch_gram(pl.mode, g, nw, c->st);
+        c->launches += launch_gram(pl.mode, g, nw, c->st);
         gram_timer_end(c, (double)nw * n * pl.Nreg * (pl.Nreg + 1.0), 1);
-        c->launches += 2;
         // M = (A'WA + I/mu)^-1 per window
         CholArgs ca{};
         ca.G = d_G;

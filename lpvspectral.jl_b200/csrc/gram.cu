@@ -463,7 +463,8 @@ __global__ void k_lpv_tables(const double* __restrict__ X, const double* __restr
 
 size_t gram_smem_bytes() { return NSTAGE * STAGE_D * sizeof(double) + 64; }
 
-void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
+int launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
+    int launched = 0;
     static bool attr_done[64] = {};  // per device: function attributes belong to the device's context
     int dev = 0;
     cudaGetDevice(&dev);
@@ -497,7 +498,9 @@ void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
             k_gram<GRAM_LPV><<<grid, NTHREADS, smem, st>>>(b);
             if (rhs) k_gram_rhs<GRAM_LPV><<<grid_rhs, NTHREADS, 0, st>>>(b);
         }
+        launched += rhs ? 2 : 1;
     }
+    return launched;
 }
 
 void launch_anchor_table(const double* t, long long s0, long long ns, const double* f, int Nf, int ngroups,

@@ -49,8 +49,8 @@ struct GramArgs {
 };
 
 size_t gram_smem_bytes();
-// grid = (nblk*(nblk+1)/2, nproblems)
-void launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st);
+// grid = (nblk*(nblk+1)/2, nproblems); returns the number of kernels launched
+int launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st);
 
 // anchors every GRP frequencies + per-sample step rotation, exact phase (double-double turns)
 void launch_anchor_table(const double* t, long long s0, long long ns, const double* f, int Nf, int ngroups,

@@ -199,9 +199,8 @@ int lpv_gram(lpvs_ctx* c, const LpvPlan& pl, const double* d_y, double* d_G, dou
         g.strideB = part_stride;
     }
     gram_timer_begin(c);
-    launch_gram(GRAM_LPV, g, nprob, c->st);
+    c->launches += launch_gram(GRAM_LPV, g, nprob, c->st);
     gram_timer_end(c, (double)pl.N * (2.0 * pl.ncc) * (2.0 * pl.ncc + 1.0), 1);
-    c->launches++;
     if (nprob > 1) {
         reduce_parts(c, d_G, parts, Np * Np, part_stride, nprob, 0);
         if (d_B) reduce_parts(c, d_B, parts + Np * Np, 2 * Np, part_stride, nprob, 0);
