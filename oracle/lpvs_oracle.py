@@ -20,7 +20,9 @@ behaviour (unpinned by the reference's own tests, see DESIGN.md "parity pins"):
 * IterativeSolvers.jl ``cg!`` (warm start, reltol=sqrt(eps) w.r.t. the initial residual, maxiter=n).
 
 ADMM parity is therefore "unpinned" by the reference (``test/test_lasso.jl`` has no assertions): this file is
-the de-facto specification for the prox steps.
+the de-facto specification for the prox steps.  What can be checked without Julia is checked in
+``tests/test_oracle_pins.py``: every prox operator against a brute-force minimisation of its Moreau objective, the ADMM
+limits against the lasso / group-lasso optimality conditions and scikit-learn, the CG restatement against scipy.
 
 Two solve modes everywhere a dense solve happens:
 
