@@ -56,5 +56,5 @@ def test_workload_generators_have_the_baseline_shapes():
 
     t, y, f, n = bench.make_cfg2(nsamp=1 << 14, nw=4, nf=128)
     assert n == 4096 and len(t) == len(y) == 1 << 14 and len(f) == 128 and f[0] == 0 and np.all(np.diff(t) >= 0)
-    t, y, f = bench.make_cfg3(N=1024)
-    assert len(f) == 512 and f[0] == 0 and len(t) == 1024
+    t, y, f = bench.make_cfg3()
+    assert len(f) == 8192 and f[0] == 0 and len(t) == 16384
