@@ -133,6 +133,17 @@ def cpu_baseline_windows(t, y, f, n, nwin, threads=None):
     return nwin / dt, dt
 
 
+def blas_threads():
+    """Threads the BLAS behind numpy/scipy uses for the CPU arm (north_star: core count AND BLAS thread count)."""
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = [int(p.get("num_threads", 0)) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else None
+    except Exception:
+        return None
+
+
 def make_cfg3(seed=3, N=16384):
     """t=sort(10*U^16384), f=default_freqs(t)[:8192], 5 tones + 0.1 noise."""
     rng = np.random.default_rng(seed)
@@ -234,7 +245,8 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg2_windowpsd", "samples": NSAMP, "nw": NW, "n": n, "noverlap": n >> 1,
                    "windows": 2 * NW - 1, "freqs": NF, "window": "hanning"},
-        "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "blas_threads": blas_threads(),
+                         "kind": "port",
                          "sample": f"{nwin} of {2 * NW - 1} windows per step, oracle reference-literal mode "
                                    f"(numpy/OpenBLAS, all host threads); Julia is not installed"},
         "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -405,7 +417,8 @@ def main():
                          "flops_per_window": float(n) * nreg * (nreg + 1), "windows_per_launch": K,
                          "gram_ms_per_step": gram_ms / args.steps, "gram_share_of_step": gram_ms / call_ms,
                          "peak_source": peak_src},
-            "cpu_baseline": {"value": cpu_val, "unit": "windows/s", "cores": os.cpu_count(), "kind": "port",
+            "cpu_baseline": {"value": cpu_val, "unit": "windows/s", "cores": os.cpu_count(),
+                             "blas_threads": blas_threads(), "kind": "port",
                              "sample": f"{cpu_windows} of {K} windows in {cpu_dt:.1f} s, oracle reference-literal "
                                        "mode (N-rhs LU per window, numpy/OpenBLAS all threads)"},
             "clocks": clocks,
