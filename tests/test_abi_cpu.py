@@ -96,3 +96,27 @@ def test_host_helpers_match_oracle():
     assert lp.check_freq(np.array([0.0, 1.0])) == 0 and lp.check_freq(np.array([1.0, 2.0])) is None
     with pytest.raises(ValueError):
         lp.check_freq(np.array([1.0, 0.0]))
+
+
+def test_plain_c_caller_compiles_links_and_fails_loudly_without_gpu(lib, tmp_path):
+    """include/lpvs.h is valid C99 and liblpvs.so links from a plain C program (examples/c_abi_example.c): host-only
+    entry points work, and without a GPU lpvs_init refuses (exit code 3) instead of computing on the host."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pkg = os.path.join(ROOT, "lpvspectral.jl_b200")
+    exe = str(tmp_path / "lpvs_example")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c",
+                    os.path.join(ROOT, "include", "lpvs.h")], check=True)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_abi_example.c"), "-L" + pkg, "-llpvs", "-lm",
+                    "-Wl,-rpath," + pkg, "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert "15 windows at 50% overlap" in out.stdout
+    if lib.load().lpvs_device_count() > 0:
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "peak at f = 20.00 Hz" in out.stdout
+    else:
+        assert out.returncode == 3 and "no CPU fallback" in out.stdout
