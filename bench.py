@@ -117,8 +117,10 @@ def fp64_peak():
         return 37.0, "nominal 37 TFLOP/s (fallback: profiles/fp64_peak_r01.json missing)"
 
 
-def cpu_baseline_windows(t, y, f, n, nwin, threads=None):
-    """Reference-literal CPU algorithm (oracle) on `nwin` windows of the workload; returns windows/s."""
+def cpu_baseline_windows(t, y, f, n, nwin, threads=None, mode="literal"):
+    """CPU algorithm (oracle) on `nwin` windows of the workload; returns windows/s.  mode="literal" is what the
+    reference executes (basis + N-rhs LU per window); mode="gram" is the stronger CPU line SURVEY 8(d) asks for (the
+    algorithm the GPU runs -- Gram + Cholesky -- on the host BLAS)."""
     from oracle import lpvs_oracle as o
 
     W = o.hanning(n)
@@ -127,7 +129,7 @@ def cpu_baseline_windows(t, y, f, n, nwin, threads=None):
     S = np.zeros(len(f))
     for k in range(nwin):
         sl = slice(k * hop, k * hop + n)
-        x, _ = o.ls_spectral(y[sl], t[sl], f, W, lam=LAMBDA, mode="literal")
+        x, _ = o.ls_spectral(y[sl], t[sl], f, W, lam=LAMBDA, mode=mode)
         S += x.real ** 2 + x.imag ** 2
     dt = time.perf_counter() - t0
     return nwin / dt, dt
@@ -399,6 +401,10 @@ def main():
         # the CPU baseline is an N=1 figure; at N>1 only a token sample keeps the other ranks from idling in NCCL
         cpu_windows = args.cpu_windows if world == 1 else min(args.cpu_windows, 8)
         cpu_val, cpu_dt = cpu_baseline_windows(t, y, f, n, cpu_windows)
+        try:  # second, stronger CPU line (Gram + Cholesky on the host BLAS); never allowed to cost the headline line
+            cpu_gram_val, _ = cpu_baseline_windows(t, y, f, n, min(cpu_windows, 48), mode="gram")
+        except Exception:
+            cpu_gram_val = None
         line = {
             "metric": "windowed LS spectra/sec", "value": value, "unit": "windows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -418,7 +424,7 @@ def main():
                          "gram_ms_per_step": gram_ms / args.steps, "gram_share_of_step": gram_ms / call_ms,
                          "peak_source": peak_src},
             "cpu_baseline": {"value": cpu_val, "unit": "windows/s", "cores": os.cpu_count(),
-                             "blas_threads": blas_threads(), "kind": "port",
+                             "blas_threads": blas_threads(), "kind": "port", "gram_cholesky_value": cpu_gram_val,
                              "sample": f"{cpu_windows} of {K} windows in {cpu_dt:.1f} s, oracle reference-literal "
                                        "mode (N-rhs LU per window, numpy/OpenBLAS all threads)"},
             "clocks": clocks,
