@@ -244,3 +244,36 @@ def test_default_freqs_three_argument_form_uses_first_n_samples():
     f = o.default_freqs(t, 64)
     fs = 1 / np.mean(np.diff(t[:64]))
     assert len(f) == 33 and f[0] == 0 and abs(f[1] - fs / 64) <= 1e-12 * fs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the oracle's two solve modes (what the reference runs / what the GPU runs) agree over random well-posed shapes
+# ---------------------------------------------------------------------------------------------------------------
+
+
+def test_literal_and_gram_modes_agree_over_random_shapes():
+    hyp = pytest.importorskip("hypothesis")
+    st = hyp.strategies
+
+    @hyp.settings(max_examples=40, deadline=None, derandomize=True)
+    @hyp.given(st.integers(0, 10 ** 6), st.integers(60, 260), st.integers(2, 14), st.booleans(), st.booleans())
+    def run(seed, N, Nf, zero_first, weighted):
+        rng = np.random.default_rng(seed)
+        t = np.sort(10.0 * rng.random(N))
+        f = (np.arange(Nf) + (0 if zero_first else 1)) * 0.37  # spacing 3.7 / record length: well conditioned
+        y = rng.standard_normal(N)
+        W = 0.2 + rng.random(N) if weighted else None
+        a, _ = o.ls_spectral(y, t, f, W, lam=1e-10, mode="literal")
+        b, _ = o.ls_spectral(y, t, f, W, lam=1e-10, mode="gram")
+        assert np.linalg.norm(a - b) <= 1e-9 * np.linalg.norm(a)
+        # windowed estimators: the ragged tail is dropped the same way in both modes, cohere(y,y) == 1 exactly (Q8)
+        u = np.roll(y, 3) + 0.5 * rng.standard_normal(N)
+        fw = f[:max(2, Nf // 2)] * 4
+        for fn in (o.ls_windowcsd, o.ls_cohere):
+            sa, _ = fn(y, u, t, fw, nw=3, mode="literal")
+            sb, _ = fn(y, u, t, fw, nw=3, mode="gram")
+            assert np.linalg.norm(sa - sb) <= 1e-8 * np.linalg.norm(sa)
+        one, _ = o.ls_cohere(y, y, t, fw, nw=3, mode="gram")
+        assert np.all(one == 1.0)
+
+    run()
