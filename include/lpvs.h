@@ -56,7 +56,8 @@ enum lpvs_option {
 };
 
 /* info flags returned by solvers */
-#define LPVS_INFO_JITTER 1
+#define LPVS_INFO_JITTER 1 /* a WEIGHTED (Gram / LU in the reference) problem was numerically singular: jitter ridge used */
+#define LPVS_INFO_QR 2     /* informational: the unweighted / LPV solve took the shifted-CholeskyQR path (ill-conditioned A) */
 
 int lpvs_version(void);
 int lpvs_device_count(void);

@@ -19,6 +19,7 @@ PROX_L1, PROX_L0, PROX_BALL_L0, PROX_GROUP_L2 = 0, 1, 2, 3
 PHASE_AUTO, PHASE_CHAIN, PHASE_DIRECT = 0, 1, 2
 OPT_PHASE_MODE, OPT_WINDOW_BATCH, OPT_JITTER, OPT_ADMM_CHECK_EVERY, OPT_ADMM_SYMV = 0, 1, 2, 3, 4
 INFO_JITTER = 1
+INFO_QR = 2
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

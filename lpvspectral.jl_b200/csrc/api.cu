@@ -129,6 +129,11 @@ __global__ void k_check_finite(const double* __restrict__ v, long long n, int* f
     if (bad) atomicOr(flag, 1);
 }
 
+// out[0] = max(ridge, scale * maxdiag[0]): jitter ridge decided on the device
+__global__ void k_jitter_ridge(const double* __restrict__ maxdiag, double ridge, double scale, double* __restrict__ out) {
+    out[0] = fmax(ridge, scale * maxdiag[0]);
+}
+
 // internal x ([nrhs][Np]) -> interleaved complex [nrhs][Nf]   (fourier2complex, src/utilities.jl:62-73)
 __global__ void k_x_to_complex(const double* __restrict__ X, int Np, int Nf, int zero_first, int nrhs,
                                double* __restrict__ out) {
@@ -326,7 +331,7 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
 }
 
 int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, double* d_B, int nrhs, double ridge,
-                 int nproblems, int* info_host, const double* d_maxdiag, double tol_scale) {
+                 int nproblems, int* info_host, const double* d_maxdiag, double tol_scale, const double* d_ridge) {
     const int nb = Np / TB;
     CholArgs ca{};
     ca.G = d_G;
@@ -348,7 +353,7 @@ int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, doub
     }
     if (!ca.Linv || !ca.info) return fail(c, LPVS_E_NOMEM, "out of device memory (factor workspace)");
     LPVS_CU(c, cudaMemsetAsync(ca.info, 0, sizeof(int) * nproblems, c->st));
-    launch_diag_prepare(d_G, ca.strideG, Np, ncc, zero_first, nullptr, ridge, nproblems, c->st);
+    launch_diag_prepare(d_G, ca.strideG, Np, ncc, zero_first, d_ridge, ridge, nproblems, c->st);
     c->launches += 1 + potrf(ca, nproblems, c->sms, c->st, &c->la);
     if (d_B && nrhs > 0) {
         launch_trsv(ca, d_B, 2LL * Np, nrhs, nproblems, c->st, fuse_fwd);
@@ -584,6 +589,22 @@ int ls_solve_dev(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const do
     if (!d_G || !d_B || !d_md) return fail(c, LPVS_E_NOMEM, "out of device memory (G)");
     int rc;
     if (info) *info = 0;
+    if (!d_W && nrhs == 1 && allow_jitter) {
+        // unweighted: the reference solves on [A; lam I] itself (SVD, src/utilities.jl:58) -> operator-accurate solve
+        auto regram = [&]() { return gram_single(c, pl, d_t, d_y, nullptr, nullptr, N, 1, d_G, d_B); };
+        if ((rc = regram())) return rc;
+        OpArgs op;
+        op.mode = GRAM_DIRECT;
+        op.t = d_t;
+        op.f = pl.d_f;
+        op.dd = pl.dd;
+        op.ncc = pl.Nf;
+        op.zero_first = pl.zero_first;
+        op.N = N;
+        if ((rc = ls_solve_accurate(c, op, pl.Np, pl.zero_first, d_y, d_G, d_B, sqrt(ridge), regram, info))) return rc;
+        *d_x = d_B;
+        return LPVS_OK;
+    }
     double* d_keep = nullptr;  // pristine copy of G, b for the jitter retry (no second Gram pass)
     for (int attempt = 0; attempt < 2; attempt++) {
         if (attempt == 0) {
@@ -673,7 +694,9 @@ int lpvs_ls_spectral(lpvs_ctx* c, const double* y, const double* t, int64_t N, c
     // ridge: lambda^2 unweighted (src/utilities.jl:58), lambda weighted (src/lsfft.jl:77)
     double ridge = W ? lambda : lambda * lambda;
     double* d_x;
-    if ((rc = ls_solve_dev(c, pl, d_t, d_y, nullptr, d_W, N, 1, ridge, !W && c->jitter, &d_x, info))) {
+    // LPVS_OPT_JITTER=1 (default): unweighted -> operator-accurate solve (lsq.cu); weighted -> Cholesky of A'WA + lambda I with
+    // a jitter retry on breakdown (the reference's LU at src/lsfft.jl:77 never throws).  0: plain Cholesky, NOT_SPD on breakdown.
+    if ((rc = ls_solve_dev(c, pl, d_t, d_y, nullptr, d_W, N, 1, ridge, c->jitter != 0, &d_x, info))) {
         if (inputs_finite(c) == LPVS_E_NONFINITE) return LPVS_E_NONFINITE;  // the more specific diagnosis
         return rc;
     }
@@ -722,7 +745,7 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
     if (c->window_batch <= 0 && batch > c->sms) batch -= batch % c->sms;
     batch = std::min<int64_t>(batch, std::max<int64_t>(1, k_end - k_begin));
     std::vector<int> hinfo((size_t)batch);
-    int bad = 0;
+    int bad = 0, jittered = 0;
     int64_t bad_window = -1;
     for (int64_t k0 = k_begin; k0 < k_end; k0 += batch) {
         const int nw = (int)std::min<int64_t>(batch, k_end - k0);
@@ -762,14 +785,44 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
         gram_timer_end(c, (double)nw * n * pl.Nreg * (pl.Nreg + 1.0), 1);
         // always the weighted estimator: ridge lambda (src/lsfft.jl:121 -> :77)
         if ((rc = factor_solve(c, pl.Nf, pl.zero_first, pl.Np, d_G, d_B, nrhs, lambda, nw, hinfo.data()))) return rc;
-        k_window_accum<<<(Nf + 127) / 128, 128, 0, c->st>>>(kind, d_B, 2 * Np, pl.Np, nw, Nf, pl.zero_first, d_sums);
-        c->launches++;
         LPVS_CU(c, cudaStreamSynchronize(c->st));
-        for (int i = 0; i < nw && !bad; i++)
-            if (hinfo[i]) {
-                bad = hinfo[i];
+        for (int i = 0; i < nw; i++) {
+            if (!hinfo[i]) continue;
+            if (!c->jitter) {
+                if (!bad) {
+                    bad = hinfo[i];
+                    bad_window = k0 + i;
+                }
+                continue;
+            }
+            // The reference's LU of A'WA + lambda I never throws (src/lsfft.jl:77); a numerically singular window is
+            // re-done alone with the jitter ridge max(lambda, Nreg eps max diag G) before the in-order accumulation.
+            double* d_g1 = ws<double>(c, BUF_YINV, (size_t)Np * Np + 2 * Np + 8);
+            if (!d_g1) return fail(c, LPVS_E_NOMEM, "out of device memory (window retry)");
+            double* d_b1 = d_g1 + Np * Np;
+            double* d_md = d_b1 + 2 * Np;
+            GramArgs g1 = g;
+            g1.start0 = g.start0 + (long long)i * hop;
+            g1.G = d_g1;
+            g1.B = d_b1;
+            c->launches += launch_gram(pl.mode, g1, 1, c->st);
+            launch_max_diag(d_g1, Np * Np, pl.Np, pl.Nf, pl.zero_first, d_md, 1, c->st);
+            k_jitter_ridge<<<1, 1, 0, c->st>>>(d_md, lambda, (double)pl.Nreg * 2.220446049250313e-16, d_md + 1);
+            c->launches += 2;
+            int pinfo = 0;
+            if ((rc = factor_solve(c, pl.Nf, pl.zero_first, pl.Np, d_g1, d_b1, nrhs, 0.0, 1, &pinfo, nullptr, 0.0, d_md + 1)))
+                return rc;
+            LPVS_CU(c, cudaMemcpyAsync(d_B + (long long)i * 2 * Np, d_b1, sizeof(double) * 2 * Np, cudaMemcpyDeviceToDevice,
+                                       c->st));
+            LPVS_CU(c, cudaStreamSynchronize(c->st));
+            if (pinfo && !bad) {
+                bad = pinfo;
                 bad_window = k0 + i;
             }
+            jittered++;
+        }
+        k_window_accum<<<(Nf + 127) / 128, 128, 0, c->st>>>(kind, d_B, 2 * Np, pl.Np, nw, Nf, pl.zero_first, d_sums);
+        c->launches++;
     }
     LPVS_CU(c, cudaMemcpyAsync(sums, d_sums, sizeof(double) * slen, cudaMemcpyDeviceToHost, c->st));
     LPVS_CU(c, cudaStreamSynchronize(c->st));
@@ -779,6 +832,7 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
         return fail(c, LPVS_E_NOT_SPD, "Cholesky breakdown in window %lld at internal pivot %d", (long long)bad_window,
                     bad);
     }
+    if (jittered && info) *info = LPVS_INFO_JITTER;
     return LPVS_OK;
 }
 

@@ -320,15 +320,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ C
 // ------------------------------------------------------------------------------------------------------------
 // global-memory NT GEMM tile: acc += A[128 x K] * B[128 x K]' with cp.async double buffering
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_tile_async(double* dst, const double* src, long long ld, int tid) {
-#pragma unroll
-    for (int i = 0; i < (TB * KC / 2) / NTHREADS; i++) {
-        int q = tid + i * NTHREADS;
-        int row = q >> 4, seg = q & 15;
-        cp_async16(dst + row * LDT + 2 * seg, src + (long long)row * ld + 2 * seg);
-    }
-}
-
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const __grid_constant__ CholArgs a, int mode, int k) {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -971,7 +962,7 @@ int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st, const Look
     return launches;
 }
 
-int potri(const CholArgs& a, int nproblems, cudaStream_t st) {
+int trtri(const CholArgs& a, int nproblems, cudaStream_t st) {
     int launches = 0;
     launch_init_y(a, nproblems, st);
     launches++;
@@ -980,6 +971,11 @@ int potri(const CholArgs& a, int nproblems, cudaStream_t st) {
         launch_gemm(GM_TRTRI_B, a, i, i, nproblems, st);
         launches += 2;
     }
+    return launches;
+}
+
+int potri(const CholArgs& a, int nproblems, cudaStream_t st) {
+    int launches = trtri(a, nproblems, st);
     launch_gemm(GM_LAUUM, a, 0, a.nb * (a.nb + 1) / 2, nproblems, st);
     launch_symmetrize(a.G, a.strideG, a.Np, nproblems, st);
     return launches + 2;

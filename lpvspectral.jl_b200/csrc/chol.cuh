@@ -66,6 +66,8 @@ void launch_max_diag(const double* G, long long strideG, int Np, int ncc, int ze
 
 // full factorisation driver (left-looking when batched, right-looking for few large problems); returns launches
 int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st, const Lookahead* la = nullptr);
+// after potrf: Y = L^-T (upper 128-tiles of a.Y; tiles below the diagonal are not written). returns launches
+int trtri(const CholArgs& a, int nproblems, cudaStream_t st);
 // after potrf: M = (L L')^{-1} written (full symmetric) into G; uses Y. returns launches
 int potri(const CholArgs& a, int nproblems, cudaStream_t st);
 

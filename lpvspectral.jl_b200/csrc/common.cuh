@@ -34,6 +34,16 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// one [TB x KC] operand tile (row-major source, leading dimension ld) into a [TB][LDT] smem tile, 16 bytes per copy
+__device__ __forceinline__ void load_tile_async(double* dst, const double* src, long long ld, int tid) {
+#pragma unroll
+    for (int i = 0; i < (TB * KC / 2) / NTHREADS; i++) {
+        int q = tid + i * NTHREADS;
+        int row = q >> 4, seg = q & 15;
+        cp_async16(dst + row * LDT + 2 * seg, src + (long long)row * ld + 2 * seg);
+    }
+}
+
 // ---- mbarrier (shared-memory barrier object): arrive is non-blocking, waiting does not count as arrival ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -20,7 +21,8 @@ struct DevBuf {
 
 enum BufSlot {
     BUF_T = 0, BUF_Y, BUF_U, BUF_W, BUF_F, BUF_ANC, BUF_DEL, BUF_G, BUF_B, BUF_LINV, BUF_INFO, BUF_PART, BUF_SUMS,
-    BUF_X, BUF_MISC, BUF_YINV, BUF_E, BUF_K, BUF_V, BUF_CENT, BUF_COUNT
+    BUF_X, BUF_MISC, BUF_YINV, BUF_E, BUF_K, BUF_V, BUF_CENT, BUF_LSQ_R, BUF_LSQ_V, BUF_LSQ_Y, BUF_LSQ_LI, BUF_LSQ_A,
+    BUF_LSQ_BT, BUF_LSQ_G2, BUF_COUNT
 };
 
 }  // namespace lpvs
@@ -109,9 +111,31 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
                 const double* d_W, int64_t N, int nrhs, double* d_G, double* d_B);
 
 // factor + solve one problem in place: d_G -> L, d_B -> x (internal layout); returns pivot info in *info_host
+// d_ridge (device, one value per problem) replaces `ridge` when given
 int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, double* d_B, int nrhs, double ridge,
                  int nproblems, int* info_host /* nproblems or null */, const double* d_maxdiag = nullptr,
-                 double tol_scale = 0.0);
+                 double tol_scale = 0.0, const double* d_ridge = nullptr);
+
+// The regressor as an operator, synthesised on the fly with the REFERENCE's rounding (lsq.cu): Fourier
+// fl(fl(cos(fl(fl(2 pi f) t))) dd) (src/lsfft.jl:34-44) or the LPV tables (src/lsfft.jl:244-248).
+struct OpArgs {
+    int mode = GRAM_DIRECT;  // GRAM_DIRECT (Fourier) or GRAM_LPV
+    const double* t = nullptr;
+    const double* f = nullptr;
+    double dd = 1.0;
+    const double2* E = nullptr;
+    const double* Kt = nullptr;
+    long long tbl_ns = 0;
+    int lpv_nf = 1;
+    int ncc = 0;  // valid complex columns
+    int zero_first = 0;
+    long long N = 0;
+};
+// x = argmin |A x - y|^2 + lam^2 |x|^2 to the accuracy of a QR / SVD of [A; lam I] (see lsq.cu).  In: d_G = Gram matrix of
+// ANY phase mode (lower tiles, destroyed), d_B[0] = A'y; out: d_B[0] = x (internal layout).  regram() must rebuild d_G / d_B
+// (only called if the shifted factorisation itself breaks down).  *info: 0, or LPVS_INFO_QR when the QR path ran.
+int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, const double* d_y, double* d_G, double* d_B,
+                      double lam, const std::function<int()>& regram, int* info);
 
 // shared helpers (api.cu)
 // reads the upload-time non-finite flag (synchronises the stream); LPVS_E_NONFINITE if any host input had NaN/Inf

@@ -33,6 +33,15 @@ struct Pref {
     bool valid;  // the weight is zeroed for invalid samples at the point of USE (no stall on the prefetch)
 };
 
+// One step of the angle-addition chain with the contraction PINNED (one rounded product, one FMA per component), so every
+// tile and every kernel that synthesises a column produces bit-identical values: the Gram matrix and the right-hand side
+// are then those of ONE well-defined matrix A~.  (With compiler-chosen contraction the same column differed in the last
+// bit between the diagonal and off-diagonal instantiations; in a null direction of A that inconsistency is amplified by
+// 1/shift ~ 1e13 -- 1.6e-5 in the Nyquist coefficient of the reference's 1000 x 1001 KAT, profiles/r02_rankdef.md.)
+__device__ __forceinline__ double2 chain_rotate(double2 z, double2 d) {
+    return make_double2(__fma_rn(z.x, d.x, -__dmul_rn(z.y, d.y)), __fma_rn(z.x, d.y, __dmul_rn(z.y, d.x)));
+}
+
 template <int MODE, bool DIAG, bool RHS = false>
 __device__ __forceinline__ Pref load_pref(const GramArgs& a, int c, long long s_begin, int lane, int w, int I,
                                           int J) {
@@ -129,14 +138,8 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
         sJ[rowc + j * LDT] = vJ.x;
         sJ[rows + j * LDT] = vJ.y;
         if (MODE == GRAM_CHAIN) {
-            double nx = zI.x * p.d.x - zI.y * p.d.y;
-            double ny = zI.x * p.d.y + zI.y * p.d.x;
-            zI = make_double2(nx, ny);
-            if (!DIAG) {
-                nx = zJ.x * p.d.x - zJ.y * p.d.y;
-                ny = zJ.x * p.d.y + zJ.y * p.d.x;
-                zJ = make_double2(nx, ny);
-            }
+            zI = chain_rotate(zI, p.d);
+            if (!DIAG) zJ = chain_rotate(zJ, p.d);
         }
     };
     auto chain_start_J = [&](const Pref& p) { return make_double2(p.aJ.x * p.wt, p.aJ.y * p.wt); };
@@ -370,11 +373,7 @@ __global__ void __launch_bounds__(NTHREADS) k_gram_rhs(const __grid_constant__ G
             ss[0][j] = fma(v.y, y0, ss[0][j]);
             sc[1][j] = fma(v.x, y1, sc[1][j]);
             ss[1][j] = fma(v.y, y1, ss[1][j]);
-            if (MODE == GRAM_CHAIN) {
-                double nx = z.x * p.d.x - z.y * p.d.y;
-                double ny = z.x * p.d.y + z.y * p.d.x;
-                z = make_double2(nx, ny);
-            }
+            if (MODE == GRAM_CHAIN) z = chain_rotate(z, p.d);
         }
     }
     const int Np = a.nblk * TB;
@@ -499,6 +498,26 @@ int launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
             if (rhs) k_gram_rhs<GRAM_LPV><<<grid_rhs, NTHREADS, 0, st>>>(b);
         }
         launched += rhs ? 2 : 1;
+    }
+    return launched;
+}
+
+int launch_gram_rhs(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
+    int launched = 0;
+    for (int p0 = 0; p0 < nproblems; p0 += 32768) {
+        int np = nproblems - p0 < 32768 ? nproblems - p0 : 32768;
+        GramArgs b = a;
+        b.start0 = a.start0 + (long long)p0 * a.hop;
+        b.B = a.B + (long long)p0 * a.strideB;
+        b.fuse_rhs = 0;
+        dim3 grid_rhs(a.nblk, np);
+        if (mode == GRAM_CHAIN)
+            k_gram_rhs<GRAM_CHAIN><<<grid_rhs, NTHREADS, 0, st>>>(b);
+        else if (mode == GRAM_DIRECT)
+            k_gram_rhs<GRAM_DIRECT><<<grid_rhs, NTHREADS, 0, st>>>(b);
+        else
+            k_gram_rhs<GRAM_LPV><<<grid_rhs, NTHREADS, 0, st>>>(b);
+        launched++;
     }
     return launched;
 }

@@ -52,6 +52,9 @@ size_t gram_smem_bytes();
 // grid = (nblk*(nblk+1)/2, nproblems); returns the number of kernels launched
 int launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st);
 
+// only b = A' diag(W) [y u] (grid = (nblk, nproblems)); the adjoint of the synthesised operator
+int launch_gram_rhs(int mode, const GramArgs& a, int nproblems, cudaStream_t st);
+
 // anchors every GRP frequencies + per-sample step rotation, exact phase (double-double turns)
 void launch_anchor_table(const double* t, long long s0, long long ns, const double* f, int Nf, int ngroups,
                          double f0, double df, double2* anc, double2* del, cudaStream_t st);

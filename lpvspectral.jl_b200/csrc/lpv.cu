@@ -229,14 +229,34 @@ int lpv_ls_core(lpvs_ctx* c, const LpvPlan& pl, const double* d_Y, double lambda
     if ((rc = lpv_gram(c, pl, d_Y, d_G, d_B))) return rc;
     if (Sigma) LPVS_CU(c, cudaMemcpyAsync(d_G + NN, d_G, sizeof(double) * NN, cudaMemcpyDeviceToDevice, c->st));
     int pinfo = 0;
-    if ((rc = factor_solve(c, pl.ncc, 0, pl.Np, d_G, d_B, 1, lambda * lambda, 1, &pinfo))) return rc;
-    if ((rc = inputs_finite(c))) return rc;  // NaN inputs / 0/0 basis normalisation: the cause, not "not SPD"
-    LPVS_CU(c, cudaStreamSynchronize(c->st));
-    if (pinfo) {
-        if (info) *info = pinfo;
-        return fail(c, LPVS_E_NOT_SPD,
-                    "Cholesky breakdown at internal pivot %d: Ar'Ar + lambda^2 I is not numerically positive definite "
-                    "(lambda=%g is too small for the Gram formulation, SURVEY Q10)", pinfo, lambda);
+    if (c->jitter) {
+        // the reference solves on [Ar; lambda I] itself (pivoted QR, src/utilities.jl:52): operator-accurate solve, so the
+        // default lambda = 1e-8 (ridge 1e-16, far below what a Cholesky of the Gram matrix can resolve) works
+        OpArgs op;
+        op.mode = GRAM_LPV;
+        op.E = pl.d_E;
+        op.Kt = pl.d_K;
+        op.tbl_ns = N;
+        op.lpv_nf = Nf;
+        op.ncc = pl.ncc;
+        op.zero_first = 0;
+        op.N = N;
+        auto regram = [&]() { return lpv_gram(c, pl, d_Y, d_G, d_B); };
+        rc = ls_solve_accurate(c, op, pl.Np, 0, d_Y, d_G, d_B, lambda, regram, info);
+        if (rc) {
+            const int rcf = inputs_finite(c);  // NaN inputs / 0/0 basis normalisation: the cause, not "not SPD"
+            return rcf ? rcf : rc;
+        }
+    } else {
+        if ((rc = factor_solve(c, pl.ncc, 0, pl.Np, d_G, d_B, 1, lambda * lambda, 1, &pinfo))) return rc;
+        if ((rc = inputs_finite(c))) return rc;
+        LPVS_CU(c, cudaStreamSynchronize(c->st));
+        if (pinfo) {
+            if (info) *info = pinfo;
+            return fail(c, LPVS_E_NOT_SPD,
+                        "Cholesky breakdown at internal pivot %d: Ar'Ar + lambda^2 I is not numerically positive definite "
+                        "(lambda=%g; LPVS_OPT_JITTER=0 disabled the QR-class solve)", pinfo, lambda);
+        }
     }
     double* d_out = ws<double>(c, BUF_X, (size_t)nref);
     double* d_e = ws<double>(c, BUF_MISC, (size_t)std::max<long long>(N, (long long)nref * nref));
@@ -560,9 +580,29 @@ int lpvs_solve_packed_dev(lpvs_ctx* c, double* d_packed, const double* f, int Nf
     if (rc) return rc;
     const long long Np = pl.Np;
     int pinfo = 0;
+    // same policy as the single-GPU weighted ls_spectral: on breakdown re-factor once with the jitter ridge
+    double* d_keep = c->jitter ? ws<double>(c, BUF_YINV, (size_t)Np * Np + 2 * Np) : nullptr;
+    if (d_keep)
+        LPVS_CU(c, cudaMemcpyAsync(d_keep, d_packed, sizeof(double) * (Np * Np + 2 * Np), cudaMemcpyDeviceToDevice, c->st));
+    double maxdiag = 0.0;
+    if (d_keep) {
+        double* d_md = ws<double>(c, BUF_SUMS, 8);
+        if (!d_md) return fail(c, LPVS_E_NOMEM, "out of device memory");
+        launch_max_diag(d_packed, Np * Np, pl.Np, pl.Nf, pl.zero_first, d_md, 1, c->st);
+        c->launches++;
+        LPVS_CU(c, cudaMemcpyAsync(&maxdiag, d_md, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    }
     if ((rc = factor_solve(c, pl.Nf, pl.zero_first, pl.Np, d_packed, d_packed + Np * Np, nrhs, ridge, 1, &pinfo)))
         return rc;
     LPVS_CU(c, cudaStreamSynchronize(c->st));
+    if (pinfo && d_keep) {
+        LPVS_CU(c, cudaMemcpyAsync(d_packed, d_keep, sizeof(double) * (Np * Np + 2 * Np), cudaMemcpyDeviceToDevice, c->st));
+        const double jr = std::max(ridge, (double)pl.Nreg * 2.220446049250313e-16 * maxdiag);
+        if ((rc = factor_solve(c, pl.Nf, pl.zero_first, pl.Np, d_packed, d_packed + Np * Np, nrhs, jr, 1, &pinfo)))
+            return rc;
+        LPVS_CU(c, cudaStreamSynchronize(c->st));
+        if (!pinfo && info) *info = LPVS_INFO_JITTER;
+    }
     if (pinfo) {
         if (info) *info = pinfo;
         return fail(c, LPVS_E_NOT_SPD, "Cholesky breakdown at internal pivot %d", pinfo);

@@ -1,0 +1,440 @@
+// Least squares on the regressor itself, for the estimators the reference does NOT solve through a Gram matrix:
+// unweighted ls_spectral -> fourier_solve = svd([A; lam I]) \ [y; 0]        (src/utilities.jl:56-60)
+// ls_spectral_lpv        -> real_complex_bs = [Ar; lam I] \ [Y; 0], pivoted QR (src/utilities.jl:49-54)
+// Those results are defined by A to cond([A; lam I])*eps; a Cholesky of A'A + lam^2 I is only good to cond^2*eps and breaks
+// down on the reference's own defaults (default_freqs gives Nreg = N+1; lam = 1e-10 / 1e-8).  The tensor-core work is
+// kept -- the Gram matrix and its Cholesky factor become a PRECONDITIONER -- and the accuracy comes from the operator:
+//
+//   1. G~ = A'A (fused synthesis + DMMA, any phase mode), L L' = G~ + max(lam^2, n eps max diag G~) I   (one factorisation)
+//   2. corrected semi-normal equations with the REFERENCE-ROUNDED operator synthesised on the fly:
+//        r = y - A x,  dx = (L L')^-1 (A' r - lam^2 x),  x += dx
+//      converges in 1-4 steps when cond(A)^2 * eps is small against the shift (every well-conditioned problem);
+//   3. otherwise (rank deficient / cond(A) >~ 1e5): shifted CholeskyQR.  Q1 = [A; lam I] L^-T has condition ~1e4 however
+//      bad A is, so the Gram matrix of the MATERIALISED Q1 can be factorised safely:
+//        Y = L^-T (TRTRI), Q1' = L^-1 [A' | lam I] (one triangular DMMA GEMM), G2 = Q1'Q1 (DMMA SYRK), G2 z = Q1'[y;0],
+//        x = Y z.
+//      Forward error ~ cond([A; lam I]) * eps, the class of the reference's SVD / QR (measured against numpy's gesdd, geqrf
+//      and gelsy, which differ among themselves by as much: tests/test_gpu_rankdef.py).
+#include <math.h>
+
+#include <algorithm>
+
+#include "ctx.h"
+
+namespace lpvs {
+
+namespace {
+
+constexpr double EPS = 2.220446049250313e-16;
+
+// element (s, cc) of the reference-rounded regressor: (Re, Im) part pair of complex column cc
+__device__ __forceinline__ double2 op_elem(const OpArgs& a, int cc, long long s, double ts) {
+    if (a.mode == GRAM_DIRECT) {
+        const double2 v = cis_reference(a.f[cc], ts);
+        return make_double2(__dmul_rn(v.x, a.dd), __dmul_rn(v.y, a.dd));  // fl(fl(cos) * dd), src/lsfft.jl:42-44
+    }
+    const int fi = cc % a.lpv_nf, ki = cc / a.lpv_nf;
+    const double2 e = a.E[(long long)fi * a.tbl_ns + s];
+    const double k = a.Kt[(long long)ki * a.tbl_ns + s];
+    return make_double2(__dmul_rn(e.x, k), __dmul_rn(e.y, k));
+}
+
+// out[s] = (y ? y[s] : 0) - sum_cc Re A[s,cc] x[p(cc)] + Im A[s,cc] x[p(cc)+64]; lane = sample, warp = column slice
+__global__ void __launch_bounds__(256) k_op_apply(const __grid_constant__ OpArgs a, const double* __restrict__ x,
+                                                  const double* __restrict__ y, double* __restrict__ out) {
+    __shared__ double part[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long s = (long long)blockIdx.x * 32 + lane;
+    const bool valid = s < a.N;
+    const long long sc = valid ? s : a.N - 1;
+    const double ts = a.mode == GRAM_DIRECT ? a.t[sc] : 0.0;
+    double acc = 0.0;
+    for (int cc = w; cc < a.ncc; cc += 8) {
+        const double2 v = op_elem(a, cc, sc, ts);
+        const int p = (cc >> 6) * 128 + (cc & 63);
+        acc = fma(v.x, x[p], acc);
+        acc = fma(v.y, x[p + 64], acc);
+    }
+    part[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && valid) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) t += part[q][lane];
+        out[s] = (y ? y[s] : 0.0) - t;
+    }
+}
+
+// Arow[s][p] = A[s, p] in the internal column layout, rows [0, Nr) (rows >= N and dummy columns are zero)
+__global__ void __launch_bounds__(256) k_materialize(const __grid_constant__ OpArgs a, double* __restrict__ Arow, int Np,
+                                                     long long Nr) {
+    const int j = threadIdx.x & 63, q = blockIdx.y, cc = q * 64 + j;
+    const long long s = (long long)blockIdx.x * 4 + (threadIdx.x >> 6);
+    if (s >= Nr) return;
+    double2 v = make_double2(0.0, 0.0);
+    if (s < a.N && cc < a.ncc) v = op_elem(a, cc, s, a.mode == GRAM_DIRECT ? a.t[s] : 0.0);
+    if (a.zero_first && cc == 0) v.y = 0.0;
+    Arow[s * Np + q * 128 + j] = v.x;
+    Arow[s * Np + q * 128 + 64 + j] = v.y;
+}
+
+// Li = Y' (lower, zero above the 128-tile diagonal) and the ridge block of Q1': Bt[i][Nr + k] = scale(k) Li[i][k],
+// scale = lam for real columns, 1 for dummy columns (their unit diagonal keeps G2 non-singular)
+__global__ void __launch_bounds__(256) k_transpose_linv(const double* __restrict__ Y, int Np, int ncc, int zero_first,
+                                                        double lam, double* __restrict__ Li, double* __restrict__ Bt,
+                                                        long long ldbt, long long Nr) {
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.y, bk = blockIdx.x;  // output rows 32*bi.., columns 32*bk..
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const bool live = (bk >> 2) <= (bi >> 2);  // 128-tile (bi/4, bk/4) on or below the diagonal
+    if (live) {
+        for (int r = ty; r < 32; r += 8) tile[r][tx] = Y[(long long)(bk * 32 + r) * Np + bi * 32 + tx];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bi * 32 + r, k = bk * 32 + tx;
+        const double v = live ? tile[tx][r] : 0.0;
+        Li[(long long)i * Np + k] = v;
+        Bt[(long long)i * ldbt + Nr + k] = v * (is_dummy_col(k, ncc, zero_first) ? 1.0 : lam);
+    }
+}
+
+// C tile = A[128 x K] * B[128 x K]' (both row-major, K contiguous): 3-stage cp.async ring, one __syncthreads per chunk.
+enum { NT_TRI = 1, NT_SYRK = 2 };
+struct NtArgs {
+    const double* A; long long lda;
+    const double* B; long long ldb;
+    double* C; long long ldc;
+    int mt, nt, mode;
+    long long K, Ksplit;
+};
+constexpr int NT_STAGES = 3;
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nt(const __grid_constant__ NtArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wm = w & 3, wn = w >> 2;
+    int I, J;
+    long long Kend;
+    if (a.mode == NT_TRI) {  // Q1' = L^-1 [A']: row block I of the lower-triangular L^-1 has (I+1)*128 columns; long tiles first
+        const int t = blockIdx.x;
+        I = a.mt - 1 - t / a.nt;
+        J = t % a.nt;
+        Kend = (long long)(I + 1) * TB;
+    } else {  // G2 = Q1'Q1, lower tiles; the ridge block of row block J ends at column Ksplit + (J+1)*128
+        tile_ij(gridDim.x - 1 - blockIdx.x, I, J);
+        Kend = a.Ksplit + (long long)(J + 1) * TB;
+        if (Kend > a.K) Kend = a.K;
+    }
+    const double* A = a.A + (long long)I * TB * a.lda;
+    const double* B = a.B + (long long)J * TB * a.ldb;
+    const int nchunks = (int)(Kend / KC);
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int p = 0; p < NT_STAGES - 1; p++) {
+        if (p < nchunks) {
+            load_tile_async(sm + p * 2 * TILE_D, A + (long long)p * KC, a.lda, tid);
+            load_tile_async(sm + p * 2 * TILE_D + TILE_D, B + (long long)p * KC, a.ldb, tid);
+        }
+        cp_async_commit();
+    }
+    const int fragA = (32 * wm + (lane >> 2)) * LDT + (lane & 3);
+    const int fragB = (64 * wn + (lane >> 2)) * LDT + (lane & 3);
+    int st_cur = 0;
+    for (int c = 0; c < nchunks; c++) {
+        cp_async_wait<NT_STAGES - 2>();  // chunk c has landed (only the newest group may still be in flight)
+        __syncthreads();                 // ... for every thread, and everyone has left the stage refilled below
+        const int st_fill = st_cur == 0 ? NT_STAGES - 1 : st_cur - 1;
+        if (c + NT_STAGES - 1 < nchunks) {
+            double* dst = sm + st_fill * 2 * TILE_D;
+            load_tile_async(dst, A + (long long)(c + NT_STAGES - 1) * KC, a.lda, tid);
+            load_tile_async(dst + TILE_D, B + (long long)(c + NT_STAGES - 1) * KC, a.ldb, tid);
+        }
+        cp_async_commit();
+        const double* pa = sm + st_cur * 2 * TILE_D + fragA;
+        const double* pb = sm + st_cur * 2 * TILE_D + TILE_D + fragB;
+#pragma unroll
+        for (int kk = 0; kk < KC / 4; kk++) mma_step(pa, pb, kk, acc);
+        st_cur = st_cur == NT_STAGES - 1 ? 0 : st_cur + 1;
+    }
+    cp_async_wait<0>();
+
+    double* C = a.C + (long long)I * TB * a.ldc + (long long)J * TB;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int row = 32 * wm + 8 * i + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int col = 64 * wn + 8 * j + 2 * (lane & 3);
+            *reinterpret_cast<double2*>(C + (long long)row * a.ldc + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+    }
+}
+
+// out[i] = sum_{s in [s0(i), len)} Mx[i][s] v[s], one warp per row; from_diag: s0 = first column of row i's 128-tile
+__global__ void __launch_bounds__(256) k_gemv_rows(const double* __restrict__ Mx, long long ld, int nrows,
+                                                   const double* __restrict__ v, long long len, int from_diag,
+                                                   double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= nrows) return;
+    const double* row = Mx + (long long)i * ld;
+    double s0 = 0.0, s1 = 0.0;
+    long long s = (from_diag ? (long long)(i & ~127) : 0) + lane;
+    for (; s + 32 < len; s += 64) {
+        s0 = fma(row[s], v[s], s0);
+        s1 = fma(row[s + 32], v[s + 32], s1);
+    }
+    if (s < len) s0 = fma(row[s], v[s], s0);
+    s0 += s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    if (lane == 0) out[i] = s0;
+}
+
+// g <- A'r - lam^2 x on the real columns, 0 on the dummies
+__global__ void k_csne_rhs(double* __restrict__ g, const double* __restrict__ x, double lam2, int Np, int ncc,
+                           int zero_first) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Np) return;
+    g[p] = is_dummy_col(p, ncc, zero_first) ? 0.0 : g[p] - lam2 * x[p];
+}
+
+// v = -lam x on the real columns, 0 on the dummies: the ridge rows of [y; 0] - [A; lam I] x
+__global__ void k_ridge_resid(double* __restrict__ v, const double* __restrict__ x, double lam, int Np, int ncc,
+                              int zero_first) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Np) return;
+    v[p] = is_dummy_col(p, ncc, zero_first) ? 0.0 : -lam * x[p];
+}
+
+// x += dx; out = {|dx|^2, |x|^2}   (one CTA, fixed summation order)
+__global__ void __launch_bounds__(1024) k_axpy_norms(double* __restrict__ x, const double* __restrict__ dx, int Np,
+                                                     double* __restrict__ out) {
+    __shared__ double r0[1024], r1[1024];
+    double a = 0.0, b = 0.0;
+    for (int p = threadIdx.x; p < Np; p += 1024) {
+        const double d = dx[p], v = x[p] + d;
+        x[p] = v;
+        a = fma(d, d, a);
+        b = fma(v, v, b);
+    }
+    r0[threadIdx.x] = a;
+    r1[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            r0[threadIdx.x] += r0[threadIdx.x + s];
+            r1[threadIdx.x] += r1[threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = r0[0];
+        out[1] = r1[0];
+    }
+}
+
+// md[1] = max(ridge, scale * md[0])
+__global__ void k_set_shift(double* md, double ridge, double scale) { md[1] = fmax(ridge, scale * md[0]); }
+
+int adjoint_apply(lpvs_ctx* c, const OpArgs& op, int Np, const double* d_r, double* d_out /* [2][Np] */) {
+    // b = A' r through the rhs kernel of the Gram pass, split over samples so the grid fills the GPU
+    const int nblk = Np / TB;
+    long long want = std::max<long long>(1, (2LL * c->sms + nblk - 1) / nblk);
+    long long nsplit = std::min<long long>(want, std::max<long long>(1, op.N / 256));
+    long long n_split = (op.N + nsplit - 1) / nsplit;
+    n_split = (n_split + KC - 1) / KC * KC;
+    const int nprob = (int)((op.N + n_split - 1) / n_split);
+    GramArgs g{};
+    g.t = op.t;
+    g.y = d_r;
+    g.u = nullptr;
+    g.W = nullptr;
+    g.w_abs = 1;
+    g.start0 = 0;
+    g.hop = n_split;
+    g.n = (int)n_split;
+    g.s_end = op.N;
+    g.ncc = op.ncc;
+    g.nblk = nblk;
+    g.nrhs = 1;
+    g.tbl_base = 0;
+    g.tbl_ns = op.tbl_ns;
+    g.f = op.f;
+    g.E = op.E;
+    g.Kt = op.Kt;
+    g.lpv_nf = op.lpv_nf;
+    g.gscale = 1.0;
+    g.bscale = op.mode == GRAM_DIRECT ? op.dd : 1.0;
+    if (nprob == 1) {
+        g.B = d_out;
+        g.strideB = 0;
+        c->launches += launch_gram_rhs(op.mode, g, 1, c->st);
+        return LPVS_OK;
+    }
+    double* parts = ws<double>(c, BUF_PART, (size_t)nprob * 2 * Np);
+    if (!parts) return fail(c, LPVS_E_NOMEM, "out of device memory (adjoint partials)");
+    g.B = parts;
+    g.strideB = 2LL * Np;
+    c->launches += launch_gram_rhs(op.mode, g, nprob, c->st);
+    reduce_parts(c, d_out, parts, Np, 2LL * Np, nprob, 0);
+    return LPVS_OK;
+}
+
+}  // namespace
+
+int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, const double* d_y, double* d_G, double* d_B,
+                      double lam, const std::function<int()>& regram, int* info) {
+    cudaStream_t st = c->st;
+    const int nb = Np / TB, ncc = op.ncc;
+    const long long NN = (long long)Np * Np, N = op.N;
+    const int nreal = 2 * ncc - zero_first;
+    const double lam2 = lam * lam;
+    int rc;
+    if (info) *info = 0;
+    double* d_md = ws<double>(c, BUF_SUMS, 8);  // [0] max diag, [1] shift, [2..3] norms
+    double* d_r = ws<double>(c, BUF_LSQ_R, (size_t)std::max<long long>(N, Np));
+    double* d_g = ws<double>(c, BUF_LSQ_V, (size_t)4 * Np);
+    if (!d_md || !d_r || !d_g) return fail(c, LPVS_E_NOMEM, "out of device memory (LS refinement vectors)");
+
+    // ---- 1. one factorisation: L L' = G~ + max(lam^2, n eps max diag) I ----
+    int pinfo = 0;
+    double mult = 1.0;
+    for (int attempt = 0;; attempt++) {
+        launch_max_diag(d_G, NN, Np, ncc, zero_first, d_md, 1, st);
+        k_set_shift<<<1, 1, 0, st>>>(d_md, lam2, mult * (double)nreal * EPS);
+        c->launches += 2;
+        if ((rc = factor_solve(c, ncc, zero_first, Np, d_G, d_B, 1, 0.0, 1, &pinfo, nullptr, 0.0, d_md + 1))) return rc;
+        LPVS_CU(c, cudaStreamSynchronize(st));
+        if (pinfo == 0) break;
+        if (attempt == 3 || !isfinite(mult)) {
+            if (info) *info = pinfo;
+            return fail(c, LPVS_E_NOT_SPD, "Cholesky breakdown at internal pivot %d even with a %g n eps shift", pinfo, mult);
+        }
+        mult *= 32.0;  // the shift only conditions the preconditioner; the solution below does not depend on it
+        if ((rc = regram())) return rc;
+    }
+    double* d_x = d_B;  // x0 = (G~ + shift)^-1 A'y
+
+    CholArgs ca{};
+    ca.G = d_G;
+    ca.strideG = NN;
+    ca.Linv = ws<double>(c, BUF_LINV, (size_t)nb * TB * TB);
+    ca.strideLinv = (long long)nb * TB * TB;
+    ca.info = ws<int>(c, BUF_INFO, 1);
+    ca.Np = Np;
+    ca.nb = nb;
+
+    // ---- 2. corrected semi-normal equations on the reference-rounded operator ----
+    double prev = 0.0;
+    bool converged = false;
+    for (int step = 1; step <= 8; step++) {
+        k_op_apply<<<(unsigned)((N + 31) / 32), 256, 0, st>>>(op, d_x, d_y, d_r);
+        c->launches++;
+        if ((rc = adjoint_apply(c, op, Np, d_r, d_g))) return rc;
+        k_csne_rhs<<<(Np + 255) / 256, 256, 0, st>>>(d_g, d_x, lam2, Np, ncc, zero_first);
+        launch_trsv(ca, d_g, 2LL * Np, 1, 1, st, false);
+        k_axpy_norms<<<1, 1024, 0, st>>>(d_x, d_g, Np, d_md + 2);
+        c->launches += 3;
+        double h[2] = {0.0, 0.0};
+        LPVS_CU(c, cudaMemcpyAsync(h, d_md + 2, sizeof h, cudaMemcpyDeviceToHost, st));
+        LPVS_CU(c, cudaStreamSynchronize(st));
+        if (!(isfinite(h[0]) && isfinite(h[1]))) break;  // NaN inputs: the caller's finite check reports the cause
+        const double rel = h[1] > 0.0 ? sqrt(h[0] / h[1]) : 0.0;
+        if (rel <= 1e-13) {
+            converged = true;
+            break;
+        }
+        if (step >= 2 && rel > 0.05 * prev) break;  // contraction too slow: cond(A)^2 eps is not small against the shift
+        prev = rel;
+    }
+    if (converged) return LPVS_OK;
+
+    // ---- 3. shifted CholeskyQR on the materialised regressor ----
+    if (info) *info = LPVS_INFO_QR;
+    const long long Nr = (N + TB - 1) / TB * TB, Mrows = Nr + Np;
+    double* d_Y = ws<double>(c, BUF_LSQ_Y, (size_t)NN);
+    double* d_Li = ws<double>(c, BUF_LSQ_LI, (size_t)NN);
+    double* d_A = ws<double>(c, BUF_LSQ_A, (size_t)Nr * Np);
+    double* d_Bt = ws<double>(c, BUF_LSQ_BT, (size_t)Np * Mrows);
+    double* d_G2 = ws<double>(c, BUF_LSQ_G2, (size_t)NN);
+    if (!d_Y || !d_Li || !d_A || !d_Bt || !d_G2)
+        return fail(c, LPVS_E_NOMEM, "out of device memory (QR path of a rank-deficient %d x %d problem)", (int)N, nreal);
+    ca.Y = d_Y;
+    ca.strideY = NN;
+    c->launches += trtri(ca, 1, st);
+    {
+        dim3 grid(Np / 32, Np / 32);
+        k_transpose_linv<<<grid, 256, 0, st>>>(d_Y, Np, ncc, zero_first, lam, d_Li, d_Bt, Mrows, Nr);
+        dim3 gm((unsigned)((Nr + 3) / 4), nb);
+        k_materialize<<<gm, 256, 0, st>>>(op, d_A, Np, Nr);
+        c->launches += 2;
+    }
+    static bool attr_done[64] = {};
+    const size_t smem = (size_t)NT_STAGES * 2 * TILE_D * sizeof(double);
+    if (!attr_done[c->device & 63]) {
+        cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done[c->device & 63] = true;
+    }
+    NtArgs t1{};
+    t1.A = d_Li; t1.lda = Np;
+    t1.B = d_A; t1.ldb = Np;
+    t1.C = d_Bt; t1.ldc = Mrows;
+    t1.mt = nb; t1.nt = (int)(Nr / TB); t1.mode = NT_TRI;
+    t1.K = Np; t1.Ksplit = 0;
+    k_gemm_nt<<<t1.mt * t1.nt, NTHREADS, smem, st>>>(t1);
+    NtArgs t2{};
+    t2.A = d_Bt; t2.lda = Mrows;
+    t2.B = d_Bt; t2.ldb = Mrows;
+    t2.C = d_G2; t2.ldc = Np;
+    t2.mt = nb; t2.nt = nb; t2.mode = NT_SYRK;
+    t2.K = Mrows; t2.Ksplit = Nr;
+    k_gemm_nt<<<nb * (nb + 1) / 2, NTHREADS, smem, st>>>(t2);
+    // c = Q1' [y; 0]
+    LPVS_CU(c, cudaMemsetAsync(d_g, 0, sizeof(double) * 4 * Np, st));
+    k_gemv_rows<<<(Np + 7) / 8, 256, 0, st>>>(d_Bt, Mrows, Np, d_y, N, 0, d_g);
+    c->launches += 3;
+    if ((rc = factor_solve(c, ncc, zero_first, Np, d_G2, d_g, 1, 0.0, 1, &pinfo))) return rc;
+    // x = L^-T z = Y z
+    k_gemv_rows<<<(Np + 7) / 8, 256, 0, st>>>(d_Y, Np, Np, d_g, Np, 1, d_x);
+    c->launches++;
+    LPVS_CU(c, cudaStreamSynchronize(st));
+    if (pinfo) {
+        if (info) *info = pinfo;
+        return fail(c, LPVS_E_NOT_SPD, "Cholesky breakdown of the preconditioned Gram matrix at internal pivot %d", pinfo);
+    }
+    // Refinement in the Q1 coordinates: dz = G2^-1 Q1'([y; 0] - [A; lam I] x), x += Y dz.  G2 is well conditioned, so this is
+    // an (almost) exact Newton step in EVERY direction -- including the ones A cannot see, where the Cholesky solve of G2
+    // leaves noise of eps |y| sqrt(shift) / lam^2 (a QR would leave eps |y| / lam).
+    double* d_v = ws<double>(c, BUF_LSQ_R, (size_t)Mrows);
+    if (!d_v) return fail(c, LPVS_E_NOMEM, "out of device memory (QR refinement)");
+    CholArgs c2 = ca;
+    c2.G = d_G2;
+    c2.Y = nullptr;
+    double* d_dx = d_g + 2 * Np;
+    for (int step = 0; step < 2; step++) {
+        k_op_apply<<<(unsigned)((N + 31) / 32), 256, 0, st>>>(op, d_x, d_y, d_v);
+        if (Nr > N) LPVS_CU(c, cudaMemsetAsync(d_v + N, 0, sizeof(double) * (Nr - N), st));
+        k_ridge_resid<<<(Np + 255) / 256, 256, 0, st>>>(d_v + Nr, d_x, lam, Np, ncc, zero_first);
+        k_gemv_rows<<<(Np + 7) / 8, 256, 0, st>>>(d_Bt, Mrows, Np, d_v, Mrows, 0, d_g);
+        launch_trsv(c2, d_g, 2LL * Np, 1, 1, st, false);
+        k_gemv_rows<<<(Np + 7) / 8, 256, 0, st>>>(d_Y, Np, Np, d_g, Np, 1, d_dx);
+        k_axpy_norms<<<1, 1024, 0, st>>>(d_x, d_dx, Np, d_md + 2);
+        c->launches += 6;
+        double h[2] = {0.0, 0.0};
+        LPVS_CU(c, cudaMemcpyAsync(h, d_md + 2, sizeof h, cudaMemcpyDeviceToHost, st));
+        LPVS_CU(c, cudaStreamSynchronize(st));
+        // a second step only when the first one moved x by more than cond(G2)*eps can explain
+        if (!(isfinite(h[0]) && isfinite(h[1])) || h[0] <= 1e-16 * h[1]) break;
+    }
+    return LPVS_OK;
+}
+
+}  // namespace lpvs

@@ -204,14 +204,23 @@ def chol_solve(G: np.ndarray, b: np.ndarray) -> np.ndarray:
     return sla.cho_solve(c, b, check_finite=False)
 
 
+def qr_solve(M: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Householder QR least squares (LAPACK geqrf/ormqr/trtrs): a second backward-stable solver of the SAME problem as
+    ``svd_solve``; the two bracket what "the reference's answer" means on an ill-conditioned problem (they differ by
+    ~cond(M)*eps).  Not a reference code path -- a comparator for tests."""
+    Q, R = np.linalg.qr(M)
+    return sla.solve_triangular(R, Q.T @ b, check_finite=False)
+
+
 def fourier_solve(A, y, zerofreq, lam=0.0, mode="literal"):
-    """src/utilities.jl:56-60: x = svd([A; lam I]) \\ [y; 0]  (ridge lam^2, Q4)."""
+    """src/utilities.jl:56-60: x = svd([A; lam I]) \\ [y; 0]  (ridge lam^2, Q4).  mode "qr": same problem by QR."""
     n = A.shape[1]
-    if mode == "literal":
+    if mode in ("literal", "qr"):
+        solve = svd_solve if mode == "literal" else qr_solve
         if lam > 0:
-            x = svd_solve(np.vstack([A, lam * np.eye(n)]), np.concatenate([y, np.zeros(n)]))
+            x = solve(np.vstack([A, lam * np.eye(n)]), np.concatenate([y, np.zeros(n)]))
         else:
-            x = svd_solve(A, y)
+            x = solve(A, y)
     else:
         x = chol_solve(A.T @ A + (lam * lam) * np.eye(n), A.T @ y)
     return fourier2complex(x, zerofreq)

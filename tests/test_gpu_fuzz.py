@@ -40,8 +40,9 @@ def test_random_ls_spectral(ctx, seed):
         pytest.skip(f"cond {cond:.1e}")
     lam = 1e-10
     x, _ = lp.ls_spectral(y, t, f, W, lam=lam, ctx=ctx) if W is not None else lp.ls_spectral(y, t, f, lam=lam, ctx=ctx)
-    xr, _ = o.ls_spectral(y, t, f, W, lam=lam, mode="gram") if W is not None else o.ls_spectral(y, t, f, lam=lam,
-                                                                                              mode="gram")
+    # comparator: the reference's own algorithm (SVD of [A; lam I] unweighted, N-rhs LU weighted), not the Gram restatement
+    xr, _ = o.ls_spectral(y, t, f, W, lam=lam, mode="literal") if W is not None else o.ls_spectral(y, t, f, lam=lam,
+                                                                                                 mode="literal")
     assert rel(x, xr) <= max(1e-10, 1e-15 * cond), (N, Nf, cond)
 
 
@@ -62,13 +63,13 @@ def test_random_windowed(ctx, seed):
     kind = seed % 3
     if kind == 0:
         S, _ = lp.ls_windowpsd(y, t, f, nw=nw, noverlap=nov, window_func=lp.hanning, ctx=ctx)
-        Sr, _ = o.ls_windowpsd(y, t, f, nw=nw, noverlap=nov, window_func=o.hanning, mode="gram")
+        Sr, _ = o.ls_windowpsd(y, t, f, nw=nw, noverlap=nov, window_func=o.hanning, mode="literal")
     elif kind == 1:
         S, _ = lp.ls_windowcsd(y, u, t, f, nw=nw, noverlap=nov, window_func=lp.hanning, ctx=ctx)
-        Sr, _ = o.ls_windowcsd(y, u, t, f, nw=nw, noverlap=nov, window_func=o.hanning, mode="gram")
+        Sr, _ = o.ls_windowcsd(y, u, t, f, nw=nw, noverlap=nov, window_func=o.hanning, mode="literal")
     else:
         S, _ = lp.ls_cohere(y, u, t, f, nw=nw, noverlap=nov, ctx=ctx)
-        Sr, _ = o.ls_cohere(y, u, t, f, nw=nw, noverlap=nov, mode="gram")
+        Sr, _ = o.ls_cohere(y, u, t, f, nw=nw, noverlap=nov, mode="literal")
     assert rel(S, Sr) <= 1e-8, (N, n, Nf, nov, kind)
 
 
@@ -107,6 +108,15 @@ def test_random_sparse_lpv(ctx, seed, symv):
     assert support(info["z"]) == support(ri["z"])
     assert rel(info["z"], ri["z"]) <= 1e-8 if np.linalg.norm(ri["z"]) > 0 else np.all(info["z"] == 0)
     assert rel(info["x"], ri["x"]) <= 1e-8
+    if symv == 1:
+        # the reference's algorithm proper: warm-started CG x-update (src/lasso.jl:151 -> ProximalOperators / cg!)
+        sl, rl = o.ls_sparse_spectral_lpv(Y, X, V, w, Nv, lam=lam, coulomb=coul, mode="literal", return_info=True,
+                                          printerval=10 ** 9, **kw)
+        assert info["iters"] == rl["iters"], (N, Nf, Nv, coul, lam)
+        assert support(info["z"]) == support(rl["z"])
+        og = o.sparse_objective(rl["Phi"], Y, info["z"], rl["proxg"])
+        ol = o.sparse_objective(rl["Phi"], Y, rl["z"], rl["proxg"])
+        assert abs(og - ol) <= 1e-8 * max(1.0, abs(ol))
 
 
 @pytest.mark.parametrize("seed", range(8))
@@ -129,6 +139,15 @@ def test_random_sparse_fourier(ctx, seed):
     assert info["iters"] == ri["iters"], (N, Nf, seed)
     assert support(info["z"]) == support(ri["z"])
     assert rel(info["z"], ri["z"]) <= 1e-8
+    # and against the reference's algorithm proper (warm-started CG x-update): iteration count, support, objective
+    xl, _, rl = o.ls_sparse_spectral(y, t, f, W, proxg=pgo, mode="literal", return_info=True, printerval=10 ** 9, **kw)
+    assert info["iters"] == rl["iters"], (N, Nf, seed)
+    assert support(info["z"]) == support(rl["z"])
+    ysign = -y if W is not None else y  # the weighted method fits -y (Q13); the objective is evaluated accordingly
+    Aw = rl["A"] * np.sqrt(W)[:, None] if W is not None else rl["A"]
+    yw = ysign * np.sqrt(W) if W is not None else ysign
+    og, ol = o.sparse_objective(Aw, yw, info["z"], pgo), o.sparse_objective(Aw, yw, rl["z"], pgo)
+    assert abs(og - ol) <= 1e-8 * max(1.0, abs(ol))
 
 
 def test_coulomb_zero_sample_is_reported(ctx):
@@ -178,7 +197,7 @@ def test_random_ls_spectral_lpv(ctx, seed):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         se = lp.ls_spectral_lpv(Y, X, V, w, Nv, lam=0.05, coulomb=coul, normalize=norm, ctx=ctx)
-        so = o.ls_spectral_lpv(Y, X, V, w, Nv, lam=0.05, coulomb=coul, normalize=norm, mode="gram")
+        so = o.ls_spectral_lpv(Y, X, V, w, Nv, lam=0.05, coulomb=coul, normalize=norm, mode="literal")
     assert se.x.shape == so.x.shape
     assert rel(se.x, so.x) <= 1e-8, (N, Nf, Nv, coul, norm)
     assert rel(se.Σ, so.Sigma) <= 1e-8
