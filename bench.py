@@ -36,6 +36,13 @@ LAMBDA = 1e-10
 FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
 
 
+def cfg2_config(n):
+    """`config` of the JSON line -- identical in the GPU arm and the reference arm (the driver compares them)."""
+    return {"workload": "cfg2_windowpsd", "samples_per_gpu": NSAMP, "nw": NW, "n": n, "noverlap": n >> 1,
+            "windows_per_gpu": 2 * NW - 1, "freqs": NF, "nreg": 2 * NF - 1, "window": "hanning",
+            "l2": "inputs+Gram workspace (4.3 GB/step) larger than L2, no flush needed"}
+
+
 def make_cfg2(seed=2, nsamp=NSAMP, nw=NW, nf=NF):
     """t=sort(10*U^N), two tones at f[40], f[100] + 0.1 noise, f=(0:nf-1)*2fs/n."""
     rng = np.random.default_rng(seed)
@@ -227,6 +234,310 @@ def admm_leg(ctx, lp, L, C, rank, world, allsum, allmax, barrier, iters=2000):
                          "note": "algorithmic bytes = lower-triangle 128x128 blocks of (G+I/mu)^-1 actually streamed"}}
 
 
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"])
+    except Exception:
+        return 6554.6
+
+
+def fp64_peak_live(torch):
+    """cuBLAS DGEMM 8192^3 through torch.matmul, best of 5 after 2 warm-ups, CUDA events -- the method MEASURED_PEAKS.json
+    uses for bf16, repeated for FP64 inside this run so the denominator sits under the same clock record."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    best = float("inf")
+    for i in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        c = torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def make_cfg1():
+    """SURVEY 8(d) cfg1 = BASELINE configs[0]: N=4096 irregular samples, default_freqs(t)[:2048], no weights, lambda=1e-10."""
+    rng = np.random.default_rng(1)
+    N = 4096
+    t = np.sort(10 * rng.random(N))
+    y = np.sin(2 * np.pi * 20 * t) + 0.5 * np.cos(2 * np.pi * 55 * t + 1) + 0.1 * rng.standard_normal(N)
+    f = (np.arange(N // 2 + 1) * (1.0 / np.mean(np.diff(t)) / N))[:2048]
+    return t, y, f
+
+
+def make_cfg5(nsamp=1 << 24, seed=5):
+    """SURVEY 8(d) cfg5 = BASELINE configs[4]: two channels of 2^24 irregular samples, n=4096, 512 freqs at spacing 2 fs / n."""
+    rng = np.random.default_rng(seed)
+    n = 4096
+    t = np.sort(10 * rng.random(nsamp))
+    fs = 1.0 / np.mean(np.diff(t))
+    f = np.arange(512) * 2 * fs / n
+    y = np.sin(2 * np.pi * f[40] * t) + 0.5 * np.cos(2 * np.pi * f[100] * t + 1) + 0.1 * rng.standard_normal(nsamp)
+    u = 0.7 * np.roll(y, 5) + 0.5 * rng.standard_normal(nsamp)
+    return t, y, u, f, n
+
+
+def cfg1_leg(ctx, lp, peak):
+    """ms per spectrum of BASELINE configs[0] through the host-buffer API (H2D/D2H inside), rank 0 only."""
+    t, y, f = make_cfg1()
+    best, info, gms, gfl = float("inf"), 0, 0.0, 0.0
+    for rep in range(6):
+        x, _, info = lp.ls_spectral(y, t, f, ctx=ctx, return_info=True)
+        ms = ctx.last_call_ms()
+        if rep >= 1 and ms < best:
+            best = ms
+            gms, _, gfl = ctx.gram_timing()
+    nreg, N = 2 * len(f) - 1, len(y)
+    flop = N * nreg * (nreg + 1.0) + nreg ** 3 / 3.0 + 2.0 * nreg ** 2  # SURVEY 8(d): Gram + Cholesky + 2 TRSV
+    np_ = (len(f) + 63) // 64 * 128
+    nr = (N + 127) // 128 * 128
+    # the QR-class path (csrc/lsq.cu) really executes: + TRTRI + triangular GEMM + SYRK of Q1 + second Cholesky
+    flop_qr = flop + np_ ** 3 / 3.0 + float(nr) * np_ * np_ + (nr + np_ / 2.0) * np_ * (np_ + 1.0) + np_ ** 3 / 3.0
+    a = x.real ** 2 + x.imag ** 2
+    return {"workload": "cfg1_ls_spectral", "N": N, "freqs": len(f), "nreg": nreg, "lambda": 1e-10,
+            "ms_per_spectrum": best, "spectra_per_s": 1e3 / best, "info": int(info),
+            "path": "shifted CholeskyQR on the materialised regressor (cond(A)~1e16: the reference's SVD answer, "
+                    "tests/test_gpu_rankdef.py)" if info == 2 else "Cholesky + refinement on the synthesised operator",
+            "gram_ms": gms, "gram_tflops": gfl / gms / 1e9 if gms else None,
+            "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak,
+                         "achieved_survey_flops": flop / best / 1e9, "frac_survey_flops": flop / best / 1e9 / peak,
+                         "achieved_executed_flops": (flop_qr if info == 2 else flop) / best / 1e9,
+                         "frac_executed_flops": (flop_qr if info == 2 else flop) / best / 1e9 / peak,
+                         "flop_survey": flop, "flop_executed": flop_qr if info == 2 else flop},
+            "peak_index": int(a.argmax())}
+
+
+def cfg4_leg(ctx, lp, L, C, iters=2000):
+    """BASELINE configs[3]: ls_sparse_spectral_lpv group lasso, N=20000, 64 freqs x Nv=50 (n=6400), lambda=0.1; rank 0 only."""
+    from oracle import lpvs_oracle as o
+
+    Y, V, X = o.generate_lpv_signal(20000, seed=4)
+    w = 2 * np.pi * np.arange(1, 65) * 0.4
+    h = C.c_void_p()
+    t0 = time.perf_counter()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    ctx.check(ctx.lib.lpvs_admm_create_lpv(ctx.h, vp(Y), vp(X), vp(V), len(Y), vp(w), len(w), 50, 0, 1, 0.1, 0.05,
+                                           C.byref(h)))
+    setup_s = time.perf_counter() - t0
+    gms, _, gfl = ctx.gram_timing()
+    solver = lp.ADMM(ctx, h)
+    solver.step(200, 0.0)
+    solver.step(iters, 0.0)
+    ms, bpi = solver.timing()
+    solver.free()
+    its = iters / (ms * 1e-3)
+    hbm = hbm_peak()
+    return {"workload": "cfg4_group_lasso_lpv", "N": 20000, "freqs": 64, "Nv": 50, "n": 6400, "iters": iters,
+            "iters_per_s": its, "us_per_iter": ms / iters * 1e3, "setup_s": setup_s, "gram_tflops": gfl / gms / 1e9,
+            "roofline": {"bound": "hbm", "achieved": bpi * its / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": bpi * its / 1e9 / hbm, "bytes_per_iter": bpi,
+                         "note": "algorithmic bytes; the inverse (164 MB lower triangle) is partly L2-resident, so DRAM "
+                                 "traffic is lower (profiles/r01c_summary.md)"}}
+
+
+def cfg5_legs(ctx, lp, L, C, D, torch, dist, rank, world, local, allmax, barrier, peak):
+    """BASELINE configs[4] on the run's N GPUs, both forms:
+    5a  ls_cohere over K=8191 windows, windows sharded over the ranks (no data-path collective), host buffers;
+    5b  the same record as ONE weighted two-channel problem: row-sharded Gram, ONE NCCL all-reduce of the packed Gram
+        (timed on its own with CUDA events), then the factorisation on every rank."""
+    t, y, u, f, n = make_cfg5()
+    NS, Nf = len(t), len(f)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    W = lp.hanning(n)
+    hop = n >> 1
+    K = lp.window_count(NS, n, hop)
+    k0, k1 = D.shard_range(K, rank, world)
+    sums = np.zeros(4 * Nf)
+    info = C.c_int(0)
+    acc = torch.zeros(4 * Nf, dtype=torch.float64, device="cuda")
+    out = {}
+    best = float("inf")
+    gram_ms = gram_fl = 0.0
+    for rep in range(3):
+        barrier()
+        w0 = time.perf_counter()
+        ctx.check(ctx.lib.lpvs_ls_window_sums(ctx.h, L.WIN_COHERE, vp(y), vp(u), vp(t), NS, vp(f), Nf, vp(W), n, hop,
+                                              LAMBDA, k0, k1, vp(sums), C.byref(info)))
+        acc.copy_(torch.from_numpy(sums))
+        if world > 1:
+            dist.all_reduce(acc)
+        coh = lp.window_finalize(L.WIN_COHERE, acc.cpu().numpy(), Nf, K)
+        dt = allmax(time.perf_counter() - w0)
+        if rep >= 1 and dt < best:
+            best = dt
+            gram_ms, _, gram_fl = ctx.gram_timing()
+    nreg = 2 * Nf - 1
+    out["cfg5a"] = {"workload": "cfg5a_ls_cohere", "samples_per_channel": NS, "windows": K, "freqs": Nf, "nreg": nreg,
+                    "sharding": "windows [K r/P, K (r+1)/P) per rank, one all-reduce of 4 Nf doubles", "n_gpus": world,
+                    "s_per_pass": best, "windows_per_s": K / best,
+                    "api": "lpvs_ls_window_sums (host pointers; H2D of this rank's sample range inside)",
+                    "gram_tflops_per_gpu": gram_fl / gram_ms / 1e9 if gram_ms else None,
+                    "gram_frac": gram_fl / gram_ms / 1e9 / peak if gram_ms else None,
+                    "coherence_in_unit_interval": bool(np.all((coh >= 0) & (coh <= 1 + 1e-12)))}
+    # ---- 5b: row-sharded ----
+    Wn = lp.hanning(NS)
+    r0, r1 = D.shard_range(NS, rank, world)
+    d_t = torch.from_numpy(t[r0:r1]).cuda()
+    d_y = torch.from_numpy(y[r0:r1]).cuda()
+    d_u = torch.from_numpy(u[r0:r1]).cuda()
+    d_W = torch.from_numpy(Wn[r0:r1]).cuda()
+    npk = int(ctx.lib.lpvs_packed_size(Nf))
+    packed = torch.empty(npk, dtype=torch.float64, device="cuda")
+    x = np.empty((2, Nf), dtype=np.complex128)
+    p = lambda a: C.c_void_p(a.data_ptr())  # noqa: E731
+    res = None
+    for rep in range(3):
+        barrier()
+        w0 = time.perf_counter()
+        ctx.check(ctx.lib.lpvs_gram_partial_dev(ctx.h, p(d_y), p(d_u), p(d_t), p(d_W), r1 - r0, vp(f), Nf, p(packed)))
+        g_ms = ctx.last_call_ms()
+        gk_ms, _, gk_fl = ctx.gram_timing()
+        ar_ms = 0.0
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(packed)
+            e1.record()
+            e1.synchronize()
+            ar_ms = e0.elapsed_time(e1)
+        ctx.check(ctx.lib.lpvs_solve_packed_dev(ctx.h, p(packed), vp(f), Nf, 2, LAMBDA, vp(x), C.byref(info)))
+        s_ms = ctx.last_call_ms()
+        wall = allmax(time.perf_counter() - w0)
+        cur = dict(wall_s=wall, gram_call_ms=allmax(g_ms), gram_kernel_ms=allmax(gk_ms), allreduce_ms=allmax(ar_ms),
+                   solve_ms=allmax(s_ms), flops_rank=gk_fl)
+        if rep >= 1 and (res is None or cur["wall_s"] < res["wall_s"]):
+            res = cur
+    flops = float(NS) * nreg * (nreg + 1.0)
+    nbytes = npk * 8
+    busbw = (2.0 * (world - 1) / world) * nbytes / (res["allreduce_ms"] * 1e-3) / 1e9 if world > 1 else None
+    out["cfg5b_rowsharded"] = {
+        "workload": "cfg5b_one_weighted_problem", "rows": NS, "freqs": Nf, "nreg": nreg, "channels": 2, "n_gpus": world,
+        "rows_per_gpu": r1 - r0, "ms_total_resident": res["wall_s"] * 1e3, "gram_ms": res["gram_call_ms"],
+        "gram_kernel_ms": res["gram_kernel_ms"], "solve_ms": res["solve_ms"],
+        "gram_tflops_aggregate": flops / (res["gram_call_ms"] * 1e-3) / 1e12,
+        "gram_kernel_frac_per_gpu": res["flops_rank"] / (res["gram_kernel_ms"] * 1e-3) / 1e12 / peak,
+        "allreduce": {"bytes": nbytes, "us": res["allreduce_ms"] * 1e3 if world > 1 else None, "busbw_gbs": busbw,
+                      "busbw_peak_gbs": 725.0, "frac": busbw / 725.0 if busbw else None,
+                      "how": "torch.distributed all_reduce (NCCL, NVLink/NVSwitch) of the packed lower-tile Gram + 2 rhs, "
+                             "CUDA events on the launching stream, max over ranks; busbw = 2(P-1)/P bytes/time against the "
+                             "725 GB/s measured 8-GPU bus bandwidth"},
+        "peak_power_yy": float((x[0].real ** 2 + x[0].imag ** 2).max())}
+    del d_t, d_y, d_u, d_W, packed
+    torch.cuda.empty_cache()
+    return out
+
+
+def strong_leg(ctx, lp, L, C, D, torch, dist, rank, world, allmax, barrier, one_gpu_ms, steps):
+    """BASELINE configs[1] as named: ONE 2^22-sample record, its K=2047 windows split over the ranks, inputs resident."""
+    t, y, f, n = make_cfg2()
+    K = lp.window_count(len(y), n, -1)
+    k0, k1 = D.shard_range(K, rank, world)
+    hop = n >> 1
+    s0, s1 = k0 * hop, (k1 - 1) * hop + n
+    d_t = torch.from_numpy(t[s0:s1]).cuda()
+    d_y = torch.from_numpy(y[s0:s1]).cuda()
+    W = lp.hanning(n)
+    sums = np.zeros(len(f))
+    acc = torch.zeros(len(f), dtype=torch.float64, device="cuda")
+    info = C.c_int(0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+
+    def step():
+        ctx.check(ctx.lib.lpvs_ls_window_sums_dev(ctx.h, L.WIN_PSD, C.c_void_p(d_y.data_ptr()), None,
+                                                  C.c_void_p(d_t.data_ptr()), s1 - s0, vp(f), len(f), vp(W), n, hop,
+                                                  LAMBDA, 0, k1 - k0, vp(sums), C.byref(info)))
+        acc.copy_(torch.from_numpy(sums))
+        dist.all_reduce(acc)
+
+    for _ in range(3):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - w0
+    ms = allmax(max(e0.elapsed_time(e1), wall * 1e3)) / steps
+    S = lp.window_finalize(L.WIN_PSD, acc.cpu().numpy(), len(f), K)
+    return {"workload": "cfg2_windowpsd", "scaling": "strong", "n_gpus": world, "windows": K, "ms_per_pass": ms,
+            "windows_per_s": K / ms * 1e3, "one_gpu_ms_per_pass": one_gpu_ms, "speedup_vs_one_gpu": one_gpu_ms / ms,
+            "peaks": np.argsort(-S)[:2].tolist(),
+            "how": "one record, windows [K r/P, K (r+1)/P) per rank, one all-reduce of Nf doubles per pass; max over ranks "
+                   "of CUDA-event / wall time; the one-GPU figure is rank 0's resident step on the same record in this run"}
+
+
+def parity_leg(ctx, lp, L, C, D, torch, dist, rank, world, local, allmax):
+    """Sharded paths against this rank's own single-GPU result (what tools/dist_check.py and tools/admm_shard_check.py
+    check), once, outside every timed region.  Returns relative errors (max over ranks)."""
+    rng = np.random.default_rng(0)
+    N = 1 << 18
+    t = np.sort(10 * rng.random(N))
+    y = np.sin(2 * np.pi * 300 * t) + 0.3 * rng.standard_normal(N)
+    u = 0.7 * np.roll(y, 2) + 0.5 * rng.standard_normal(N)
+    n = 2048
+    f = np.arange(64) * 2.0 / (t[n] - t[0])
+    W = lp.hanning(n)
+    dev = torch.device("cuda", local)
+    rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))  # noqa: E731
+    res, _ = D.ls_window_sharded(L.WIN_PSD, y, None, t, f, n=n, W=W, lam=LAMBDA, ctx=ctx, reduce_device=dev)
+    ref, _ = lp.ls_windowpsd(y, t, f, nw=N // n, window_func=lp.hanning, ctx=ctx)
+    e_win = rel(res, ref)
+    res, _ = D.ls_window_sharded(L.WIN_COHERE, y, u, t, f, n=n, W=W, lam=LAMBDA, ctx=ctx, reduce_device=dev)
+    ref, _ = lp.ls_cohere(y, u, t, f, nw=N // n, ctx=ctx)
+    e_win = max(e_win, rel(res, ref))
+    f2 = np.arange(128) * 40.0
+    Wn = 0.5 + rng.random(N)
+    xs = D.ls_spectral_rowsharded(y, t, f2, Wn, u=u, lam=LAMBDA, ctx=ctx)
+    x1, _ = lp.ls_spectral(y, t, f2, Wn, ctx=ctx)
+    e_row = rel(xs[0], x1)
+    # ADMM: ONE 4095-unknown L1 problem sharded over the ranks vs the same problem on this GPU alone
+    rng = np.random.default_rng(3)
+    Na = 4096
+    ta = np.sort(10 * rng.random(Na))
+    fa = (np.arange(Na // 2 + 1) * (1.0 / np.mean(np.diff(ta)) / Na))[:2048]
+    ya = sum(np.cos(2 * np.pi * fa[k] * ta + k) for k in (100, 500, 900)) + 0.1 * rng.standard_normal(Na)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+
+    def create():
+        h = C.c_void_p()
+        ctx.check(ctx.lib.lpvs_admm_create_fourier(ctx.h, vp(ya), vp(ta), Na, vp(fa), len(fa), None, L.PROX_L1, 0.1, 0.05,
+                                                   None, 0, 0.0, C.byref(h)))
+        return lp.ADMM(ctx, h)
+
+    one = create()
+    one.step(600, 1e-9)
+    x1a, z1a = one.get()
+    it1 = one.iters
+    one.free()
+    sh = D.admm_shard(create())
+    sh.step(600, 1e-9)
+    dist.barrier()
+    xsa, zsa = sh.get()
+    its = sh.iters
+    dist.barrier()
+    sh.free()
+    e_admm = max(rel(zsa, z1a), rel(xsa, x1a))
+    same = bool(np.array_equal(zsa != 0, z1a != 0)) and its == it1
+    out = {"window_sharded": allmax(e_win), "row_sharded": allmax(e_row), "admm_sharded": allmax(e_admm),
+           "admm_same_support_and_iterations": allmax(0.0 if same else 1.0) == 0.0, "bar": 1e-12,
+           "how": "every rank compares the sharded result with its own single-GPU result on the same inputs (windowed PSD + "
+                  "coherence, row-sharded weighted LS with one NCCL all-reduce, one L1 ADMM problem sharded by peer stores); "
+                  "relative l2, max over ranks"}
+    out["ok"] = bool(out["window_sharded"] <= 1e-12 and out["row_sharded"] <= 1e-12 and out["admm_sharded"] <= 1e-12
+                     and out["admm_same_support_and_iterations"])
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port; Julia is not installed) on host cores."""
     if rank != 0:
@@ -245,8 +556,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "windowed LS spectra/sec", "value": val, "unit": "windows/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2_windowpsd", "samples": NSAMP, "nw": NW, "n": n, "noverlap": n >> 1,
-                   "windows": 2 * NW - 1, "freqs": NF, "window": "hanning"},
+        "config": cfg2_config(n),
         "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "blas_threads": blas_threads(),
                          "kind": "port",
                          "sample": f"{nwin} of {2 * NW - 1} windows per step, oracle reference-literal mode "
@@ -264,6 +574,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cpu-windows", type=int, default=96)
     ap.add_argument("--no-admm", action="store_true", help="skip the cfg3 ADMM leg (extra.admm)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the other BASELINE configs (extra.cfg1 / cfg4 / cfg5a / cfg5b_rowsharded / strong / parity)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -369,6 +681,7 @@ def main():
     dev_ms = ev0.elapsed_time(ev1)  # CUDA events on the launching stream around exactly K steps
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launches - launches0
+    one_gpu_ms = allsum(dev_ms / args.steps if rank == 0 else 0.0)  # rank 0's record is make_cfg2()'s default seed
     dev_ms = allmax(dev_ms)
     wall = allmax(wall)
     ms_per_step = dev_ms / args.steps
@@ -394,8 +707,33 @@ def main():
     if not args.no_admm:
         admm = admm_leg(ctx, lp, L, C, rank, world, allsum=lambda v: allsum(v), allmax=allmax, barrier=barrier)
 
+    peak, peak_src = fp64_peak()
+    extra = {"admm": admm}
+    parity_ok = True
+    if not args.no_extra:
+        from lpvspectral_jl_b200 import _dist as D
+
+        peak_live = fp64_peak_live(torch)
+        extra["fp64_dgemm_8192_live_tflops"] = peak_live
+        if rank == 0:
+            for name, fn in (("cfg1", lambda: cfg1_leg(ctx, lp, peak)), ("cfg4", lambda: cfg4_leg(ctx, lp, L, C))):
+                try:
+                    extra[name] = fn()
+                except Exception as e:  # never lose the headline line to an extra leg
+                    extra[name] = {"error": repr(e)[:300]}
+        barrier()
+        extra.update(cfg5_legs(ctx, lp, L, C, D, torch, dist, rank, world, local, allmax, barrier, peak))
+        if world > 1:
+            extra["strong"] = strong_leg(ctx, lp, L, C, D, torch, dist, rank, world, allmax, barrier, one_gpu_ms,
+                                         max(3, args.steps // 2))
+            extra["parity"] = parity_leg(ctx, lp, L, C, D, torch, dist, rank, world, local, allmax)
+            parity_ok = extra["parity"]["ok"]
+        else:
+            extra["strong"] = {"workload": "cfg2_windowpsd", "scaling": "strong", "n_gpus": 1,
+                               "ms_per_pass": one_gpu_ms, "speedup_vs_one_gpu": 1.0}
+            extra["parity"] = {"note": "sharded-path parity is checked at --gpus N > 1"}
+
     if rank == 0:
-        peak, peak_src = fp64_peak()
         achieved = gram_fl / (gram_ms * 1e-3) / 1e12
         nreg = 2 * NF - 1
         # the CPU baseline is an N=1 figure; at N>1 only a token sample keeps the other ranks from idling in NCCL
@@ -409,11 +747,9 @@ def main():
             "metric": "windowed LS spectra/sec", "value": value, "unit": "windows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg2_windowpsd", "samples_per_gpu": NSAMP, "nw": NW, "n": n,
-                       "noverlap": noverlap, "windows_per_gpu": K, "freqs": NF, "nreg": nreg, "window": "hanning",
-                       "l2": "inputs+Gram workspace (4.3 GB/step) larger than L2, no flush needed",
-                       "timing": "torch CUDA events on the shared launching stream around exactly K steps (barrier + synchronize both sides), max over ranks",
-                       "wall_ms_per_step": wall / args.steps * 1e3},
+            "config": cfg2_config(n),
+            "timing": {"how": "torch CUDA events on the shared launching stream around exactly K steps (barrier + "
+                              "synchronize both sides), max over ranks", "wall_ms_per_step": wall / args.steps * 1e3},
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(2 * NSAMP * 8 + n * 8 + NF * 8),
                     "d2h_bytes_per_step": int(NF * 8), "steps": e2e_steps,
                     "api": "lpvs_ls_window_sums (host pointers, pinned)"},
@@ -422,17 +758,22 @@ def main():
                          "frac": achieved / peak, "traffic": ncu_traffic("k_gram"), "kernel": "k_gram<GRAM_CHAIN>",
                          "flops_per_window": float(n) * nreg * (nreg + 1), "windows_per_launch": K,
                          "gram_ms_per_step": gram_ms / args.steps, "gram_share_of_step": gram_ms / call_ms,
-                         "peak_source": peak_src},
+                         "peak_source": peak_src, "peak_live": extra.get("fp64_dgemm_8192_live_tflops"),
+                         "frac_of_peak_live": (achieved / extra["fp64_dgemm_8192_live_tflops"]
+                                               if extra.get("fp64_dgemm_8192_live_tflops") else None),
+                         "peak_live_how": "cuBLAS DGEMM 8192^3 via torch.matmul, best of 5, CUDA events, inside this run"},
             "cpu_baseline": {"value": cpu_val, "unit": "windows/s", "cores": os.cpu_count(),
                              "blas_threads": blas_threads(), "kind": "port", "gram_cholesky_value": cpu_gram_val,
                              "sample": f"{cpu_windows} of {K} windows in {cpu_dt:.1f} s, oracle reference-literal "
                                        "mode (N-rhs LU per window, numpy/OpenBLAS all threads)"},
             "clocks": clocks,
-            "extra": {"admm": admm},
+            "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if not parity_ok:
+        sys.exit(3)  # a sharded path disagreed with the single-GPU result beyond 1e-12: the run is not valid
 
 
 if __name__ == "__main__":

@@ -19,7 +19,11 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "windowed LS spectra/sec" and d["unit"] == "windows/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
-    assert d["config"]["workload"] == "cfg2_windowpsd" and d["config"]["windows"] == 2047
+    assert d["config"]["workload"] == "cfg2_windowpsd" and d["config"]["windows_per_gpu"] == 2047
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.cfg2_config(4096)  # the GPU arm prints the same dict (the driver compares the two)
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
@@ -58,3 +62,7 @@ def test_workload_generators_have_the_baseline_shapes():
     assert n == 4096 and len(t) == len(y) == 1 << 14 and len(f) == 128 and f[0] == 0 and np.all(np.diff(t) >= 0)
     t, y, f = bench.make_cfg3()
     assert len(f) == 8192 and f[0] == 0 and len(t) == 16384
+    t, y, f = bench.make_cfg1()
+    assert len(t) == 4096 and len(f) == 2048 and f[0] == 0
+    t, y, u, f, n = bench.make_cfg5(nsamp=1 << 14)
+    assert n == 4096 and len(f) == 512 and len(t) == len(y) == len(u) == 1 << 14

@@ -105,20 +105,41 @@ def test_cfg4_full_size_against_oracle(ctx):
 
     Y, V, X = o.generate_lpv_signal(20000, seed=4)
     w = 2 * np.pi * np.arange(1, 65) * 0.4
-    kw = dict(lam=0.1, iters=6000, tol=1e-5, printerval=10 ** 9)
-    se, gi = lp.ls_sparse_spectral_lpv(Y, X, V, w, 50, ctx=ctx, return_info=True, **kw)
-    sr, ri = o.ls_sparse_spectral_lpv(Y, X, V, w, 50, mode="gram", return_info=True, **kw)
-    sl, rl = o.ls_sparse_spectral_lpv(Y, X, V, w, 50, mode="literal", return_info=True, **kw)
-    print(f"cfg4: gpu {gi['iters']} its, exact host {ri['iters']}, CG host {rl['iters']}; z gpu-vs-exact "
-          f"{rel(gi['z'], ri['z']):.2e}, gpu-vs-CG {rel(gi['z'], rl['z']):.2e}")
-    assert gi["iters"] == ri["iters"] == rl["iters"]
-    assert support(gi["z"]) == support(ri["z"]) == support(rl["z"])
-    assert rel(gi["z"], ri["z"]) <= 1e-9 and rel(se.x, sr.x) <= 1e-9
-    og = o.sparse_objective(ri["Phi"], Y, gi["z"], ri["proxg"])
-    for r in (ri, rl):
-        oo = o.sparse_objective(r["Phi"], Y, r["z"], r["proxg"])
-        assert abs(og - oo) <= 1e-8 * max(1.0, abs(oo))
-    assert rel(gi["z"], rl["z"]) <= 1e-7
+    Nv, Nf = 50, 64
+    Ar = o.lpv_regressor(X, V, w, Nv, True, False)
+    inds = o.lpv_group_perm(Nf, Ar.shape[1])
+    Phi = Ar[:, inds]  # src/lasso.jl:47-50
+    G, b = Phi.T @ Phi, Phi.T @ Y
+    n = Phi.shape[1]
+    assert n == 6400
+    pg = o.GroupNormL2(0.1, 2 * Nv, Nf)
+    unperm = np.argsort(inds, kind="stable")
+    exact = InverseProx(G, b, 0.05)
+    # (a) the config as named: natural stop at the default tol = 1e-5 within iters = 6000, against the exact host x-update
+    se, gs = lp.ls_sparse_spectral_lpv(Y, X, V, w, Nv, lam=0.1, iters=6000, tol=1e-5, printerval=10 ** 9, ctx=ctx,
+                                       return_info=True)
+    xs, zs, its_s, res_s = o.admm(np.zeros(n), exact, pg, iters=6000, tol=1e-5, mu=0.05, printerval=10 ** 9)
+    print(f"cfg4 natural stop: gpu {gs['iters']} its, host {its_s} its, residual {gs['residual']:.3e} / {res_s:.3e}")
+    assert gs["iters"] == its_s
+    assert support(gs["z"]) == support(zs) and rel(gs["z"], zs) <= 1e-9 and rel(gs["x"], xs) <= 1e-9
+    zr = zs[unperm]
+    assert rel(se.x, zr[: n // 2] + 1j * zr[n // 2:]) <= 1e-9  # un-permuted complex parameters (src/lasso.jl:67-68)
+    og, oo = o.sparse_objective(Phi, Y, gs["z"], pg), o.sparse_objective(Phi, Y, zs, pg)
+    assert abs(og - oo) <= 1e-8 * max(1.0, abs(oo))
+    # (b) the reference's algorithm proper (warm-started CG x-update) for 250 iterations
+    ITS = 250
+    _, gi = lp.ls_sparse_spectral_lpv(Y, X, V, w, Nv, lam=0.1, iters=ITS, tol=0.0, printerval=10 ** 9, ctx=ctx,
+                                      return_info=True)
+    pl = o.QuadProx(G, b, "ls", "literal")
+    xl, zl, _, resl = o.admm(np.zeros(n), pl, pg, iters=ITS, tol=0.0, mu=0.05, printerval=10 ** 9)
+    print(f"cfg4: {ITS} iterations, CG iterations per x-update {pl.cg_its / ITS:.2f}, z gpu-vs-CG {rel(gi['z'], zl):.2e}, "
+          f"residual {gi['residual']:.6e} / {resl:.6e}")
+    assert support(gi["z"]) == support(zl)
+    og, ol = o.sparse_objective(Phi, Y, gi["z"], pg), o.sparse_objective(Phi, Y, zl, pg)
+    assert abs(og - ol) <= 1e-8 * max(1.0, abs(ol))
+    assert rel(gi["z"], zl) <= 1e-7 and abs(gi["residual"] - resl) <= 1e-7 * resl
+    p = lp.psd(se)
+    assert set((np.argsort(-p)[:3] + 1).tolist()) == {5, 25, 50}  # 2, 10, 20 Hz on the 0.4 Hz grid
 
 
 def _window_pick(t, n, hop, K, nrand, seed):
