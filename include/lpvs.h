@@ -41,9 +41,12 @@ enum lpvs_status {
 enum lpvs_window_kind { LPVS_WIN_PSD = 0, LPVS_WIN_CSD = 1, LPVS_WIN_COHERE = 2 };
 enum lpvs_prox_kind { LPVS_PROX_L1 = 0, LPVS_PROX_L0 = 1, LPVS_PROX_BALL_L0 = 2, LPVS_PROX_GROUP_L2 = 3 };
 enum lpvs_phase_mode {
-    LPVS_PHASE_AUTO = 0,  /* chain when f is a uniform grid, else direct */
-    LPVS_PHASE_CHAIN = 1, /* exact anchors + angle-addition chains (fast path) */
-    LPVS_PHASE_DIRECT = 2 /* per-element sincos of fl(fl(2*pi*f)*t), the reference's rounding (src/lsfft.jl:41) */
+    LPVS_PHASE_AUTO = 0,     /* chain_ref when f is a uniform grid, else direct: always the reference's phase rounding */
+    LPVS_PHASE_CHAIN = 1,    /* exact anchors + angle-addition chains with the mathematically EXACT phase 2*pi*f*t: closer to
+                                the true basis than the reference, differs from it by up to eps*2*pi*f*t per element */
+    LPVS_PHASE_DIRECT = 2,   /* per-element sincos of fl(fl(2*pi*f)*t), the reference's rounding (src/lsfft.jl:34,41) */
+    LPVS_PHASE_CHAIN_REF = 3 /* the chains of mode 1, each element turned by fl(fl(2*pi*f)*t) - 2*pi*f*t (5 FP64 ops): the
+                                reference's rounding at chain speed */
 };
 enum lpvs_option {
     LPVS_OPT_PHASE_MODE = 0,   /* lpvs_phase_mode */
@@ -182,6 +185,12 @@ int lpvs_admm_result(lpvs_admm* h, double* out);
 /* device time [ms] of the last lpvs_admm_run loop kernel and its algorithmic bytes per iteration */
 int lpvs_admm_last_timing(const lpvs_admm* h, double* ms, double* bytes_per_iter);
 void lpvs_admm_free(lpvs_admm* h);
+
+/* ---- parity entry: z = prox_{gamma g}(v) computed by the ADMM loop's own device routines (the g-update of
+ * src/lasso.jl:153: ProximalOperators prox!(z, proxg, x+u, mu)).  v, z: Nreg = 2Nf - (zero_first != 0) doubles in the
+ * reference's order [cos block; sin block].  NormL1 / NormL0 / IndBallL0; ties of IndBallL0 go to the lower REFERENCE index. */
+int lpvs_prox_fourier(lpvs_ctx* ctx, int prox_kind, double prox_param, double gamma, const double* v, int Nf,
+                      int zero_first, double* z);
 
 /* one-shot conveniences mirroring the Julia functions */
 int lpvs_ls_sparse_spectral(lpvs_ctx* ctx, const double* y, const double* t, int64_t N, const double* f, int Nf,

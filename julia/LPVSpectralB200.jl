@@ -94,7 +94,9 @@ function _windowed(kind, y, u, t, freqs, nw, noverlap, window_func, estimator, k
     uv = u === nothing ? nothing : vecf(u)
     length(yv) == length(tv) || throw(AssertionError("y and t has to be the same length"))  # src/windows.jl:31
     noverlap < 0 && (noverlap = n >> 1)
+    noverlap < n || throw(ArgumentError("noverlap must be smaller than the window length n"))  # DSP.arraysplit
     Wv = vecf(window_func(n))
+    length(Wv) == n || throw(DimensionMismatch("window_func(n) must return n = $n weights, got $(length(Wv))"))
     out = kind == WIN_CSD ? Vector{ComplexF64}(undef, length(fv)) : Vector{Float64}(undef, length(fv))
     K = Ref{Int64}(0); info = Ref{Cint}(0)
     GC.@preserve yv uv tv fv Wv out begin
@@ -113,7 +115,10 @@ function _windowed_generic(kind, y, u, t, freqs, n, noverlap, window_func, estim
     estimator === ls_sparse_spectral ||
         throw(ArgumentError("estimator must be ls_spectral or ls_sparse_spectral (no CPU fallback)"))
     noverlap < 0 && (noverlap = n >> 1)
+    noverlap < n || throw(ArgumentError("noverlap must be smaller than the window length n"))  # DSP.arraysplit
     W = vecf(window_func(n)); hop = n - noverlap
+    length(W) == n || throw(DimensionMismatch("window_func(n) must return n = $n weights, got $(length(W))"))
+    # K == 0 (signal shorter than one window): empty sums divided by K^2 / K give NaN spectra, as in the reference
     K = length(y) >= n ? (length(y) - n) ÷ hop + 1 : 0
     kw = Dict{Symbol,Any}(kwargs)
     iters = get(kw, :iters, 10000); tol = get(kw, :tol, 1e-5); printerval = get(kw, :printerval, 100)

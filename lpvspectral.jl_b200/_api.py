@@ -21,7 +21,7 @@ __all__ = [
     "Context", "default_context", "default_freqs", "check_freq", "rect", "hanning", "hamming", "window_count",
     "ls_spectral", "ls_windowpsd", "ls_windowcsd", "ls_cohere", "ls_spectral_lpv", "ls_sparse_spectral",
     "ls_sparse_spectral_lpv", "ls_windowpsd_lpv", "gram_fourier", "SpectralExt", "psd", "NormL1", "NormL0",
-    "IndBallL0", "ADMM", "LpvsError", "NotPositiveDefinite", "window_sums", "window_sparse_sums", "window_finalize",
+    "IndBallL0", "ADMM", "prox", "LpvsError", "NotPositiveDefinite", "window_sums", "window_sparse_sums", "window_finalize",
 ]
 
 LpvsError = L.LpvsError
@@ -282,7 +282,13 @@ def _windowed(kind, y, u, t, freqs, nw, noverlap, window_func, estimator, ctx, k
     if noverlap < 0:
         noverlap = n >> 1
     Wv = _f64(window_func(n))
+    if len(Wv) != n:  # the reference broadcasts W against an n-sample window: DimensionMismatch (src/lsfft.jl:77)
+        raise ValueError(f"window_func(n) must return n = {n} weights, got {len(Wv)}")
     K = window_count(len(yv), n, noverlap)
+    if K < 0:  # DSP.arraysplit: ArgumentError
+        raise ValueError("noverlap must be smaller than the window length n")
+    # K == 0 (signal shorter than one window): the reference divides empty sums by K^2 / K -> NaN spectra; so do
+    # lpvs_ls_window / window_finalize (0/0), deliberately not an error
     if estimator is None or estimator is ls_spectral:
         lam = _lam(kw, 1e-10)
         if kw:
@@ -485,6 +491,18 @@ def _prox_desc(proxg):
     if isinstance(proxg, IndBallL0):
         return L.PROX_BALL_L0, float(proxg.r)
     raise ValueError("proxg must be NormL1, NormL0 or IndBallL0 (no host-side fallback for other operators)")
+
+
+def prox(proxg, v, gamma, Nf, zero_first, ctx: Optional[Context] = None):
+    """prox!(z, proxg, v, gamma) on the device, with the ADMM loop's own routines (lpvs_prox_fourier): v in the
+    reference's order [cos block; sin block], length 2*Nf - zero_first."""
+    ctx = ctx or default_context()
+    vv = _f64(v)
+    kind, param = _prox_desc(proxg)
+    z = np.empty_like(vv)
+    ctx.check(ctx.lib.lpvs_prox_fourier(ctx.h, kind, param, float(gamma), _ptr(vv), int(Nf), int(bool(zero_first)),
+                                        _ptr(z)))
+    return z
 
 
 class ADMM:

@@ -50,6 +50,26 @@ def _allreduce_sum_np(arr: np.ndarray, group=None, device=None) -> np.ndarray:
     return tt.cpu().numpy()
 
 
+def _raise_together(err: Optional[BaseException], group=None, device=None):
+    """A rank-local failure (NOT_SPD in one window range, NONFINITE, NOMEM) must not leave the other ranks blocked in the
+    data all-reduce until the NCCL timeout: every rank first all-reduces a status flag and all of them raise."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if err is not None:
+            raise err
+        return
+    flag = torch.tensor([1.0 if err is not None else 0.0], dtype=torch.float64)
+    if device is not None:
+        flag = flag.to(device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if err is not None:
+        raise err
+    if float(flag.item()) > 0:
+        raise RuntimeError("a sharded liblpvs call failed on another rank (see that rank's exception)")
+
+
 def ls_window_sharded(kind, y, u, t, freqs, *, n, noverlap=-1, W, lam=1e-10, ctx: Optional[A.Context] = None,
                       group=None, sums_fn: Optional[Callable] = None, reduce_device=None):
     """Windowed PSD/CSD/coherence with the windows sharded across ranks.
@@ -66,7 +86,12 @@ def ls_window_sharded(kind, y, u, t, freqs, *, n, noverlap=-1, W, lam=1e-10, ctx
         sums_fn = lambda *a: A.window_sums(*a, ctx=ctx)  # noqa: E731
     nf = len(freqs)
     slen = {L.WIN_PSD: 1, L.WIN_CSD: 2, L.WIN_COHERE: 4}[kind] * nf
-    sums = sums_fn(kind, y, u, t, freqs, W, n, noverlap, lam, k0, k1) if k1 > k0 else np.zeros(slen)
+    err = None
+    try:
+        sums = sums_fn(kind, y, u, t, freqs, W, n, noverlap, lam, k0, k1) if k1 > k0 else np.zeros(slen)
+    except Exception as e:  # noqa: BLE001 -- re-raised on every rank below
+        err, sums = e, np.zeros(slen)
+    _raise_together(err, group, reduce_device)
     sums = _allreduce_sum_np(np.asarray(sums, dtype=np.float64), group, reduce_device)
     return A.window_finalize(kind, sums, nf, K), K
 
@@ -106,8 +131,13 @@ def ls_spectral_rowsharded(y, t, f, W=None, *, u=None, lam=1e-10, ctx: Optional[
     packed = torch.empty(npk, dtype=torch.float64, device=dev)
     p = lambda x: None if x is None else C.c_void_p(x.data_ptr())  # noqa: E731
     torch.cuda.synchronize(dev)
-    ctx.check(ctx.lib.lpvs_gram_partial_dev(ctx.h, p(d_y), p(d_u), p(d_t), p(d_W), r1 - r0, A._ptr(fv), len(fv),
-                                            p(packed)))
+    err = None
+    try:
+        ctx.check(ctx.lib.lpvs_gram_partial_dev(ctx.h, p(d_y), p(d_u), p(d_t), p(d_W), r1 - r0, A._ptr(fv), len(fv),
+                                                p(packed)))
+    except Exception as e:  # noqa: BLE001 -- re-raised on every rank below
+        err = e
+    _raise_together(err, group, dev)
     if world > 1:
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
         torch.cuda.synchronize(dev)

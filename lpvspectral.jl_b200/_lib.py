@@ -9,14 +9,14 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblpvs.so")
+LIB_PATH = os.environ.get("LPVS_LIB") or os.path.join(_HERE, "liblpvs.so")  # LPVS_LIB: kernel-variant experiments only
 HEADER_PATH = os.path.join(_HERE, "..", "include", "lpvs.h")
 
 OK = 0
 E_BAD_ARG, E_NOT_SPD, E_NONFINITE, E_CUDA, E_NCCL, E_UNSUPPORTED, E_NOMEM = -1, -2, -3, -4, -5, -6, -7
 WIN_PSD, WIN_CSD, WIN_COHERE = 0, 1, 2
 PROX_L1, PROX_L0, PROX_BALL_L0, PROX_GROUP_L2 = 0, 1, 2, 3
-PHASE_AUTO, PHASE_CHAIN, PHASE_DIRECT = 0, 1, 2
+PHASE_AUTO, PHASE_CHAIN, PHASE_DIRECT, PHASE_CHAIN_REF = 0, 1, 2, 3
 OPT_PHASE_MODE, OPT_WINDOW_BATCH, OPT_JITTER, OPT_ADMM_CHECK_EVERY, OPT_ADMM_SYMV = 0, 1, 2, 3, 4
 INFO_JITTER = 1
 INFO_QR = 2
@@ -77,6 +77,7 @@ _PROTOS = {
     "lpvs_ls_sparse_spectral_lpv": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, C.c_int, C.c_int,
                                               C.c_int, C.c_double, C.c_double, C.c_int64, C.c_double, _vp, _i64p,
                                               _dp]),
+    "lpvs_prox_fourier": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp, C.c_int, C.c_int, _vp]),
     "lpvs_packed_size": (C.c_int64, [C.c_int]),
     "lpvs_gram_partial_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, _vp]),
     "lpvs_solve_packed_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_double, _vp, _ip]),

@@ -46,6 +46,8 @@ struct AdmmArgs {
     double tol;
     int check_every;
     int rbuf0;  // which r buffer holds the current rhs at entry
+    // Fourier problems: reference position of an internal index (tie order of IndBallL0); ref_half = Nf
+    int ref_half, zero_first;
     // outputs
     long long* iters_out;
     double* res_out;
@@ -67,6 +69,18 @@ __device__ __forceinline__ double prox_elem(int kind, double v, double gl, doubl
     }
     // NormL0: keep v iff |v| > sqrt(2 mu lambda)
     return fabs(v) > thr0 ? v : 0.0;
+}
+
+// reference position ([cos block; -sin block], src/lsfft.jl:36-47) <-> internal tiled index, Fourier problems
+__device__ __forceinline__ int admm_ref_to_internal(int j, int half, int zero_first) {
+    if (j < half) return (j >> 6) * 128 + (j & 63);
+    const int k = j - half + zero_first;
+    return (k >> 6) * 128 + 64 + (k & 63);
+}
+__device__ __forceinline__ int admm_internal_to_ref(int p, int half, int zero_first) {
+    const int q = p >> 7, r = p & 127, part = r >> 6, cc = q * 64 + (r & 63);
+    if (cc >= half || (zero_first && part == 1 && cc == 0)) return 0x7fffffff;  // dummy column
+    return part == 0 ? cc : half + cc - zero_first;
 }
 
 __device__ __forceinline__ double next_rhs(const AdmmArgs& a, int i, double z, double u) {
@@ -175,16 +189,33 @@ __device__ __forceinline__ double admm_phase_nonelem(const AdmmArgs& a, double* 
             __syncthreads();
         }
         const unsigned long long kth = s_prefix;  // key of the r-th largest
-        const unsigned ties_to_take = s_want;     // entries equal to kth that are kept (lowest index first)
+        const unsigned ties_to_take = s_want;     // entries equal to kth that are kept
+        // Ties are broken in the REFERENCE's index order -- sortperm(abs.(x), rev=true) is stable over [cos block; sin block]
+        // (ProximalOperators IndBallL0) -- not in the order of the internal tiled layout, which interleaves the two blocks
+        // in groups of 64 and would keep a different support for Nf > 64.  Usually every tie is kept (the r-th largest is
+        // unique): the serial scan in reference order only runs when it is not.
+        __shared__ unsigned s_nties;
+        if (tid == 0) s_nties = 0u;
+        __syncthreads();
+        if (rkeep > 0 && rkeep < (unsigned)Np) {
+            unsigned mine = 0;
+            for (int i = tid; i < Np; i += ADMM_THREADS)
+                mine += ((unsigned long long)__double_as_longlong(fabs(__ldcg(a.v + i))) == kth) ? 1u : 0u;
+            if (mine) atomicAdd(&s_nties, mine);
+        }
+        __syncthreads();
         if (tid == 0) {
-            int cut = -1;
-            if (rkeep > 0 && rkeep < (unsigned)Np) {
+            int cut = 0x7fffffff;  // reference index of the last tie kept; default: all of them
+            if (rkeep > 0 && rkeep < (unsigned)Np && ties_to_take < s_nties) {
+                cut = -1;
                 unsigned seen = 0;
-                for (int i = 0; i < Np && seen < ties_to_take; i++) {
+                const int nref = 2 * a.ref_half - a.zero_first;
+                for (int j = 0; j < nref && seen < ties_to_take; j++) {
+                    const int i = admm_ref_to_internal(j, a.ref_half, a.zero_first);
                     unsigned long long key = (unsigned long long)__double_as_longlong(fabs(__ldcg(a.v + i)));
                     if (key == kth) {
                         seen++;
-                        cut = i;
+                        cut = j;
                     }
                 }
             }
@@ -198,7 +229,8 @@ __device__ __forceinline__ double admm_phase_nonelem(const AdmmArgs& a, double* 
             bool keep;
             if (rkeep == 0) keep = false;
             else if (rkeep >= (unsigned)Np) keep = true;
-            else keep = key > kth || (key == kth && i <= cut);
+            else keep = key > kth || (key == kth && (cut == 0x7fffffff ||
+                                                     admm_internal_to_ref(i, a.ref_half, a.zero_first) <= cut));
             double zi = keep ? vi : 0.0;
             double di = xi - zi;
             ui += di;
@@ -643,6 +675,7 @@ struct AdmmBatchArgs {
     double mu;
     int quad, prox;
     double pparam;
+    int ref_half, zero_first;  // tie order of IndBallL0 (see AdmmArgs)
     long long max_iters;
     double tol;
     long long* iters_out;  // [nw][nrhs]
@@ -674,6 +707,8 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_batch(const __grid_con
         ch[c].quad = ba.quad;
         ch[c].prox = ba.prox;
         ch[c].pparam = ba.pparam;
+        ch[c].ref_half = ba.ref_half;
+        ch[c].zero_first = ba.zero_first;
     }
     const bool elementwise = (ba.prox == LPVS_PROX_L1 || ba.prox == LPVS_PROX_L0);
     const double gl = ba.mu * ba.pparam;
@@ -797,6 +832,8 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_batch_symv(const __gri
     ch.quad = ba.quad;
     ch.prox = ba.prox;
     ch.pparam = ba.pparam;
+    ch.ref_half = ba.ref_half;
+    ch.zero_first = ba.zero_first;
     const bool elementwise = (ba.prox == LPVS_PROX_L1 || ba.prox == LPVS_PROX_L0);
     const double gl = ba.mu * ba.pparam;
     const double thr0 = sqrt(2.0 * ba.mu * ba.pparam);
@@ -898,7 +935,8 @@ __global__ void k_admm_batch_collect(const double* __restrict__ vecs, int Np, in
 // All windows of a batch: M already holds (G + I/mu)^-1 per window, B the weighted right-hand sides A'W[y u].
 // On return B holds z (internal layout) per window and channel.
 int admm_batch_run(lpvs_ctx* c, const double* d_M, double* d_B, int Np, int nrhs, int nw, int prox, double pparam,
-                   double mu, int quad, long long iters, double tol, long long* d_iters, double* d_res) {
+                   double mu, int quad, long long iters, double tol, long long* d_iters, double* d_res, int ref_half,
+                   int zero_first) {
     double* vecs = ws<double>(c, BUF_MISC, (size_t)nw * nrhs * 7 * Np);
     if (!vecs) return fail(c, LPVS_E_NOMEM, "out of device memory (ADMM state of %d windows)", nw);
     const size_t smem = sizeof(double) * 4 * (size_t)Np;
@@ -919,6 +957,8 @@ int admm_batch_run(lpvs_ctx* c, const double* d_M, double* d_B, int Np, int nrhs
     ba.quad = quad;
     ba.prox = prox;
     ba.pparam = pparam;
+    ba.ref_half = ref_half;
+    ba.zero_first = zero_first;
     ba.max_iters = iters;
     ba.tol = tol;
     ba.iters_out = d_iters;
@@ -1233,6 +1273,17 @@ __global__ void k_gather_vec(const double* __restrict__ xin, int nref, int half,
     }
     const int idx = (cc >> 6) * 128 + part * 64 + (cc & 63);
     out[j] = xin[pos ? pos[idx] : idx];
+}
+
+// z = prox_{gamma g}(v) with the loop's own device routines (parity entry lpvs_prox_fourier), one CTA
+__global__ void __launch_bounds__(ADMM_THREADS, 1) k_prox_only(const __grid_constant__ AdmmArgs a, double* rn) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const double gl = a.mu * a.pparam, thr0 = sqrt(2.0 * a.mu * a.pparam);
+    if (a.prox == LPVS_PROX_L1 || a.prox == LPVS_PROX_L0) {
+        for (int i = tid; i < a.Np; i += ADMM_THREADS) a.z[i] = prox_elem(a.prox, a.v[i], gl, thr0);
+    } else {
+        admm_phase_nonelem(a, rn, 0, 1, tid, lane, w, gl);
+    }
 }
 
 // ADMM order: Mp[p][q] = M[order[p]][order[q]] (M symmetric), vp[p] = v[order[p]]
@@ -1628,6 +1679,8 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
     a.quad = h->quad;
     a.prox = h->prox;
     a.pparam = h->pparam;
+    a.ref_half = h->half;
+    a.zero_first = h->zero_first;
     a.goff = h->goff;
     a.gmem = h->gmem;
     a.ngroups = h->ngroups;
@@ -1640,8 +1693,17 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
     a.res_out = h->d_res;
     a.conv_out = h->d_flags;
     a.rbuf_out = h->d_flags + 1;
-    long long* d_trace = nullptr;
-    const char* trace_path = getenv("LPVS_ADMM_TRACE");
+    // clock-stamp trace of a few iterations (tools/admm_trace.py): a developer build only (-DLPVS_ADMM_TRACE_HOOK); the
+    // production library neither reads the environment nor writes files
+    struct TraceBuf {
+        long long* p = nullptr;
+        ~TraceBuf() { if (p) cudaFree(p); }  // freed on every exit path
+    } trace_buf;
+    long long*& d_trace = trace_buf.p;
+    const char* trace_path = nullptr;
+#ifdef LPVS_ADMM_TRACE_HOOK
+    trace_path = getenv("LPVS_ADMM_TRACE");
+#endif
     if (trace_path && *trace_path && max_iters > 16) {
         LPVS_CU(c, cudaMalloc(&d_trace, sizeof(long long) * TRACE_ITERS * h->grid * 8));
         LPVS_CU(c, cudaMemsetAsync(d_trace, 0, sizeof(long long) * TRACE_ITERS * h->grid * 8, c->st));
@@ -1726,7 +1788,6 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
     if (d_trace) {
         std::vector<long long> tr((size_t)TRACE_ITERS * h->grid * 8);
         cudaMemcpy(tr.data(), d_trace, sizeof(long long) * tr.size(), cudaMemcpyDeviceToHost);
-        cudaFree(d_trace);
         if (FILE* fp = fopen(trace_path, "wb")) {
             int hdr[2] = {TRACE_ITERS, h->grid};
             fwrite(hdr, sizeof(int), 2, fp);
@@ -1833,6 +1894,44 @@ int lpvs_admm_shard_connect(lpvs_admm* h, const void* handles) {
 }
 
 int lpvs_admm_size(const lpvs_admm* h) { return h ? h->nref : 0; }
+
+int lpvs_prox_fourier(lpvs_ctx* c, int prox_kind, double prox_param, double gamma, const double* v, int Nf,
+                      int zero_first, double* z) {
+    if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
+    cudaSetDevice(c->device);
+    if (!v || !z || Nf <= 0 || !(gamma > 0.0)) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
+    if (prox_kind < LPVS_PROX_L1 || prox_kind > LPVS_PROX_BALL_L0)
+        return fail(c, LPVS_E_BAD_ARG, "prox kind %d not valid for the Fourier layout", prox_kind);
+    zero_first = zero_first ? 1 : 0;
+    const int nref = 2 * Nf - zero_first, Np = (Nf + FB - 1) / FB * TB;
+    double* d_ref;
+    int rc;
+    if ((rc = upload(c, BUF_MISC, v, nref, &d_ref))) return rc;
+    double* w = ws<double>(c, BUF_X, (size_t)7 * Np + nref);  // v, x, u, z, q, rn, (unused), out
+    if (!w) return fail(c, LPVS_E_NOMEM, "out of device memory");
+    LPVS_CU(c, cudaMemsetAsync(w, 0, sizeof(double) * (7 * (size_t)Np + nref), c->st));
+    launch_scatter_ref_vec(c, d_ref, Nf, zero_first, nref, Np, w);
+    LPVS_CU(c, cudaMemcpyAsync(w + Np, w, sizeof(double) * Np, cudaMemcpyDeviceToDevice, c->st));  // x = v, u = 0
+    AdmmArgs a{};
+    a.Np = Np;
+    a.v = w;
+    a.x = w + Np;
+    a.u = w + 2 * Np;
+    a.z = w + 3 * Np;
+    a.q = w + 4 * Np;
+    a.mu = gamma;
+    a.prox = prox_kind;
+    a.pparam = prox_param;
+    a.ref_half = Nf;
+    a.zero_first = zero_first;
+    k_prox_only<<<1, ADMM_THREADS, 0, c->st>>>(a, w + 5 * Np);
+    k_gather_vec<<<(nref + 255) / 256, 256, 0, c->st>>>(a.z, nref, Nf, zero_first, nullptr, w + 7 * Np);
+    c->launches += 2;
+    LPVS_CU(c, cudaMemcpyAsync(z, w + 7 * Np, sizeof(double) * nref, cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    return inputs_finite(c);
+}
 
 int lpvs_admm_get(lpvs_admm* h, double* x, double* z) {
     if (!h) return LPVS_E_BAD_ARG;

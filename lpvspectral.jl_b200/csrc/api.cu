@@ -99,14 +99,37 @@ int make_fourier_plan(lpvs_ctx* c, const double* f, int Nf, FourierPlan* pl) {
     }
     bool uniform = dev <= 8.0 * 2.220446049250313e-16 * fmaxabs;
     int mode = c->phase_mode;
-    if (mode == LPVS_PHASE_AUTO) mode = uniform ? LPVS_PHASE_CHAIN : LPVS_PHASE_DIRECT;
-    if (mode == LPVS_PHASE_CHAIN && !uniform)
-        return fail(c, LPVS_E_BAD_ARG, "LPVS_PHASE_CHAIN requires a uniformly spaced frequency grid");
-    pl->mode = (mode == LPVS_PHASE_CHAIN) ? GRAM_CHAIN : GRAM_DIRECT;
+    if (mode == LPVS_PHASE_AUTO) mode = uniform ? LPVS_PHASE_CHAIN_REF : LPVS_PHASE_DIRECT;
+    if ((mode == LPVS_PHASE_CHAIN || mode == LPVS_PHASE_CHAIN_REF) && !uniform)
+        return fail(c, LPVS_E_BAD_ARG, "LPVS_PHASE_CHAIN / LPVS_PHASE_CHAIN_REF require a uniformly spaced frequency grid");
+    pl->mode = mode == LPVS_PHASE_CHAIN ? GRAM_CHAIN : (mode == LPVS_PHASE_CHAIN_REF ? GRAM_CHAINREF : GRAM_DIRECT);
     double* d_f = ws<double>(c, BUF_F, Nf);
     if (!d_f) return fail(c, LPVS_E_NOMEM, "out of device memory (f)");
     LPVS_CU(c, cudaMemcpyAsync(d_f, f, sizeof(double) * Nf, cudaMemcpyHostToDevice, c->st));
     pl->d_f = d_f;
+    if (pl->mode == GRAM_CHAINREF) {
+        // per column k = 8g + j: w = fl(2 pi f_k) (src/lsfft.jl:34) and dw = w - 2 pi (f_8g + j df), the difference between
+        // the reference's angular frequency and the one the chain realises, in double-double
+        const double P_HI = 6.283185307179586, P_LO = 2.4492935982947064e-16;
+        const int ncol = pl->nblk * FB;
+        c->wtab_host.assign((size_t)2 * ncol, 0.0);
+        for (int k = 0; k < Nf; k++) {
+            const int g8 = (k / GRP) * GRP, j = k - g8;
+            const double w = P_HI * f[k];
+            const double jd = (double)j * pl->df, jd_lo = fma((double)j, pl->df, -jd);
+            const double s_hi = f[g8] + jd;
+            const double bb = s_hi - f[g8];
+            const double s_lo = ((f[g8] - (s_hi - bb)) + (jd - bb)) + jd_lo;  // two_sum(f_8g, j df) + the product's tail
+            const double ph = P_HI * s_hi, pe = fma(P_HI, s_hi, -ph);
+            const double pl_lo = fma(P_LO, s_hi, pe) + P_HI * s_lo;
+            c->wtab_host[2 * k] = w;
+            c->wtab_host[2 * k + 1] = (w - ph) - pl_lo;
+        }
+        double* d_w = ws<double>(c, BUF_WTAB, (size_t)2 * ncol);
+        if (!d_w) return fail(c, LPVS_E_NOMEM, "out of device memory (phase table)");
+        LPVS_CU(c, cudaMemcpyAsync(d_w, c->wtab_host.data(), sizeof(double) * 2 * ncol, cudaMemcpyHostToDevice, c->st));
+        pl->d_wtab = reinterpret_cast<const double2*>(d_w);
+    }
     return LPVS_OK;
 }
 
@@ -231,6 +254,7 @@ void fill_basis_args(const FourierPlan& pl, GramArgs& g) {
     g.ncc = pl.Nf;
     g.nblk = pl.nblk;
     g.f = pl.d_f;
+    g.wtab = pl.d_wtab;
     g.gscale = pl.dd * pl.dd;
     g.bscale = pl.dd;
     g.E = nullptr;
@@ -251,7 +275,7 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
     }
     // segment the sample axis so the anchor table stays below ~2 GiB
     long long seg_cap = N;
-    if (pl.mode == GRAM_CHAIN) {
+    if (gram_is_chain(pl.mode)) {
         long long per_sample = (long long)(pl.ngroups + 1) * sizeof(double2);
         seg_cap = std::max<long long>(65536, (2LL << 30) / per_sample);
     }
@@ -277,7 +301,7 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
         long long s0 = sgi * seg_len, s1 = std::min<long long>(N, s0 + seg_len);
         if (s1 <= s0) break;
         long long ns = s1 - s0;
-        if (pl.mode == GRAM_CHAIN) {
+        if (gram_is_chain(pl.mode)) {
             anc = ws<double2>(c, BUF_ANC, (size_t)pl.ngroups * ns);
             del = ws<double2>(c, BUF_DEL, (size_t)ns);
             if (!anc || !del) return fail(c, LPVS_E_NOMEM, "out of device memory (anchor table)");
@@ -356,7 +380,8 @@ int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, doub
     launch_diag_prepare(d_G, ca.strideG, Np, ncc, zero_first, d_ridge, ridge, nproblems, c->st);
     c->launches += 1 + potrf(ca, nproblems, c->sms, c->st, &c->la);
     if (d_B && nrhs > 0) {
-        launch_trsv(ca, d_B, 2LL * Np, nrhs, nproblems, c->st, fuse_fwd);
+        launch_trsv(ca, d_B, 2LL * Np, nrhs, nproblems, c->st, fuse_fwd,
+                    nproblems == 1 ? ws<int>(c, BUF_FLAGS, (size_t)2 * nb) : nullptr);
         c->launches++;
     }
     LPVS_CU(c, cudaGetLastError());
@@ -755,7 +780,7 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
         if (!d_G || !d_B) return fail(c, LPVS_E_NOMEM, "out of device memory (window batch of %d)", nw);
         GramArgs g{};
         fill_basis_args(pl, g);
-        if (pl.mode == GRAM_CHAIN) {
+        if (gram_is_chain(pl.mode)) {
             double2* anc = ws<double2>(c, BUF_ANC, (size_t)pl.ngroups * ns);
             double2* del = ws<double2>(c, BUF_DEL, (size_t)ns);
             if (!anc || !del) return fail(c, LPVS_E_NOMEM, "out of device memory (anchor table)");
@@ -942,7 +967,7 @@ int lpvs_ls_window_sparse_sums(lpvs_ctx* c, int kind, const double* y, const dou
         }
         GramArgs g{};
         fill_basis_args(pl, g);
-        if (pl.mode == GRAM_CHAIN) {
+        if (gram_is_chain(pl.mode)) {
             double2* anc = ws<double2>(c, BUF_ANC, (size_t)pl.ngroups * ns);
             double2* del = ws<double2>(c, BUF_DEL, (size_t)ns);
             if (!anc || !del) {
@@ -994,7 +1019,7 @@ int lpvs_ls_window_sparse_sums(lpvs_ctx* c, int kind, const double* y, const dou
         c->launches += potri(ca, nw, c->st);
         cudaMemcpyAsync(hinfo.data(), ca.info, sizeof(int) * nw, cudaMemcpyDeviceToHost, c->st);
         if ((rc = admm_batch_run(c, d_G, d_B, pl.Np, nrhs, nw, prox_kind, prox_param, mu, /*quad=*/1, iters, tol, d_its,
-                                 d_res))) {
+                                 d_res, pl.Nf, pl.zero_first))) {
             cleanup();
             return rc;
         }

@@ -822,6 +822,127 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trsv_big(const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Dataflow TRSV for ONE large problem: CTA i owns row block i, all nb CTAs co-resident (cooperative launch).  Instead of a
+// grid barrier per block step (k_trsv_big: ~15 us per step, 1 ms per solve at nb = 32, profiles/r02_cfg1_launches_v1.csv)
+// the blocks are chained by flags: CTA i streams the tiles L[i,k] (forward) / L[k,i] (backward) in order, has the NEXT
+// tile's loads in registers before it waits for y_k / x_k, and publishes its own block with a release store.  The inverse
+// of its diagonal block sits in shared memory for the whole kernel.  Critical path per block step: flag hop + one 1 KB
+// vector read + a 128x128 GEMV from registers + a 128x128 GEMV from shared memory.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int LDI = TB + 1;  // smem stride of the diagonal inverse (conflict-free for row- and column-wise access)
+__device__ __forceinline__ void flag_wait(const int* f) {
+    if (threadIdx.x == 0) {
+        int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        } while (v == 0);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void flag_set(int* f) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_trsv_flow(const __grid_constant__ CholArgs a, double* b, int nrhs,
+                                                          int fwd_done, int* flags /* [2][nb], zero on entry */) {
+    extern __shared__ __align__(16) double sm[];
+    double* Li = sm;               // [128][LDI] inverse of the diagonal block
+    double* rs = Li + TB * LDI;    // [2][128] this block's running right-hand side
+    double* vs = rs + 2 * TB;      // [2][128] the published block of the current step
+    double* part = vs + 2 * TB;    // [4][2][128] partial sums
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x, nb = a.nb;
+    const long long Np = a.Np;
+    const double* L = a.G;
+    if (__ldcg(a.info) != 0) return;  // broken factorisation (set before this launch): every CTA leaves
+    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+        const int r = idx >> 7, c = idx & 127;
+        Li[r * LDI + c] = a.Linv[(long long)i * TB * TB + idx];
+    }
+    for (int q = tid; q < 2 * TB; q += NTHREADS) rs[q] = (q >> 7) < nrhs ? b[(long long)(q >> 7) * Np + i * TB + (q & 127)] : 0.0;
+    __syncthreads();
+    if (!fwd_done) {
+        // ---- forward: r_i -= L[i,k] y_k for k < i, then y_i = Linv_ii r_i ----
+        const int row = tid >> 1, half = tid & 1;
+        const double* Lrow = L + ((long long)i * TB + row) * Np + half * 64;
+        for (int k = 0; k < i; k++) {
+            double2 tl[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) tl[j] = __ldg(reinterpret_cast<const double2*>(Lrow + (long long)k * TB) + j);
+            flag_wait(flags + k);
+            for (int q = tid; q < 2 * TB; q += NTHREADS)
+                vs[q] = (q >> 7) < nrhs ? __ldcg(b + (long long)(q >> 7) * Np + k * TB + (q & 127)) : 0.0;
+            __syncthreads();
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int c = half * 64 + 2 * j;
+                s0 = fma(tl[j].x, vs[c], fma(tl[j].y, vs[c + 1], s0));
+                s1 = fma(tl[j].x, vs[TB + c], fma(tl[j].y, vs[TB + c + 1], s1));
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            if (half == 0) {
+                rs[row] -= s0;
+                rs[TB + row] -= s1;
+            }
+            __syncthreads();
+        }
+        {
+            const int r = tid & 127, h = tid >> 7;  // rhs h
+            double s = 0.0;
+            for (int c = 0; c <= r; c++) s = fma(Li[r * LDI + c], rs[h * TB + c], s);
+            __syncthreads();
+            rs[h * TB + r] = s;  // y_i: also the backward right-hand side of this block
+            if (h < nrhs) b[(long long)h * Np + i * TB + r] = s;
+        }
+        flag_set(flags + i);
+    }
+    // ---- backward: r_i -= L[k,i]' x_k for k > i, then x_i = Linv_ii' r_i ----
+    {
+        const int c2 = tid & 63, rq = tid >> 6;
+        for (int k = nb - 1; k > i; k--) {
+            double2 tl[32];
+            const double* T = L + ((long long)k * TB + rq * 32) * Np + (long long)i * TB + 2 * c2;
+#pragma unroll
+            for (int j = 0; j < 32; j++) tl[j] = __ldg(reinterpret_cast<const double2*>(T + (long long)j * Np));
+            flag_wait(flags + nb + k);
+            for (int q = tid; q < 2 * TB; q += NTHREADS)
+                vs[q] = (q >> 7) < nrhs ? __ldcg(b + (long long)(q >> 7) * Np + k * TB + (q & 127)) : 0.0;
+            __syncthreads();
+            double p00 = 0.0, p01 = 0.0, p10 = 0.0, p11 = 0.0;  // [rhs][column of the pair]
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const double x0 = vs[rq * 32 + j], x1 = vs[TB + rq * 32 + j];
+                p00 = fma(tl[j].x, x0, p00);
+                p01 = fma(tl[j].y, x0, p01);
+                p10 = fma(tl[j].x, x1, p10);
+                p11 = fma(tl[j].y, x1, p11);
+            }
+            part[(rq * 2 + 0) * TB + 2 * c2] = p00;
+            part[(rq * 2 + 0) * TB + 2 * c2 + 1] = p01;
+            part[(rq * 2 + 1) * TB + 2 * c2] = p10;
+            part[(rq * 2 + 1) * TB + 2 * c2 + 1] = p11;
+            __syncthreads();
+            {
+                const int c = tid & 127, h = tid >> 7;
+                rs[h * TB + c] -= (part[(0 * 2 + h) * TB + c] + part[(1 * 2 + h) * TB + c]) +
+                                  (part[(2 * 2 + h) * TB + c] + part[(3 * 2 + h) * TB + c]);
+            }
+            __syncthreads();
+        }
+        const int c = tid & 127, h = tid >> 7;
+        double s = 0.0;
+        for (int m = c; m < TB; m++) s = fma(Li[m * LDI + c], rs[h * TB + m], s);
+        if (h < nrhs) b[(long long)h * Np + i * TB + c] = s;
+        flag_set(flags + nb + i);
+    }
+}
+constexpr size_t TRSV_FLOW_SMEM = sizeof(double) * (TB * LDI + 2 * TB + 2 * TB + 8 * TB);
+
 bool attrs_done[64] = {};  // per device
 void set_attrs() {
     int dev = 0;
@@ -887,11 +1008,26 @@ void launch_symmetrize(double* G, long long strideG, int Np, int nproblems, cuda
 }
 
 void launch_trsv(const CholArgs& a, double* B, long long strideB, int nrhs, int nproblems, cudaStream_t st,
-                 bool fwd_done) {
+                 bool fwd_done, int* flow_flags) {
     if (nproblems == 1 && a.nb >= 8) {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (a.nb <= sms && flow_flags) {  // all row blocks co-resident: flag-chained dataflow substitution
+            static bool flow_attr[64] = {};
+            if (!flow_attr[dev & 63]) {
+                cudaFuncSetAttribute(k_trsv_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_FLOW_SMEM);
+                flow_attr[dev & 63] = true;
+            }
+            cudaMemsetAsync(flow_flags, 0, sizeof(int) * 2 * a.nb, st);
+            CholArgs aa = a;
+            int fd = fwd_done ? 1 : 0;
+            void* args[] = {(void*)&aa, (void*)&B, (void*)&nrhs, (void*)&fd, (void*)&flow_flags};
+            if (cudaLaunchCooperativeKernel((void*)k_trsv_flow, dim3(a.nb), dim3(NTHREADS), args, TRSV_FLOW_SMEM, st) ==
+                cudaSuccess)
+                return;
+            cudaGetLastError();
+        }
         if (a.nb <= sms) {  // all row blocks co-resident: cooperative multi-CTA substitution
             CholArgs aa = a;
             int fd = fwd_done ? 1 : 0;

@@ -58,8 +58,9 @@ void launch_init_y(const CholArgs& a, int nproblems, cudaStream_t st);
 void launch_symmetrize(double* G, long long strideG, int Np, int nproblems, cudaStream_t st);
 // B[p][r][Np] <- (L L')^{-1} B, nrhs <= 2, one CTA per problem
 // fwd_done: B already holds y = L^-1 b (fused forward substitution), only L' x = y remains
+// flow_flags (2*nb ints of device scratch, nullable): enables the flag-chained single-problem kernel
 void launch_trsv(const CholArgs& a, double* B, long long strideB, int nrhs, int nproblems, cudaStream_t st,
-                 bool fwd_done = false);
+                 bool fwd_done = false, int* flow_flags = nullptr);
 // max_i G[i][i] over non-dummy i  -> out[prob]
 void launch_max_diag(const double* G, long long strideG, int Np, int ncc, int zero_first, double* out,
                      int nproblems, cudaStream_t st);

@@ -22,7 +22,7 @@ struct DevBuf {
 enum BufSlot {
     BUF_T = 0, BUF_Y, BUF_U, BUF_W, BUF_F, BUF_ANC, BUF_DEL, BUF_G, BUF_B, BUF_LINV, BUF_INFO, BUF_PART, BUF_SUMS,
     BUF_X, BUF_MISC, BUF_YINV, BUF_E, BUF_K, BUF_V, BUF_CENT, BUF_LSQ_R, BUF_LSQ_V, BUF_LSQ_Y, BUF_LSQ_LI, BUF_LSQ_A,
-    BUF_LSQ_BT, BUF_LSQ_G2, BUF_COUNT
+    BUF_LSQ_BT, BUF_LSQ_G2, BUF_WTAB, BUF_FLAGS, BUF_COUNT
 };
 
 }  // namespace lpvs
@@ -51,6 +51,7 @@ struct lpvs_ctx {
     cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
     int call_depth = 0;
     int* d_nonfinite = nullptr;  // set by the upload-time scan of host inputs
+    std::vector<double> wtab_host;      // staging of the GRAM_CHAINREF phase table (kept alive across the async upload)
     std::vector<lpvs_admm*> live_admm;  // handles created on this context and not yet freed
 };
 
@@ -96,6 +97,7 @@ struct FourierPlan {
     int mode = GRAM_CHAIN;
     double f0 = 0.0, df = 0.0, dd = 1.0;
     const double* d_f = nullptr;
+    const double2* d_wtab = nullptr;  // GRAM_CHAINREF: (fl(2 pi f), fl(2 pi f) - 2 pi (f_anchor + j df)) per complex column
 };
 int make_fourier_plan(lpvs_ctx* c, const double* f, int Nf, FourierPlan* plan);
 inline int pcol(int k) { return (k >> 6) * 128 + (k & 63); }
@@ -176,6 +178,7 @@ int admm_set_groups(lpvs_ctx* c, lpvs_admm* h, const std::vector<int>& goff, con
 int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q, const double* d_x0);
 // one CTA per window: d_M [nw] Np x Np inverses, d_B [nw][2][Np] rhs in / z out; d_iters, d_res: [nw][nrhs]
 int admm_batch_run(lpvs_ctx* c, const double* d_M, double* d_B, int Np, int nrhs, int nw, int prox, double pparam,
-                   double mu, int quad, long long iters, double tol, long long* d_iters, double* d_res);
+                   double mu, int quad, long long iters, double tol, long long* d_iters, double* d_res, int ref_half,
+                   int zero_first);
 
 }  // namespace lpvs

@@ -42,6 +42,16 @@ __device__ __forceinline__ double2 chain_rotate(double2 z, double2 d) {
     return make_double2(__fma_rn(z.x, d.x, -__dmul_rn(z.y, d.y)), __fma_rn(z.x, d.y, __dmul_rn(z.y, d.x)));
 }
 
+// GRAM_CHAINREF: z = e^{-i theta} with the exact phase theta = 2 pi (f_anchor + j df) t -> e^{-i phi}, phi = fl(w t) the
+// reference's rounded phase.  phi - theta = dw t - (w t - fl(w t)); the product error is exact through one FMA, and the
+// rotation by that angle (<= ~1e-8 rad) is first order: second-order terms are < 1e-16.  Pinned arithmetic (see above).
+__device__ __forceinline__ double2 chain_ref_correct(double2 z, double2 wk, double t) {
+    const double phr = __dmul_rn(wk.x, t);
+    const double err = __fma_rn(wk.x, t, -phr);
+    const double dlt = __fma_rn(wk.y, t, -err);
+    return make_double2(__fma_rn(z.y, dlt, z.x), __fma_rn(-z.x, dlt, z.y));
+}
+
 template <int MODE, bool DIAG, bool RHS = false>
 __device__ __forceinline__ Pref load_pref(const GramArgs& a, int c, long long s_begin, int lane, int w, int I,
                                           int J) {
@@ -56,10 +66,11 @@ __device__ __forceinline__ Pref load_pref(const GramArgs& a, int c, long long s_
     if (a.W) p.wt = a.W[a.w_abs ? s : (long long)idc];
     p.valid = valid;
     if (RHS) p.yv = a.y[s];
-    if (MODE == GRAM_CHAIN) {
+    if (gram_is_chain(MODE)) {
         p.aI = a.anc[(long long)(I * (FB / GRP) + w) * a.tbl_ns + p.si];
         if (!DIAG) p.aJ = a.anc[(long long)(J * (FB / GRP) + w) * a.tbl_ns + p.si];
         p.d = a.del[p.si];
+        if (MODE == GRAM_CHAINREF) p.tt = a.t[s];
     } else if (MODE == GRAM_DIRECT) {
         p.tt = a.t[s];
     }
@@ -69,6 +80,7 @@ __device__ __forceinline__ Pref load_pref(const GramArgs& a, int c, long long s_
 // value of complex column cc at the prefetched sample (slow paths)
 template <int MODE>
 __device__ __forceinline__ double2 synth_elem(const GramArgs& a, const Pref& p, int cc) {
+    if (gram_is_chain(MODE)) return make_double2(0.0, 0.0);  // never taken: chain modes do not synthesise per element
     if (MODE == GRAM_DIRECT) {
         return cis_reference(a.f[cc], p.tt);
     } else {
@@ -94,6 +106,8 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     const int wm = w & 3, wn = w >> 2;
     const long long s_begin = a.start0 + (long long)prob * a.hop;
     const int nchunks = (a.n + KC - 1) / KC;
+    // GRAM_CHAINREF: (w, dw) of the I block's and the J block's 64 complex columns, staged below
+    const double2* sWtab = reinterpret_cast<const double2*>(smem + NSTAGE * STAGE_D + 8);
 
     double acc[4][8][2];   // off-diagonal: [i][j][e]; diagonal: viewed as [piece(3)][i(2)*4+j(4)][e(2)] = 48 used
 #pragma unroll
@@ -118,6 +132,9 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
         if (MODE == GRAM_CHAIN) {
             vI = zI;
             vJ = DIAG ? make_double2(zI.x * p.wt, zI.y * p.wt) : zJ;
+        } else if (MODE == GRAM_CHAINREF) {
+            vI = chain_ref_correct(zI, sWtab[w * GRP + j], p.tt);
+            vJ = DIAG ? make_double2(vI.x * p.wt, vI.y * p.wt) : chain_ref_correct(zJ, sWtab[FB + w * GRP + j], p.tt);
         } else {
             vI = synth_elem<MODE>(a, p, min(ccI0 + j, a.ncc - 1));
             vJ = DIAG ? vI : synth_elem<MODE>(a, p, min(ccJ0 + j, a.ncc - 1));
@@ -137,7 +154,7 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
         sI[rows + j * LDT] = vI.y;
         sJ[rowc + j * LDT] = vJ.x;
         sJ[rows + j * LDT] = vJ.y;
-        if (MODE == GRAM_CHAIN) {
+        if (gram_is_chain(MODE)) {
             zI = chain_rotate(zI, p.d);
             if (!DIAG) zJ = chain_rotate(zJ, p.d);
         }
@@ -156,6 +173,10 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     if (tid == 0) {
 #pragma unroll
         for (int q = 0; q < NSTAGE; q++) mbar_init(&full[q], NTHREADS / 32);
+    }
+    if (MODE == GRAM_CHAINREF && tid < 2 * FB) {
+        double2* dst = reinterpret_cast<double2*>(smem + NSTAGE * STAGE_D + 8);
+        dst[tid] = a.wtab[(tid < FB ? I : J) * FB + (tid & (FB - 1))];
     }
     __syncthreads();
     // prologue: chunk 0 into stage 0
@@ -210,7 +231,22 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
 #pragma unroll
         for (int kk = 0; kk < KC / 4; kk++) {
             if (have_next) {
-                if (SYNTH_BURST) {
+                if (SYNTH_BURST == 2) {
+                    // two half bursts (kk = 0 and kk = 4), published after the second
+                    if (kk == 0 || kk == 4) {
+                        const int j0 = kk == 0 ? 0 : GRP / 2;
+                        if (any_mask) {
+#pragma unroll
+                            for (int j = 0; j < GRP / 2; j++) synth_step(std::true_type{}, p1, zI, zJ, j0 + j, nxt);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < GRP / 2; j++) synth_step(std::false_type{}, p1, zI, zJ, j0 + j, nxt);
+                        }
+                    } else if (kk == 5) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full[st_nxt]);
+                    }
+                } else if (SYNTH_BURST) {
                     // whole next chunk in one burst: fewer DMMA<->DFMA interleave points (79.1 -> 77.7 ms)
                     if (kk == burst_kk) {
                         if (any_mask) {  // warp-uniform: the masked variant costs 128 selects per chunk
@@ -368,12 +404,13 @@ __global__ void __launch_bounds__(NTHREADS) k_gram_rhs(const __grid_constant__ G
 #pragma unroll
         for (int j = 0; j < GRP; j++) {
             double2 v = z;
-            if (MODE != GRAM_CHAIN) v = (cc0 + j < a.ncc) ? synth_elem<MODE>(a, p, cc0 + j) : make_double2(0.0, 0.0);
+            if (MODE == GRAM_CHAINREF) v = chain_ref_correct(z, a.wtab[cc0 + j], p.tt);
+            if (!gram_is_chain(MODE)) v = (cc0 + j < a.ncc) ? synth_elem<MODE>(a, p, cc0 + j) : make_double2(0.0, 0.0);
             sc[0][j] = fma(v.x, y0, sc[0][j]);
             ss[0][j] = fma(v.y, y0, ss[0][j]);
             sc[1][j] = fma(v.x, y1, sc[1][j]);
             ss[1][j] = fma(v.y, y1, ss[1][j]);
-            if (MODE == GRAM_CHAIN) z = chain_rotate(z, p.d);
+            if (gram_is_chain(MODE)) z = chain_rotate(z, p.d);
         }
     }
     const int Np = a.nblk * TB;
@@ -460,7 +497,7 @@ __global__ void k_lpv_tables(const double* __restrict__ X, const double* __restr
 
 }  // namespace
 
-size_t gram_smem_bytes() { return NSTAGE * STAGE_D * sizeof(double) + 64; }
+size_t gram_smem_bytes() { return NSTAGE * STAGE_D * sizeof(double) + 64 + 2 * FB * sizeof(double2); }
 
 int launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
     int launched = 0;
@@ -472,6 +509,7 @@ int launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
         cudaFuncSetAttribute(k_gram<GRAM_CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_gram<GRAM_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_gram<GRAM_LPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_gram<GRAM_CHAINREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done[dev & 63] = true;
     }
     int ntiles = a.nblk * (a.nblk + 1) / 2;
@@ -490,6 +528,9 @@ int launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st) {
         if (mode == GRAM_CHAIN) {
             k_gram<GRAM_CHAIN><<<grid, NTHREADS, smem, st>>>(b);
             if (rhs) k_gram_rhs<GRAM_CHAIN><<<grid_rhs, NTHREADS, 0, st>>>(b);
+        } else if (mode == GRAM_CHAINREF) {
+            k_gram<GRAM_CHAINREF><<<grid, NTHREADS, smem, st>>>(b);
+            if (rhs) k_gram_rhs<GRAM_CHAINREF><<<grid_rhs, NTHREADS, 0, st>>>(b);
         } else if (mode == GRAM_DIRECT) {
             k_gram<GRAM_DIRECT><<<grid, NTHREADS, smem, st>>>(b);
             if (rhs) k_gram_rhs<GRAM_DIRECT><<<grid_rhs, NTHREADS, 0, st>>>(b);
@@ -513,6 +554,8 @@ int launch_gram_rhs(int mode, const GramArgs& a, int nproblems, cudaStream_t st)
         dim3 grid_rhs(a.nblk, np);
         if (mode == GRAM_CHAIN)
             k_gram_rhs<GRAM_CHAIN><<<grid_rhs, NTHREADS, 0, st>>>(b);
+        else if (mode == GRAM_CHAINREF)
+            k_gram_rhs<GRAM_CHAINREF><<<grid_rhs, NTHREADS, 0, st>>>(b);
         else if (mode == GRAM_DIRECT)
             k_gram_rhs<GRAM_DIRECT><<<grid_rhs, NTHREADS, 0, st>>>(b);
         else

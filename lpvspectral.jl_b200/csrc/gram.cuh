@@ -7,7 +7,11 @@
 
 namespace lpvs {
 
-enum GramMode { GRAM_CHAIN = 0, GRAM_DIRECT = 1, GRAM_LPV = 2 };
+// GRAM_CHAIN: exact-phase anchors + angle-addition chains.  GRAM_CHAINREF: the same chains, each element then turned by the
+// tiny angle fl(fl(2 pi f) t) - 2 pi f t, so the basis carries the REFERENCE's phase rounding (src/lsfft.jl:34,41) -- 5 FP64
+// ops per element instead of a sincos.  GRAM_DIRECT: per-element sincos of the reference-rounded phase (any grid).
+enum GramMode { GRAM_CHAIN = 0, GRAM_DIRECT = 1, GRAM_LPV = 2, GRAM_CHAINREF = 3 };
+__host__ __device__ constexpr bool gram_is_chain(int mode) { return mode == GRAM_CHAIN || mode == GRAM_CHAINREF; }
 
 // Internal column layout (size Np = 128*nblk): block q holds "complex columns" cc = 64q .. 64q+63;
 // internal index p = 128q + (cc%64) for the real part (cos, or Re A for LPV) and 128q + 64 + (cc%64) for the
@@ -33,6 +37,8 @@ struct GramArgs {
     const double2* del;
     long long tbl_base;
     long long tbl_ns;
+    // GRAM_CHAINREF: per complex column (w, dw): w = fl(2 pi f), dw = w - 2 pi (f_anchor + j df) (double-double, host)
+    const double2* wtab;
     // GRAM_DIRECT
     const double* f;
     // GRAM_LPV tables: E[fi * tbl_ns + s'], Kt[ki * tbl_ns + s']

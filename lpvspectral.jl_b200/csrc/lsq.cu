@@ -78,28 +78,160 @@ __global__ void __launch_bounds__(256) k_materialize(const __grid_constant__ OpA
     Arow[s * Np + q * 128 + 64 + j] = v.y;
 }
 
-// Li = Y' (lower, zero above the 128-tile diagonal) and the ridge block of Q1': Bt[i][Nr + k] = scale(k) Li[i][k],
-// scale = lam for real columns, 1 for dummy columns (their unit diagonal keeps G2 non-singular)
-__global__ void __launch_bounds__(256) k_transpose_linv(const double* __restrict__ Y, int Np, int ncc, int zero_first,
-                                                        double lam, double* __restrict__ Li, double* __restrict__ Bt,
+// Y = X' (upper) and the ridge block of Q1': Bt[i][Nr + k] = scale(k) X[i][k], scale = lam for real columns, 1 for dummy
+// columns (their unit diagonal keeps G2 non-singular).  X is lower triangular with explicit zeros above the diagonal.
+__global__ void __launch_bounds__(256) k_transpose_linv(const double* __restrict__ X, int Np, int ncc, int zero_first,
+                                                        double lam, double* __restrict__ Y, double* __restrict__ Bt,
                                                         long long ldbt, long long Nr) {
     __shared__ double tile[32][33];
-    const int bi = blockIdx.y, bk = blockIdx.x;  // output rows 32*bi.., columns 32*bk..
+    const int bi = blockIdx.y, bk = blockIdx.x;  // input rows 32*bi.., columns 32*bk..
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const bool live = (bk >> 2) <= (bi >> 2);  // 128-tile (bi/4, bk/4) on or below the diagonal
-    if (live) {
-        for (int r = ty; r < 32; r += 8) tile[r][tx] = Y[(long long)(bk * 32 + r) * Np + bi * 32 + tx];
-    }
-    __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         const int i = bi * 32 + r, k = bk * 32 + tx;
-        const double v = live ? tile[tx][r] : 0.0;
-        Li[(long long)i * Np + k] = v;
+        const double v = X[(long long)i * Np + k];
+        tile[r][tx] = v;
         Bt[(long long)i * ldbt + Nr + k] = v * (is_dummy_col(k, ncc, zero_first) ? 1.0 : lam);
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) Y[(long long)(bk * 32 + r) * Np + bi * 32 + tx] = tile[tx][r];
+}
+
+// B operand stored [K][N] (N contiguous): a [KC x 128] slab into a [KC][LDN] smem tile; LDN == 4 (mod 16) keeps the DMMA
+// fragment loads (k = lane & 3, n = lane >> 2) conflict-free per half warp
+constexpr int LDN = TB + 4;
+static_assert(KC * LDN <= TILE_D, "the [k][n] tile must fit the [n][k] tile's slot");
+__device__ __forceinline__ void load_tile_async_kn(double* dst, const double* src, long long ld, int tid) {
+#pragma unroll
+    for (int i = 0; i < (TB * KC / 2) / NTHREADS; i++) {
+        const int q = tid + i * NTHREADS;
+        const int row = q >> 6, seg = q & 63;
+        cp_async16(dst + row * LDN + 2 * seg, src + (long long)row * ld + 2 * seg);
+    }
+}
+__device__ __forceinline__ void mma_step_kn(const double* __restrict__ pa, const double* __restrict__ pb, int kk,
+                                            double (&acc)[4][8][2]) {
+    double a[4], b[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = pa[i * 8 * LDT + 4 * kk];
+#pragma unroll
+    for (int j = 0; j < 8; j++) b[j] = pb[4 * kk * LDN + 8 * j];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+}
+
+// acc += A[128 x (k0..k1)] * op(B): BKN ? B[(k0..k1) x 128] (row-major, ldb) : B[128 x (k0..k1)]' -- 3-stage cp.async ring,
+// one __syncthreads per chunk.  A / B point at column / row k0 already.
+constexpr int NT_STAGES = 3;
+template <bool BKN>
+__device__ __forceinline__ void gemm_mainloop(const double* A, long long lda, const double* B, long long ldb, int nchunks,
+                                              double* sm, double (&acc)[4][8][2]) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wm = w & 3, wn = w >> 2;
+    auto load = [&](int stage, int chunk) {
+        double* dst = sm + stage * 2 * TILE_D;
+        load_tile_async(dst, A + (long long)chunk * KC, lda, tid);
+        if (BKN)
+            load_tile_async_kn(dst + TILE_D, B + (long long)chunk * KC * ldb, ldb, tid);
+        else
+            load_tile_async(dst + TILE_D, B + (long long)chunk * KC, ldb, tid);
+    };
+#pragma unroll
+    for (int p = 0; p < NT_STAGES - 1; p++) {
+        if (p < nchunks) load(p, p);
+        cp_async_commit();
+    }
+    const int fragA = (32 * wm + (lane >> 2)) * LDT + (lane & 3);
+    const int fragB = BKN ? (lane & 3) * LDN + 64 * wn + (lane >> 2) : (64 * wn + (lane >> 2)) * LDT + (lane & 3);
+    int st_cur = 0;
+    for (int c = 0; c < nchunks; c++) {
+        cp_async_wait<NT_STAGES - 2>();  // chunk c has landed (only the newest group may still be in flight)
+        __syncthreads();                 // ... for every thread, and everyone has left the stage refilled below
+        const int st_fill = st_cur == 0 ? NT_STAGES - 1 : st_cur - 1;
+        if (c + NT_STAGES - 1 < nchunks) load(st_fill, c + NT_STAGES - 1);
+        cp_async_commit();
+        const double* pa = sm + st_cur * 2 * TILE_D + fragA;
+        const double* pb = sm + st_cur * 2 * TILE_D + TILE_D + fragB;
+#pragma unroll
+        for (int kk = 0; kk < KC / 4; kk++) {
+            if (BKN)
+                mma_step_kn(pa, pb, kk, acc);
+            else
+                mma_step(pa, pb, kk, acc);
+        }
+        st_cur = st_cur == NT_STAGES - 1 ? 0 : st_cur + 1;
+    }
+    cp_async_wait<0>();
+}
+
+__device__ __forceinline__ void store_tile(double* C, long long ldc, double alpha, const double (&acc)[4][8][2]) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int wm = w & 3, wn = w >> 2;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int row = 32 * wm + 8 * i + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int col = 64 * wn + 8 * j + 2 * (lane & 3);
+            *reinterpret_cast<double2*>(C + (long long)row * ldc + col) =
+                make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+        }
     }
 }
 
-// C tile = A[128 x K] * B[128 x K]' (both row-major, K contiguous): 3-stage cp.async ring, one __syncthreads per chunk.
+// Triangular inverse X = L^-1 (lower, row-major) by recursive doubling over 128-blocks: with X11, X22 known for the two
+// halves of a pair,  X21 = -X22 (L21 X11).  One launch per product and level handles every pair of the level
+// (2 ceil(log2 nb) launches, each a grid of full DMMA tiles) -- the block-column sweep of trtri() exposes at most nb-1
+// CTAs per launch and took 10 of the 31 ms of a cfg1 solve (profiles/r02_cfg1_launches_v1.csv).
+struct RdArgs {
+    const double* L;  // Cholesky factor (lower), ld = Np
+    double* X;        // inverse (lower), ld = Np; diagonal 128-blocks pre-filled
+    double* S;        // scratch, ld = Np: T = L21 X11 at the coordinates of X21
+    int Np, nb, hb;   // hb = blocks per half at this level
+    int phase;        // 0: T = L21 X11, 1: X21 = -X22 T
+};
+__global__ void __launch_bounds__(NTHREADS, 1) k_trtri_rd(const __grid_constant__ RdArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const int per = a.hb * a.hb;
+    const int p = blockIdx.x / per, r = blockIdx.x - p * per;
+    const int ti = r / a.hb, tj = r - ti * a.hb;
+    const int o = 2 * a.hb * p;
+    const int h2 = min(a.hb, a.nb - o - a.hb);  // blocks in the second half (ragged last pair)
+    if (ti >= h2) return;
+    const long long Np = a.Np;
+    const int row = o + a.hb + ti, col = o + tj;
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    if (a.phase == 0) {
+        // T[row, col] = sum_{k = col .. o+hb-1} L[row, k] X[k, col]   (X11 lower triangular)
+        const int k0 = col, k1 = o + a.hb;
+        gemm_mainloop<true>(a.L + (long long)row * TB * Np + (long long)k0 * TB, Np,
+                            a.X + (long long)k0 * TB * Np + (long long)col * TB, Np, (k1 - k0) * (TB / KC), sm, acc);
+        store_tile(a.S + (long long)row * TB * Np + (long long)col * TB, Np, 1.0, acc);
+    } else {
+        // X[row, col] = - sum_{k = o+hb .. row} X[row, k] T[k, col]   (X22 lower triangular)
+        const int k0 = o + a.hb, k1 = row + 1;
+        gemm_mainloop<true>(a.X + (long long)row * TB * Np + (long long)k0 * TB, Np,
+                            a.S + (long long)k0 * TB * Np + (long long)col * TB, Np, (k1 - k0) * (TB / KC), sm, acc);
+        store_tile(a.X + (long long)row * TB * Np + (long long)col * TB, Np, -1.0, acc);
+    }
+}
+
+// X diagonal 128-blocks <- the per-block inverses the factorisation kept (Linv, ld 128)
+__global__ void __launch_bounds__(256) k_copy_diag_inv(const double* __restrict__ Linv, double* __restrict__ X, int Np) {
+    const int kb = blockIdx.x;
+    for (int idx = threadIdx.x; idx < TB * TB / 2; idx += 256) {
+        const int r = idx >> 6, c2 = (idx & 63) * 2;
+        *reinterpret_cast<double2*>(X + (long long)(kb * TB + r) * Np + kb * TB + c2) =
+            *reinterpret_cast<const double2*>(Linv + (long long)kb * TB * TB + r * TB + c2);
+    }
+}
+
+// C tile = A[128 x K] * B[128 x K]' (both row-major, K contiguous)
 enum { NT_TRI = 1, NT_SYRK = 2 };
 struct NtArgs {
     const double* A; long long lda;
@@ -108,12 +240,8 @@ struct NtArgs {
     int mt, nt, mode;
     long long K, Ksplit;
 };
-constexpr int NT_STAGES = 3;
-
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nt(const __grid_constant__ NtArgs a) {
     extern __shared__ __align__(16) double sm[];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int wm = w & 3, wn = w >> 2;
     int I, J;
     long long Kend;
     if (a.mode == NT_TRI) {  // Q1' = L^-1 [A']: row block I of the lower-triangular L^-1 has (I+1)*128 columns; long tiles first
@@ -126,55 +254,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nt(const __grid_constant__
         Kend = a.Ksplit + (long long)(J + 1) * TB;
         if (Kend > a.K) Kend = a.K;
     }
-    const double* A = a.A + (long long)I * TB * a.lda;
-    const double* B = a.B + (long long)J * TB * a.ldb;
-    const int nchunks = (int)(Kend / KC);
-
     double acc[4][8][2];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-#pragma unroll
-    for (int p = 0; p < NT_STAGES - 1; p++) {
-        if (p < nchunks) {
-            load_tile_async(sm + p * 2 * TILE_D, A + (long long)p * KC, a.lda, tid);
-            load_tile_async(sm + p * 2 * TILE_D + TILE_D, B + (long long)p * KC, a.ldb, tid);
-        }
-        cp_async_commit();
-    }
-    const int fragA = (32 * wm + (lane >> 2)) * LDT + (lane & 3);
-    const int fragB = (64 * wn + (lane >> 2)) * LDT + (lane & 3);
-    int st_cur = 0;
-    for (int c = 0; c < nchunks; c++) {
-        cp_async_wait<NT_STAGES - 2>();  // chunk c has landed (only the newest group may still be in flight)
-        __syncthreads();                 // ... for every thread, and everyone has left the stage refilled below
-        const int st_fill = st_cur == 0 ? NT_STAGES - 1 : st_cur - 1;
-        if (c + NT_STAGES - 1 < nchunks) {
-            double* dst = sm + st_fill * 2 * TILE_D;
-            load_tile_async(dst, A + (long long)(c + NT_STAGES - 1) * KC, a.lda, tid);
-            load_tile_async(dst + TILE_D, B + (long long)(c + NT_STAGES - 1) * KC, a.ldb, tid);
-        }
-        cp_async_commit();
-        const double* pa = sm + st_cur * 2 * TILE_D + fragA;
-        const double* pb = sm + st_cur * 2 * TILE_D + TILE_D + fragB;
-#pragma unroll
-        for (int kk = 0; kk < KC / 4; kk++) mma_step(pa, pb, kk, acc);
-        st_cur = st_cur == NT_STAGES - 1 ? 0 : st_cur + 1;
-    }
-    cp_async_wait<0>();
-
-    double* C = a.C + (long long)I * TB * a.ldc + (long long)J * TB;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int row = 32 * wm + 8 * i + (lane >> 2);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int col = 64 * wn + 8 * j + 2 * (lane & 3);
-            *reinterpret_cast<double2*>(C + (long long)row * a.ldc + col) = make_double2(acc[i][j][0], acc[i][j][1]);
-        }
-    }
+    gemm_mainloop<false>(a.A + (long long)I * TB * a.lda, a.lda, a.B + (long long)J * TB * a.ldb, a.ldb, (int)(Kend / KC),
+                         sm, acc);
+    store_tile(a.C + (long long)I * TB * a.ldc + (long long)J * TB, a.ldc, 1.0, acc);
 }
 
 // out[i] = sum_{s in [s0(i), len)} Mx[i][s] v[s], one warp per row; from_diag: s0 = first column of row i's 128-tile
@@ -239,6 +326,25 @@ __global__ void __launch_bounds__(1024) k_axpy_norms(double* __restrict__ x, con
         out[0] = r0[0];
         out[1] = r1[0];
     }
+}
+
+// out[0] = min over the real columns of L[i][i]^2 (the pivots of the factorisation)
+__global__ void __launch_bounds__(256) k_min_pivot(const double* __restrict__ L, int Np, int ncc, int zero_first,
+                                                   double* __restrict__ out) {
+    __shared__ double red[256];
+    double m = 1.0e300;
+    for (int i = threadIdx.x; i < Np; i += 256)
+        if (!is_dummy_col(i, ncc, zero_first)) {
+            const double l = L[(long long)i * Np + i];
+            m = fmin(m, l * l);
+        }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] = fmin(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
 }
 
 // md[1] = max(ridge, scale * md[0])
@@ -307,11 +413,16 @@ int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, con
     // ---- 1. one factorisation: L L' = G~ + max(lam^2, n eps max diag) I ----
     int pinfo = 0;
     double mult = 1.0;
+    double hmin[2] = {0.0, 0.0};  // smallest squared pivot of the factor, the shift
     for (int attempt = 0;; attempt++) {
         launch_max_diag(d_G, NN, Np, ncc, zero_first, d_md, 1, st);
         k_set_shift<<<1, 1, 0, st>>>(d_md, lam2, mult * (double)nreal * EPS);
         c->launches += 2;
         if ((rc = factor_solve(c, ncc, zero_first, Np, d_G, d_B, 1, 0.0, 1, &pinfo, nullptr, 0.0, d_md + 1))) return rc;
+        k_min_pivot<<<1, 256, 0, st>>>(d_G, Np, ncc, zero_first, d_md + 4);
+        c->launches++;
+        LPVS_CU(c, cudaMemcpyAsync(&hmin[0], d_md + 4, sizeof(double), cudaMemcpyDeviceToHost, st));
+        LPVS_CU(c, cudaMemcpyAsync(&hmin[1], d_md + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
         LPVS_CU(c, cudaStreamSynchronize(st));
         if (pinfo == 0) break;
         if (attempt == 3 || !isfinite(mult)) {
@@ -322,6 +433,9 @@ int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, con
         if ((rc = regram())) return rc;
     }
     double* d_x = d_B;  // x0 = (G~ + shift)^-1 A'y
+    // Pivots at the level of the shift mean directions with sigma^2 <~ shift, where the refinement contracts by shift / (sigma^2
+    // + shift) ~ 1 per step: go straight to the QR path (which is also exact where the refinement would have converged).
+    const bool hopeless = hmin[0] < 8.0 * hmin[1];
 
     CholArgs ca{};
     ca.G = d_G;
@@ -335,12 +449,12 @@ int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, con
     // ---- 2. corrected semi-normal equations on the reference-rounded operator ----
     double prev = 0.0;
     bool converged = false;
-    for (int step = 1; step <= 8; step++) {
+    for (int step = 1; step <= 8 && !hopeless; step++) {
         k_op_apply<<<(unsigned)((N + 31) / 32), 256, 0, st>>>(op, d_x, d_y, d_r);
         c->launches++;
         if ((rc = adjoint_apply(c, op, Np, d_r, d_g))) return rc;
         k_csne_rhs<<<(Np + 255) / 256, 256, 0, st>>>(d_g, d_x, lam2, Np, ncc, zero_first);
-        launch_trsv(ca, d_g, 2LL * Np, 1, 1, st, false);
+        launch_trsv(ca, d_g, 2LL * Np, 1, 1, st, false, ws<int>(c, BUF_FLAGS, (size_t)2 * nb));
         k_axpy_norms<<<1, 1024, 0, st>>>(d_x, d_g, Np, d_md + 2);
         c->launches += 3;
         double h[2] = {0.0, 0.0};
@@ -367,21 +481,37 @@ int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, con
     double* d_G2 = ws<double>(c, BUF_LSQ_G2, (size_t)NN);
     if (!d_Y || !d_Li || !d_A || !d_Bt || !d_G2)
         return fail(c, LPVS_E_NOMEM, "out of device memory (QR path of a rank-deficient %d x %d problem)", (int)N, nreal);
-    ca.Y = d_Y;
-    ca.strideY = NN;
-    c->launches += trtri(ca, 1, st);
-    {
-        dim3 grid(Np / 32, Np / 32);
-        k_transpose_linv<<<grid, 256, 0, st>>>(d_Y, Np, ncc, zero_first, lam, d_Li, d_Bt, Mrows, Nr);
-        dim3 gm((unsigned)((Nr + 3) / 4), nb);
-        k_materialize<<<gm, 256, 0, st>>>(op, d_A, Np, Nr);
-        c->launches += 2;
-    }
     static bool attr_done[64] = {};
     const size_t smem = (size_t)NT_STAGES * 2 * TILE_D * sizeof(double);
     if (!attr_done[c->device & 63]) {
         cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_trtri_rd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done[c->device & 63] = true;
+    }
+    {
+        // X = L^-1 into d_Li by recursive doubling (d_G2 is free until the SYRK below: scratch for T)
+        LPVS_CU(c, cudaMemsetAsync(d_Li, 0, sizeof(double) * NN, st));
+        k_copy_diag_inv<<<nb, 256, 0, st>>>(ca.Linv, d_Li, Np);
+        c->launches++;
+        RdArgs rd{};
+        rd.L = d_G;
+        rd.X = d_Li;
+        rd.S = d_G2;
+        rd.Np = Np;
+        rd.nb = nb;
+        for (int hb = 1; hb < nb; hb <<= 1) {
+            const int npairs = (nb + 2 * hb - 1) / (2 * hb);
+            rd.hb = hb;
+            for (rd.phase = 0; rd.phase < 2; rd.phase++) {
+                k_trtri_rd<<<npairs * hb * hb, NTHREADS, smem, st>>>(rd);
+                c->launches++;
+            }
+        }
+        dim3 grid(Np / 32, Np / 32);
+        k_transpose_linv<<<grid, 256, 0, st>>>(d_Li, Np, ncc, zero_first, lam, d_Y, d_Bt, Mrows, Nr);
+        dim3 gm((unsigned)((Nr + 3) / 4), nb);
+        k_materialize<<<gm, 256, 0, st>>>(op, d_A, Np, Nr);
+        c->launches += 2;
     }
     NtArgs t1{};
     t1.A = d_Li; t1.lda = Np;
@@ -424,7 +554,7 @@ int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, con
         if (Nr > N) LPVS_CU(c, cudaMemsetAsync(d_v + N, 0, sizeof(double) * (Nr - N), st));
         k_ridge_resid<<<(Np + 255) / 256, 256, 0, st>>>(d_v + Nr, d_x, lam, Np, ncc, zero_first);
         k_gemv_rows<<<(Np + 7) / 8, 256, 0, st>>>(d_Bt, Mrows, Np, d_v, Mrows, 0, d_g);
-        launch_trsv(c2, d_g, 2LL * Np, 1, 1, st, false);
+        launch_trsv(c2, d_g, 2LL * Np, 1, 1, st, false, ws<int>(c, BUF_FLAGS, (size_t)2 * nb));
         k_gemv_rows<<<(Np + 7) / 8, 256, 0, st>>>(d_Y, Np, Np, d_g, Np, 1, d_dx);
         k_axpy_norms<<<1, 1024, 0, st>>>(d_x, d_dx, Np, d_md + 2);
         c->launches += 6;

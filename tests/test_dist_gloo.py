@@ -108,3 +108,48 @@ def test_window_and_row_sharding_world2():
     A, _ = o.get_fourier_regressor(t, f)
     full = np.concatenate([(A.T @ A).ravel(), A.T @ y])
     assert np.allclose(out["gram"], full, rtol=1e-12, atol=1e-12)
+
+
+def _failing_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lpvspectral_jl_b200 import _dist as D
+
+    rng = np.random.default_rng(6)
+    N, n = 1200, 100
+    t = np.sort(10 * rng.random(N))
+    y = rng.standard_normal(N)
+    f = np.arange(4) * 2.0 / (t[n] - t[0])
+
+    def sums(kind, yy, uu, tt, ff, W, nn, nov, lam, k0, k1):
+        if rank == 1:
+            raise ValueError("rank-local failure (stands in for NOT_SPD / NONFINITE / NOMEM in one window range)")
+        return _oracle_sums(kind, yy, uu, tt, ff, W, nn, nov, lam, k0, k1)
+
+    try:
+        D.ls_window_sharded(0, y, None, t, f, n=n, W=o.hanning(n), lam=1e-10, sums_fn=sums)
+        q.put((rank, "returned"))
+    except ValueError:
+        q.put((rank, "own"))
+    except RuntimeError as e:
+        q.put((rank, "peer" if "another rank" in str(e) else "other"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank_local_failure_raises_on_every_rank():
+    """A liblpvs error on one rank used to leave the others blocked in the accumulator all-reduce."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_failing_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == {0: "peer", 1: "own"}

@@ -22,7 +22,7 @@ def signal(N, seed, tones=((20.0, 1.0, 0.0), (55.0, 0.5, 1.0)), noise=0.1, T=10.
     return t, y
 
 
-@pytest.mark.parametrize("phase", [1, 2])
+@pytest.mark.parametrize("phase", [1, 2, 3])
 @pytest.mark.parametrize("N,Nf,zero", [(1000, 100, True), (777, 70, False), (300, 129, True)])
 def test_gram_matches_oracle(ctx, phase, N, Nf, zero):
     import lpvspectral_jl_b200 as lp
@@ -42,6 +42,38 @@ def test_gram_matches_oracle(ctx, phase, N, Nf, zero):
     assert np.abs(G - Gr).max() <= 2e-13 * np.abs(Gr).max()
     assert np.abs(b - br).max() <= 2e-13 * np.abs(br).max()
     assert np.array_equal(G, G.T)
+
+
+def test_chain_ref_reproduces_reference_phase_rounding(ctx):
+    """SURVEY H3 at its hardest: large absolute time and high frequency (phi = 2 pi f t ~ 2.6e7 rad, the scale of cfg5a's
+    last windows), where the reference's fl(fl(2 pi f) t) is off the true phase by up to 2.9e-9 rad.  The Gram matrix of the
+    default mode (chain_ref) must match the oracle's (reference rounding) as closely as the per-element mode does; the
+    exact-phase chain must differ by about the phase rounding, and no more."""
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+
+    rng = np.random.default_rng(12)
+    N, Nf = 4096, 200
+    t = 9.99 + np.sort(2.4e-3 * rng.random(N))
+    fs = N / 2.4e-3
+    f = np.arange(Nf) * (fs / N) * 5.0
+    W = o.hanning(N)
+    y = rng.standard_normal(N)
+    A, _ = o.get_fourier_regressor(t, f)
+    Gr, br = (A.T * W) @ A, (A.T * W) @ y
+    err = {}
+    for mode in (L.PHASE_AUTO, L.PHASE_DIRECT, L.PHASE_CHAIN):
+        ctx.set_option(L.OPT_PHASE_MODE, mode)
+        try:
+            G, b = lp.gram_fourier(t, f, W, y, ctx=ctx)
+        finally:
+            ctx.set_option(L.OPT_PHASE_MODE, 0)
+        err[mode] = max(np.abs(G - Gr).max() / np.abs(Gr).max(), np.abs(b - br).max() / np.abs(br).max())
+    phimax = 2 * np.pi * f[-1] * t[-1]
+    print(f"phi_max {phimax:.2e} rad, phase rounding {phimax * 2.2e-16 / 2:.1e}; Gram error vs oracle: auto {err[0]:.1e} "
+          f"direct {err[2]:.1e} exact-phase chain {err[1]:.1e}")
+    assert err[L.PHASE_AUTO] <= 5e-13 and err[L.PHASE_DIRECT] <= 5e-13
+    assert 1e-11 < err[L.PHASE_CHAIN] <= 4 * phimax * 2.2e-16
 
 
 def test_parity1_unweighted_and_weighted(ctx):

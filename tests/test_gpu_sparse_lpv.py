@@ -311,3 +311,33 @@ def test_sparse_lpv_coulomb_quirk(ctx):
     assert support(info["z"]) == support(ri["z"])
     assert rel(info["z"], ri["z"]) <= 1e-9
     assert np.all(ri["z"][len(ri["z"]) // 2:] == 0) and np.all(info["z"][len(info["z"]) // 2:] == 0)
+
+
+@pytest.mark.parametrize("Nf,zero", [(40, True), (200, True), (130, False)])
+def test_device_prox_matches_oracle_bitwise_with_ties(ctx, Nf, zero):
+    """The g-update of the ADMM loop on its own (lpvs_prox_fourier) against the oracle's prox operators, bit for bit,
+    on vectors with EXACT ties.  IndBallL0 keeps the r largest |v| with ties going to the lower index of the REFERENCE
+    order [cos block; sin block] (stable sortperm, ProximalOperators) -- the device works on a tiled layout that
+    interleaves the two blocks in groups of 64, so for Nf > 64 the two orders differ."""
+    import lpvspectral_jl_b200 as lp
+
+    rng = np.random.default_rng(Nf)
+    nreg = 2 * Nf - (1 if zero else 0)
+    v = np.round(rng.standard_normal(nreg) * 4) / 4  # quarter-integer values: many exact ties in |v|
+    v[rng.random(nreg) < 0.1] = 0.0
+    for pg_d, pg_o in [(lp.NormL1(0.3), o.NormL1(0.3)), (lp.NormL0(0.4), o.NormL0(0.4))]:
+        z = lp.prox(pg_d, v, 0.05, Nf, zero, ctx=ctx)
+        assert np.array_equal(z, pg_o.prox(v, 0.05))
+    for r in (0, 1, 5, nreg // 3, nreg - 1, nreg, nreg + 3):
+        z = lp.prox(lp.IndBallL0(r), v, 0.05, Nf, zero, ctx=ctx)
+        zr = o.IndBallL0(r).prox(v, 0.05)
+        assert np.array_equal(z, zr), (Nf, zero, r)
+    # a tie that straddles the two orders: sin of frequency 3 (reference index Nf+3-zero) against cos of frequency 70
+    if Nf > 70:
+        v = np.zeros(nreg)
+        v[70] = 2.0
+        v[Nf + 3 - (1 if zero else 0)] = -2.0
+        v[5] = 3.0
+        z = lp.prox(lp.IndBallL0(2), v, 0.05, Nf, zero, ctx=ctx)
+        assert np.array_equal(z, o.IndBallL0(2).prox(v, 0.05))
+        assert z[70] == 2.0 and z[Nf + 3 - (1 if zero else 0)] == 0.0  # the cos entry has the lower reference index
