@@ -54,6 +54,8 @@ enum lpvs_option {
     LPVS_OPT_JITTER = 2,       /* 1 (default): on Cholesky breakdown of the UNWEIGHTED ls_spectral re-factor on device
                                   with ridge max(lambda^2, Nreg*eps*max diag G) and set *info=1; 0: fail */
     LPVS_OPT_ADMM_CHECK_EVERY = 3, /* residual test cadence inside the device loop; 1 (default) = every iteration (Q12) */
+    LPVS_OPT_TRSV_FLOW = 5,        /* triangular solves of ONE large problem: 1 (default) flag-chained dataflow kernel,
+                                      0 the grid-barrier kernel (one barrier per 128-block step) */
     LPVS_OPT_ADMM_SYMV = 4         /* x-update kernel: -1 auto (default), 0 GEMV over the full symmetric inverse (8 Np^2 B/iter),
                                       1 SYMV over its lower triangle (4 Np^2 B/iter) */
 };
@@ -101,6 +103,18 @@ int lpvs_gram_fourier(lpvs_ctx* ctx, const double* y, const double* t, int64_t N
  * x: Nf complex (fourier2complex, src/utilities.jl:62-73). */
 int lpvs_ls_spectral(lpvs_ctx* ctx, const double* y, const double* t, int64_t N, const double* f, int Nf,
                      const double* W, double lambda, double* x, int* info);
+
+/* ---- Base.merge(yf, w::Windows2), the re-assembly step of mapwindows (src/windows.jl:50-70) ----
+ * pieces: K x n doubles (window k = samples [k (n-noverlap), +n), as lpvs_window_count counts them), out: N doubles =
+ * the overlap-average: covering windows added in window order, divided by max(count, 1) (uncovered tail samples stay 0). */
+int lpvs_merge_windows(lpvs_ctx* ctx, const double* pieces, int64_t K, int n, int noverlap, int64_t N, double* out);
+
+/* ---- tls_spectral(y,t,f) (src/lsfft.jl:87-99) ----
+ * Total least squares: x = -V[1:n, n+1] / V[n+1, n+1], V the right singular vectors of [A y].  Computed as the eigenvector of
+ * the smallest eigenvalue of [A y]'[A y] (the Gram pass gives A'A and A'y) by inverse iteration on the factorised bordered
+ * matrix; *iters (may be NULL) = inverse-iteration steps taken.  The reference's default f is default_freqs(t)[1:end-1]. */
+int lpvs_tls_spectral(lpvs_ctx* ctx, const double* y, const double* t, int64_t N, const double* f, int Nf, double* x,
+                      int* iters);
 
 /* ---- ls_windowpsd / ls_windowcsd / ls_cohere (src/lsfft.jl:112-126, 140-156, 176-193) ----
  * One weighted ls_spectral per window (window weights W[n], shared), reduced on device.

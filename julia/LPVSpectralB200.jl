@@ -15,8 +15,8 @@ using LinearAlgebra, Statistics, Printf
 import LPVSpectral: SpectralExt, default_freqs, check_freq   # host-side pieces stay untouched Julia
 import DSP: rect, hanning
 
-export ls_spectral, ls_windowpsd, ls_windowcsd, ls_cohere, ls_sparse_spectral, ls_spectral_lpv,
-       ls_sparse_spectral_lpv, ls_windowpsd_lpv
+export ls_spectral, tls_spectral, ls_windowpsd, ls_windowcsd, ls_cohere, ls_sparse_spectral, ls_spectral_lpv,
+       ls_sparse_spectral_lpv, ls_windowpsd_lpv, mapwindows_b200
 
 const liblpvs = get(ENV, "LIBLPVS", "liblpvs")
 const WIN_PSD, WIN_CSD, WIN_COHERE = Cint(0), Cint(1), Cint(2)
@@ -78,8 +78,48 @@ function _ls_spectral(y, t, f, W, λ)
              Ptr{ComplexF64}, Ptr{Cint}),
             ctx(), yv, tv, length(yv), fv, length(fv), nullable(Wv), Float64(λ), x, info))
     end
-    info[] == 1 && @warn "Gram matrix numerically rank deficient: solved with a jitter ridge (see DESIGN.md H1)"
+    # info 1: a WEIGHTED problem was numerically singular and re-factorised with a jitter ridge (the reference's LU returns
+    # something there too); info 2 (informational): the unweighted solve took the QR-class path of csrc/lsq.cu
+    info[] == 1 && @warn "weighted Gram matrix numerically singular: solved with a jitter ridge (DESIGN.md section 1)"
     like(y, x), f                                    # the caller's own f object, untouched
+end
+
+# ---- tls_spectral (src/lsfft.jl:87-99) ---------------------------------------------------------------------
+function tls_spectral(y, t, f=default_freqs(t)[1:end-1])
+    check_freq(f)
+    yv, tv, fv = vecf(y), vecf(t), vecf(f)
+    length(yv) == length(tv) || throw(ArgumentError("y and t has to be the same length"))
+    x = Vector{ComplexF64}(undef, length(fv))
+    its = Ref{Cint}(0)
+    GC.@preserve yv tv fv x begin
+        check(ccall((:lpvs_tls_spectral, liblpvs), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Ptr{ComplexF64}, Ptr{Cint}),
+            ctx(), yv, tv, length(yv), fv, length(fv), x, its))
+    end
+    like(y, x), f
+end
+
+# ---- mapwindows / merge (src/windows.jl:50-70): the closure runs on the host as in the reference, the overlap-average
+# re-assembly on the device ------------------------------------------------------------------------------------
+function mapwindows_b200(fn::Function, y, t, n::Integer, noverlap::Integer=-1)
+    yv, tv = vecf(y), vecf(t)
+    length(yv) == length(tv) || throw(AssertionError("y and t has to be the same length"))   # src/windows.jl:31
+    noverlap < 0 && (noverlap = n >> 1)
+    noverlap < n || throw(ArgumentError("noverlap must be smaller than the window length n"))
+    hop = n - noverlap
+    K = length(yv) >= n ? (length(yv) - n) ÷ hop + 1 : 0
+    pieces = Matrix{Float64}(undef, n, K)             # column k = window k: K x n row-major for the C side
+    for k in 0:K-1
+        r = k*hop+1:k*hop+n
+        pieces[:, k+1] = fn(yv[r], tv[r])
+    end
+    out = Vector{Float64}(undef, length(yv))
+    GC.@preserve pieces out begin
+        check(ccall((:lpvs_merge_windows, liblpvs), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Cint, Int64, Ptr{Float64}),
+            ctx(), pieces, K, n, noverlap, length(yv), out))
+    end
+    like(y, out)
 end
 
 # ---- windowed estimators (src/lsfft.jl:112-193) -----------------------------------------------------------

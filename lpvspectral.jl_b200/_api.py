@@ -19,7 +19,7 @@ from . import _lib as L
 
 __all__ = [
     "Context", "default_context", "default_freqs", "check_freq", "rect", "hanning", "hamming", "window_count",
-    "ls_spectral", "ls_windowpsd", "ls_windowcsd", "ls_cohere", "ls_spectral_lpv", "ls_sparse_spectral",
+    "ls_spectral", "tls_spectral", "merge_windows", "mapwindows", "ls_windowpsd", "ls_windowcsd", "ls_cohere", "ls_spectral_lpv", "ls_sparse_spectral",
     "ls_sparse_spectral_lpv", "ls_windowpsd_lpv", "gram_fourier", "SpectralExt", "psd", "NormL1", "NormL0",
     "IndBallL0", "ADMM", "prox", "LpvsError", "NotPositiveDefinite", "window_sums", "window_sparse_sums", "window_finalize",
 ]
@@ -219,6 +219,58 @@ def ls_spectral(y, t, f=None, W=None, *, verbose=False, ctx: Optional[Context] =
     if return_info:
         return x, f_in, info.value
     return x, f_in
+
+
+@_preserve_eltype
+def tls_spectral(y, t, f=None, *, ctx: Optional[Context] = None, return_info=False):
+    """tls_spectral(y,t,f=default_freqs(t)[1:end-1]) -> (x, f)   (src/lsfft.jl:87-99): total least squares."""
+    ctx = ctx or default_context()
+    yv, tv = _f64(y), _f64(t)
+    if len(yv) != len(tv):
+        raise ValueError("y and t has to be the same length")
+    f_in = default_freqs(tv)[:-1] if f is None else f
+    fv = _f64(f_in)
+    check_freq(fv)
+    x = np.empty(len(fv), dtype=np.complex128)
+    its = C.c_int(0)
+    ctx.check(ctx.lib.lpvs_tls_spectral(ctx.h, _ptr(yv), _ptr(tv), len(yv), _ptr(fv), len(fv), _ptr(x), C.byref(its)))
+    if return_info:
+        return x, f_in, its.value
+    return x, f_in
+
+
+def merge_windows(pieces, N, n, noverlap=-1, ctx: Optional[Context] = None):
+    """Base.merge(yf, w::Windows2) (src/windows.jl:58-70): overlap-average re-assembly of per-window outputs on the device."""
+    ctx = ctx or default_context()
+    P = np.ascontiguousarray(np.asarray(pieces, dtype=np.float64))
+    if P.ndim != 2 or (P.size and P.shape[1] != n):
+        raise ValueError("pieces must be K arrays of n samples")  # the reference: DimensionMismatch in ym[inds] .+= yf[i]
+    out = np.empty(int(N))
+    ctx.check(ctx.lib.lpvs_merge_windows(ctx.h, _ptr(P), P.shape[0], int(n), int(noverlap), int(N), _ptr(out)))
+    return out
+
+
+def mapwindows(fn: Callable, y, t, n, noverlap=-1, window_func: Callable = rect, ctx: Optional[Context] = None):
+    """mapwindows(f, y, t, n, noverlap, window_func) (src/windows.jl:50-56): apply ``fn(y_i, t_i) -> yhat_i`` (an arbitrary
+    host closure, as in the reference) to every window of Windows2 and merge the outputs (device overlap-average)."""
+    yv, tv = _f64(y), _f64(t)
+    if len(yv) != len(tv):
+        raise ValueError("y and t has to be the same length")  # src/windows.jl:31
+    n = int(n)
+    if noverlap < 0:
+        noverlap = n >> 1
+    K = window_count(len(yv), n, noverlap)
+    if K < 0:
+        raise ValueError("noverlap must be smaller than the window length n")
+    hop = n - noverlap
+    pieces = np.empty((K, n))
+    for k in range(K):
+        sl = slice(k * hop, k * hop + n)
+        out = np.asarray(fn(yv[sl], tv[sl]), dtype=np.float64)
+        if out.shape != (n,):
+            raise ValueError("f must return an output of the window's length")
+        pieces[k] = out
+    return merge_windows(pieces, len(yv), n, noverlap, ctx=ctx)
 
 
 def window_sums(kind, y, u, t, freqs, W, n, noverlap, lam, k_begin, k_end, ctx: Optional[Context] = None):

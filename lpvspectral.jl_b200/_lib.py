@@ -17,7 +17,7 @@ E_BAD_ARG, E_NOT_SPD, E_NONFINITE, E_CUDA, E_NCCL, E_UNSUPPORTED, E_NOMEM = -1, 
 WIN_PSD, WIN_CSD, WIN_COHERE = 0, 1, 2
 PROX_L1, PROX_L0, PROX_BALL_L0, PROX_GROUP_L2 = 0, 1, 2, 3
 PHASE_AUTO, PHASE_CHAIN, PHASE_DIRECT, PHASE_CHAIN_REF = 0, 1, 2, 3
-OPT_PHASE_MODE, OPT_WINDOW_BATCH, OPT_JITTER, OPT_ADMM_CHECK_EVERY, OPT_ADMM_SYMV = 0, 1, 2, 3, 4
+OPT_PHASE_MODE, OPT_WINDOW_BATCH, OPT_JITTER, OPT_ADMM_CHECK_EVERY, OPT_ADMM_SYMV, OPT_TRSV_FLOW = 0, 1, 2, 3, 4, 5
 INFO_JITTER = 1
 INFO_QR = 2
 
@@ -45,6 +45,8 @@ _PROTOS = {
     "lpvs_window_count": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "lpvs_gram_fourier": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, C.c_int, _vp, _vp, _vp]),
     "lpvs_ls_spectral": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, _vp, _ip]),
+    "lpvs_merge_windows": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int64, _vp]),
+    "lpvs_tls_spectral": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, C.c_int, _vp, _ip]),
     "lpvs_ls_window_sums": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int, C.c_int,
                                       C.c_double, C.c_int64, C.c_int64, _vp, _ip]),
     "lpvs_ls_window_sums_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int,

@@ -157,6 +157,24 @@ __global__ void k_jitter_ridge(const double* __restrict__ maxdiag, double ridge,
     out[0] = fmax(ridge, scale * maxdiag[0]);
 }
 
+// Base.merge(yf, w::Windows2) (src/windows.jl:58-70): overlap-average of per-window outputs; one thread per sample, the
+// covering windows added in window order (the reference's `ym[inds] .+= yf[i]` loop), then ./ max(count, 1)
+__global__ void k_merge_windows(const double* __restrict__ pieces, long long K, int n, int hop, long long N,
+                                double* __restrict__ out) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    long long k0 = s >= n ? (s - n + hop) / hop : 0;  // first window with k*hop + n > s
+    long long k1 = s / hop;                           // last window with k*hop <= s
+    if (k1 > K - 1) k1 = K - 1;
+    double acc = 0.0;
+    long long cnt = 0;
+    for (long long k = k0; k <= k1; k++) {
+        acc += pieces[k * n + (s - k * hop)];
+        cnt++;
+    }
+    out[s] = acc / (double)(cnt > 0 ? cnt : 1);
+}
+
 // internal x ([nrhs][Np]) -> interleaved complex [nrhs][Nf]   (fourier2complex, src/utilities.jl:62-73)
 __global__ void k_x_to_complex(const double* __restrict__ X, int Np, int Nf, int zero_first, int nrhs,
                                double* __restrict__ out) {
@@ -381,7 +399,7 @@ int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, doub
     c->launches += 1 + potrf(ca, nproblems, c->sms, c->st, &c->la);
     if (d_B && nrhs > 0) {
         launch_trsv(ca, d_B, 2LL * Np, nrhs, nproblems, c->st, fuse_fwd,
-                    nproblems == 1 ? ws<int>(c, BUF_FLAGS, (size_t)2 * nb) : nullptr);
+                    nproblems == 1 ? trsv_flags(c, nb) : nullptr);
         c->launches++;
     }
     LPVS_CU(c, cudaGetLastError());
@@ -490,6 +508,7 @@ int lpvs_set_option(lpvs_ctx* c, int key, double value) {
         case LPVS_OPT_JITTER: c->jitter = (int)value; break;
         case LPVS_OPT_ADMM_CHECK_EVERY: c->admm_check_every = std::max(1, (int)value); break;
         case LPVS_OPT_ADMM_SYMV: c->admm_symv = (int)value; break;
+        case LPVS_OPT_TRSV_FLOW: c->trsv_flow = (int)value != 0; break;
         default: return fail(c, LPVS_E_BAD_ARG, "unknown option %d", key);
     }
     return LPVS_OK;
@@ -729,6 +748,61 @@ int lpvs_ls_spectral(lpvs_ctx* c, const double* y, const double* t, int64_t N, c
     if (!d_out) return fail(c, LPVS_E_NOMEM, "out of device memory (x)");
     k_x_to_complex<<<(Nf + 127) / 128, 128, 0, c->st>>>(d_x, pl.Np, Nf, pl.zero_first, 1, d_out);
     c->launches++;
+    LPVS_CU(c, cudaMemcpyAsync(x, d_out, sizeof(double) * 2 * Nf, cudaMemcpyDeviceToHost, c->st));
+    if ((rc = inputs_finite(c))) return rc;
+    gram_timer_resolve(c);
+    return LPVS_OK;
+}
+
+int lpvs_merge_windows(lpvs_ctx* c, const double* pieces, int64_t K, int n, int noverlap, int64_t N, double* out) {
+    if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
+    CallTimer call_timer(c);
+    cudaSetDevice(c->device);
+    if (!out || N <= 0 || n <= 0 || K < 0 || (K > 0 && !pieces)) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
+    if (noverlap < 0) noverlap = n >> 1;
+    if (noverlap >= n) return fail(c, LPVS_E_BAD_ARG, "noverlap must be < n");
+    const int hop = n - noverlap;
+    if (K > 0 && (K - 1) * (int64_t)hop + n > N) return fail(c, LPVS_E_BAD_ARG, "windows extend beyond the signal");
+    double* d_p = nullptr;
+    int rc;
+    if (K > 0 && (rc = upload(c, BUF_MISC, pieces, K * (int64_t)n, &d_p))) return rc;
+    double* d_o = ws<double>(c, BUF_X, (size_t)N);
+    if (!d_o) return fail(c, LPVS_E_NOMEM, "out of device memory");
+    k_merge_windows<<<(unsigned)((N + 255) / 256), 256, 0, c->st>>>(d_p, K, n, hop, N, d_o);
+    c->launches++;
+    LPVS_CU(c, cudaMemcpyAsync(out, d_o, sizeof(double) * N, cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    return LPVS_OK;
+}
+
+int lpvs_tls_spectral(lpvs_ctx* c, const double* y, const double* t, int64_t N, const double* f, int Nf, double* x,
+                      int* iters) {
+    if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
+    CallTimer call_timer(c);
+    cudaSetDevice(c->device);
+    if (iters) *iters = 0;
+    if (!y || !t || !x || N <= 0) return fail(c, LPVS_E_BAD_ARG, "bad arguments");
+    gram_timer_reset(c);
+    FourierPlan pl;
+    int rc = make_fourier_plan(c, f, Nf, &pl);
+    if (rc) return rc;
+    double *d_t, *d_y;
+    if ((rc = upload(c, BUF_T, t, N, &d_t))) return rc;
+    if ((rc = upload(c, BUF_Y, y, N, &d_y))) return rc;
+    const long long Np = pl.Np;
+    double* d_G = ws<double>(c, BUF_G, (size_t)Np * Np);
+    double* d_B = ws<double>(c, BUF_B, (size_t)2 * Np);
+    if (!d_G || !d_B) return fail(c, LPVS_E_NOMEM, "out of device memory (G)");
+    if ((rc = gram_single(c, pl, d_t, d_y, nullptr, nullptr, N, 1, d_G, d_B))) return rc;
+    if ((rc = tls_solve(c, pl.Np, pl.Nf, pl.zero_first, d_y, N, d_G, d_B, iters))) {
+        if (inputs_finite(c) == LPVS_E_NONFINITE) return LPVS_E_NONFINITE;
+        return rc;
+    }
+    double* d_out = ws<double>(c, BUF_X, (size_t)2 * Nf);
+    if (!d_out) return fail(c, LPVS_E_NOMEM, "out of device memory (x)");
+    launch_x_to_complex(c, d_B, pl.Np, Nf, pl.zero_first, 1, d_out);
     LPVS_CU(c, cudaMemcpyAsync(x, d_out, sizeof(double) * 2 * Nf, cudaMemcpyDeviceToHost, c->st));
     if ((rc = inputs_finite(c))) return rc;
     gram_timer_resolve(c);

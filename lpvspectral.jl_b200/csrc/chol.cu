@@ -876,12 +876,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trsv_flow(const __grid_constant
             for (int q = tid; q < 2 * TB; q += NTHREADS)
                 vs[q] = (q >> 7) < nrhs ? __ldcg(b + (long long)(q >> 7) * Np + k * TB + (q & 127)) : 0.0;
             __syncthreads();
-            double s0 = 0.0, s1 = 0.0;
+            double s0, s1;
+            {
+                double e0[4] = {0.0, 0.0, 0.0, 0.0}, e1[4] = {0.0, 0.0, 0.0, 0.0};  // 4 chains: latency and rounding
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int c = half * 64 + 2 * j;
-                s0 = fma(tl[j].x, vs[c], fma(tl[j].y, vs[c + 1], s0));
-                s1 = fma(tl[j].x, vs[TB + c], fma(tl[j].y, vs[TB + c + 1], s1));
+                for (int j = 0; j < 32; j++) {
+                    const int c = half * 64 + 2 * j;
+                    e0[j & 3] = fma(tl[j].x, vs[c], fma(tl[j].y, vs[c + 1], e0[j & 3]));
+                    e1[j & 3] = fma(tl[j].x, vs[TB + c], fma(tl[j].y, vs[TB + c + 1], e1[j & 3]));
+                }
+                s0 = (e0[0] + e0[1]) + (e0[2] + e0[3]);
+                s1 = (e1[0] + e1[1]) + (e1[2] + e1[3]);
             }
             s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
             s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
@@ -893,8 +898,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trsv_flow(const __grid_constant
         }
         {
             const int r = tid & 127, h = tid >> 7;  // rhs h
-            double s = 0.0;
-            for (int c = 0; c <= r; c++) s = fma(Li[r * LDI + c], rs[h * TB + c], s);
+            double e[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int c = 0; c <= r; c++) e[c & 3] = fma(Li[r * LDI + c], rs[h * TB + c], e[c & 3]);
+            const double s = (e[0] + e[1]) + (e[2] + e[3]);
             __syncthreads();
             rs[h * TB + r] = s;  // y_i: also the backward right-hand side of this block
             if (h < nrhs) b[(long long)h * Np + i * TB + r] = s;
@@ -913,15 +919,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trsv_flow(const __grid_constant
             for (int q = tid; q < 2 * TB; q += NTHREADS)
                 vs[q] = (q >> 7) < nrhs ? __ldcg(b + (long long)(q >> 7) * Np + k * TB + (q & 127)) : 0.0;
             __syncthreads();
-            double p00 = 0.0, p01 = 0.0, p10 = 0.0, p11 = 0.0;  // [rhs][column of the pair]
+            double q00[2] = {0.0, 0.0}, q01[2] = {0.0, 0.0}, q10[2] = {0.0, 0.0}, q11[2] = {0.0, 0.0};
 #pragma unroll
             for (int j = 0; j < 32; j++) {
                 const double x0 = vs[rq * 32 + j], x1 = vs[TB + rq * 32 + j];
-                p00 = fma(tl[j].x, x0, p00);
-                p01 = fma(tl[j].y, x0, p01);
-                p10 = fma(tl[j].x, x1, p10);
-                p11 = fma(tl[j].y, x1, p11);
+                q00[j & 1] = fma(tl[j].x, x0, q00[j & 1]);
+                q01[j & 1] = fma(tl[j].y, x0, q01[j & 1]);
+                q10[j & 1] = fma(tl[j].x, x1, q10[j & 1]);
+                q11[j & 1] = fma(tl[j].y, x1, q11[j & 1]);
             }
+            const double p00 = q00[0] + q00[1], p01 = q01[0] + q01[1];  // [rhs][column of the pair]
+            const double p10 = q10[0] + q10[1], p11 = q11[0] + q11[1];
             part[(rq * 2 + 0) * TB + 2 * c2] = p00;
             part[(rq * 2 + 0) * TB + 2 * c2 + 1] = p01;
             part[(rq * 2 + 1) * TB + 2 * c2] = p10;
@@ -935,8 +943,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trsv_flow(const __grid_constant
             __syncthreads();
         }
         const int c = tid & 127, h = tid >> 7;
-        double s = 0.0;
-        for (int m = c; m < TB; m++) s = fma(Li[m * LDI + c], rs[h * TB + m], s);
+        double e[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int m = c; m < TB; m++) e[m & 3] = fma(Li[m * LDI + c], rs[h * TB + m], e[m & 3]);
+        const double s = (e[0] + e[1]) + (e[2] + e[3]);
         if (h < nrhs) b[(long long)h * Np + i * TB + c] = s;
         flag_set(flags + nb + i);
     }

@@ -40,6 +40,7 @@ struct lpvs_ctx {
     int jitter = 1;
     int admm_check_every = 1;
     int admm_symv = -1;  // -1 auto, 0 GEMV over full M, 1 SYMV over the lower triangle
+    int trsv_flow = 1;   // single-problem triangular solves: dataflow kernel (1) or grid-barrier kernel (0)
     lpvs::DevBuf buf[lpvs::BUF_COUNT];
     int64_t launches = 0;
     // Gram kernel timing of the last API call
@@ -133,11 +134,17 @@ struct OpArgs {
     int zero_first = 0;
     long long N = 0;
 };
+// tls_spectral on device: in d_G = A'A (lower tiles, destroyed), d_B[0] = A'y; out d_B[0] = x (internal layout)
+int tls_solve(lpvs_ctx* c, int Np, int ncc, int zero_first, const double* d_y, long long N, double* d_G, double* d_B,
+              int* iters_out);
 // x = argmin |A x - y|^2 + lam^2 |x|^2 to the accuracy of a QR / SVD of [A; lam I] (see lsq.cu).  In: d_G = Gram matrix of
 // ANY phase mode (lower tiles, destroyed), d_B[0] = A'y; out: d_B[0] = x (internal layout).  regram() must rebuild d_G / d_B
 // (only called if the shifted factorisation itself breaks down).  *info: 0, or LPVS_INFO_QR when the QR path ran.
 int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, const double* d_y, double* d_G, double* d_B,
                       double lam, const std::function<int()>& regram, int* info);
+
+// device scratch for the flag-chained TRSV (null = use the grid-barrier kernel)
+inline int* trsv_flags(lpvs_ctx* c, int nb) { return c->trsv_flow ? ws<int>(c, BUF_FLAGS, (size_t)2 * nb) : nullptr; }
 
 // shared helpers (api.cu)
 // reads the upload-time non-finite flag (synchronises the stream); LPVS_E_NONFINITE if any host input had NaN/Inf

@@ -248,6 +248,21 @@ def ls_spectral(y, t, f=None, W=None, lam=1e-10, mode="literal"):
     return fourier2complex(x, zerofreq), f
 
 
+def tls_spectral(y, t, f=None):
+    """src/lsfft.jl:87-99: total least squares by the SVD of [A y] (LAPACK gesvd 'S','S'): x = -V21 / V22 with
+    V21 = Vt[n+1, 1:n], V22 = Vt[n+1, n+1].  Default frequencies default_freqs(t)[1:end-1]."""
+    y = np.asarray(y, dtype=np.float64)
+    t = np.asarray(t, dtype=np.float64)
+    if f is None:
+        f = default_freqs(t)[:-1]
+    f = np.asarray(f, dtype=np.float64)
+    A, zerofreq = get_fourier_regressor(t, f)
+    n = A.shape[1]
+    _, _, Vt = sla.svd(np.column_stack([A, y]), full_matrices=False, lapack_driver="gesvd")
+    x = -Vt[n, :n] / Vt[n, n]
+    return fourier2complex(x, zerofreq), f
+
+
 # --------------------------------------------------------------------------------------------------------
 # windowed estimators -- src/lsfft.jl:112-193
 # --------------------------------------------------------------------------------------------------------

@@ -31,3 +31,12 @@ for nf in (1024, 2048):
         x, _, info = lp.ls_spectral(y, t, f, ctx=ctx, return_info=True)
         wall = time.perf_counter() - t0
     print(f"N=4096 Nf={nf}: info={info} call {ctx.last_call_ms():.3f} ms wall {wall*1e3:.3f} ms gram {ctx.gram_timing()[0]:.3f} ms")
+# dataflow vs grid-barrier TRSV on the same well-conditioned problem
+f = lp.default_freqs(t)[:1024]
+for flow in (1, 0):
+    ctx.set_option(L.OPT_TRSV_FLOW, flow)
+    x, _, info = lp.ls_spectral(y, t, f, ctx=ctx, return_info=True)
+    if flow:
+        x1 = x
+    print(f"trsv_flow={flow}: info={info} call {ctx.last_call_ms():.3f} ms" + ("" if flow else f" rel diff {rel(x1, x):.2e}"))
+ctx.set_option(L.OPT_TRSV_FLOW, 1)
