@@ -51,8 +51,11 @@ enum lpvs_phase_mode {
 enum lpvs_option {
     LPVS_OPT_PHASE_MODE = 0,   /* lpvs_phase_mode */
     LPVS_OPT_WINDOW_BATCH = 1, /* windows factorised per batch (bounds workspace), default auto */
-    LPVS_OPT_JITTER = 2,       /* 1 (default): on Cholesky breakdown of the UNWEIGHTED ls_spectral re-factor on device
-                                  with ridge max(lambda^2, Nreg*eps*max diag G) and set *info=1; 0: fail */
+    LPVS_OPT_JITTER = 2,       /* 1 (default): unweighted ls_spectral / ls_spectral_lpv are solved to the accuracy of the
+                                  reference's SVD / pivoted QR of [A; lambda I] (refinement on the operator, shifted CholeskyQR
+                                  when needed: rank-deficient defaults work, *info = LPVS_INFO_QR); weighted / windowed solves
+                                  re-factor a numerically singular problem with ridge max(lambda, Nreg*eps*max diag G)
+                                  (*info = LPVS_INFO_JITTER).  0: plain Cholesky everywhere, LPVS_E_NOT_SPD on breakdown */
     LPVS_OPT_ADMM_CHECK_EVERY = 3, /* residual test cadence inside the device loop; 1 (default) = every iteration (Q12) */
     LPVS_OPT_TRSV_FLOW = 5,        /* triangular solves of ONE large problem: 1 (default) flag-chained dataflow kernel,
                                       0 the grid-barrier kernel (one barrier per 128-block step) */
@@ -98,7 +101,8 @@ int lpvs_gram_fourier(lpvs_ctx* ctx, const double* y, const double* t, int64_t N
                       const double* W, double* G, double* b);
 
 /* ---- ls_spectral(y,t,f; lambda) and ls_spectral(y,t,f,W; lambda)  (src/lsfft.jl:62-80) ----
- * W == NULL: x = (A'A + lambda^2 I)^-1 A'y  (fourier_solve, src/utilities.jl:56-60)
+ * W == NULL: x = argmin |Ax-y|^2 + lambda^2 |x|^2, to the accuracy of svd([A; lambda I]) \ [y; 0]
+ *            (fourier_solve, src/utilities.jl:56-60); the default call with Nreg = N+1 > N is fine
  * W != NULL: x = (A'WA + lambda I)^-1 A'Wy  (src/lsfft.jl:77)
  * x: Nf complex (fourier2complex, src/utilities.jl:62-73). */
 int lpvs_ls_spectral(lpvs_ctx* ctx, const double* y, const double* t, int64_t N, const double* f, int Nf,

@@ -57,6 +57,20 @@ __global__ void k_sum_sq(const double* __restrict__ v, long long N, double shift
     }
 }
 
+// S[f] += abs2(sum_k x[f + k Nf])   (psd(::SpectralExt), src/lsfft.jl:214-217, accumulated as src/lsfft.jl:273-274)
+__global__ void k_lpv_psd_accum(const double* __restrict__ xint, int Nf, int Nvv, double* __restrict__ S) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= Nf) return;
+    double re = 0.0, im = 0.0;
+    for (int k = 0; k < Nvv; k++) {
+        const int cc = f + k * Nf;
+        const int p = (cc >> 6) * 128 + (cc & 63);
+        re += xint[p];
+        im += xint[p + 64];
+    }
+    S[f] = __dadd_rn(S[f], __dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im)));
+}
+
 __global__ void k_scale(double* v, long long n, double s) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] *= s;
@@ -215,8 +229,9 @@ namespace lpvs {
 namespace {
 
 // ls_spectral_lpv on prepared tables and a device-resident Y (src/lsfft.jl:248-257); params / Sigma / fva are host outputs
+// params (host, nullable) and / or d_psd (device, nullable: S[f] += abs2(sum_k x[f,k]) stays on the device)
 int lpv_ls_core(lpvs_ctx* c, const LpvPlan& pl, const double* d_Y, double lambda, double* params, double* Sigma,
-                double* fva, int* info) {
+                double* fva, int* info, double* d_psd = nullptr) {
     const int64_t N = pl.N;
     const int Nf = pl.Nf;
     int rc;
@@ -261,8 +276,14 @@ int lpv_ls_core(lpvs_ctx* c, const LpvPlan& pl, const double* d_Y, double lambda
     double* d_out = ws<double>(c, BUF_X, (size_t)nref);
     double* d_e = ws<double>(c, BUF_MISC, (size_t)std::max<long long>(N, (long long)nref * nref));
     if (!d_out || !d_e) return fail(c, LPVS_E_NOMEM, "out of device memory");
-    launch_x_to_complex(c, d_B, pl.Np, pl.ncc, 0, 1, d_out);
-    LPVS_CU(c, cudaMemcpyAsync(params, d_out, sizeof(double) * nref, cudaMemcpyDeviceToHost, c->st));
+    if (params) {
+        launch_x_to_complex(c, d_B, pl.Np, pl.ncc, 0, 1, d_out);
+        LPVS_CU(c, cudaMemcpyAsync(params, d_out, sizeof(double) * nref, cudaMemcpyDeviceToHost, c->st));
+    }
+    if (d_psd) {
+        k_lpv_psd_accum<<<(Nf + 127) / 128, 128, 0, c->st>>>(d_B, Nf, pl.Nvv, d_psd);
+        c->launches++;
+    }
     // residual, variances, fraction of variance explained (src/lsfft.jl:252-256)
     double ve = 0.0, vy = 0.0;
     if (fva || Sigma) {
@@ -359,23 +380,25 @@ int lpvs_ls_windowpsd_lpv(lpvs_ctx* c, const double* Y, const double* X, const d
     if ((rc = upload(c, BUF_T, X, N, &d_X))) return rc;
     if ((rc = upload(c, BUF_V, V, N, &d_V))) return rc;
     if ((rc = upload(c, BUF_F, w, Nf, &d_w))) return rc;
-    const int nvv = coulomb ? 2 * Nv : Nv;
-    std::vector<double> p((size_t)2 * Nf * nvv);
+    // S accumulates on the device in window order (k_lpv_psd_accum); the parameters never travel to the host
+    double* d_S = ws<double>(c, BUF_PSD, (size_t)Nf);
+    if (!d_S) return fail(c, LPVS_E_NOMEM, "out of device memory");
+    LPVS_CU(c, cudaMemsetAsync(d_S, 0, sizeof(double) * Nf, c->st));
+    int any_info = 0;
     for (int64_t k = 0; k < nwin; k++) {
         const int64_t off = k * hop;
         LpvPlan pl;
         if ((rc = lpv_prepare_dev(c, V + off, d_X + off, d_V + off, n, d_w, Nf, Nv, coulomb, normalize, &pl))) return rc;
-        // the core ends with a stream synchronisation, so p is complete when it returns
-        if ((rc = lpv_ls_core(c, pl, d_Y + off, lambda, p.data(), nullptr, fva ? fva + k : nullptr, info))) return rc;
-        for (int f = 0; f < Nf; f++) {  // abs2(sum(reshape_params(x, Nf), dims=2)), src/lsfft.jl:273-274
-            double re = 0.0, im = 0.0;
-            for (int kk = 0; kk < nvv; kk++) {
-                re += p[2 * ((size_t)f + (size_t)kk * Nf)];
-                im += p[2 * ((size_t)f + (size_t)kk * Nf) + 1];
-            }
-            S[f] += re * re + im * im;
+        int winfo = 0;
+        if ((rc = lpv_ls_core(c, pl, d_Y + off, lambda, nullptr, nullptr, fva ? fva + k : nullptr, &winfo, d_S))) {
+            if (info) *info = winfo;
+            return rc;
         }
+        any_info |= winfo;
     }
+    if (info) *info = any_info;
+    LPVS_CU(c, cudaMemcpyAsync(S, d_S, sizeof(double) * Nf, cudaMemcpyDeviceToHost, c->st));
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
     gram_timer_resolve(c);
     return LPVS_OK;
 }
