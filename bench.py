@@ -107,9 +107,9 @@ class ClockSampler:
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic.json)."""
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r02_traffic.json)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
             return float(json.load(fh)[kernel]["dram_bytes_per_launch"])
     except Exception:
         return None
