@@ -219,8 +219,9 @@ def admm_leg(ctx, lp, L, C, rank, world, allsum, allmax, barrier, iters=2000):
             ms_max = allmax(ms_s)
             sharded = {"iters_per_s": iters / (ms_max * 1e-3), "us_per_iter": ms_max / iters * 1e3,
                        "vs_one_gpu": (iters / (ms_max * 1e-3)) / its_min,
-                       "how": "one problem over all GPUs: reduce-scatter of partial products + all-gather of the rhs by "
-                              "peer stores over NVLink inside the persistent kernel, max over ranks of the device time"}
+                       "how": "one problem over all GPUs: ONE all-reduce of the partial products per iteration by peer stores "
+                              "over NVLink inside the persistent kernel (prox computed redundantly on every rank), max over "
+                              "ranks of the device time"}
         except Exception as e:  # never lose the headline line to the optional leg
             sharded = {"error": repr(e)[:200]}
     return {"workload": "cfg3_l1_admm", "nreg": 2 * len(f) - 1, "iters": iters, "iters_per_s": total,
@@ -340,6 +341,35 @@ def cfg4_leg(ctx, lp, L, C, iters=2000):
                          "frac": bpi * its / 1e9 / hbm, "bytes_per_iter": bpi,
                          "note": "algorithmic bytes; the inverse (164 MB lower triangle) is partly L2-resident, so DRAM "
                                  "traffic is lower (profiles/r01c_summary.md)"}}
+
+
+def cfg4_sharded_leg(ctx, lp, L, C, D, dist, world, allmax, barrier, one_gpu_its, iters=2000):
+    """BASELINE configs[3] as ONE problem over the run's N GPUs (exchange 2: all-reduce of the partial products by peer stores,
+    group prox computed redundantly on every rank).  Every rank creates the same problem."""
+    from oracle import lpvs_oracle as o
+
+    Y, V, X = o.generate_lpv_signal(20000, seed=4)
+    w = 2 * np.pi * np.arange(1, 65) * 0.4
+    h = C.c_void_p()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rc = ctx.lib.lpvs_admm_create_lpv(ctx.h, vp(Y), vp(X), vp(V), len(Y), vp(w), len(w), 50, 0, 1, 0.1, 0.05, C.byref(h))
+    if allmax(1.0 if rc else 0.0) > 0:
+        if not rc:
+            ctx.lib.lpvs_admm_free(h)
+        return {"error": "problem creation failed on some rank"}
+    ss = D.admm_shard(lp.ADMM(ctx, h))
+    ss.step(200, 0.0)
+    barrier()
+    ss.step(iters, 0.0)
+    ms, _ = ss.timing()
+    barrier()
+    ss.free()
+    ms = allmax(ms)
+    its = iters / (ms * 1e-3)
+    return {"workload": "cfg4_group_lasso_lpv", "n_gpus": world, "iters_per_s": its, "us_per_iter": ms / iters * 1e3,
+            "vs_one_gpu": its / one_gpu_its if one_gpu_its else None,
+            "how": "one problem over all GPUs: one all-reduce of the partial products per iteration by peer stores over NVLink "
+                   "inside the persistent kernel, whole groups per CTA; max over ranks of the device time"}
 
 
 def cfg5_legs(ctx, lp, L, C, D, torch, dist, rank, world, local, allmax, barrier, peak):
@@ -528,13 +558,40 @@ def parity_leg(ctx, lp, L, C, D, torch, dist, rank, world, local, allmax):
     sh.free()
     e_admm = max(rel(zsa, z1a), rel(xsa, x1a))
     same = bool(np.array_equal(zsa != 0, z1a != 0)) and its == it1
+    # group lasso (ls_sparse_spectral_lpv): ONE 640-unknown problem sharded vs this GPU alone
+    from oracle import lpvs_oracle as o
+
+    Yg, Vg, Xg = o.generate_lpv_signal(4000, seed=4)
+    wg = 2 * np.pi * np.arange(1, 17) * 0.4
+
+    def create_lpv():
+        h = C.c_void_p()
+        ctx.check(ctx.lib.lpvs_admm_create_lpv(ctx.h, vp(Yg), vp(Xg), vp(Vg), len(Yg), vp(wg), len(wg), 20, 0, 1, 0.1, 0.05,
+                                               C.byref(h)))
+        return lp.ADMM(ctx, h)
+
+    one = create_lpv()
+    one.step(400, 1e-7)
+    x1g, z1g = one.get()
+    it1g = one.iters
+    one.free()
+    sh = D.admm_shard(create_lpv())
+    sh.step(400, 1e-7)
+    dist.barrier()
+    xsg, zsg = sh.get()
+    itsg = sh.iters
+    dist.barrier()
+    sh.free()
+    e_group = max(rel(zsg, z1g), rel(xsg, x1g))
+    same = same and bool(np.array_equal(zsg != 0, z1g != 0)) and itsg == it1g
     out = {"window_sharded": allmax(e_win), "row_sharded": allmax(e_row), "admm_sharded": allmax(e_admm),
+           "admm_group_sharded": allmax(e_group),
            "admm_same_support_and_iterations": allmax(0.0 if same else 1.0) == 0.0, "bar": 1e-12,
            "how": "every rank compares the sharded result with its own single-GPU result on the same inputs (windowed PSD + "
                   "coherence, row-sharded weighted LS with one NCCL all-reduce, one L1 ADMM problem sharded by peer stores); "
                   "relative l2, max over ranks"}
     out["ok"] = bool(out["window_sharded"] <= 1e-12 and out["row_sharded"] <= 1e-12 and out["admm_sharded"] <= 1e-12
-                     and out["admm_same_support_and_iterations"])
+                     and out["admm_group_sharded"] <= 1e-12 and out["admm_same_support_and_iterations"])
     return out
 
 
@@ -744,6 +801,8 @@ def main():
         barrier()
         extra.update(cfg5_legs(ctx, lp, L, C, D, torch, dist, rank, world, local, allmax, barrier, peak))
         if world > 1:
+            one4 = allsum(extra["cfg4"].get("iters_per_s", 0.0) if rank == 0 and isinstance(extra.get("cfg4"), dict) else 0.0)
+            extra["cfg4_sharded"] = cfg4_sharded_leg(ctx, lp, L, C, D, dist, world, allmax, barrier, one4)
             extra["strong"] = strong_leg(ctx, lp, L, C, D, torch, dist, rank, world, allmax, barrier, one_gpu_ms,
                                          max(3, args.steps // 2))
             extra["parity"] = parity_leg(ctx, lp, L, C, D, torch, dist, rank, world, local, allmax)

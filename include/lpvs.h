@@ -57,6 +57,11 @@ enum lpvs_option {
                                   re-factor a numerically singular problem with ridge max(lambda, Nreg*eps*max diag G)
                                   (*info = LPVS_INFO_JITTER).  0: plain Cholesky everywhere, LPVS_E_NOT_SPD on breakdown */
     LPVS_OPT_ADMM_CHECK_EVERY = 3, /* residual test cadence inside the device loop; 1 (default) = every iteration (Q12) */
+    LPVS_OPT_SHARD_EXCHANGE = 6,   /* one ADMM problem over several GPUs, exchange per iteration (set identically on every rank):
+                                      2 (default) all-reduce of the partial products by peer stores, prox computed redundantly on
+                                        every rank: ONE cross-GPU step and two grid barriers per iteration;
+                                      1 reduce-scatter + all-gather with per-CTA arrival counters (two steps, one barrier);
+                                      0 reduce-scatter + all-gather with flags raised by CTA 0 (two steps, three barriers) */
     LPVS_OPT_TRSV_FLOW = 5,        /* triangular solves of ONE large problem: 1 (default) flag-chained dataflow kernel,
                                       0 the grid-barrier kernel (one barrier per 128-block step) */
     LPVS_OPT_ADMM_SYMV = 4         /* x-update kernel: -1 auto (default), 0 GEMV over the full symmetric inverse (8 Np^2 B/iter),

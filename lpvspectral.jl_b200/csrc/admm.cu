@@ -996,7 +996,14 @@ struct ShardArgs {
     int rows_max;                  // max rows owned by a rank
     long long it_base;             // iterations done before this launch (flags are absolute iteration counters)
     long long spin_limit;          // clock64 budget of one flag wait
+    // exchange v2 (LPVS_OPT_SHARD_EXCHANGE = 1, default): every CTA arrives on counters at every peer instead of
+    // "grid barrier -> CTA 0 raises a flag": one grid barrier per iteration instead of three
+    int v2;
+    long long off_cnt;             // [2] u64 arrival counters: A (partials delivered), B (new rhs + residual partial delivered)
+    long long off_resid2;          // [2][SHARD_MAXP][SHARD_MAXGRID] residual partial of every CTA of every rank
+    long long off_recv2;           // v3: [2][world][Np] partial of every row from every rank, by iteration parity
 };
+constexpr int SHARD_MAXGRID = 256;
 
 __device__ __forceinline__ void st_release_sys(long long* p, long long v) {
     asm volatile("st.global.release.sys.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -1025,6 +1032,30 @@ __device__ __forceinline__ void shard_wait(const ShardArgs& sh, long long off_fl
     }
     __syncthreads();
 }
+// v2: this CTA's stores to every peer are done -> one arrival on each peer's counter.  The bar.sync orders the CTA's stores
+// before the arriving threads' release, which is cumulative over them.
+__device__ __forceinline__ void shard_arrive(const ShardArgs& sh, int which, int tid) {
+    __syncthreads();
+    if (tid < sh.world) {
+        unsigned long long* cnt = reinterpret_cast<unsigned long long*>(sh.base[tid] + sh.off_cnt) + which;
+        asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(cnt), "l"(1ull) : "memory");
+    }
+}
+// v2: wait until `target` arrivals reached this rank's counter (bounded like shard_wait; a timeout is only recorded)
+__device__ __forceinline__ void shard_wait_count(const ShardArgs& sh, int which, unsigned long long target, int tid) {
+    if (tid == 0) {
+        const long long* cnt = reinterpret_cast<const long long*>(sh.base[sh.rank] + sh.off_cnt) + which;
+        long long* ab = reinterpret_cast<long long*>(sh.base[sh.rank] + sh.off_abort);
+        const long long t0 = clock64();
+        while ((unsigned long long)ld_acquire_sys(cnt) < target) {
+            if (clock64() - t0 > sh.spin_limit || ld_acquire_sys(ab) != 0) {
+                atomicExch(reinterpret_cast<unsigned long long*>(ab + 1), 1ull);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
 __device__ __forceinline__ void shard_fold_abort(const ShardArgs& sh, int b, int tid) {
     if (b == 0 && tid == 0) {
         long long* ab = reinterpret_cast<long long*>(sh.base[sh.rank] + sh.off_abort);
@@ -1044,11 +1075,14 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv_sharded(const __g
     extern __shared__ __align__(16) double sm[];
     double* ys = sm;
     double* cred = sm + a.Np;
+    double* xs = cred + ADMM_WARPS * 128;  // [max_item] x of the current group item (group prox, exchange v3 only)
     __shared__ double wsum[ADMM_WARPS];
+    __shared__ double gsum[ADMM_WARPS];
     __shared__ double red4[4][128];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int nblocks = gridDim.x, b = blockIdx.x;
     const int Np = a.Np, P = sh.world, me = sh.rank;
+    const int item0 = sp.cta_item[b], item1 = sp.cta_item[b + 1];
     const double gl = a.mu * a.pparam;
     const double thr0 = sqrt(2.0 * a.mu * a.pparam);
     const int sg0 = sp.cta_seg[b], sg1 = sp.cta_seg[b + 1];
@@ -1123,6 +1157,127 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv_sharded(const __g
             break;
         }
         ADMM_TR(2)
+        if (sh.v2 == 2) {
+            // ---- exchange v3: ONE cross-GPU step per iteration.  Every rank sends its partial of EVERY row to every peer
+            // (an all-reduce by peer stores, Np doubles per peer), then computes x, prox, u and the next right-hand side for
+            // all rows itself (redundantly but bit-identically: fixed summation order), so no all-gather and no residual
+            // exchange is needed.  Receive buffers alternate with the iteration parity.
+            const int par = (int)(tick & 1);
+            for (int rb0 = 0; rb0 < an; rb0 += 128) {
+                const int rl = rb0 + (tid & 127), q = tid >> 7;
+                red4[q][tid & 127] = rl < an ? symv_row_sum(sp, a0 + rl, q) : 0.0;
+                __syncthreads();
+                if (tid < 128 && rl < an) {
+                    const int i = a0 + rl;
+                    const double yi = (red4[0][tid] + red4[1][tid]) + (red4[2][tid] + red4[3][tid]);
+                    const long long off = sh.off_recv2 + ((long long)(par * P + me)) * Np + i;
+                    for (int sdst = 0; sdst < P; sdst++) sh.base[sdst][off] = yi;  // peer (or local) stores over NVLink
+                }
+                __syncthreads();
+            }
+            ADMM_TR(3)
+            shard_arrive(sh, 0, tid);
+            ADMM_TR(4)
+            shard_wait_count(sh, 0, (unsigned long long)tick * (unsigned long long)(P * nblocks), tid);
+            ADMM_TR(5)
+            const int nxt3 = cur ^ 1;
+            double d2 = 0.0;
+            const double* rbase = mine + sh.off_recv2 + (long long)par * P * Np;
+            double* rn3 = mine + sh.off_rhs + (long long)nxt3 * Np;
+            if (a.prox != LPVS_PROX_GROUP_L2) {
+                for (int r = tid; r < an; r += ADMM_THREADS) {
+                    const int i = a0 + r;
+                    double xi = 0.0;
+                    for (int sr = 0; sr < P; sr++) xi += __ldcg(rbase + (long long)sr * Np + i);
+                    a.x[i] = xi;
+                    double ui = a.u[i];
+                    const double zi = prox_elem(a.prox, xi + ui, gl, thr0);
+                    const double di = xi - zi;
+                    ui += di;
+                    a.z[i] = zi;
+                    a.u[i] = ui;
+                    rn3[i] = next_rhs(a, i, zi, ui);
+                    d2 += di * di;
+                }
+            } else {
+                // group prox (src/lasso.jl:53-55): whole groups per CTA in ADMM order, as in k_admm_symv -- every rank holds
+                // every row after the all-reduce, so groups never straddle ranks.  ys is free after barrier 1.
+                for (int itx = item0; itx < item1; itx++) {
+                    const int lo = __ldg(sp.item_lo + itx), hi = __ldg(sp.item_hi + itx), kind = __ldg(sp.item_kind + itx);
+                    for (int m = tid; m < hi - lo; m += ADMM_THREADS) {
+                        const int i = lo + m;
+                        double xi = 0.0;
+                        for (int sr = 0; sr < P; sr++) xi += __ldcg(rbase + (long long)sr * Np + i);
+                        a.x[i] = xi;
+                        xs[m] = xi;
+                        ys[m] = xi + a.u[i];
+                    }
+                    __syncthreads();
+                    double scale = 0.0;
+                    if (kind == 0) {
+                        double ss = 0.0;
+                        for (int m = tid; m < hi - lo; m += ADMM_THREADS) ss = fma(ys[m], ys[m], ss);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                        if (lane == 0) gsum[w] = ss;
+                        __syncthreads();
+                        double tot = 0.0;
+#pragma unroll
+                        for (int k = 0; k < ADMM_WARPS; k++) tot += gsum[k];
+                        const double nrm = sqrt(tot);
+                        scale = nrm > 0.0 ? fmax(0.0, 1.0 - gl / nrm) : 0.0;
+                    }
+                    for (int m = tid; m < hi - lo; m += ADMM_THREADS) {
+                        const int i = lo + m;
+                        const double xi = xs[m], zi = scale * ys[m];
+                        double ui = a.u[i];
+                        const double di = xi - zi;
+                        ui += di;
+                        a.z[i] = zi;
+                        a.u[i] = ui;
+                        rn3[i] = next_rhs(a, i, zi, ui);
+                        d2 += di * di;
+                    }
+                    __syncthreads();
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+            if (lane == 0) wsum[w] = d2;
+            __syncthreads();
+            if (tid == 0) {
+                double sacc = 0.0;
+                for (int k = 0; k < ADMM_WARPS; k++) sacc += wsum[k];
+                a.part[(it & 1) * nblocks + b] = sacc;
+            }
+            ADMM_TR(6)
+            shard_fold_abort(sh, b, tid);
+            grid.sync();
+            if (shard_aborted(sh)) {
+                failed = 1;
+                break;
+            }
+            ADMM_TR(7)
+            if (w == 0) {
+                double sacc = 0.0;
+                for (int k = lane; k < nblocks; k += 32) sacc += __ldcg(a.part + (it & 1) * nblocks + k);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                if (lane == 0) wsum[0] = sacc;
+            }
+            __syncthreads();
+            nxz = sqrt(wsum[0]);
+            __syncthreads();
+            cur = nxt3;
+            if ((it + 1) % a.check_every == 0 || it + 1 == a.max_iters) {
+                if (nxz < a.tol) {
+                    converged = 1;
+                    it++;
+                    break;
+                }
+            }
+            continue;
+        }
         // ---- phase 2a: this rank's partial of every row -> the owner's receive slot [me] (reduce-scatter) ----
         for (int rb0 = 0; rb0 < an; rb0 += 128) {
             const int rl = rb0 + (tid & 127), q = tid >> 7;
@@ -1142,16 +1297,22 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv_sharded(const __g
         // no per-thread system fence: the stores above happen-before the grid barrier, and the signalling thread's
         // release.sys store after it is cumulative over everything that happened before it
         ADMM_TR(3)
-        shard_fold_abort(sh, b, tid);
-        grid.sync();
-        if (shard_aborted(sh)) {
-            failed = 1;
-            break;
+        if (sh.v2) {
+            shard_arrive(sh, 0, tid);
+            ADMM_TR(4)
+            shard_wait_count(sh, 0, (unsigned long long)tick * (unsigned long long)(P * nblocks), tid);
+        } else {
+            shard_fold_abort(sh, b, tid);
+            grid.sync();
+            if (shard_aborted(sh)) {
+                failed = 1;
+                break;
+            }
+            if (b == 0 && tid < P)
+                st_release_sys(reinterpret_cast<long long*>(sh.base[tid] + sh.off_flagA) + me, tick);
+            ADMM_TR(4)
+            shard_wait(sh, sh.off_flagA, tick, tid);
         }
-        if (b == 0 && tid < P)
-            st_release_sys(reinterpret_cast<long long*>(sh.base[tid] + sh.off_flagA) + me, tick);
-        ADMM_TR(4)
-        shard_wait(sh, sh.off_flagA, tick, tid);
         ADMM_TR(5)
         // ---- phase 2b: owned rows: x = sum over ranks (fixed order), prox, dual update, new rhs -> every rank ----
         const int nxt = cur ^ 1;
@@ -1176,36 +1337,65 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv_sharded(const __g
         for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
         if (lane == 0) wsum[w] = d2;
         __syncthreads();
-        if (tid == 0) {
-            double s = 0.0;
-            for (int k = 0; k < ADMM_WARPS; k++) s += wsum[k];
-            a.part[(it & 1) * nblocks + b] = s;
-        }
-        shard_fold_abort(sh, b, tid);
-        grid.sync();
-        if (shard_aborted(sh)) {
-            failed = 1;
-            break;
-        }
-        ADMM_TR(6)
-        if (b == 0) {
-            if (w == 0) {  // this rank's residual partial, fixed order, to every rank; then the flag
+        if (sh.v2) {
+            // this CTA's residual partial into its slot at every rank, then one arrival per peer; after the wait every CTA of
+            // every rank sums the same P * nblocks slots in the same order -> the same stop decision everywhere
+            if (tid < P) {
                 double s = 0.0;
-                for (int k = lane; k < nblocks; k += 32) s += __ldcg(a.part + (it & 1) * nblocks + k);
+                for (int k = 0; k < ADMM_WARPS; k++) s += wsum[k];
+                sh.base[tid][sh.off_resid2 + ((long long)(it & 1) * SHARD_MAXP + me) * SHARD_MAXGRID + b] = s;
+            }
+            ADMM_TR(6)
+            shard_arrive(sh, 1, tid);
+            shard_wait_count(sh, 1, (unsigned long long)tick * (unsigned long long)(P * nblocks), tid);
+            ADMM_TR(7)
+            if (w == 0) {
+                double s = 0.0;
+                for (int r = 0; r < P; r++) {
+                    const double* slot = mine + sh.off_resid2 + ((long long)(it & 1) * SHARD_MAXP + r) * SHARD_MAXGRID;
+                    double sr = 0.0;
+                    for (int k = lane; k < nblocks; k += 32) sr += __ldcg(slot + k);
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane < P) {
-                    sh.base[lane][sh.off_resid + (it & 1) * SHARD_MAXP + me] = s;
-                    st_release_sys(reinterpret_cast<long long*>(sh.base[lane] + sh.off_flagB) + me, tick);
+                    for (int o = 16; o > 0; o >>= 1) sr += __shfl_xor_sync(0xffffffffu, sr, o);
+                    s += sr;
+                }
+                if (lane == 0) wsum[0] = s;
+            }
+            __syncthreads();
+            nxz = sqrt(wsum[0]);
+            __syncthreads();
+        } else {
+            if (tid == 0) {
+                double s = 0.0;
+                for (int k = 0; k < ADMM_WARPS; k++) s += wsum[k];
+                a.part[(it & 1) * nblocks + b] = s;
+            }
+            shard_fold_abort(sh, b, tid);
+            grid.sync();
+            if (shard_aborted(sh)) {
+                failed = 1;
+                break;
+            }
+            ADMM_TR(6)
+            if (b == 0) {
+                if (w == 0) {  // this rank's residual partial, fixed order, to every rank; then the flag
+                    double s = 0.0;
+                    for (int k = lane; k < nblocks; k += 32) s += __ldcg(a.part + (it & 1) * nblocks + k);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane < P) {
+                        sh.base[lane][sh.off_resid + (it & 1) * SHARD_MAXP + me] = s;
+                        st_release_sys(reinterpret_cast<long long*>(sh.base[lane] + sh.off_flagB) + me, tick);
+                    }
                 }
             }
-        }
-        shard_wait(sh, sh.off_flagB, tick, tid);
-        ADMM_TR(7)
-        {
-            double s = 0.0;
-            for (int k = 0; k < P; k++) s += __ldcg(mine + sh.off_resid + (it & 1) * SHARD_MAXP + k);
-            nxz = sqrt(s);
+            shard_wait(sh, sh.off_flagB, tick, tid);
+            ADMM_TR(7)
+            {
+                double s = 0.0;
+                for (int k = 0; k < P; k++) s += __ldcg(mine + sh.off_resid + (it & 1) * SHARD_MAXP + k);
+                nxz = sqrt(s);
+            }
         }
         cur = nxt;
         if ((it + 1) % a.check_every == 0 || it + 1 == a.max_iters) {
@@ -1337,6 +1527,7 @@ struct lpvs_admm {
     double* peer_base[8] = {};
     int shard_rb[9] = {};
     long long off_recv = 0, off_rhs = 0, off_resid = 0, off_flagA = 0, off_flagB = 0, off_abort = 0, off_xzu = 0;
+    long long off_cnt = 0, off_resid2 = 0, off_recv2 = 0;
     int shard_rows_max = 0;
     double* ypart = nullptr;
     int rbuf = 0;
@@ -1739,12 +1930,18 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
         sh.off_flagA = h->off_flagA;
         sh.off_flagB = h->off_flagB;
         sh.off_abort = h->off_abort;
+        sh.off_cnt = h->off_cnt;
+        sh.off_resid2 = h->off_resid2;
+        sh.off_recv2 = h->off_recv2;
+        sh.v2 = h->grid <= SHARD_MAXGRID ? c->shard_exchange : 0;
         sh.rows_max = h->shard_rows_max;
         sh.it_base = h->iters_total;
         sh.spin_limit = 6000000000LL;  // ~3 s of SM clocks: a peer that is this late is gone
         void* args[] = {&a, &sp, &sh};
+        if (h->prox == LPVS_PROX_GROUP_L2 && sh.v2 != 2)
+            return fail(c, LPVS_E_UNSUPPORTED, "sharded group prox needs LPVS_OPT_SHARD_EXCHANGE = 2 on every rank");
         LPVS_CU(c, cudaLaunchCooperativeKernel((void*)k_admm_symv_sharded, dim3(h->grid), dim3(ADMM_THREADS), args,
-                                               admm_smem_symv(Np, 0), c->st));
+                                               admm_smem_symv(Np, h->max_item), c->st));
         const int own0 = h->shard_rb[h->shard_rank] * 128;
         const int ownn = (h->shard_rb[h->shard_rank + 1] - h->shard_rb[h->shard_rank]) * 128;
         k_shard_broadcast<<<(ownn + 255) / 256, 256, 0, c->st>>>(a.x, a.z, a.u, own0, ownn, Np, sh, h->off_xzu);
@@ -1819,21 +2016,25 @@ int lpvs_admm_shard_begin(lpvs_admm* h, int rank, int world) {
     const int Np = h->Np, nb = Np / TB;
     if (world < 2 || world > SHARD_MAXP || rank < 0 || rank >= world)
         return fail(c, LPVS_E_BAD_ARG, "sharded ADMM: world must be 2..%d and 0 <= rank < world", SHARD_MAXP);
-    if (h->prox != LPVS_PROX_L1 && h->prox != LPVS_PROX_L0)
-        return fail(c, LPVS_E_UNSUPPORTED, "sharded ADMM supports the element-wise prox operators (NormL1, NormL0)");
-    if (!h->h_order.empty() || nb < world || h->shard_world > 1 || h->iters_total > 0)
-        return fail(c, LPVS_E_UNSUPPORTED, "sharded ADMM: needs a fresh Fourier problem with at least `world` 128-blocks");
-    if (admm_smem_symv(Np, 0) > 220 * 1024) return fail(c, LPVS_E_UNSUPPORTED, "sharded ADMM: Np=%d too large", Np);
-    LPVS_CU(c, cudaFuncSetAttribute(k_admm_symv_sharded, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)admm_smem_symv(Np, 0)));
-    // this rank's contiguous share of the lower-triangle blocks, and the 128-row blocks every rank owns
-    const long long T = (long long)nb * (nb + 1) / 2;
+    // element-wise prox operators with every exchange; the group prox (ls_sparse_spectral_lpv, BASELINE configs[3]) with
+    // exchange 2, where every rank holds every row after the all-reduce and groups cannot straddle ranks
+    const bool group = h->prox == LPVS_PROX_GROUP_L2 && c->shard_exchange == 2;
+    if (h->prox != LPVS_PROX_L1 && h->prox != LPVS_PROX_L0 && !group)
+        return fail(c, LPVS_E_UNSUPPORTED,
+                    "sharded ADMM supports NormL1 / NormL0, and the group prox with LPVS_OPT_SHARD_EXCHANGE = 2");
+    if ((!h->h_order.empty() && !group) || nb < world || h->shard_world > 1 || h->iters_total > 0)
+        return fail(c, LPVS_E_UNSUPPORTED, "sharded ADMM: needs a fresh problem with at least `world` 128-blocks");
     h->symv = 1;
     h->grid = c->sms;
-    h->max_item = 0;
-    GroupItems none;
-    none.cta_item.assign((size_t)c->sms + 1, 0);
-    int rc = build_symv_plan(c, h, none, T * rank / world, T * (rank + 1) / world);
+    GroupItems gitems = build_group_items(h, c->sms);  // empty unless the prox is the group one
+    h->max_item = gitems.max_item;
+    if (admm_smem_symv(Np, h->max_item) > 220 * 1024)
+        return fail(c, LPVS_E_UNSUPPORTED, "sharded ADMM: Np=%d too large", Np);
+    LPVS_CU(c, cudaFuncSetAttribute(k_admm_symv_sharded, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)admm_smem_symv(Np, h->max_item)));
+    // this rank's contiguous share of the lower-triangle blocks, and the 128-row blocks every rank owns
+    const long long T = (long long)nb * (nb + 1) / 2;
+    int rc = build_symv_plan(c, h, gitems, T * rank / world, T * (rank + 1) / world);
     if (rc) return rc;
     cudaFree(h->part);
     h->part = nullptr;
@@ -1848,6 +2049,9 @@ int lpvs_admm_shard_begin(lpvs_admm* h, int rank, int world) {
     h->off_flagA = off;  off += SHARD_MAXP;
     h->off_flagB = off;  off += SHARD_MAXP;
     h->off_abort = off;  off += 4;
+    h->off_cnt = off;    off += 2;
+    h->off_resid2 = off; off += 2LL * SHARD_MAXP * SHARD_MAXGRID;
+    h->off_recv2 = off;  off += 2LL * world * Np;
     h->off_xzu = off;    off += 3LL * Np;
     LPVS_CU(c, cudaMalloc(&h->xchg, sizeof(double) * off));
     LPVS_CU(c, cudaMemsetAsync(h->xchg, 0, sizeof(double) * off, c->st));

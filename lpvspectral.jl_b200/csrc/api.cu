@@ -284,28 +284,38 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
                 const double* d_W, int64_t N, int nrhs, double* d_G, double* d_B) {
     const long long Np = pl.Np;
     const int ntiles = pl.nblk * (pl.nblk + 1) / 2;
-    // split over samples when tiles alone cannot fill the machine; each split >= 2048 samples
-    int nsplit = 1;
-    if (ntiles < 4 * c->sms) {
-        long long want = (4LL * c->sms + ntiles - 1) / ntiles;
-        long long maxs = std::max<long long>(1, N / 2048);
-        nsplit = (int)std::min(want, maxs);
-    }
-    // segment the sample axis so the anchor table stays below ~2 GiB
+    // split over samples when tiles alone cannot fill the machine; each split >= 2048 samples.  Among the admissible split
+    // counts take the one whose CTA count wastes the least of its last wave (36 tiles x 17 splits = 4.14 waves ran cfg5b's
+    // Gram at 76 % of peak; x 37 = exactly 9 waves)
+    auto pick_split = [&](long long nsamp) {
+        if (ntiles >= 4 * c->sms) return 1;
+        const long long want = (4LL * c->sms + ntiles - 1) / ntiles;
+        const long long maxs = std::max<long long>(1, nsamp / 2048);
+        if (maxs <= want) return (int)maxs;
+        int best = (int)want;
+        double best_eff = 0.0;
+        for (long long sct = want; sct <= std::min(maxs, 3 * want); sct++) {
+            const long long ctas = sct * ntiles, waves = (ctas + c->sms - 1) / c->sms;
+            const double eff = (double)ctas / (double)(waves * c->sms);
+            if (eff > best_eff + 1e-9) {
+                best_eff = eff;
+                best = (int)sct;
+            }
+        }
+        return best;
+    };
+    const int nsplit = pick_split(N);
+    // segment the sample axis so the anchor table stays below ~16 GiB (of 180 GB HBM)
     long long seg_cap = N;
     if (gram_is_chain(pl.mode)) {
         long long per_sample = (long long)(pl.ngroups + 1) * sizeof(double2);
-        seg_cap = std::max<long long>(65536, (2LL << 30) / per_sample);
+        seg_cap = std::max<long long>(65536, (16LL << 30) / per_sample);
     }
     int nseg = (int)((N + seg_cap - 1) / seg_cap);
     if (nseg < 1) nseg = 1;
     long long seg_len = (N + nseg - 1) / nseg;
     // segments run one after the other, so EACH must be split enough to fill the machine on its own
-    int split_per_seg = nseg == 1 ? nsplit : 1;
-    if (nseg > 1 && ntiles < 4 * c->sms) {
-        long long want = (4LL * c->sms + ntiles - 1) / ntiles;
-        split_per_seg = (int)std::min(want, std::max<long long>(1, seg_len / 2048));
-    }
+    const int split_per_seg = nseg == 1 ? nsplit : pick_split(seg_len);
     const bool direct_out = (nseg == 1 && split_per_seg == 1);
     double* parts = nullptr;
     const long long part_stride = Np * Np + 2 * Np;
@@ -509,6 +519,10 @@ int lpvs_set_option(lpvs_ctx* c, int key, double value) {
         case LPVS_OPT_ADMM_CHECK_EVERY: c->admm_check_every = std::max(1, (int)value); break;
         case LPVS_OPT_ADMM_SYMV: c->admm_symv = (int)value; break;
         case LPVS_OPT_TRSV_FLOW: c->trsv_flow = (int)value != 0; break;
+        case LPVS_OPT_SHARD_EXCHANGE:
+            if ((int)value < 0 || (int)value > 2) return fail(c, LPVS_E_BAD_ARG, "LPVS_OPT_SHARD_EXCHANGE must be 0, 1 or 2");
+            c->shard_exchange = (int)value;
+            break;
         default: return fail(c, LPVS_E_BAD_ARG, "unknown option %d", key);
     }
     return LPVS_OK;

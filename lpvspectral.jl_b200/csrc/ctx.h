@@ -41,6 +41,8 @@ struct lpvs_ctx {
     int admm_check_every = 1;
     int admm_symv = -1;  // -1 auto, 0 GEMV over full M, 1 SYMV over the lower triangle
     int trsv_flow = 1;   // single-problem triangular solves: dataflow kernel (1) or grid-barrier kernel (0)
+    int shard_exchange = 2;  // sharded ADMM exchange: 0 flag hops (3 barriers, 2 exchanges), 1 arrival counters, 2 all-reduce by
+                             // peer stores + redundant prox (2 barriers, 1 exchange per iteration)
     lpvs::DevBuf buf[lpvs::BUF_COUNT];
     int64_t launches = 0;
     // Gram kernel timing of the last API call

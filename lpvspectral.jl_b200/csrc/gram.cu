@@ -215,7 +215,9 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     const int offA0 = 16 * pr0 * LDT, offA1 = 16 * pr1 * LDT;
     const int offB0 = 32 * pc0 * LDT, offB1 = 32 * pc1 * LDT, offB2 = 32 * pc2 * LDT;
 
-    const int burst_kk = 0;  // staggering the bursts of an SMSP's two warps (0 / 4) measured no better (78.0 vs 77.7 ms)
+    // staggering the bursts of an SMSP's two warps (kk = 0 / 4) measured no better: 78.0 vs 77.7 ms with the exact-phase
+    // burst, SYNTH_BURST=3 re-measures it with the longer reference-phase burst (profiles/r02_summary.md)
+    const int burst_kk = SYNTH_BURST == 3 ? (w >> 2) * 4 : 0;
     int st_cur = 0;
     for (int c = 0; c < nchunks; c++) {
         const int st_nxt = st_cur == NSTAGE - 1 ? 0 : st_cur + 1;

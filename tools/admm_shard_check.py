@@ -21,8 +21,18 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 ctx = lp.Context(local)
+if "LPVS_SHARD_EXCHANGE" in os.environ:  # 1 (default): per-CTA arrival counters; 0: grid barrier + flag hops
+    ctx.set_option(L.OPT_SHARD_EXCHANGE, int(os.environ["LPVS_SHARD_EXCHANGE"]))
 full = len(sys.argv) > 1 and sys.argv[1] == "full"
-if full:
+lpv = len(sys.argv) > 1 and sys.argv[1] in ("lpv", "lpvfull")  # group lasso (BASELINE cfg4 with "lpvfull")
+if lpv:
+    from oracle import lpvs_oracle as o
+
+    big = sys.argv[1] == "lpvfull"
+    Y, V, X = o.generate_lpv_signal(20000 if big else 4000, seed=4)
+    w = 2 * np.pi * np.arange(1, (64 if big else 16) + 1) * 0.4
+    Nv = 50 if big else 20
+elif full:
     t, y, f = bench.make_cfg3()
 else:
     rng = np.random.default_rng(3)
@@ -34,6 +44,11 @@ else:
 
 def create():
     h = C.c_void_p()
+    if lpv:
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        ctx.check(ctx.lib.lpvs_admm_create_lpv(ctx.h, vp(Y), vp(X), vp(V), len(Y), vp(w), len(w), Nv, 0, 1, 0.1, 0.05,
+                                               C.byref(h)))
+        return lp.ADMM(ctx, h)
     ctx.check(ctx.lib.lpvs_admm_create_fourier(ctx.h, y.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p),
                                                len(y), f.ctypes.data_as(C.c_void_p), len(f), None, L.PROX_L1, 0.1,
                                                0.05, None, 0, 0.0, C.byref(h)))
@@ -41,15 +56,16 @@ def create():
 
 
 iters = 400 if full else 600
+tol_run = 1e-9 if not lpv else 1e-7
 one = create()
-one.step(iters, 1e-9)
+one.step(iters, tol_run)
 x1, z1 = one.get()
 it1 = one.iters
 one.step(iters, 0.0)
 ms1, _ = one.timing()
 one.free()
 sh = D.admm_shard(create())
-sh.step(iters, 1e-9)
+sh.step(iters, tol_run)
 dist.barrier()
 xs, zs = sh.get()
 its = sh.iters
@@ -66,7 +82,8 @@ dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 t_all = torch.tensor([mss], device=torch.device("cuda", local))
 dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print(json.dumps({"workload": "cfg3_l1_admm" if full else "l1_admm_4095", "n_gpus": world, "iters": iters,
+    print(json.dumps({"workload": ("cfg4_group_lasso" if big else "group_lasso_640") if lpv else
+                      ("cfg3_l1_admm" if full else "l1_admm_4095"), "n_gpus": world, "iters": iters,
                       "one_gpu_it_per_s": iters / ms1 * 1e3, "sharded_it_per_s": iters / t_all.item() * 1e3,
                       "speedup": ms1 / t_all.item(), "rel_err_z": err, "rel_err_x": errx, "iters_one": it1,
                       "iters_sharded": its, "same_support": supp, "ok": bool(flag.item() == 1.0)}))
