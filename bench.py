@@ -558,11 +558,11 @@ def parity_leg(ctx, lp, L, C, D, torch, dist, rank, world, local, allmax):
     sh.free()
     e_admm = max(rel(zsa, z1a), rel(xsa, x1a))
     same = bool(np.array_equal(zsa != 0, z1a != 0)) and its == it1
-    # group lasso (ls_sparse_spectral_lpv): ONE 640-unknown problem sharded vs this GPU alone
+    # group lasso (ls_sparse_spectral_lpv): ONE 1280-unknown problem (10 blocks of 128 >= 8 ranks) sharded vs this GPU alone
     from oracle import lpvs_oracle as o
 
     Yg, Vg, Xg = o.generate_lpv_signal(4000, seed=4)
-    wg = 2 * np.pi * np.arange(1, 17) * 0.4
+    wg = 2 * np.pi * np.arange(1, 33) * 0.4
 
     def create_lpv():
         h = C.c_void_p()
