@@ -186,6 +186,29 @@ def admm_leg(ctx, lp, L, C, rank, world, allsum, allmax, barrier, iters=2000):
     its = iters / (ms * 1e-3)
     its_min = -allmax(-its)
     total = allsum(its)
+    # the Float32 instantiation: the same problem with the inverse stored in single precision
+    f32 = None
+    if rank == 0:
+        try:
+            ctx.set_option(L.OPT_ADMM_M32, 1)
+            h32 = C.c_void_p()
+            ctx.check(ctx.lib.lpvs_admm_create_fourier(ctx.h, y.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p),
+                                                       len(y), f.ctypes.data_as(C.c_void_p), len(f), None, L.PROX_L1, 0.1,
+                                                       0.05, None, 0, 0.0, C.byref(h32)))
+            ctx.set_option(L.OPT_ADMM_M32, 0)
+            s32 = lp.ADMM(ctx, h32)
+            s32.step(100, 0.0)
+            s32.step(iters, 0.0)
+            ms32, bpi32 = s32.timing()
+            s32.free()
+            f32 = {"iters_per_s": iters / (ms32 * 1e-3), "bytes_per_iter": bpi32,
+                   "hbm_gbs": bpi32 * iters / (ms32 * 1e-3) / 1e9,
+                   "note": "LPVS_OPT_ADMM_M32: (G+I/mu)^-1 stored in single precision, double accumulation -- what Float32 "
+                           "callers of ls_sparse_spectral get"}
+        except Exception as e:
+            f32 = {"error": repr(e)[:200]}
+        finally:
+            ctx.set_option(L.OPT_ADMM_M32, 0)
     hbm = 6554.6
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -226,7 +249,7 @@ def admm_leg(ctx, lp, L, C, rank, world, allsum, allmax, barrier, iters=2000):
             sharded = {"error": repr(e)[:200]}
     return {"workload": "cfg3_l1_admm", "nreg": 2 * len(f) - 1, "iters": iters, "iters_per_s": total,
             "iters_per_s_per_gpu_min": its_min, "scaling": "replicas (weak); `sharded` = one problem (strong)",
-            "sharded": sharded, "setup_s": setup_s,
+            "sharded": sharded, "float32_storage": f32, "setup_s": setup_s,
             "gram_tflops": gfl / gms / 1e9,
             "roofline": {"bound": "hbm", "achieved": bpi * its_min / 1e9, "peak": hbm, "unit": "GB/s",
                          "frac": bpi * its_min / 1e9 / hbm, "traffic": ncu_traffic("k_admm_symv"),

@@ -62,6 +62,10 @@ enum lpvs_option {
                                         every rank: ONE cross-GPU step and two grid barriers per iteration;
                                       1 reduce-scatter + all-gather with per-CTA arrival counters (two steps, one barrier);
                                       0 reduce-scatter + all-gather with flags raised by CTA 0 (two steps, three barriers) */
+    LPVS_OPT_ADMM_M32 = 7,         /* 1: ADMM problems created while set store the inverse (G + I/mu)^-1 in single precision and
+                                      accumulate in double -- half the bytes per iteration; what the Float32 instantiation of
+                                      ls_sparse_spectral[_lpv] (src/lasso.jl:85, eltype-generic) uses.  Single GPU, SYMV loop.
+                                      0 (default): double */
     LPVS_OPT_TRSV_FLOW = 5,        /* triangular solves of ONE large problem: 1 (default) flag-chained dataflow kernel,
                                       0 the grid-barrier kernel (one barrier per 128-block step) */
     LPVS_OPT_ADMM_SYMV = 4         /* x-update kernel: -1 auto (default), 0 GEMV over the full symmetric inverse (8 Np^2 B/iter),

@@ -49,6 +49,20 @@ function check(rc)
     error("liblpvs error $rc: $msg")
 end
 
+# LPVS_OPT_ADMM_M32 (include/lpvs.h): ADMM problems created while set keep their inverse in single precision.  The Float32
+# instantiations of the sparse estimators switch it on around the create call.
+const OPT_ADMM_M32 = Cint(7)
+setopt(key, v) = check(ccall((:lpvs_set_option, liblpvs), Cint, (Ptr{Cvoid}, Cint, Float64), ctx(), key, Float64(v)))
+function with_m32(fn, T)
+    T === Float32 || return fn()
+    setopt(OPT_ADMM_M32, 1)
+    try
+        return fn()
+    finally
+        setopt(OPT_ADMM_M32, 0)
+    end
+end
+
 vecf(x) = collect(Float64, x)
 nullable(x) = x === nothing ? Ptr{Float64}(C_NULL) : pointer(x)
 # Float32 instantiation of the generic signatures (e.g. src/lasso.jl:85 `AbstractArray{T}`): results carry the signal's
@@ -291,7 +305,7 @@ function ls_sparse_spectral(y::AbstractArray{T}, t, f=default_freqs(t), W=nothin
     yv, tv, fv = vecf(y), vecf(t), vecf(f)
     Wv = W === nothing ? nothing : vecf(W)
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve yv tv fv Wv begin
+    GC.@preserve yv tv fv Wv with_m32(T) do
         check(ccall((:lpvs_admm_create_fourier, liblpvs), Cint,
             (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Float64, Float64,
              Ptr{Float64}, Cint, Float64, Ptr{Ptr{Cvoid}}),
@@ -312,7 +326,7 @@ function ls_sparse_spectral_lpv(y::AbstractVector{S}, X::AbstractVector{S}, V::A
                                 λ=1, coulomb=false, normalize=true, μ=S(0.05), kwargs...) where S
     yv, Xv, Vv, wv = vecf(y), vecf(X), vecf(V), vecf(w[:])
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve yv Xv Vv wv begin
+    GC.@preserve yv Xv Vv wv with_m32(S) do
         check(ccall((:lpvs_admm_create_lpv, liblpvs), Cint,
             (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Cint, Cint, Cint,
              Float64, Float64, Ptr{Ptr{Cvoid}}),

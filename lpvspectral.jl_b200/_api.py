@@ -44,14 +44,17 @@ def _cast_like(val, single):
 
 def _preserve_eltype(fn):
     """Float32 instantiation of the generic signatures (e.g. src/lasso.jl:85 `AbstractArray{T}`): a
-    Float32 signal gives Float32 / ComplexF32 results, as the reference's eltype-generic code does.  The arithmetic is
-    still the library's FP64 path on the up-converted inputs (no FP32 kernels), so the result is the correctly
-    rounded-to-single FP64 answer -- at least as accurate as the reference's Float32 arithmetic."""
+    Float32 signal gives Float32 / ComplexF32 results, as the reference's eltype-generic code does.  The dense solves run
+    the library's FP64 path on the up-converted inputs; the sparse estimators additionally keep the ADMM inverse in single
+    precision (half the bytes per iteration, double accumulation) -- either way at least as accurate as the reference's
+    Float32 arithmetic."""
     import functools
 
     @functools.wraps(fn)
     def wrapper(y, *a, **k):
         single = isinstance(y, np.ndarray) and y.dtype == np.float32
+        if single and fn.__name__ in ("ls_sparse_spectral", "ls_sparse_spectral_lpv"):
+            k.setdefault("_m32", True)  # the ADMM loop streams the inverse in single precision (LPVS_OPT_ADMM_M32)
         out = fn(y, *a, **k)
         if not single:
             return out
@@ -626,7 +629,7 @@ class ADMM:
 
 @_preserve_eltype
 def ls_sparse_spectral(y, t, f=None, W=None, *, init=False, proxg=None, iters=10000, tol=1e-5, printerval=100,
-                       cb=None, μ=None, mu=None, verbose=False, ctx=None, return_info=False, **kw):
+                       cb=None, μ=None, mu=None, verbose=False, ctx=None, return_info=False, _m32=False, **kw):
     """ls_sparse_spectral(y,t,f[,W]; init=false, λ=1, proxg=NormL1(λ), iters, tol, printerval, cb, μ)
     -> (x, f)   (src/lasso.jl:85-126).  The weighted method keeps the reference's sign quirk (Q13)."""
     lam = _lam(kw, 1.0)
@@ -645,8 +648,14 @@ def ls_sparse_spectral(y, t, f=None, W=None, *, init=False, proxg=None, iters=10
     Wv = None if W is None else _f64(W)
     kind, param = _prox_desc(proxg if proxg is not None else NormL1(lam))
     h = C.c_void_p()
-    ctx.check(ctx.lib.lpvs_admm_create_fourier(ctx.h, _ptr(yv), _ptr(tv), len(yv), _ptr(fv), len(fv), _ptr(Wv), kind,
-                                               param, mu, None, int(bool(init)), lam, C.byref(h)))
+    if _m32:
+        ctx.set_option(L.OPT_ADMM_M32, 1)
+    try:
+        ctx.check(ctx.lib.lpvs_admm_create_fourier(ctx.h, _ptr(yv), _ptr(tv), len(yv), _ptr(fv), len(fv), _ptr(Wv), kind,
+                                                   param, mu, None, int(bool(init)), lam, C.byref(h)))
+    finally:
+        if _m32:
+            ctx.set_option(L.OPT_ADMM_M32, 0)
     solver = ADMM(ctx, h)
     try:
         solver.run(iters=iters, tol=tol, printerval=printerval, cb=cb, verbose=verbose)
@@ -664,7 +673,7 @@ def ls_sparse_spectral(y, t, f=None, W=None, *, init=False, proxg=None, iters=10
 
 @_preserve_eltype
 def ls_sparse_spectral_lpv(y, X, V, w, Nv, *, coulomb=False, normalize=True, iters=10000, tol=1e-5, printerval=100,
-                           cb=None, μ=None, mu=None, verbose=False, ctx=None, return_info=False, **kw):
+                           cb=None, μ=None, mu=None, verbose=False, ctx=None, return_info=False, _m32=False, **kw):
     """ls_sparse_spectral_lpv(y,X,V,w,Nv; λ=1, coulomb=false, normalize=true, ADMM kwargs) -> SpectralExt
     (src/lasso.jl:27-70): group lasso over frequencies."""
     lam = _lam(kw, 1.0)
@@ -676,8 +685,14 @@ def ls_sparse_spectral_lpv(y, X, V, w, Nv, *, coulomb=False, normalize=True, ite
     ctx = ctx or default_context()
     yv, Xv, Vv, wv = _f64(y), _f64(X), _f64(V), _f64(w)
     h = C.c_void_p()
-    ctx.check(ctx.lib.lpvs_admm_create_lpv(ctx.h, _ptr(yv), _ptr(Xv), _ptr(Vv), len(yv), _ptr(wv), len(wv), int(Nv),
-                                           int(bool(coulomb)), int(bool(normalize)), lam, mu, C.byref(h)))
+    if _m32:
+        ctx.set_option(L.OPT_ADMM_M32, 1)
+    try:
+        ctx.check(ctx.lib.lpvs_admm_create_lpv(ctx.h, _ptr(yv), _ptr(Xv), _ptr(Vv), len(yv), _ptr(wv), len(wv), int(Nv),
+                                               int(bool(coulomb)), int(bool(normalize)), lam, mu, C.byref(h)))
+    finally:
+        if _m32:
+            ctx.set_option(L.OPT_ADMM_M32, 0)
     solver = ADMM(ctx, h)
     try:
         solver.run(iters=iters, tol=tol, printerval=printerval, cb=cb, verbose=verbose)

@@ -29,6 +29,7 @@ constexpr int ADMM_WARPS = ADMM_THREADS / 32;
 
 struct AdmmArgs {
     const double* M;
+    const float* M32;  // the inverse rounded to single (LPVS_OPT_ADMM_M32: Float32 callers; half the bytes per iteration)
     int Np;
     const double* q;
     double *x, *z, *u, *v;  // Np each (v = x+u scratch for non-elementwise prox)
@@ -408,12 +409,23 @@ __device__ __forceinline__ double2 ld_hint(const double* p, unsigned long long p
     return v;
 }
 
+__device__ __forceinline__ double2 ld_hint(const float* p, unsigned long long pol) {
+    float2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+    return make_double2((double)v.x, (double)v.y);
+}
+__device__ __forceinline__ double2 ld_ro(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ double2 ld_ro(const float* p) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    return make_double2((double)v.x, (double)v.y);
+}
+
 // One 128x128 block of M, this warp's 8 rows (blk -> row 8w, the lane's columns 2*lane, 2*lane+1, 64+2*lane, 65+2*lane):
 // row part M[rows, cols] * r_J reduced over the lanes (returned value is valid in lanes with (lane & 3) == 0, for row
 // ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1) of the 8), column part M[rows, cols]' * r_I accumulated into c0..c3.
 // 16 independent 16-byte loads per lane.
-template <bool HINT>
-__device__ __forceinline__ double symv_block(const double* blk, long long Np, unsigned long long pol,
+template <bool HINT, typename MT = double>
+__device__ __forceinline__ double symv_block(const MT* blk, long long Np, unsigned long long pol,
                                              const double (&rs8)[8], double2 rj0, double2 rj1, double& c0, double& c1,
                                              double& c2, double& c3, int lane) {
     double2 m0[8], m1[8];
@@ -423,8 +435,8 @@ __device__ __forceinline__ double symv_block(const double* blk, long long Np, un
             m0[r] = ld_hint(blk + (long long)r * Np, pol);
             m1[r] = ld_hint(blk + (long long)r * Np + 64, pol);
         } else {
-            m0[r] = __ldg(reinterpret_cast<const double2*>(blk + (long long)r * Np));
-            m1[r] = __ldg(reinterpret_cast<const double2*>(blk + (long long)r * Np + 64));
+            m0[r] = ld_ro(blk + (long long)r * Np);
+            m1[r] = ld_ro(blk + (long long)r * Np + 64);
         }
     }
     double s[8];
@@ -489,8 +501,10 @@ __device__ __forceinline__ double symv_row_sum(const SymvPlan& sp, int i, int q)
     return t;
 }
 
+template <typename MT>
 __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv(const __grid_constant__ AdmmArgs a,
                                                                const __grid_constant__ SymvPlan sp) {
+    const MT* Mst = sizeof(MT) == 4 ? reinterpret_cast<const MT*>(a.M32) : reinterpret_cast<const MT*>(a.M);
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double sm[];
     double* ys = sm;             // Np: CTA-private partial y
@@ -541,13 +555,13 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv(const __grid_cons
             const double2 rj1 = __ldcg(reinterpret_cast<const double2*>(rc + J * 128 + 64 + 2 * lane));
             double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
             for (int I = i0; I < i1; I++) {
-                const double* blk = a.M + ((long long)I * 128 + 8 * w) * Np + (long long)J * 128 + 2 * lane;
+                const MT* blk = Mst + ((long long)I * 128 + 8 * w) * Np + (long long)J * 128 + 2 * lane;
                 const unsigned long long pol = (bcount++ < my_persist) ? pol_keep : pol_stream;
                 const bool offdiag = I != J;
                 double rs8[8];
 #pragma unroll
                 for (int r = 0; r < 8; r++) rs8[r] = offdiag ? __ldcg(rc + I * 128 + 8 * w + r) : 0.0;
-                const double srow = symv_block<true>(blk, Np, pol, rs8, rj0, rj1, c0, c1, c2, c3, lane);
+                const double srow = symv_block<true, MT>(blk, Np, pol, rs8, rj0, rj1, c0, c1, c2, c3, lane);
                 // lanes with (lane & 3) == 0 hold row index ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)
                 if ((lane & 3) == 0) {
                     int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
@@ -1476,6 +1490,11 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_prox_only(const __grid_cons
     }
 }
 
+__global__ void k_to_float(const double* __restrict__ in, float* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
 // ADMM order: Mp[p][q] = M[order[p]][order[q]] (M symmetric), vp[p] = v[order[p]]
 __global__ void k_permute_sym(const double* __restrict__ M, double* __restrict__ Mp, const int* __restrict__ order,
                               int Np) {
@@ -1512,6 +1531,7 @@ struct lpvs_admm {
     int* d_flags = nullptr;
     // SYMV variant (lower triangle only)
     int symv = 0;
+    float* M32 = nullptr;    // LPVS_OPT_ADMM_M32: the inverse rounded to single, replaces M in the SYMV loop
     int* seg_buf = nullptr;  // all SymvPlan index tables, one allocation
     int nseg = 0;
     size_t off_cta_seg = 0, off_persist = 0, off_cta_slot = 0, off_slot_blk = 0, off_red_ptr = 0, off_red_slot = 0,
@@ -1549,6 +1569,7 @@ static void admm_release(lpvs_admm* h) {
     cudaSetDevice(h->ctx->device);
     cudaStreamSynchronize(h->ctx->st);
     cudaFree(h->M);
+    cudaFree(h->M32);
     cudaFree(h->vecs);
     cudaFree(h->goff);
     cudaFree(h->gmem);
@@ -1658,7 +1679,7 @@ static int build_symv_plan(lpvs_ctx* c, lpvs_admm* h, const GroupItems& gitems, 
         // L2-resident share: 88 MB of blocks spread evenly over the CTAs
         std::vector<int> persist(grid, 0);
         {
-            const double keep_bytes = 88.0 * 1024 * 1024, blk_bytes = 128.0 * 128.0 * 8.0;
+            const double keep_bytes = 88.0 * 1024 * 1024, blk_bytes = 128.0 * 128.0 * (h->M32 ? 4.0 : 8.0);
             const double frac = std::min(1.0, keep_bytes / ((double)Tr * blk_bytes));
             for (int cta_i = 0; cta_i < grid; cta_i++) {
                 long long nblk = Tr * (cta_i + 1) / grid - Tr * cta_i / grid;
@@ -1820,8 +1841,22 @@ int admm_finish_create(lpvs_ctx* c, lpvs_admm* h, double* d_G, const double* d_q
     }
     if (h->symv) {
         size_t sm2 = admm_smem_symv(Np, h->max_item);
-        LPVS_CU(c, cudaFuncSetAttribute(k_admm_symv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        LPVS_CU(c, cudaFuncSetAttribute(k_admm_symv<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        LPVS_CU(c, cudaFuncSetAttribute(k_admm_symv<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
         h->grid = grid = c->sms;
+        if (c->admm_m32) {
+            // Float32 callers: the inverse is stored in single precision -- half the bytes every iteration
+            // streams -- and accumulated in double; the double copy is released
+            if (cudaMalloc(&h->M32, sizeof(float) * NN) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(c, LPVS_E_NOMEM, "out of device memory (single-precision inverse)");
+            }
+            k_to_float<<<(unsigned)((NN + 255) / 256), 256, 0, c->st>>>(h->M, h->M32, NN);
+            c->launches++;
+            LPVS_CU(c, cudaStreamSynchronize(c->st));
+            cudaFree(h->M);
+            h->M = nullptr;
+        }
         int rcp = build_symv_plan(c, h, gitems, 0, (long long)nb * (nb + 1) / 2);
         if (rcp) return rcp;
     }
@@ -1859,6 +1894,7 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
     const int Np = h->Np;
     AdmmArgs a{};
     a.M = h->M;
+    a.M32 = h->M32;
     a.Np = Np;
     a.q = h->vecs;
     a.x = h->vecs + Np;
@@ -1963,8 +1999,8 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
         sp.item_kind = h->seg_buf + h->off_item_kind;
         sp.ypart = h->ypart;
         void* args[] = {&a, &sp};
-        LPVS_CU(c, cudaLaunchCooperativeKernel((void*)k_admm_symv, dim3(h->grid), dim3(ADMM_THREADS), args,
-                                               admm_smem_symv(Np, h->max_item), c->st));
+        LPVS_CU(c, cudaLaunchCooperativeKernel(h->M32 ? (void*)k_admm_symv<float> : (void*)k_admm_symv<double>, dim3(h->grid),
+                                               dim3(ADMM_THREADS), args, admm_smem_symv(Np, h->max_item), c->st));
     } else {
         int rows_max = (Np + h->grid - 1) / h->grid;
         size_t smem = admm_smem(Np, rows_max + 1);
@@ -2016,6 +2052,7 @@ int lpvs_admm_shard_begin(lpvs_admm* h, int rank, int world) {
     const int Np = h->Np, nb = Np / TB;
     if (world < 2 || world > SHARD_MAXP || rank < 0 || rank >= world)
         return fail(c, LPVS_E_BAD_ARG, "sharded ADMM: world must be 2..%d and 0 <= rank < world", SHARD_MAXP);
+    if (h->M32) return fail(c, LPVS_E_UNSUPPORTED, "sharded ADMM: not with the single-precision inverse (LPVS_OPT_ADMM_M32)");
     // element-wise prox operators with every exchange; the group prox (ls_sparse_spectral_lpv, BASELINE configs[3]) with
     // exchange 2, where every rank holds every row after the all-reduce and groups cannot straddle ranks
     const bool group = h->prox == LPVS_PROX_GROUP_L2 && c->shard_exchange == 2;
@@ -2201,7 +2238,8 @@ int lpvs_admm_last_timing(const lpvs_admm* h, double* ms, double* bytes_per_iter
     if (bytes_per_iter) {
         // algorithmic bytes of the variant actually run: full M (GEMV) or the lower-triangle blocks (SYMV)
         double nb = h->Np / 128.0;
-        *bytes_per_iter = h->symv ? nb * (nb + 1.0) / 2.0 * 128.0 * 128.0 * 8.0 : 8.0 * (double)h->Np * (double)h->Np;
+        *bytes_per_iter = h->symv ? nb * (nb + 1.0) / 2.0 * 128.0 * 128.0 * (h->M32 ? 4.0 : 8.0)
+                                  : 8.0 * (double)h->Np * (double)h->Np;
     }
     return LPVS_OK;
 }

@@ -519,6 +519,7 @@ int lpvs_set_option(lpvs_ctx* c, int key, double value) {
         case LPVS_OPT_ADMM_CHECK_EVERY: c->admm_check_every = std::max(1, (int)value); break;
         case LPVS_OPT_ADMM_SYMV: c->admm_symv = (int)value; break;
         case LPVS_OPT_TRSV_FLOW: c->trsv_flow = (int)value != 0; break;
+        case LPVS_OPT_ADMM_M32: c->admm_m32 = (int)value != 0; break;
         case LPVS_OPT_SHARD_EXCHANGE:
             if ((int)value < 0 || (int)value > 2) return fail(c, LPVS_E_BAD_ARG, "LPVS_OPT_SHARD_EXCHANGE must be 0, 1 or 2");
             c->shard_exchange = (int)value;

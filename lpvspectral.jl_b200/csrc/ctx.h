@@ -40,6 +40,7 @@ struct lpvs_ctx {
     int jitter = 1;
     int admm_check_every = 1;
     int admm_symv = -1;  // -1 auto, 0 GEMV over full M, 1 SYMV over the lower triangle
+    int admm_m32 = 0;    // ADMM handles created while set keep the inverse in single precision (Float32 callers)
     int trsv_flow = 1;   // single-problem triangular solves: dataflow kernel (1) or grid-barrier kernel (0)
     int shard_exchange = 2;  // sharded ADMM exchange: 0 flag hops (3 barriers, 2 exchanges), 1 arrival counters, 2 all-reduce by
                              // peer stores + redundant prox (2 barriers, 1 exchange per iteration)
