@@ -74,6 +74,7 @@ enum lpvs_option {
 
 /* info flags returned by solvers */
 #define LPVS_INFO_JITTER 1 /* a WEIGHTED (Gram / LU in the reference) problem was numerically singular: jitter ridge used */
+#define LPVS_INFO_DUAL 3   /* informational: Nreg >= N, solved in the sample space: x = A'(A A' + lambda^2 I)^-1 y */
 #define LPVS_INFO_QR 2     /* informational: the unweighted / LPV solve took the shifted-CholeskyQR path (ill-conditioned A) */
 
 int lpvs_version(void);

@@ -20,6 +20,7 @@ PHASE_AUTO, PHASE_CHAIN, PHASE_DIRECT, PHASE_CHAIN_REF = 0, 1, 2, 3
 OPT_PHASE_MODE, OPT_WINDOW_BATCH, OPT_JITTER, OPT_ADMM_CHECK_EVERY, OPT_ADMM_SYMV, OPT_TRSV_FLOW, OPT_SHARD_EXCHANGE, OPT_ADMM_M32 = 0, 1, 2, 3, 4, 5, 6, 7
 INFO_JITTER = 1
 INFO_QR = 2
+INFO_DUAL = 3
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

@@ -18,7 +18,10 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
+#include <vector>
 
 #include "ctx.h"
 
@@ -284,6 +287,68 @@ __global__ void __launch_bounds__(256) k_gemv_rows(const double* __restrict__ Mx
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
     if (lane == 0) out[i] = s0;
+}
+
+// dual (sample-space) Gram: diagonal += lam^2 on the N real samples, unit diagonal on the padding rows
+__global__ void k_diag_dual(double* __restrict__ Gd, long long Nr, long long N, double lam2) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= Nr) return;
+    double* g = Gd + s * Nr + s;
+    *g = s < N ? *g + lam2 : 1.0;
+}
+// out[0] = min_i L[i][i]^2, out[1] = max_i L[i][i]^2 over the first n rows of a factor with leading dimension ld
+__global__ void __launch_bounds__(256) k_pivot_range(const double* __restrict__ L, long long ld, long long n,
+                                                     double* __restrict__ out) {
+    __shared__ double r0[256], r1[256];
+    double lo = 1.0e300, hi = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) {
+        const double l = L[i * ld + i], p = l * l;
+        lo = fmin(lo, p);
+        hi = fmax(hi, p);
+    }
+    r0[threadIdx.x] = lo;
+    r1[threadIdx.x] = hi;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            r0[threadIdx.x] = fmin(r0[threadIdx.x], r0[threadIdx.x + s]);
+            r1[threadIdx.x] = fmax(r1[threadIdx.x], r1[threadIdx.x + s]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = r0[0];
+        out[1] = r1[0];
+    }
+}
+// out[p] = sum_s Mx[s][p] v[s]  (column sums over `rows` rows; coalesced across p), grid.y splits the rows, partials summed
+// in fixed order by the caller's second pass (k_colsum_finish)
+__global__ void __launch_bounds__(256) k_gemv_cols(const double* __restrict__ Mx, long long ld, long long rows, int ncols,
+                                                   const double* __restrict__ v, double* __restrict__ part) {
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    const long long per = (rows + gridDim.y - 1) / gridDim.y;
+    const long long s0 = blockIdx.y * per, s1 = s0 + per < rows ? s0 + per : rows;
+    if (p >= ncols) return;
+    double a0 = 0.0, a1 = 0.0;
+    long long s = s0;
+    for (; s + 1 < s1; s += 2) {
+        a0 = fma(Mx[s * ld + p], v[s], a0);
+        a1 = fma(Mx[(s + 1) * ld + p], v[s + 1], a1);
+    }
+    if (s < s1) a0 = fma(Mx[s * ld + p], v[s], a0);
+    part[(long long)blockIdx.y * ncols + p] = a0 + a1;
+}
+__global__ void k_colsum_finish(const double* __restrict__ part, int nparts, int ncols, double* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ncols) return;
+    double t = 0.0;
+    for (int q = 0; q < nparts; q++) t += part[(long long)q * ncols + p];
+    out[p] = t;
+}
+// r <- r - lam2 * w (first n entries)
+__global__ void k_axpy_neg(double* __restrict__ r, const double* __restrict__ w, double lam2, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) r[i] = fma(-lam2, w[i], r[i]);
 }
 
 // g <- A'r - lam^2 x on the real columns, 0 on the dummies
@@ -553,6 +618,107 @@ int tls_solve(lpvs_ctx* c, int Np, int ncc, int zero_first, const double* d_y, l
     return LPVS_OK;
 }
 
+namespace {
+// Underdetermined problems (Nreg >= N): x = A'(A A' + lam^2 I)^-1 y -- the same ridge solution through the N x N Gram
+// matrix of the ROWS.  With more functions than samples the row space is the well-conditioned side (the reference's KAT,
+// 1000 x 1001, has cond(A A') = 2 against a singular A'A); the sample-space Gram matrix is one NT DMMA pass over the
+// materialised regressor, and iterative refinement on the operator brings the answer to cond(A) eps.  Returns 1 when the
+// factorisation is too ill-conditioned to trust (the caller falls back to the column-space path), 0 on success.
+int ls_solve_dual(lpvs_ctx* c, const OpArgs& op, int Np, const double* d_y, double lam, double* d_x, int* rc_out) {
+    cudaStream_t st = c->st;
+    const long long N = op.N, Nr = (N + TB - 1) / TB * TB;
+    const int nbd = (int)(Nr / TB), nb = Np / TB;
+    const double lam2 = lam * lam;
+    *rc_out = LPVS_OK;
+    double* d_A = ws<double>(c, BUF_LSQ_A, (size_t)Nr * Np);
+    double* d_Gd = ws<double>(c, BUF_LSQ_G2, (size_t)std::max<long long>(Nr * Nr, (long long)Np * Np));
+    double* d_w = ws<double>(c, BUF_LSQ_R, (size_t)std::max<long long>(6 * Nr, Nr + Np));  // w | r (2 Nr: trsv layout) | spare
+    double* d_md = ws<double>(c, BUF_SUMS, 8);
+    const int nsplit = 32;
+    double* d_part = ws<double>(c, BUF_PART, (size_t)nsplit * Np);
+    if (!d_A || !d_Gd || !d_w || !d_md || !d_part) {
+        *rc_out = fail(c, LPVS_E_NOMEM, "out of device memory (sample-space solve of a %lld x %d problem)", N, Np);
+        return 0;
+    }
+    static bool attr_done[64] = {};
+    const size_t smem = (size_t)NT_STAGES * 2 * TILE_D * sizeof(double);
+    if (!attr_done[c->device & 63]) {
+        cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_trtri_rd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done[c->device & 63] = true;
+    }
+    dim3 gm((unsigned)((Nr + 3) / 4), nb);
+    k_materialize<<<gm, 256, 0, st>>>(op, d_A, Np, Nr);
+    NtArgs t{};
+    t.A = d_A; t.lda = Np;
+    t.B = d_A; t.ldb = Np;
+    t.C = d_Gd; t.ldc = Nr;
+    t.mt = nbd; t.nt = nbd; t.mode = NT_SYRK;
+    t.K = Np; t.Ksplit = Np;
+    k_gemm_nt<<<nbd * (nbd + 1) / 2, NTHREADS, smem, st>>>(t);
+    k_diag_dual<<<(unsigned)((Nr + 255) / 256), 256, 0, st>>>(d_Gd, Nr, N, lam2);
+    c->launches += 3;
+    CholArgs ca{};
+    ca.G = d_Gd;
+    ca.strideG = Nr * Nr;
+    ca.Linv = ws<double>(c, BUF_LINV, (size_t)std::max(nbd, nb) * TB * TB);
+    ca.strideLinv = (long long)nbd * TB * TB;
+    ca.info = ws<int>(c, BUF_INFO, 1);
+    ca.Np = (int)Nr;
+    ca.nb = nbd;
+    if (!ca.Linv || !ca.info) {
+        *rc_out = fail(c, LPVS_E_NOMEM, "out of device memory (factor workspace)");
+        return 0;
+    }
+    cudaMemsetAsync(ca.info, 0, sizeof(int), st);
+    c->launches += potrf(ca, 1, c->sms, st, &c->la);
+    k_pivot_range<<<1, 256, 0, st>>>(d_Gd, Nr, N, d_md + 4);
+    c->launches++;
+    int pinfo = 0;
+    double pr[2] = {0.0, 0.0};
+    cudaMemcpyAsync(&pinfo, ca.info, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(pr, d_md + 4, sizeof pr, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        *rc_out = fail(c, LPVS_E_CUDA, "sample-space factorisation failed");
+        return 0;
+    }
+    // iterative refinement converges while cond(A A' + lam^2 I) eps << 1; the pivot ratio is a (lower) estimate of that cond
+    if (pinfo != 0 || !(pr[0] > 1e-10 * pr[1])) return 1;
+    double* d_r = d_w + Nr;  // [2][Nr] right-hand side / solution of the triangular solves
+    cudaMemsetAsync(d_w, 0, sizeof(double) * 3 * Nr, st);
+    cudaMemsetAsync(d_x, 0, sizeof(double) * Np, st);
+    double prev = 0.0;
+    bool ok = false;
+    for (int step = 0; step < 6; step++) {
+        // r = y - A x - lam^2 w  (first step: x = w = 0 -> r = y)
+        k_op_apply<<<(unsigned)((N + 31) / 32), 256, 0, st>>>(op, d_x, d_y, d_r);
+        k_axpy_neg<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_r, d_w, lam2, N);
+        if (Nr > N) cudaMemsetAsync(d_r + N, 0, sizeof(double) * (Nr - N), st);
+        launch_trsv(ca, d_r, 2 * Nr, 1, 1, st, false, trsv_flags(c, nbd));
+        k_axpy_norms<<<1, 1024, 0, st>>>(d_w, d_r, (int)Nr, d_md + 2);  // w += dw
+        dim3 gc((Np + 255) / 256, nsplit);
+        k_gemv_cols<<<gc, 256, 0, st>>>(d_A, Np, N, Np, d_w, d_part);
+        k_colsum_finish<<<(Np + 255) / 256, 256, 0, st>>>(d_part, nsplit, Np, d_x);  // x = A' w
+        c->launches += 6;
+        double h[2] = {0.0, 0.0};
+        cudaMemcpyAsync(h, d_md + 2, sizeof h, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) {
+            *rc_out = fail(c, LPVS_E_CUDA, "sample-space refinement failed");
+            return 0;
+        }
+        if (!(isfinite(h[0]) && isfinite(h[1]))) return 0;  // NaN inputs: the caller's finite check reports the cause
+        const double rel = h[1] > 0.0 ? sqrt(h[0] / h[1]) : 0.0;
+        if (step > 0 && rel <= 1e-12) {
+            ok = true;
+            break;
+        }
+        if (step > 1 && rel > 0.25 * prev) break;  // not contracting: too ill-conditioned for this side
+        prev = rel;
+    }
+    return ok ? 0 : 1;
+}
+}  // namespace
+
 int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, const double* d_y, double* d_G, double* d_B,
                       double lam, const std::function<int()>& regram, int* info) {
     cudaStream_t st = c->st;
@@ -567,6 +733,18 @@ int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, con
     double* d_g = ws<double>(c, BUF_LSQ_V, (size_t)4 * Np);
     if (!d_md || !d_r || !d_g) return fail(c, LPVS_E_NOMEM, "out of device memory (LS refinement vectors)");
 
+    // ---- 0. more functions than samples: the sample-space (dual) solve; falls through when that side is ill-conditioned ----
+    if (nreal >= N && lam > 0.0) {
+        int rcd = LPVS_OK;
+        const int fallback = ls_solve_dual(c, op, Np, d_y, lam, d_g, &rcd);  // x into scratch: d_B (A'y) survives a fallback
+        if (rcd) return rcd;
+        if (!fallback) {
+            LPVS_CU(c, cudaMemcpyAsync(d_B, d_g, sizeof(double) * Np, cudaMemcpyDeviceToDevice, st));
+            LPVS_CU(c, cudaStreamSynchronize(st));
+            if (info) *info = LPVS_INFO_DUAL;
+            return LPVS_OK;
+        }
+    }
     // ---- 1. one factorisation: L L' = G~ + max(lam^2, n eps max diag) I ----
     int pinfo = 0;
     double mult = 1.0;
@@ -691,6 +869,23 @@ int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, con
     t2.mt = nb; t2.nt = nb; t2.mode = NT_SYRK;
     t2.K = Mrows; t2.Ksplit = Nr;
     k_gemm_nt<<<nb * (nb + 1) / 2, NTHREADS, smem, st>>>(t2);
+#ifdef LPVS_DEBUG_LSQ
+    if (const char* dump = getenv("LPVS_DEBUG_DUMP")) {  // developer build only: the QR path's matrices for offline comparison
+        cudaStreamSynchronize(st);
+        std::vector<double> hb((size_t)std::max<long long>(NN, (long long)Np * Mrows));
+        if (FILE* fp = fopen(dump, "wb")) {
+            long long hdr[4] = {Np, Mrows, Nr, N};
+            fwrite(hdr, sizeof(long long), 4, fp);
+            for (const double* src : {(const double*)d_G, (const double*)d_Li, (const double*)d_G2}) {
+                cudaMemcpy(hb.data(), src, sizeof(double) * NN, cudaMemcpyDeviceToHost);
+                fwrite(hb.data(), sizeof(double), (size_t)NN, fp);
+            }
+            cudaMemcpy(hb.data(), d_Bt, sizeof(double) * Np * Mrows, cudaMemcpyDeviceToHost);
+            fwrite(hb.data(), sizeof(double), (size_t)Np * Mrows, fp);
+            fclose(fp);
+        }
+    }
+#endif
     // c = Q1' [y; 0]
     LPVS_CU(c, cudaMemsetAsync(d_g, 0, sizeof(double) * 4 * Np, st));
     k_gemv_rows<<<(Np + 7) / 8, 256, 0, st>>>(d_Bt, Mrows, Np, d_y, N, 0, d_g);
@@ -701,8 +896,23 @@ int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, con
     c->launches++;
     LPVS_CU(c, cudaStreamSynchronize(st));
     if (pinfo) {
-        if (info) *info = pinfo;
-        return fail(c, LPVS_E_NOT_SPD, "Cholesky breakdown of the preconditioned Gram matrix at internal pivot %d", pinfo);
+        // Last resort.  The blocked factorisation applies its diagonal blocks through explicit inverses, so a matrix with MANY
+        // null directions (Nreg well above N, with near-coincident sample times making the row space ill-conditioned too) needs
+        // a shift ~1e-9 max diag to factorise, and lam^2 / shift then falls below what G2 can resolve.  The reference's SVD
+        // still returns a (noise-dominated, |x| ~ |y| / lam) vector there; this library returns the shift-regularised solution
+        // (G~ + shift I)^-1 A'y and says so: *info = LPVS_INFO_JITTER.
+        if ((rc = regram())) return rc;
+        launch_max_diag(d_G, NN, Np, ncc, zero_first, d_md, 1, st);
+        k_set_shift<<<1, 1, 0, st>>>(d_md, lam2, mult * (double)nreal * EPS);
+        c->launches += 2;
+        if ((rc = factor_solve(c, ncc, zero_first, Np, d_G, d_B, 1, 0.0, 1, &pinfo, nullptr, 0.0, d_md + 1))) return rc;
+        LPVS_CU(c, cudaStreamSynchronize(st));
+        if (pinfo) {
+            if (info) *info = pinfo;
+            return fail(c, LPVS_E_NOT_SPD, "Cholesky breakdown at internal pivot %d (rank-deficient problem, last resort)", pinfo);
+        }
+        if (info) *info = LPVS_INFO_JITTER;
+        return LPVS_OK;
     }
     // Refinement in the Q1 coordinates: dz = G2^-1 Q1'([y; 0] - [A; lam I] x), x += Y dz.  G2 is well conditioned, so this is
     // an (almost) exact Newton step in EVERY direction -- including the ones A cannot see, where the Cholesky solve of G2

@@ -167,3 +167,45 @@ def test_windowed_singular_window_is_jittered_not_fatal(ctx):
     f = lp.default_freqs(t, n)  # n/2+1 frequencies on n Hann-weighted samples: rank deficient
     S, _ = lp.ls_windowpsd(y, t, f, nw=nw, window_func=lp.hanning, ctx=ctx)
     assert np.all(np.isfinite(S))
+
+
+@pytest.mark.parametrize("seed", range(14))
+def test_random_shapes_through_the_qr_path(ctx, seed):
+    """Random (N, Nf) around and beyond square -- underdetermined (Nreg up to 2N), barely determined, padded tile counts,
+    sample counts that are not multiples of anything, with and without a zero frequency -- against the QR and SVD solves of
+    the same [A; lam I].  Catches indexing mistakes in the materialised-regressor / triangular-GEMM / recursive-doubling
+    kernels that the fixed shapes above can miss (compute-sanitizer is closed on this pool)."""
+    import lpvspectral_jl_b200 as lp
+
+    rng = np.random.default_rng(4000 + seed)
+    N = int(rng.integers(40, 900))
+    ratio = [0.55, 0.8, 1.0, 1.3, 2.0][seed % 5]
+    Nf = max(2, int(ratio * N / 2))
+    zero = bool(seed % 2)
+    t = np.sort(10 * rng.random(N))
+    fs = N / 10.0
+    f = (np.arange(Nf) + (0 if zero else 1)) * (fs / 2 / Nf) * (0.9 if seed % 3 else 1.0)
+    y = np.sin(2 * np.pi * f[Nf // 3] * t) + 0.3 * rng.standard_normal(N)
+    lam = [1e-10, 1e-8, 1e-6][seed % 3]
+    x, _, info = lp.ls_spectral(y, t, f, lam=lam, ctx=ctx, return_info=True)
+    A, zf = o.get_fourier_regressor(t, f)
+    cm = cond_aug(A, lam)
+    x_qr, _ = o.ls_spectral(y, t, f, lam=lam, mode="qr")
+    x_svd, _ = o.ls_spectral(y, t, f, lam=lam, mode="literal")
+    # The bar is the condition number of the LEAST-SQUARES PROBLEM (Wedin): kappa_LS = cond (1 + cond |r| / (|M| |x|)).  The
+    # regressor the GPU synthesises differs from numpy's in the last bit of some entries (CUDA sincospi vs libm), and a
+    # large-residual ill-conditioned problem amplifies that by cond^2 |r| / (|M||x|), not by cond -- for ANY solver.
+    xr = o.complex2fourier(x_qr, zf)
+    res = np.sqrt(np.linalg.norm(A @ xr - y) ** 2 + (lam * np.linalg.norm(xr)) ** 2)
+    kls = cm * (1.0 + cm * res / (np.hypot(np.linalg.norm(A, 2), lam) * np.linalg.norm(xr)))
+    tol = max(1e-9, 10.0 * kls * EPS)
+    print(f"seed {seed}: {A.shape[0]} x {A.shape[1]} lam {lam:g} cond(M) {cm:.1e} kappa_LS {kls:.1e} info {info} "
+          f"gpu-qr {rel(x, x_qr):.2e} gpu-svd {rel(x, x_svd):.2e} svd-qr {rel(x_svd, x_qr):.2e} tol {tol:.1e}")
+    assert np.all(np.isfinite(x))
+    if info == 1:
+        # LPVS_INFO_JITTER, the documented last resort: many null directions (Nreg >= 1.3 N) AND an ill-conditioned row space
+        # (near-coincident sample times at the full Nyquist band).  The reference's answer there is |y| / lam noise; the
+        # library returns the shift-regularised solution and flags it.  Only these shapes may take it.
+        assert A.shape[1] >= 1.25 * A.shape[0] and cm > 1e9
+        return
+    assert rel(x, x_qr) <= tol and rel(x, x_svd) <= tol
