@@ -209,3 +209,26 @@ def test_random_shapes_through_the_qr_path(ctx, seed):
         assert A.shape[1] >= 1.25 * A.shape[0] and cm > 1e9
         return
     assert rel(x, x_qr) <= tol and rel(x, x_svd) <= tol
+
+
+@pytest.mark.parametrize("N,Nf,zero", [(3, 1, True), (3, 2, False), (5, 3, True), (8, 8, True), (17, 5, False), (17, 40, True),
+                                       (64, 33, True), (129, 64, False), (130, 200, True)])
+def test_tiny_and_ragged_shapes(ctx, N, Nf, zero):
+    """Shapes around the tile / chunk sizes (1..130 samples, 1..200 frequencies, both sides of square): every path of the
+    unweighted solver (refinement, sample-space, QR) must index correctly when almost everything is padding."""
+    import lpvspectral_jl_b200 as lp
+
+    rng = np.random.default_rng(100 * N + Nf)
+    t = np.sort(rng.random(N)) + 0.01 * np.arange(N)
+    f = (np.arange(Nf) + (0 if zero else 1)) * 0.37
+    y = rng.standard_normal(N)
+    lam = 1e-3  # keeps every shape well-posed: the point here is indexing, not conditioning
+    x, _, info = lp.ls_spectral(y, t, f, lam=lam, ctx=ctx, return_info=True)
+    x_qr, _ = o.ls_spectral(y, t, f, lam=lam, mode="qr")
+    A, _ = o.get_fourier_regressor(t, f)
+    tol = max(1e-9, C_TOL * cond_aug(A, lam) * EPS)
+    assert info != 1 and rel(x, x_qr) <= tol, (N, Nf, zero, info, rel(x, x_qr))
+    W = 0.5 + rng.random(N)
+    xw, _ = lp.ls_spectral(y, t, f, W, lam=lam, ctx=ctx)
+    xwr, _ = o.ls_spectral(y, t, f, W, lam=lam, mode="literal")
+    assert rel(xw, xwr) <= 1e-9 * max(1.0, np.linalg.cond((A.T * W) @ A + lam * np.eye(A.shape[1])) / 1e6)

@@ -47,7 +47,8 @@ def cfg1(ctx, args):
     flop = N * nreg * (nreg + 1) + nreg ** 3 / 3 + 2 * nreg ** 2
     res.update(spectra_per_s=1e3 / res["call_ms"], flop_per_spectrum=flop,
                tflops_e2e=flop / res["call_ms"] / 1e9, frac_gram=res["gram_tflops"] / FP64_PEAK,
-               note="cond(A)~1e16: timing + breakdown policy only (SURVEY H1); info=1 means jitter ridge used")
+               note="cond(A)~1e16: info=2 means the shifted-CholeskyQR path of csrc/lsq.cu ran (the reference's SVD-class "
+                    "answer, tests/test_gpu_rankdef.py::test_cfg1_full_size)")
     a = x.real ** 2 + x.imag ** 2
     res["peak_index"] = int(a.argmax())
     res["peak_freq"] = float(f[a.argmax()])
