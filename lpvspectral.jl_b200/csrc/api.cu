@@ -383,7 +383,8 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
 }
 
 int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, double* d_B, int nrhs, double ridge,
-                 int nproblems, int* info_host, const double* d_maxdiag, double tol_scale, const double* d_ridge) {
+                 int nproblems, int* info_host, const double* d_maxdiag, double tol_scale, const double* d_ridge,
+                 bool robust) {
     const int nb = Np / TB;
     CholArgs ca{};
     ca.G = d_G;
@@ -397,7 +398,12 @@ int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, doub
     ca.nb = nb;
     ca.maxdiag = d_maxdiag;
     ca.tol_scale = tol_scale;
-    const bool fuse_fwd = d_B && nrhs > 0;  // L y = b rides along with the factorisation
+    robust = robust && nproblems == 1;
+    if (robust) {
+        ca.trsm_scratch = ws<double>(c, BUF_TRSM, (size_t)nb * TB * TB);
+        if (!ca.trsm_scratch) return fail(c, LPVS_E_NOMEM, "out of device memory (TRSM refinement scratch)");
+    }
+    const bool fuse_fwd = d_B && nrhs > 0 && !robust;  // L y = b rides along with the factorisation
     if (fuse_fwd) {
         ca.rhs = d_B;
         ca.strideRhs = 2LL * Np;

@@ -333,10 +333,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const __grid_constant__ Ch
 
     const double *A, *B;
     double* C;
-    long long lda, ldb;
+    long long lda, ldb, ldc = Np;
     int K;
     double alpha, beta;
     switch (mode) {
+        case GM_TRSM_RES: {
+            int i = k + 1 + t;
+            A = G + (long long)i * TB * Np + (long long)k * TB; lda = Np;
+            B = G + (long long)k * TB * Np + (long long)k * TB; ldb = Np;  // L_kk (zeros above its diagonal)
+            C = a.trsm_scratch + (long long)t * TB * TB; ldc = TB;
+            K = TB; alpha = -1.0; beta = 1.0;
+        } break;
+        case GM_TRSM_FIX: {
+            int i = k + 1 + t;
+            A = a.trsm_scratch + (long long)t * TB * TB; lda = TB;
+            B = Linv + (long long)k * TB * TB; ldb = TB;
+            C = G + (long long)i * TB * Np + (long long)k * TB;
+            K = TB; alpha = 1.0; beta = 1.0;
+        } break;
         case GM_TRSM: {
             int i = k + 1 + t;
             A = G + (long long)i * TB * Np + (long long)k * TB; lda = Np;
@@ -447,7 +461,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const __grid_constant__ Ch
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             int col = 64 * wn + 8 * j + 2 * (lane & 3);
-            double2* pc = reinterpret_cast<double2*>(C + (long long)row * Np + col);
+            double2* pc = reinterpret_cast<double2*>(C + (long long)row * ldc + col);
             double2 v = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
             if (beta != 0.0) {
                 double2 o = *pc;
@@ -1061,6 +1075,23 @@ void launch_trsv(const CholArgs& a, double* B, long long strideB, int nrhs, int 
     k_trsv<<<nproblems, NTHREADS, 0, st>>>(a, B, strideB, nrhs, fwd_done ? 1 : 0);
 }
 
+// TRSM of block column k (m tiles), optionally with one step of iterative refinement (CholArgs::trsm_scratch)
+static int trsm_column(const CholArgs& a, int k, int m, int nproblems, cudaStream_t st) {
+    if (!a.trsm_scratch || nproblems != 1) {
+        launch_gemm(GM_TRSM, a, k, m, nproblems, st);
+        return 1;
+    }
+    // keep the pre-TRSM tiles: a 128-wide column panel of G, rows (k+1)*128 .., into the dense scratch
+    cudaMemcpy2DAsync(a.trsm_scratch, TB * sizeof(double), a.G + (long long)(k + 1) * TB * a.Np + (long long)k * TB,
+                      (size_t)a.Np * sizeof(double), TB * sizeof(double), (size_t)m * TB, cudaMemcpyDeviceToDevice, st);
+    CholArgs b = a;
+    b.rhs = nullptr;  // the fused forward substitution would use the unrefined tiles: the caller runs the full solve
+    launch_gemm(GM_TRSM, b, k, m, 1, st);
+    launch_gemm(GM_TRSM_RES, b, k, m, 1, st);
+    launch_gemm(GM_TRSM_FIX, b, k, m, 1, st);
+    return 3;
+}
+
 int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st, const Lookahead* la) {
     int launches = 0;
     const int nb = a.nb;
@@ -1071,7 +1102,7 @@ int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st, const Look
         launches++;
         for (int k = 0; k + 1 < nb; k++) {
             const int m = nb - k - 1;
-            launch_gemm(GM_TRSM, a, k, m, nproblems, st);
+            launches += trsm_column(a, k, m, nproblems, st) - 1;
             cudaEventRecord(la->e_trsm, st);
             if (k > 0) cudaStreamWaitEvent(st, la->e_rest, 0);  // block column k+1 carries the updates up to k-1
             launch_gemm(GM_SYRK_COL, a, k, m, nproblems, st);
@@ -1095,8 +1126,7 @@ int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st, const Look
         launch_potf2(a, k, nproblems, st);
         launches++;
         if (k + 1 < nb) {
-            launch_gemm(GM_TRSM, a, k, nb - k - 1, nproblems, st);
-            launches++;
+            launches += trsm_column(a, k, nb - k - 1, nproblems, st);
             if (!left) {
                 int m = nb - k - 1;
                 launch_gemm(GM_SYRK_RIGHT, a, k, m * (m + 1) / 2, nproblems, st);

@@ -15,7 +15,9 @@ enum GemmMode {
     GM_TRTRI_B = 4,    // Y_ki <- -Y_ki * Linv_ii'
     GM_LAUUM = 5,      // M_ab  = Y[a, a:nb) * Y[b, a:nb)'              (a >= b), M written into G
     GM_SYRK_COL = 6,   // GM_SYRK_RIGHT restricted to block column k+1  (the next panel: look-ahead)
-    GM_SYRK_REST = 7   // GM_SYRK_RIGHT for block columns >= k+2
+    GM_SYRK_REST = 7,  // GM_SYRK_RIGHT for block columns >= k+2
+    GM_TRSM_RES = 8,   // S_i <- S_i - A_ik L_kk'   (S = copy of the pre-TRSM tile: the residual of the inverse-based TRSM)
+    GM_TRSM_FIX = 9    // A_ik <- A_ik + S_i Linv_kk'   (one step of iterative refinement of the TRSM)
 };
 
 // Look-ahead for ONE large problem (right-looking): the trailing update of columns >= k+2 runs on `aux` while the next
@@ -37,6 +39,11 @@ struct CholArgs {
     const double* maxdiag;
     double tol_scale;
     int Np, nb;
+    // optional (ONE problem): nb x 128 x 128 doubles.  When set, every TRSM tile A_ik Linv_kk' is refined once against L_kk
+    // (A_ik += (A_ik0 - A_ik L_kk') Linv_kk').  Applying a diagonal block through its explicit inverse loses cond(L_kk) eps;
+    // on matrices with many tiny pivots (rank-deficient Gram matrices with a 1e-13 shift) that is enough to drive later
+    // pivots negative -- a substitution-based TRSM (LAPACK) or this one refinement step does not (tools).
+    double* trsm_scratch;
     // optional right-hand sides [nrhs][Np] per problem: the forward substitution L y = b rides along with the
     // factorisation (k_potf2 finishes y_k = Linv_kk r_k, the TRSM tiles apply r_i -= L_ik y_k), b is overwritten by y
     double* rhs;

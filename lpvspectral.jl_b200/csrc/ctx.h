@@ -22,7 +22,7 @@ struct DevBuf {
 enum BufSlot {
     BUF_T = 0, BUF_Y, BUF_U, BUF_W, BUF_F, BUF_ANC, BUF_DEL, BUF_G, BUF_B, BUF_LINV, BUF_INFO, BUF_PART, BUF_SUMS,
     BUF_X, BUF_MISC, BUF_YINV, BUF_E, BUF_K, BUF_V, BUF_CENT, BUF_LSQ_R, BUF_LSQ_V, BUF_LSQ_Y, BUF_LSQ_LI, BUF_LSQ_A,
-    BUF_LSQ_BT, BUF_LSQ_G2, BUF_WTAB, BUF_FLAGS, BUF_PSD, BUF_COUNT
+    BUF_LSQ_BT, BUF_LSQ_G2, BUF_WTAB, BUF_FLAGS, BUF_PSD, BUF_TRSM, BUF_COUNT
 };
 
 }  // namespace lpvs
@@ -118,9 +118,10 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
 
 // factor + solve one problem in place: d_G -> L, d_B -> x (internal layout); returns pivot info in *info_host
 // d_ridge (device, one value per problem) replaces `ridge` when given
+// robust (ONE problem): TRSM tiles refined once (CholArgs::trsm_scratch), full forward + backward solve afterwards
 int factor_solve(lpvs_ctx* c, int ncc, int zero_first, int Np, double* d_G, double* d_B, int nrhs, double ridge,
                  int nproblems, int* info_host /* nproblems or null */, const double* d_maxdiag = nullptr,
-                 double tol_scale = 0.0, const double* d_ridge = nullptr);
+                 double tol_scale = 0.0, const double* d_ridge = nullptr, bool robust = false);
 
 // The regressor as an operator, synthesised on the fly with the REFERENCE's rounding (lsq.cu): Fourier
 // fl(fl(cos(fl(fl(2 pi f) t))) dd) (src/lsfft.jl:34-44) or the LPV tables (src/lsfft.jl:244-248).

@@ -753,18 +753,21 @@ int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, con
         launch_max_diag(d_G, NN, Np, ncc, zero_first, d_md, 1, st);
         k_set_shift<<<1, 1, 0, st>>>(d_md, lam2, mult * (double)nreal * EPS);
         c->launches += 2;
-        if ((rc = factor_solve(c, ncc, zero_first, Np, d_G, d_B, 1, 0.0, 1, &pinfo, nullptr, 0.0, d_md + 1))) return rc;
+        // attempt 0: plain; a breakdown is first answered with the SAME shift and refined TRSM tiles (attempt 1), and only then
+        // with larger shifts -- the shift bounds lam^2 / shift, the smallest eigenvalue the QR path's G2 has to resolve
+        if ((rc = factor_solve(c, ncc, zero_first, Np, d_G, d_B, 1, 0.0, 1, &pinfo, nullptr, 0.0, d_md + 1, attempt > 0)))
+            return rc;
         k_min_pivot<<<1, 256, 0, st>>>(d_G, Np, ncc, zero_first, d_md + 4);
         c->launches++;
         LPVS_CU(c, cudaMemcpyAsync(&hmin[0], d_md + 4, sizeof(double), cudaMemcpyDeviceToHost, st));
         LPVS_CU(c, cudaMemcpyAsync(&hmin[1], d_md + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
         LPVS_CU(c, cudaStreamSynchronize(st));
         if (pinfo == 0) break;
-        if (attempt == 3 || !isfinite(mult)) {
+        if (attempt == 4 || !isfinite(mult)) {
             if (info) *info = pinfo;
             return fail(c, LPVS_E_NOT_SPD, "Cholesky breakdown at internal pivot %d even with a %g n eps shift", pinfo, mult);
         }
-        mult *= 32.0;  // the shift only conditions the preconditioner; the solution below does not depend on it
+        if (attempt > 0) mult *= 32.0;  // the shift only conditions the preconditioner, not the solution
         if ((rc = regram())) return rc;
     }
     double* d_x = d_B;  // x0 = (G~ + shift)^-1 A'y
@@ -891,6 +894,14 @@ int ls_solve_accurate(lpvs_ctx* c, const OpArgs& op, int Np, int zero_first, con
     k_gemv_rows<<<(Np + 7) / 8, 256, 0, st>>>(d_Bt, Mrows, Np, d_y, N, 0, d_g);
     c->launches += 3;
     if ((rc = factor_solve(c, ncc, zero_first, Np, d_G2, d_g, 1, 0.0, 1, &pinfo))) return rc;
+    LPVS_CU(c, cudaStreamSynchronize(st));
+    if (pinfo) {  // once more with refined TRSM tiles (G2 has eigenvalues down to lam^2 / shift)
+        k_gemm_nt<<<nb * (nb + 1) / 2, NTHREADS, smem, st>>>(t2);
+        LPVS_CU(c, cudaMemsetAsync(d_g, 0, sizeof(double) * 4 * Np, st));
+        k_gemv_rows<<<(Np + 7) / 8, 256, 0, st>>>(d_Bt, Mrows, Np, d_y, N, 0, d_g);
+        c->launches += 2;
+        if ((rc = factor_solve(c, ncc, zero_first, Np, d_G2, d_g, 1, 0.0, 1, &pinfo, nullptr, 0.0, nullptr, true))) return rc;
+    }
     // x = L^-T z = Y z
     k_gemv_rows<<<(Np + 7) / 8, 256, 0, st>>>(d_Y, Np, Np, d_g, Np, 1, d_x);
     c->launches++;

@@ -202,12 +202,9 @@ def test_random_shapes_through_the_qr_path(ctx, seed):
     print(f"seed {seed}: {A.shape[0]} x {A.shape[1]} lam {lam:g} cond(M) {cm:.1e} kappa_LS {kls:.1e} info {info} "
           f"gpu-qr {rel(x, x_qr):.2e} gpu-svd {rel(x, x_svd):.2e} svd-qr {rel(x_svd, x_qr):.2e} tol {tol:.1e}")
     assert np.all(np.isfinite(x))
-    if info == 1:
-        # LPVS_INFO_JITTER, the documented last resort: many null directions (Nreg >= 1.3 N) AND an ill-conditioned row space
-        # (near-coincident sample times at the full Nyquist band).  The reference's answer there is |y| / lam noise; the
-        # library returns the shift-regularised solution and flags it.  Only these shapes may take it.
-        assert A.shape[1] >= 1.25 * A.shape[0] and cm > 1e9
-        return
+    # LPVS_INFO_JITTER is the flagged last resort (shift-regularised solution).  Seeds 3 and 9 (Nreg >= 1.3 N on irregular
+    # samples, many tiny pivots) needed it until the factorisation learned to refine its TRSM tiles; nothing here may take it.
+    assert info != 1
     assert rel(x, x_qr) <= tol and rel(x, x_svd) <= tol
 
 
