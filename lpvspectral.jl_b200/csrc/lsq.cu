@@ -253,8 +253,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nt(const __grid_constant__
         I = a.mt - 1 - t / a.nt;
         J = t % a.nt;
         Kend = (long long)(I + 1) * TB;
-    } else {  // G2 = Q1'Q1, lower tiles; the ridge block of row block J ends at column Ksplit + (J+1)*128
-        tile_ij(gridDim.x - 1 - blockIdx.x, I, J);
+    } else {  // G2 = Q1'Q1, lower tiles; the ridge block of row block J ends at column Ksplit + (J+1)*128.  Longest tiles
+              // (largest J) first: block columns from the last one backwards
+        int cidx, ridx;
+        tile_ij(blockIdx.x, cidx, ridx);
+        J = a.nt - 1 - cidx;
+        I = J + ridx;
         Kend = a.Ksplit + (long long)(J + 1) * TB;
         if (Kend > a.K) Kend = a.K;
     }
