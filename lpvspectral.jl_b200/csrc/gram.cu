@@ -217,8 +217,13 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
 
     // staggering the bursts of an SMSP's two warps (kk = 0 / 4) measured no better: 78.0 vs 77.7 ms with the exact-phase
     // burst, SYNTH_BURST=3 re-measures it with the longer reference-phase burst (profiles/r02_summary.md)
-    const int burst_kk = SYNTH_BURST == 3 ? (w >> 2) * 4 : 0;
     int st_cur = 0;
+    // SYNTH_BURST == 4: the two warps of an SM sub-partition (w and w+4) burst half a chunk apart, with the burst position a
+    // COMPILE-TIME constant of two specialised copies of the loop (a run-time position makes every unrolled k-step carry a
+    // predicated copy of the burst: SYNTH_BURST == 3, measured slower)
+    auto chunk_loop = [&](auto bk_tag) {
+    constexpr int BKC = decltype(bk_tag)::value;
+    const int burst_kk = SYNTH_BURST == 3 ? (w >> 2) * 4 : BKC;
     for (int c = 0; c < nchunks; c++) {
         const int st_nxt = st_cur == NSTAGE - 1 ? 0 : st_cur + 1;
         double* cur = smem + st_cur * STAGE_D;
@@ -312,6 +317,11 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
         if (have_next) mbar_wait(&full[st_nxt], ((c + 1) / NSTAGE) & 1);
         st_cur = st_nxt;
     }
+    };
+    if (SYNTH_BURST == 4 && w >= 4)
+        chunk_loop(std::integral_constant<int, 4>{});
+    else
+        chunk_loop(std::integral_constant<int, 0>{});
 
     // epilogue
     const int Np = a.nblk * TB;
