@@ -99,6 +99,9 @@ int lpvs_dev_free(lpvs_ctx* ctx, void* dptr);
 int lpvs_dev_upload(lpvs_ctx* ctx, void* dptr, const void* hptr, int64_t bytes);
 int lpvs_dev_download(lpvs_ctx* ctx, void* hptr, const void* dptr, int64_t bytes);
 int lpvs_sync(lpvs_ctx* ctx);
+/* the context's device workspaces are grow-only (a cfg5b-sized call leaves ~17 GB of tables behind): give them back.  ADMM
+ * handles keep their own memory and stay valid. */
+int lpvs_release_workspace(lpvs_ctx* ctx);
 
 /* ---- window bookkeeping: DSP.arraysplit semantics used by Windows2/Windows3 (src/windows.jl:27-36,94-104) ---- */
 /* K = N >= n ? (N-n) div (n-noverlap) + 1 : 0 ; noverlap < 0 means n>>1 */

@@ -53,6 +53,8 @@ end
 # instantiations of the sparse estimators switch it on around the create call.
 const OPT_ADMM_M32 = Cint(7)
 setopt(key, v) = check(ccall((:lpvs_set_option, liblpvs), Cint, (Ptr{Cvoid}, Cint, Float64), ctx(), key, Float64(v)))
+"Give the context's grow-only device workspaces back (re-allocated on demand by the next call)."
+release_workspace() = check(ccall((:lpvs_release_workspace, liblpvs), Cint, (Ptr{Cvoid},), ctx()))
 function with_m32(fn, T)
     T === Float32 || return fn()
     setopt(OPT_ADMM_M32, 1)

@@ -107,6 +107,10 @@ class Context:
         self.check(self.lib.lpvs_last_call_ms(self.h, C.byref(ms)))
         return ms.value
 
+    def release_workspace(self):
+        """Give the grow-only device workspaces back (they are re-allocated on demand)."""
+        self.check(self.lib.lpvs_release_workspace(self.h))
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.lpvs_destroy(self.h)

@@ -43,6 +43,7 @@ _PROTOS = {
     "lpvs_dev_upload": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "lpvs_dev_download": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "lpvs_sync": (C.c_int, [_vp]),
+    "lpvs_release_workspace": (C.c_int, [_vp]),
     "lpvs_window_count": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "lpvs_gram_fourier": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, C.c_int, _vp, _vp, _vp]),
     "lpvs_ls_spectral": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, _vp, _ip]),

@@ -592,6 +592,18 @@ int lpvs_dev_download(lpvs_ctx* c, void* hptr, const void* dptr, int64_t bytes) 
     LPVS_CU(c, cudaStreamSynchronize(c->st));
     return LPVS_OK;
 }
+int lpvs_release_workspace(lpvs_ctx* c) {
+    if (!c) return LPVS_E_BAD_ARG;
+    Lock lk(c->mu);
+    cudaSetDevice(c->device);
+    LPVS_CU(c, cudaStreamSynchronize(c->st));
+    for (auto& b : c->buf) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    return LPVS_OK;
+}
 int lpvs_sync(lpvs_ctx* c) {
     if (!c) return LPVS_E_BAD_ARG;
     LPVS_CU(c, cudaStreamSynchronize(c->st));

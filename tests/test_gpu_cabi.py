@@ -192,3 +192,16 @@ def test_sharded_admm_entry_points_single_gpu(ctx):
     h = create(L.PROX_BALL_L0, 5.0)
     assert ctx.lib.lpvs_admm_shard_begin(h, 0, 2) == L.E_UNSUPPORTED    # element-wise prox operators only
     ctx.lib.lpvs_admm_free(h)
+
+
+def test_release_workspace_then_reuse(ctx):
+    """lpvs_release_workspace frees the grow-only tables; the next call re-allocates and returns the same answer."""
+    import lpvspectral_jl_b200 as lp
+
+    t, y = sig(600, 11)
+    f = np.arange(0, 40.0)
+    x0 = lp.ls_spectral(y, t, f, ctx=ctx)[0]
+    ctx.release_workspace()
+    x1 = lp.ls_spectral(y, t, f, ctx=ctx)[0]
+    assert np.array_equal(x0, x1)
+    assert ctx.lib.lpvs_release_workspace(None) != 0
