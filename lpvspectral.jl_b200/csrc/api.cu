@@ -1,6 +1,7 @@
 // C ABI of liblpvs.so (see include/lpvs.h): context, Fourier LS estimators, windowed estimators.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -88,7 +89,7 @@ int make_fourier_plan(lpvs_ctx* c, const double* f, int Nf, FourierPlan* pl) {
     pl->Nreg = 2 * Nf - pl->zero_first;
     pl->nblk = (Nf + FB - 1) / FB;
     pl->Np = pl->nblk * TB;
-    pl->ngroups = pl->nblk * (FB / GRP);
+    pl->ngroups = anchor_rows(pl->nblk);  // rows of the chain anchor table
     pl->dd = 1.0 / sqrt(2.0 * (double)Nf);  // src/lsfft.jl:35
     pl->f0 = f[0];
     pl->df = Nf > 1 ? (f[Nf - 1] - f[0]) / (double)(Nf - 1) : 0.0;
@@ -108,18 +109,25 @@ int make_fourier_plan(lpvs_ctx* c, const double* f, int Nf, FourierPlan* pl) {
     LPVS_CU(c, cudaMemcpyAsync(d_f, f, sizeof(double) * Nf, cudaMemcpyHostToDevice, c->st));
     pl->d_f = d_f;
     if (pl->mode == GRAM_CHAINREF) {
-        // per column k = 8g + j: w = fl(2 pi f_k) (src/lsfft.jl:34) and dw = w - 2 pi (f_8g + j df), the difference between
-        // the reference's angular frequency and the one the chain realises, in double-double
+        // per column k = 64 b + 8 g + j: w = fl(2 pi f_k) (src/lsfft.jl:34) and dw = w - 2 pi (f_64b + fl(8 g df) + j df), the
+        // difference between the reference's angular frequency and the one the chain realises (block anchor x group power,
+        // then j steps of df: launch_anchor_table), in double-double
         const double P_HI = 6.283185307179586, P_LO = 2.4492935982947064e-16;
         const int ncol = pl->nblk * FB;
         c->wtab_host.assign((size_t)2 * ncol, 0.0);
+        auto two_sum = [](double a, double b, double& lo) {
+            const double s = a + b, bb = s - a;
+            lo = (a - (s - bb)) + (b - bb);
+            return s;
+        };
         for (int k = 0; k < Nf; k++) {
-            const int g8 = (k / GRP) * GRP, j = k - g8;
+            const int b64 = (k / FB) * FB, g = (k - b64) / GRP, j = k - b64 - g * GRP;
             const double w = P_HI * f[k];
+            double e1, e2;
+            const double a_hi = two_sum(f[b64], anchor_group_step(g, pl->df), e1);
             const double jd = (double)j * pl->df, jd_lo = fma((double)j, pl->df, -jd);
-            const double s_hi = f[g8] + jd;
-            const double bb = s_hi - f[g8];
-            const double s_lo = ((f[g8] - (s_hi - bb)) + (jd - bb)) + jd_lo;  // two_sum(f_8g, j df) + the product's tail
+            const double s_hi = two_sum(a_hi, jd, e2);
+            const double s_lo = (e1 + e2) + jd_lo;
             const double ph = P_HI * s_hi, pe = fma(P_HI, s_hi, -ph);
             const double pl_lo = fma(P_LO, s_hi, pe) + P_HI * s_lo;
             c->wtab_host[2 * k] = w;
@@ -333,7 +341,7 @@ int gram_single(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const dou
             anc = ws<double2>(c, BUF_ANC, (size_t)pl.ngroups * ns);
             del = ws<double2>(c, BUF_DEL, (size_t)ns);
             if (!anc || !del) return fail(c, LPVS_E_NOMEM, "out of device memory (anchor table)");
-            launch_anchor_table(d_t, s0, ns, pl.d_f, pl.Nf, pl.ngroups, pl.f0, pl.df, anc, del, c->st);
+            launch_anchor_table(d_t, s0, ns, pl.d_f, pl.nblk, pl.df, anc, del, c->st);
             c->launches++;
         }
         long long n_split = (ns + split_per_seg - 1) / split_per_seg;
@@ -485,7 +493,18 @@ int lpvs_init(int device, lpvs_ctx** out) {
         return LPVS_E_CUDA;
     }
     c->st = c->own_st;
-    cudaStreamCreateWithFlags(&c->la.aux, cudaStreamNonBlocking);
+    {
+        int prio_least = 0, prio_greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+        cudaStreamCreateWithPriority(&c->la.aux, cudaStreamNonBlocking, prio_least);
+        if (prio_greatest != prio_least && getenv("LPVS_NO_CRIT_STREAM") == nullptr &&
+            cudaStreamCreateWithPriority(&c->la.crit, cudaStreamNonBlocking, prio_greatest) == cudaSuccess) {
+            cudaEventCreateWithFlags(&c->la.e_in, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&c->la.e_out, cudaEventDisableTiming);
+        } else {
+            c->la.crit = nullptr;
+        }
+    }
     cudaEventCreateWithFlags(&c->la.e_trsm, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->la.e_rest, cudaEventDisableTiming);
     cudaEventCreate(&c->ev_call0);
@@ -508,6 +527,9 @@ void lpvs_destroy(lpvs_ctx* c) {
     cudaEventDestroy(c->ev_call1);
     cudaStreamDestroy(c->own_st);
     if (c->la.aux) cudaStreamDestroy(c->la.aux);
+    if (c->la.crit) cudaStreamDestroy(c->la.crit);
+    if (c->la.e_in) cudaEventDestroy(c->la.e_in);
+    if (c->la.e_out) cudaEventDestroy(c->la.e_out);
     if (c->la.e_trsm) cudaEventDestroy(c->la.e_trsm);
     if (c->la.e_rest) cudaEventDestroy(c->la.e_rest);
     delete c;
@@ -891,7 +913,7 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
             double2* anc = ws<double2>(c, BUF_ANC, (size_t)pl.ngroups * ns);
             double2* del = ws<double2>(c, BUF_DEL, (size_t)ns);
             if (!anc || !del) return fail(c, LPVS_E_NOMEM, "out of device memory (anchor table)");
-            launch_anchor_table(d_t, s0, ns, pl.d_f, pl.Nf, pl.ngroups, pl.f0, pl.df, anc, del, c->st);
+            launch_anchor_table(d_t, s0, ns, pl.d_f, pl.nblk, pl.df, anc, del, c->st);
             c->launches++;
             g.anc = anc;
             g.del = del;
@@ -1048,20 +1070,13 @@ int lpvs_ls_window_sparse_sums(lpvs_ctx* c, int kind, const double* y, const dou
     batch = std::min<int64_t>(batch, nwin);
     std::vector<int> hinfo((size_t)batch);
     std::vector<long long> hits((size_t)batch * nrhs);
-    long long* d_its = nullptr;
-    double* d_res = nullptr;
-    LPVS_CU(c, cudaMalloc(&d_its, sizeof(long long) * batch * nrhs));
-    if (cudaMalloc(&d_res, sizeof(double) * batch * nrhs) != cudaSuccess) {
-        cudaFree(d_its);
-        return fail(c, LPVS_E_NOMEM, "out of device memory");
-    }
+    // per-window iteration counts and residuals live in the context's grow-only workspace (no allocation per call)
+    long long* d_its = ws<long long>(c, BUF_WIN_ITS, (size_t)batch * nrhs);
+    double* d_res = ws<double>(c, BUF_WIN_RES, (size_t)batch * nrhs);
+    if (!d_its || !d_res) return fail(c, LPVS_E_NOMEM, "out of device memory");
     int bad = 0;
     int64_t bad_window = -1;
-    auto cleanup = [&]() {
-        cudaStreamSynchronize(c->st);
-        cudaFree(d_its);
-        cudaFree(d_res);
-    };
+    auto cleanup = [&]() { cudaStreamSynchronize(c->st); };
     for (int64_t k0 = 0; k0 < nwin && !bad; k0 += batch) {
         const int nw = (int)std::min<int64_t>(batch, nwin - k0);
         const long long s0 = k0 * hop, ns = (long long)(nw - 1) * hop + n;
@@ -1081,7 +1096,7 @@ int lpvs_ls_window_sparse_sums(lpvs_ctx* c, int kind, const double* y, const dou
                 cleanup();
                 return fail(c, LPVS_E_NOMEM, "out of device memory (anchor table)");
             }
-            launch_anchor_table(d_t, s0, ns, pl.d_f, pl.Nf, pl.ngroups, pl.f0, pl.df, anc, del, c->st);
+            launch_anchor_table(d_t, s0, ns, pl.d_f, pl.nblk, pl.df, anc, del, c->st);
             c->launches++;
             g.anc = anc;
             g.del = del;

@@ -107,68 +107,56 @@ __device__ __forceinline__ void warp_mma_row(double* C, int ldc, const double* A
         }
 }
 
-// One warp factorises a 16x16 SPD block (lane & 15 = row) and inverts the factor (lane & 15 = column).
-// The critical path per column is pivot -> rsqrt -> two multiplies -> one FMA: the column is broadcast UNSCALED
-// through shared memory (double-buffered, one __syncwarp per column) while the pivot travels by shuffle, and the
-// scaling by rsqrt(pivot) is applied to the multiplier instead of to the column (an LDL'-style update).
-// Measured (tools/potf2_probe.cu): the previous all-shuffle version spent 15.9 K cycles per panel here.
-__device__ __forceinline__ void warp_potf2_inv(double* D, int ldd, double* Di, int ldi, double* LT, double* colbuf,
-                                               int lane, int* info, int pivot_base, double tol) {
+// One warp factorises a 16x16 SPD block AND inverts the factor, in lockstep: lanes 0-15 own row (lane) of the block, lanes
+// 16-31 own column (lane - 16) of X = L^-1.  Column c of the factor is broadcast UNSCALED through shared memory (double-
+// buffered, one __syncwarp per column) while the pivot travels by shuffle; the scaling by rsqrt(pivot) is applied to the
+// multiplier instead of to the column (an LDL'-style update), so the critical path per column is pivot -> rsqrt -> two
+// multiplies -> one FMA.  The inverse needs exactly that broadcast column: its running sums s[i] = sum_{k<=c} L[i][k] x[k]
+// advance by the same FMA with the multiplier rsqrt(pivot) * x[c], and x[c] = -s[c] rsqrt(pivot) is ready when column c is.
+// Both halves therefore execute ONE instruction stream (the inverse no longer runs as a second 16-step serial loop:
+// 5.7 K -> about 3 K cycles per panel, tools/potf2_probe.cu).
+__device__ __forceinline__ void warp_potf2_inv(double* D, int ldd, double* Di, int ldi, double* colbuf, int lane,
+                                               int* info, int pivot_base, double tol) {
     const unsigned full = 0xffffffffu;
     const int row = lane & (PB - 1);
-    double d[PB], rs[PB];
+    const bool inv = lane >= PB;
+    double a[PB];  // factor lanes: A[row][.] -> L[row][.]; inverse lanes: running sums -> X[.][row]
 #pragma unroll
-    for (int c = 0; c < PB; c++) d[c] = (c <= row) ? D[row * ldd + c] : 0.0;
+    for (int c = 0; c < PB; c++) a[c] = (!inv && c <= row) ? D[row * ldd + c] : 0.0;
 #pragma unroll
     for (int c = 0; c < PB; c++) {
         double* cb = colbuf + (c & 1) * PB;
-        if (lane < PB) cb[row] = d[c];
-        double piv = __shfl_sync(full, d[c], c);
+        if (!inv) cb[row] = a[c];
+        double piv = __shfl_sync(full, a[c], c);
         if (!(piv > tol) || !isfinite(piv)) {
             if (lane == 0) atomicCAS(info, 0, pivot_base + c + 1);
             piv = (fabs(piv) > 0.0 && isfinite(piv)) ? fabs(piv) : 1.0;
         }
         const double ri = rsqrt(piv);
-        rs[c] = ri;
-        const double l = (row == c) ? piv * ri : d[c] * ri;  // L[row][c]
-        const double w = l * ri;                             // a[row][c] / pivot
-        d[c] = l;
+        double keep, mult;
+        if (!inv) {
+            keep = (row == c) ? piv * ri : a[c] * ri;  // L[row][c]
+            mult = -(keep * ri);                        // -a[row][c] / pivot
+        } else {
+            keep = (c == row) ? ri : ((c > row) ? -a[c] * ri : 0.0);  // X[c][row]
+            mult = ri * keep;
+        }
+        a[c] = keep;
         __syncwarp();
 #pragma unroll
         for (int kk = (c + 1) / 2; kk < PB / 2; kk++) {
             const double2 v = reinterpret_cast<const double2*>(cb)[kk];
-            if (2 * kk > c) d[2 * kk] = fma(-w, v.x, d[2 * kk]);
-            d[2 * kk + 1] = fma(-w, v.y, d[2 * kk + 1]);
+            if (2 * kk > c) a[2 * kk] = fma(mult, v.x, a[2 * kk]);
+            a[2 * kk + 1] = fma(mult, v.y, a[2 * kk + 1]);
         }
     }
-    // L back to the block (rows) and transposed to LT (LT[c][row] = L[row][c]) for the broadcast reads below
-    if (lane < PB) {
+    if (!inv) {
 #pragma unroll
-        for (int c = 0; c < PB; c++) {
-            if (c <= row) D[row * ldd + c] = d[c];
-            LT[c * PB + row] = (c <= row) ? d[c] : 0.0;
-        }
-    }
-    __syncwarp();
-    // inverse, lane & 15 = column j: x[m] = -rs[m] * sum_{k<m} L[m][k] x[k]; the sums are kept running so that one
-    // FMA and one multiply separate consecutive x[m]
-    double sacc[PB], x[PB];
+        for (int c = 0; c < PB; c++)
+            if (c <= row) D[row * ldd + c] = a[c];
+    } else {
 #pragma unroll
-    for (int i = 0; i < PB; i++) sacc[i] = 0.0;
-#pragma unroll
-    for (int m = 0; m < PB; m++) {
-        const double xm = (m == row) ? rs[m] : ((m > row) ? -sacc[m] * rs[m] : 0.0);
-        x[m] = xm;
-#pragma unroll
-        for (int kk = (m + 1) / 2; kk < PB / 2; kk++) {
-            const double2 v = reinterpret_cast<const double2*>(LT + m * PB)[kk];  // L[2kk][m], L[2kk+1][m]
-            if (2 * kk > m) sacc[2 * kk] = fma(v.x, xm, sacc[2 * kk]);
-            sacc[2 * kk + 1] = fma(v.y, xm, sacc[2 * kk + 1]);
-        }
-    }
-    if (lane < PB) {
-#pragma unroll
-        for (int c = 0; c < PB; c++) Di[c * ldi + row] = x[c];
+        for (int c = 0; c < PB; c++) Di[c * ldi + row] = a[c];
     }
 }
 
@@ -185,8 +173,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ C
     double* S = sm;
     double* T = sm + 128 * LDS;
     double* Dinv = T + 64 * LDH;
-    double* LT = Dinv + (TB / PB) * PB * LDP;
-    double* colbuf = LT + PB * PB;
+    double* colbuf = Dinv + (TB / PB) * PB * LDP + PB * PB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int prob = blockIdx.x;
     double* Gd = a.G + (long long)prob * a.strideG + ((long long)k * TB) * a.Np + (long long)k * TB;
@@ -215,7 +202,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ C
         double* Di = Dinv + p * PB * LDP;
         const int nt = (TB - j0 - PB) >> 3;  // 8-row tiles below the panel's diagonal block
         if (warp == 0) {
-            warp_potf2_inv(S + j0 * LDS + j0, LDS, Di, LDP, LT, colbuf, lane, &a.info[prob], k * TB + j0, tol);
+            warp_potf2_inv(S + j0 * LDS + j0, LDS, Di, LDP, colbuf, lane, &a.info[prob], k * TB + j0, tol);
         } else if (nt > 0 && j0 > 0) {
             // panel p+1 (columns j0+16 .. j0+31, rows >= j0+16) -= L[rows, 0:j0) * L[j0+16 .. j0+31, 0:j0)'
             const double* Brow = S + (j0 + PB) * LDS;
@@ -1097,16 +1084,22 @@ int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st, const Look
     const int nb = a.nb;
     const bool left = (long long)nproblems * nb >= 2LL * sms;
     if (!left && la && nb >= 4) {
-        // right-looking with look-ahead: main stream = potf2 / TRSM / next-panel update, aux = the rest of the update
-        launch_potf2(a, 0, nproblems, st);
+        // right-looking with look-ahead: critical stream = potf2 / TRSM / next-panel update, aux = the rest of the update
+        cudaStream_t ms = st;
+        if (la->crit) {
+            cudaEventRecord(la->e_in, st);
+            cudaStreamWaitEvent(la->crit, la->e_in, 0);
+            ms = la->crit;
+        }
+        launch_potf2(a, 0, nproblems, ms);
         launches++;
         for (int k = 0; k + 1 < nb; k++) {
             const int m = nb - k - 1;
-            launches += trsm_column(a, k, m, nproblems, st) - 1;
-            cudaEventRecord(la->e_trsm, st);
-            if (k > 0) cudaStreamWaitEvent(st, la->e_rest, 0);  // block column k+1 carries the updates up to k-1
-            launch_gemm(GM_SYRK_COL, a, k, m, nproblems, st);
-            launch_potf2(a, k + 1, nproblems, st);
+            launches += trsm_column(a, k, m, nproblems, ms) - 1;
+            cudaEventRecord(la->e_trsm, ms);
+            if (k > 0) cudaStreamWaitEvent(ms, la->e_rest, 0);  // block column k+1 carries the updates up to k-1
+            launch_gemm(GM_SYRK_COL, a, k, m, nproblems, ms);
+            launch_potf2(a, k + 1, nproblems, ms);
             launches += 3;
             if (m > 1) {
                 cudaStreamWaitEvent(la->aux, la->e_trsm, 0);
@@ -1115,7 +1108,11 @@ int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st, const Look
             }
             cudaEventRecord(la->e_rest, la->aux);
         }
-        cudaStreamWaitEvent(st, la->e_rest, 0);
+        cudaStreamWaitEvent(ms, la->e_rest, 0);
+        if (ms != st) {
+            cudaEventRecord(la->e_out, ms);
+            cudaStreamWaitEvent(st, la->e_out, 0);
+        }
         return launches;
     }
     for (int k = 0; k < nb; k++) {

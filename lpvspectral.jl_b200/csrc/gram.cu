@@ -6,8 +6,10 @@
 // (software pipelined inside the k4-step loop because DMMA and DFMA share one pipe -- tools/fp64_probe.cu).
 //
 // GRAM_CHAIN synthesis (uniform frequency grid): thread (warp w, lane l) owns sample l of the chunk and the 8
-// frequencies 64*blk+8w .. +7; it starts from an exact anchor e^{-i 2 pi f t} (table, double-double phase) and
-// advances with the per-sample rotation e^{-i 2 pi df t}: 4 FP64 ops per (cos,-sin) pair instead of ~35.
+// frequencies 64*blk+8w .. +7; it starts from an exact anchor e^{-i 2 pi f t} and advances with the per-sample
+// rotation e^{-i 2 pi df t}: 4 FP64 ops per (cos,-sin) pair instead of ~35.  The anchor is the product of two table
+// entries (double-double phases): one per (64-frequency block, sample) and one per (warp, sample) -- the block's first
+// frequency turned by 8 w df -- so the table holds nblk + 8 rows per sample instead of 8 nblk.
 #include "gram.cuh"
 
 #include <stdlib.h>
@@ -26,6 +28,7 @@ constexpr int NSTAGE = 3;             // smem ring of the 8-warp kernel (per-sta
 
 struct Pref {
     double2 aI, aJ, d;  // chain: anchors + step rotation
+    double2 pw;         // chain: e^{-i 2 pi (8 w df) t}, folded into aI / aJ by resolve()
     double tt;          // direct: sample position
     long long si;       // table sample index
     double wt;
@@ -67,8 +70,9 @@ __device__ __forceinline__ Pref load_pref(const GramArgs& a, int c, long long s_
     p.valid = valid;
     if (RHS) p.yv = a.y[s];
     if (gram_is_chain(MODE)) {
-        p.aI = a.anc[(long long)(I * (FB / GRP) + w) * a.tbl_ns + p.si];
-        if (!DIAG) p.aJ = a.anc[(long long)(J * (FB / GRP) + w) * a.tbl_ns + p.si];
+        p.aI = a.anc[(long long)I * a.tbl_ns + p.si];
+        if (!DIAG) p.aJ = a.anc[(long long)J * a.tbl_ns + p.si];
+        p.pw = a.anc[(long long)(a.nblk + w) * a.tbl_ns + p.si];
         p.d = a.del[p.si];
         if (MODE == GRAM_CHAINREF) p.tt = a.t[s];
     } else if (MODE == GRAM_DIRECT) {
@@ -165,6 +169,10 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     auto resolve = [](Pref& p) {
         p.wt = p.valid ? p.wt : 0.0;
         if (RHS) p.yv *= p.wt;
+        if (gram_is_chain(MODE)) {  // anchor of this warp's 8-frequency group = block anchor x group power (pinned product)
+            p.aI = chain_rotate(p.aI, p.pw);
+            if (!DIAG) p.aJ = chain_rotate(p.aJ, p.pw);
+        }
     };
     // 3-stage ring: full[s] completes when all 8 warps have stored their part of the chunk living in stage s.
     // A stage is rewritten two chunks after it was last read; passing full[] of the chunk in between proves every
@@ -412,7 +420,7 @@ __global__ void __launch_bounds__(NTHREADS) k_gram_rhs(const __grid_constant__ G
             pm = load_pref<MODE, true>(a, c + 2, s_begin, lane, w, I, I);
             load_y(pm, ym0, ym1);
         }
-        double2 z = p.aI;
+        double2 z = gram_is_chain(MODE) ? chain_rotate(p.aI, p.pw) : p.aI;
 #pragma unroll
         for (int j = 0; j < GRP; j++) {
             double2 v = z;
@@ -460,18 +468,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gram(const __grid_constant__ Gr
     }
 }
 
+// rows [0, nblk): e^{-i 2 pi f_{64 b} t_s} (the block's first frequency); rows [nblk, nblk + GRP): e^{-i 2 pi (8 j df) t_s}
+// (the turn from the block's first frequency to the first frequency of chain group j; `pstep[j]` = fl(8 j df) is computed
+// on the host so that the reference-phase table of make_fourier_plan describes exactly the frequency realised here);
+// del[s] = e^{-i 2 pi df t_s}.  All phases are reduced in double-double turns.
+struct PowSteps {
+    double v[GRP];
+};
 __global__ void k_anchor_table(const double* __restrict__ t, long long s0, long long ns,
-                               const double* __restrict__ f, int Nf, int ngroups, double f0, double df,
+                               const double* __restrict__ f, int nblk, const __grid_constant__ PowSteps pstep, double df,
                                double2* __restrict__ anc, double2* __restrict__ del) {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= ns) return;
     int g = blockIdx.y;
     double tt = t[s0 + s];
-    if (g == ngroups) {
+    if (g == nblk + GRP) {
         del[s] = cis_turns_exact(df, tt);
     } else {
-        int k = g * GRP;
-        double fk = (k < Nf) ? f[k] : fma((double)k, df, f0);
+        const double fk = g < nblk ? f[g * FB] : pstep.v[g - nblk];
         anc[(long long)g * ns + s] = cis_turns_exact(fk, tt);
     }
 }
@@ -577,10 +591,12 @@ int launch_gram_rhs(int mode, const GramArgs& a, int nproblems, cudaStream_t st)
     return launched;
 }
 
-void launch_anchor_table(const double* t, long long s0, long long ns, const double* f, int Nf, int ngroups,
-                         double f0, double df, double2* anc, double2* del, cudaStream_t st) {
-    dim3 grid((unsigned)((ns + 255) / 256), ngroups + 1);
-    k_anchor_table<<<grid, 256, 0, st>>>(t, s0, ns, f, Nf, ngroups, f0, df, anc, del);
+void launch_anchor_table(const double* t, long long s0, long long ns, const double* f, int nblk, double df,
+                         double2* anc, double2* del, cudaStream_t st) {
+    PowSteps ps;
+    for (int j = 0; j < GRP; j++) ps.v[j] = anchor_group_step(j, df);
+    dim3 grid((unsigned)((ns + 255) / 256), nblk + GRP + 1);
+    k_anchor_table<<<grid, 256, 0, st>>>(t, s0, ns, f, nblk, ps, df, anc, del);
 }
 
 void launch_lpv_tables(const double* X, const double* V, long long N, const double* w, int Nf, int Nvv,

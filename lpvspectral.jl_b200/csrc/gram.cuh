@@ -32,12 +32,13 @@ struct GramArgs {
     int nblk; // Np / 128
     int nrhs;
     int fuse_rhs;  // set by launch_gram: b for nrhs == 1 is accumulated inside the diagonal tiles
-    // GRAM_CHAIN tables, indexed [g * tbl_ns + (s - tbl_base)]
+    // GRAM_CHAIN tables, indexed [row * tbl_ns + (s - tbl_base)]: anc rows [0, nblk) block anchors, [nblk, nblk + GRP)
+    // group powers (launch_anchor_table)
     const double2* anc;
     const double2* del;
     long long tbl_base;
     long long tbl_ns;
-    // GRAM_CHAINREF: per complex column (w, dw): w = fl(2 pi f), dw = w - 2 pi (f_anchor + j df) (double-double, host)
+    // GRAM_CHAINREF: per complex column (w, dw): w = fl(2 pi f), dw = w - 2 pi (f_block + fl(8 g df) + j df) (double-double, host)
     const double2* wtab;
     // GRAM_DIRECT
     const double* f;
@@ -61,9 +62,14 @@ int launch_gram(int mode, const GramArgs& a, int nproblems, cudaStream_t st);
 // only b = A' diag(W) [y u] (grid = (nblk, nproblems)); the adjoint of the synthesised operator
 int launch_gram_rhs(int mode, const GramArgs& a, int nproblems, cudaStream_t st);
 
-// anchors every GRP frequencies + per-sample step rotation, exact phase (double-double turns)
-void launch_anchor_table(const double* t, long long s0, long long ns, const double* f, int Nf, int ngroups,
-                         double f0, double df, double2* anc, double2* del, cudaStream_t st);
+// Chain anchor tables, exact phase (double-double turns): anc has nblk + GRP rows of ns entries -- rows [0, nblk) the first
+// frequency of every 64-frequency block, rows [nblk, nblk + GRP) the turn by anchor_group_step(j, df) from there to chain
+// group j -- and del the per-sample step rotation e^{-i 2 pi df t}.  (Round 1 kept one anchor per 8 frequencies: 8 nblk rows,
+// 2.1 GB at BASELINE cfg2; this layout is 0.8 GB and costs one complex multiply per 8 synthesised elements.)
+constexpr int anchor_rows(int nblk) { return nblk + GRP; }
+inline double anchor_group_step(int j, double df) { return (double)(GRP * j) * df; }  // the double the device phase uses
+void launch_anchor_table(const double* t, long long s0, long long ns, const double* f, int nblk, double df, double2* anc,
+                         double2* del, cudaStream_t st);
 // LPV factor tables: E[fi][s] = (cos, -sin)(w_fi * X_s) (reference rounding), Kt[ki][s] = RBF activations
 void launch_lpv_tables(const double* X, const double* V, long long N, const double* w, int Nf, int Nvv,
                        const double* centers, double gamma, int coulomb, int normalize, double2* E, double* Kt,
