@@ -561,26 +561,32 @@ def parity_leg(ctx, lp, L, C, D, torch, dist, rank, world, local, allmax):
     ya = sum(np.cos(2 * np.pi * fa[k] * ta + k) for k in (100, 500, 900)) + 0.1 * rng.standard_normal(Na)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
 
-    def create():
+    def create(prox=None, pparam=0.1):
         h = C.c_void_p()
-        ctx.check(ctx.lib.lpvs_admm_create_fourier(ctx.h, vp(ya), vp(ta), Na, vp(fa), len(fa), None, L.PROX_L1, 0.1, 0.05,
-                                                   None, 0, 0.0, C.byref(h)))
+        ctx.check(ctx.lib.lpvs_admm_create_fourier(ctx.h, vp(ya), vp(ta), Na, vp(fa), len(fa), None,
+                                                   L.PROX_L1 if prox is None else prox, pparam, 0.05, None, 0, 0.0,
+                                                   C.byref(h)))
         return lp.ADMM(ctx, h)
 
-    one = create()
-    one.step(600, 1e-9)
-    x1a, z1a = one.get()
-    it1 = one.iters
-    one.free()
-    sh = D.admm_shard(create())
-    sh.step(600, 1e-9)
-    dist.barrier()
-    xsa, zsa = sh.get()
-    its = sh.iters
-    dist.barrier()
-    sh.free()
-    e_admm = max(rel(zsa, z1a), rel(xsa, x1a))
-    same = bool(np.array_equal(zsa != 0, z1a != 0)) and its == it1
+    def one_vs_sharded(make, iters, tol):
+        one = make()
+        one.step(iters, tol)
+        x1, z1 = one.get()
+        it1 = one.iters
+        one.free()
+        sh = D.admm_shard(make())
+        sh.step(iters, tol)
+        dist.barrier()
+        xs_, zs_ = sh.get()
+        its = sh.iters
+        dist.barrier()
+        sh.free()
+        return max(rel(zs_, z1), rel(xs_, x1)), bool(np.array_equal(zs_ != 0, z1 != 0)) and its == it1
+
+    e_admm, same = one_vs_sharded(create, 600, 1e-9)
+    # IndBallL0 (keep the 24 largest): the selection runs redundantly on every rank after the all-reduce
+    e_ball, same_ball = one_vs_sharded(lambda: create(L.PROX_BALL_L0, 24.0), 300, 1e-9)
+    same = same and same_ball
     # group lasso (ls_sparse_spectral_lpv): ONE 1280-unknown problem (10 blocks of 128 >= 8 ranks) sharded vs this GPU alone
     from oracle import lpvs_oracle as o
 
@@ -593,28 +599,17 @@ def parity_leg(ctx, lp, L, C, D, torch, dist, rank, world, local, allmax):
                                                C.byref(h)))
         return lp.ADMM(ctx, h)
 
-    one = create_lpv()
-    one.step(400, 1e-7)
-    x1g, z1g = one.get()
-    it1g = one.iters
-    one.free()
-    sh = D.admm_shard(create_lpv())
-    sh.step(400, 1e-7)
-    dist.barrier()
-    xsg, zsg = sh.get()
-    itsg = sh.iters
-    dist.barrier()
-    sh.free()
-    e_group = max(rel(zsg, z1g), rel(xsg, x1g))
-    same = same and bool(np.array_equal(zsg != 0, z1g != 0)) and itsg == it1g
+    e_group, same_group = one_vs_sharded(create_lpv, 400, 1e-7)
+    same = same and same_group
     out = {"window_sharded": allmax(e_win), "row_sharded": allmax(e_row), "admm_sharded": allmax(e_admm),
-           "admm_group_sharded": allmax(e_group),
+           "admm_group_sharded": allmax(e_group), "admm_ball_l0_sharded": allmax(e_ball),
            "admm_same_support_and_iterations": allmax(0.0 if same else 1.0) == 0.0, "bar": 1e-12,
            "how": "every rank compares the sharded result with its own single-GPU result on the same inputs (windowed PSD + "
-                  "coherence, row-sharded weighted LS with one NCCL all-reduce, one L1 ADMM problem sharded by peer stores); "
+                  "coherence, row-sharded weighted LS with one NCCL all-reduce, one L1 / IndBallL0 / group-lasso ADMM problem each, sharded by peer stores); "
                   "relative l2, max over ranks"}
     out["ok"] = bool(out["window_sharded"] <= 1e-12 and out["row_sharded"] <= 1e-12 and out["admm_sharded"] <= 1e-12
-                     and out["admm_group_sharded"] <= 1e-12 and out["admm_same_support_and_iterations"])
+                     and out["admm_group_sharded"] <= 1e-12 and out["admm_ball_l0_sharded"] <= 1e-12
+                     and out["admm_same_support_and_iterations"])
     return out
 
 

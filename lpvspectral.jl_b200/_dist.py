@@ -151,7 +151,7 @@ def ls_spectral_rowsharded(y, t, f, W=None, *, u=None, lam=1e-10, ctx: Optional[
 
 
 def admm_shard(solver: "A.ADMM", group=None):
-    """Shard ONE ADMM problem over the ranks of a node (every rank must have created the same problem; NormL1 / NormL0).
+    """Shard ONE ADMM problem over the ranks of a node (every rank must have created the same problem; NormL1 / NormL0, and -- with the default one-exchange scheme -- IndBallL0 and the group prox).
 
     The loop then runs as a persistent kernel per GPU that exchanges partial products and the new right-hand side with
     device-initiated peer stores over NVLink (lpvs_admm_shard_*); torch.distributed only carries the 64-byte CUDA IPC

@@ -1198,7 +1198,25 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm_symv_sharded(const __g
             double d2 = 0.0;
             const double* rbase = mine + sh.off_recv2 + (long long)par * P * Np;
             double* rn3 = mine + sh.off_rhs + (long long)nxt3 * Np;
-            if (a.prox != LPVS_PROX_GROUP_L2) {
+            if (a.prox == LPVS_PROX_BALL_L0) {
+                // IndBallL0 (keep the r largest |x + u|): every rank holds every row after the all-reduce, so each rank runs
+                // the single-GPU selection (radix select in block 0, ties in the reference's index order) on its own copy --
+                // redundantly and bit-identically, like the element-wise prox; one more local grid barrier, no extra exchange
+                for (int r = tid; r < an; r += ADMM_THREADS) {
+                    const int i = a0 + r;
+                    double xi = 0.0;
+                    for (int sr = 0; sr < P; sr++) xi += __ldcg(rbase + (long long)sr * Np + i);
+                    a.x[i] = xi;
+                    a.v[i] = xi + a.u[i];
+                }
+                shard_fold_abort(sh, b, tid);
+                grid.sync();
+                if (shard_aborted(sh)) {
+                    failed = 1;
+                    break;
+                }
+                d2 = admm_phase_nonelem(a, rn3, b, nblocks, tid, lane, w, gl);
+            } else if (a.prox != LPVS_PROX_GROUP_L2) {
                 for (int r = tid; r < an; r += ADMM_THREADS) {
                     const int i = a0 + r;
                     double xi = 0.0;
@@ -1974,8 +1992,8 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
         sh.it_base = h->iters_total;
         sh.spin_limit = 6000000000LL;  // ~3 s of SM clocks: a peer that is this late is gone
         void* args[] = {&a, &sp, &sh};
-        if (h->prox == LPVS_PROX_GROUP_L2 && sh.v2 != 2)
-            return fail(c, LPVS_E_UNSUPPORTED, "sharded group prox needs LPVS_OPT_SHARD_EXCHANGE = 2 on every rank");
+        if ((h->prox == LPVS_PROX_GROUP_L2 || h->prox == LPVS_PROX_BALL_L0) && sh.v2 != 2)
+            return fail(c, LPVS_E_UNSUPPORTED, "sharded group prox / IndBallL0 need LPVS_OPT_SHARD_EXCHANGE = 2 on every rank");
         LPVS_CU(c, cudaLaunchCooperativeKernel((void*)k_admm_symv_sharded, dim3(h->grid), dim3(ADMM_THREADS), args,
                                                admm_smem_symv(Np, h->max_item), c->st));
         const int own0 = h->shard_rb[h->shard_rank] * 128;
@@ -2056,9 +2074,10 @@ int lpvs_admm_shard_begin(lpvs_admm* h, int rank, int world) {
     // element-wise prox operators with every exchange; the group prox (ls_sparse_spectral_lpv, BASELINE configs[3]) with
     // exchange 2, where every rank holds every row after the all-reduce and groups cannot straddle ranks
     const bool group = h->prox == LPVS_PROX_GROUP_L2 && c->shard_exchange == 2;
-    if (h->prox != LPVS_PROX_L1 && h->prox != LPVS_PROX_L0 && !group)
+    const bool ball = h->prox == LPVS_PROX_BALL_L0 && c->shard_exchange == 2;  // redundant selection on every rank
+    if (h->prox != LPVS_PROX_L1 && h->prox != LPVS_PROX_L0 && !group && !ball)
         return fail(c, LPVS_E_UNSUPPORTED,
-                    "sharded ADMM supports NormL1 / NormL0, and the group prox with LPVS_OPT_SHARD_EXCHANGE = 2");
+                    "sharded ADMM supports NormL1 / NormL0, and the group prox / IndBallL0 with LPVS_OPT_SHARD_EXCHANGE = 2");
     if ((!h->h_order.empty() && !group) || nb < world || h->shard_world > 1 || h->iters_total > 0)
         return fail(c, LPVS_E_UNSUPPORTED, "sharded ADMM: needs a fresh problem with at least `world` 128-blocks");
     h->symv = 1;

@@ -493,18 +493,7 @@ int lpvs_init(int device, lpvs_ctx** out) {
         return LPVS_E_CUDA;
     }
     c->st = c->own_st;
-    {
-        int prio_least = 0, prio_greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-        cudaStreamCreateWithPriority(&c->la.aux, cudaStreamNonBlocking, prio_least);
-        if (prio_greatest != prio_least && getenv("LPVS_NO_CRIT_STREAM") == nullptr &&
-            cudaStreamCreateWithPriority(&c->la.crit, cudaStreamNonBlocking, prio_greatest) == cudaSuccess) {
-            cudaEventCreateWithFlags(&c->la.e_in, cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&c->la.e_out, cudaEventDisableTiming);
-        } else {
-            c->la.crit = nullptr;
-        }
-    }
+    cudaStreamCreateWithFlags(&c->la.aux, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&c->la.e_trsm, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->la.e_rest, cudaEventDisableTiming);
     cudaEventCreate(&c->ev_call0);
@@ -527,9 +516,6 @@ void lpvs_destroy(lpvs_ctx* c) {
     cudaEventDestroy(c->ev_call1);
     cudaStreamDestroy(c->own_st);
     if (c->la.aux) cudaStreamDestroy(c->la.aux);
-    if (c->la.crit) cudaStreamDestroy(c->la.crit);
-    if (c->la.e_in) cudaEventDestroy(c->la.e_in);
-    if (c->la.e_out) cudaEventDestroy(c->la.e_out);
     if (c->la.e_trsm) cudaEventDestroy(c->la.e_trsm);
     if (c->la.e_rest) cudaEventDestroy(c->la.e_rest);
     delete c;

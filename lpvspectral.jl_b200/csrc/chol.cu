@@ -1084,22 +1084,18 @@ int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st, const Look
     const int nb = a.nb;
     const bool left = (long long)nproblems * nb >= 2LL * sms;
     if (!left && la && nb >= 4) {
-        // right-looking with look-ahead: critical stream = potf2 / TRSM / next-panel update, aux = the rest of the update
-        cudaStream_t ms = st;
-        if (la->crit) {
-            cudaEventRecord(la->e_in, st);
-            cudaStreamWaitEvent(la->crit, la->e_in, 0);
-            ms = la->crit;
-        }
-        launch_potf2(a, 0, nproblems, ms);
+        // right-looking with look-ahead: main stream = potf2 / TRSM / next-panel update, aux = the rest of the update.
+        // (Measured in round 2: running the critical path on a separate highest-priority stream and the rest on a lowest-
+        // priority one does not help -- cfg1 19.6 ms against 19.4 ms; profiles/r02_summary.md.)
+        launch_potf2(a, 0, nproblems, st);
         launches++;
         for (int k = 0; k + 1 < nb; k++) {
             const int m = nb - k - 1;
-            launches += trsm_column(a, k, m, nproblems, ms) - 1;
-            cudaEventRecord(la->e_trsm, ms);
-            if (k > 0) cudaStreamWaitEvent(ms, la->e_rest, 0);  // block column k+1 carries the updates up to k-1
-            launch_gemm(GM_SYRK_COL, a, k, m, nproblems, ms);
-            launch_potf2(a, k + 1, nproblems, ms);
+            launches += trsm_column(a, k, m, nproblems, st) - 1;
+            cudaEventRecord(la->e_trsm, st);
+            if (k > 0) cudaStreamWaitEvent(st, la->e_rest, 0);  // block column k+1 carries the updates up to k-1
+            launch_gemm(GM_SYRK_COL, a, k, m, nproblems, st);
+            launch_potf2(a, k + 1, nproblems, st);
             launches += 3;
             if (m > 1) {
                 cudaStreamWaitEvent(la->aux, la->e_trsm, 0);
@@ -1108,11 +1104,7 @@ int potrf(const CholArgs& a, int nproblems, int sms, cudaStream_t st, const Look
             }
             cudaEventRecord(la->e_rest, la->aux);
         }
-        cudaStreamWaitEvent(ms, la->e_rest, 0);
-        if (ms != st) {
-            cudaEventRecord(la->e_out, ms);
-            cudaStreamWaitEvent(st, la->e_out, 0);
-        }
+        cudaStreamWaitEvent(st, la->e_rest, 0);
         return launches;
     }
     for (int k = 0; k < nb; k++) {

@@ -22,15 +22,9 @@ enum GemmMode {
 
 // Look-ahead for ONE large problem (right-looking): the trailing update of columns >= k+2 runs on `aux` while the next
 // diagonal block is factorised on the main stream.  Null = plain in-order factorisation.
-// Streams of the right-looking factorisation with look-ahead.  `crit` (highest priority) carries the critical path -- diagonal
-// block, TRSM column, update of the next block column -- and `aux` (lowest priority) the rest of the trailing update, so a
-// critical-path CTA takes the next SM that frees up instead of queueing behind up to three waves of update tiles.  Both are
-// joined to the caller's stream by events (e_in / e_out), whatever priority that stream has.
 struct Lookahead {
     cudaStream_t aux;
     cudaEvent_t e_trsm, e_rest;
-    cudaStream_t crit = nullptr;
-    cudaEvent_t e_in = nullptr, e_out = nullptr;
 };
 
 struct CholArgs {

@@ -95,12 +95,19 @@ __device__ __forceinline__ double2 synth_elem(const GramArgs& a, const Pref& p, 
     }
 }
 
-// DIAG tiles (I == J) compute only the 20 of 32 pieces (16 rows x 32 columns) that touch the lower triangle:
-// piece (r, c) is needed iff r >= 2c.  Pieces are dealt so that every SM sub-partition (warps w and w+4) issues
-// 5 pieces = 40 DMMAs per k4-step instead of 64: warps 0-3 take three pieces of one row strip (rows 4..7, columns
-// 0..2: one A fragment pair, three B fragment quads), warps 4-7 take the remaining pairs {(6,3),(7,3)}, {(2,0),(2,1)},
-// {(3,0),(3,1)}, {(0,0),(1,0)} which share either the A or the B fragments.  (Computing the three lower 64x64
-// sub-blocks instead costs 48 per sub-partition: measured 77.8 ms vs this layout on cfg2, see profiles/.)
+// DIAG tiles (I == J) compute only the 20 of 32 pieces (16 rows x 32 columns) that touch the lower triangle: piece (r, c)
+// is needed iff r >= 2c -- and of the four pieces that start ON the diagonal (r == 2c) only the left 16 columns, the right
+// half lying strictly above it: 144 DMMAs per k4-step instead of 256.  The deal matters as much as the count.  (i) The two
+// warps of an SM sub-partition (w and w+4) share one FP64 pipe and keep it busy only while BOTH have DMMAs to issue: a warp
+// that finishes its chunk early waits at the stage barrier and leaves its partner to run alone.  (ii) A predicated-off DMMA
+// still occupies the pipe (measured, profiles/r02_summary.md: a 36-DMMA deal with 4 of 40 predicated off ran exactly as
+// long as the 40-DMMA deal and ncu counted 40), so every warp must execute the SAME instruction stream.  Hence: every warp
+// takes two whole pieces that share their A or B fragments (16 DMMAs) plus 8 rows of one diagonal half piece (2 DMMAs; of
+// the upper 8 rows the second is the one wasted 8x8 block): 18 per warp, 36 per sub-partition, no predicates.
+//   w0 (7,0)(7,1)+(6,3)lo   w1 (6,0)(6,1)+(4,2)lo   w2 (5,0)(5,1)+(2,1)lo   w3 (6,2)(5,2)+(0,0)lo
+//   w4 (7,2)(7,3)+(6,3)up   w5 (4,0)(4,1)+(4,2)up   w6 (3,0)(3,1)+(2,1)up   w7 (1,0)(2,0)+(0,0)up
+// (History on cfg2, diagonal tiles alone: three lower 64x64 sub-blocks 48 per sub-partition; 40 with warp pairs 24 + 12:
+// 24.6 ms at 71 % useful pipe time; 36 as 20 + 16 with predicates: 23.4 ms; this deal: see profiles/r02_summary.md.)
 // RHS (diagonal tiles only, nrhs == 1): b_I = A_I' W y is accumulated by the threads that synthesise A_I anyway --
 // 2 FMAs per synthesised element in the 16 accumulator registers the diagonal layout leaves free -- instead of a second
 // pass over the anchor table (k_gram_rhs: 2.2 ms of a 85 ms step on cfg2).
@@ -205,23 +212,13 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
     const int fragB = DIAG ? (lane >> 2) * LDT + (lane & 3) : (64 * wn + (lane >> 2)) * LDT + (lane & 3);
     // diagonal tile: this warp's pieces (16-row strip pr, 32-column strip pc); the third piece of warps 0-3 shares
     // the A fragments of the first
-    int pr0, pr1, pc0, pc1, pc2 = 2;
-    if (w < 4) {
-        pr0 = pr1 = 4 + w;
-        pc0 = 0;
-        pc1 = 1;
-    } else if (w == 4) {
-        pr0 = 6; pr1 = 7; pc0 = pc1 = 3;
-    } else if (w == 7) {
-        pr0 = 0; pr1 = 1; pc0 = pc1 = 0;
-    } else {
-        pr0 = pr1 = w - 3;  // 2, 3
-        pc0 = 0;
-        pc1 = 1;
-    }
-    const bool three = w < 4, sameA = pr0 == pr1, sameB = pc0 == pc1;
-    const int offA0 = 16 * pr0 * LDT, offA1 = 16 * pr1 * LDT;
-    const int offB0 = 32 * pc0 * LDT, offB1 = 32 * pc1 * LDT, offB2 = 32 * pc2 * LDT;
+    // nibble w of each constant = the value for warp w (table in the comment above gram_tile)
+    const int pr0 = (0x13476567u >> (4 * w)) & 15, pc0 = (0x00022000u >> (4 * w)) & 15;
+    const int pr1 = (0x23475567u >> (4 * w)) & 15, pc1 = (0x01132111u >> (4 * w)) & 15;
+    const int prh = (0x02460246u >> (4 * w)) & 15, pch = (0x01230123u >> (4 * w)) & 15;
+    const int ih = w < 4 ? 1 : 0;  // which 8 rows of the diagonal half piece (1 = lower)
+    const int offA0 = 16 * pr0 * LDT, offA1 = 16 * pr1 * LDT, offAh = (16 * prh + 8 * ih) * LDT;
+    const int offB0 = 32 * pc0 * LDT, offB1 = 32 * pc1 * LDT, offBh = 32 * pch * LDT;
 
     // staggering the bursts of an SMSP's two warps (kk = 0 / 4) measured no better: 78.0 vs 77.7 ms with the exact-phase
     // burst, SYNTH_BURST=3 re-measures it with the longer reference-phase burst (profiles/r02_summary.md)
@@ -286,39 +283,31 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
             if (!DIAG) {
                 mma_step(pa, pb, kk, acc);
             } else {
-                double fa0[2], fa1[2], fb[4];
+                // every fragment of the k-step is requested up front, in its own registers (the diagonal path holds 40
+                // accumulators against the off-diagonal path's 64, so there is room): one exposed shared-memory latency per
+                // k-step instead of one per piece.  Pieces that share a row / column strip simply load it twice.
+                double fa0[2], fa1[2], fah, fb0[4], fb1[4], fbh[2];
 #pragma unroll
                 for (int i = 0; i < 2; i++) fa0[i] = pa[offA0 + 8 * i * LDT + 4 * kk];
 #pragma unroll
-                for (int j = 0; j < 4; j++) fb[j] = pb[offB0 + 8 * j * LDT + 4 * kk];
-                if (sameA) {
-                    fa1[0] = fa0[0];
-                    fa1[1] = fa0[1];
-                } else {
+                for (int j = 0; j < 4; j++) fb0[j] = pb[offB0 + 8 * j * LDT + 4 * kk];
 #pragma unroll
-                    for (int i = 0; i < 2; i++) fa1[i] = pa[offA1 + 8 * i * LDT + 4 * kk];
-                }
+                for (int i = 0; i < 2; i++) fa1[i] = pa[offA1 + 8 * i * LDT + 4 * kk];
 #pragma unroll
-                for (int i = 0; i < 2; i++)
+                for (int j = 0; j < 4; j++) fb1[j] = pb[offB1 + 8 * j * LDT + 4 * kk];
+                fah = pa[offAh + 4 * kk];  // 8 rows x left 16 columns of a piece that starts on the diagonal
 #pragma unroll
-                    for (int j = 0; j < 4; j++) dmma884(acc[0][i * 4 + j][0], acc[0][i * 4 + j][1], fa0[i], fb[j]);
-                if (!sameB) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) fb[j] = pb[offB1 + 8 * j * LDT + 4 * kk];
-                }
+                for (int j = 0; j < 2; j++) fbh[j] = pb[offBh + 8 * j * LDT + 4 * kk];
 #pragma unroll
                 for (int i = 0; i < 2; i++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++) dmma884(acc[1][i * 4 + j][0], acc[1][i * 4 + j][1], fa1[i], fb[j]);
-                if (three) {
+                    for (int j = 0; j < 4; j++) dmma884(acc[0][i * 4 + j][0], acc[0][i * 4 + j][1], fa0[i], fb0[j]);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) fb[j] = pb[offB2 + 8 * j * LDT + 4 * kk];
+                for (int i = 0; i < 2; i++)
 #pragma unroll
-                    for (int i = 0; i < 2; i++)
+                    for (int j = 0; j < 4; j++) dmma884(acc[1][i * 4 + j][0], acc[1][i * 4 + j][1], fa1[i], fb1[j]);
 #pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            dmma884(acc[2][i * 4 + j][0], acc[2][i * 4 + j][1], fa0[i], fb[j]);
-                }
+                for (int j = 0; j < 2; j++) dmma884(acc[2][j][0], acc[2][j][1], fah, fbh[j]);
             }
         }
         p1 = p2;
@@ -364,9 +353,8 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
         }
     } else {
 #pragma unroll
-        for (int pz = 0; pz < 3; pz++) {
-            if (pz == 2 && !three) break;
-            const int pr = pz == 1 ? pr1 : pr0, pc = pz == 0 ? pc0 : (pz == 1 ? pc1 : pc2);
+        for (int pz = 0; pz < 2; pz++) {
+            const int pr = pz == 0 ? pr0 : pr1, pc = pz == 0 ? pc0 : pc1;
 #pragma unroll
             for (int i = 0; i < 2; i++) {
                 int row = I * TB + 16 * pr + 8 * i + (lane >> 2);
@@ -376,6 +364,16 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
                     double2 v = make_double2(acc[pz][i * 4 + j][0] * a.gscale, acc[pz][i * 4 + j][1] * a.gscale);
                     *reinterpret_cast<double2*>(Gp + (long long)row * Np + col) = v;
                 }
+            }
+        }
+        {  // 8 rows of a diagonal half piece; the 8x8 block right of the diagonal block's upper rows is not stored
+            const int row = I * TB + 16 * prh + 8 * ih + (lane >> 2);
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                if (j > ih) break;
+                const int col = I * TB + 32 * pch + 8 * j + 2 * (lane & 3);
+                double2 v = make_double2(acc[2][j][0] * a.gscale, acc[2][j][1] * a.gscale);
+                *reinterpret_cast<double2*>(Gp + (long long)row * Np + col) = v;
             }
         }
     }
@@ -458,6 +456,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gram(const __grid_constant__ Gr
     extern __shared__ __align__(16) double smem[];
     int I, J;
     tile_ij(blockIdx.x, I, J);
+#ifdef GRAM_DBG_SKIP  // timing experiments only (tools/build_variants.sh): 1 = skip diagonal tiles, 2 = skip the others
+    if ((GRAM_DBG_SKIP == 1) == (I == J)) return;
+#endif
     if (I == J) {
         if (a.fuse_rhs)
             gram_tile<MODE, true, true>(a, I, J, blockIdx.y, smem);

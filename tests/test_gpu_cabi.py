@@ -189,8 +189,14 @@ def test_sharded_admm_entry_points_single_gpu(ctx):
     assert rc == L.E_BAD_ARG and b"not connected" in ctx.lib.lpvs_last_error(ctx.h)
     assert ctx.lib.lpvs_admm_shard_begin(h, 1, 2) == L.E_UNSUPPORTED    # already sharded
     ctx.lib.lpvs_admm_free(h)
+    # IndBallL0 and the group prox shard only with the one-exchange scheme (every rank then holds every row)
     h = create(L.PROX_BALL_L0, 5.0)
-    assert ctx.lib.lpvs_admm_shard_begin(h, 0, 2) == L.E_UNSUPPORTED    # element-wise prox operators only
+    ctx.set_option(L.OPT_SHARD_EXCHANGE, 0)
+    try:
+        assert ctx.lib.lpvs_admm_shard_begin(h, 0, 2) == L.E_UNSUPPORTED
+    finally:
+        ctx.set_option(L.OPT_SHARD_EXCHANGE, 2)
+    assert ctx.lib.lpvs_admm_shard_begin(h, 0, 2) == L.OK
     ctx.lib.lpvs_admm_free(h)
 
 

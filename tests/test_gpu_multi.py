@@ -22,9 +22,10 @@ def _torchrun(script, n, port, *args):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
 
 
-@pytest.mark.parametrize("script,port", [("dist_check.py", 29561), ("admm_shard_check.py", 29562)])
-def test_two_gpu_paths(script, port):
+@pytest.mark.parametrize("script,port,arg", [("dist_check.py", 29561, None), ("admm_shard_check.py", 29562, None),
+                                             ("admm_shard_check.py", 29563, "ball"), ("admm_shard_check.py", 29564, "lpv")])
+def test_two_gpu_paths(script, port, arg):
     if _ngpu() < 2:
         pytest.skip("needs >= 2 GPUs")
-    r = _torchrun(script, 2, port)
+    r = _torchrun(script, 2, port, *([arg] if arg else []))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

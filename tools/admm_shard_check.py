@@ -1,6 +1,7 @@
 """torchrun --nproc-per-node P tools/admm_shard_check.py [full]: ONE L1 ADMM problem sharded over P GPUs (device-initiated
 peer stores over NVLink) vs the same problem on one GPU: iterates, iteration count, iterations/s.
-`full` = BASELINE cfg3 (16 383 unknowns); default = a 4 095-unknown problem (quick)."""
+`full` = BASELINE cfg3 (16 383 unknowns); default = a 4 095-unknown problem (quick); `ball` = the same quick problem with the
+IndBallL0 prox (keep the 24 largest); `lpv` / `lpvfull` = the group lasso of ls_sparse_spectral_lpv."""
 import ctypes as C
 import json
 import os
@@ -24,6 +25,7 @@ ctx = lp.Context(local)
 if "LPVS_SHARD_EXCHANGE" in os.environ:  # 1 (default): per-CTA arrival counters; 0: grid barrier + flag hops
     ctx.set_option(L.OPT_SHARD_EXCHANGE, int(os.environ["LPVS_SHARD_EXCHANGE"]))
 full = len(sys.argv) > 1 and sys.argv[1] == "full"
+ball = len(sys.argv) > 1 and sys.argv[1] == "ball"
 lpv = len(sys.argv) > 1 and sys.argv[1] in ("lpv", "lpvfull")  # group lasso (BASELINE cfg4 with "lpvfull")
 if lpv:
     from oracle import lpvs_oracle as o
@@ -50,8 +52,9 @@ def create():
                                                C.byref(h)))
         return lp.ADMM(ctx, h)
     ctx.check(ctx.lib.lpvs_admm_create_fourier(ctx.h, y.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p),
-                                               len(y), f.ctypes.data_as(C.c_void_p), len(f), None, L.PROX_L1, 0.1,
-                                               0.05, None, 0, 0.0, C.byref(h)))
+                                               len(y), f.ctypes.data_as(C.c_void_p), len(f), None,
+                                               L.PROX_BALL_L0 if ball else L.PROX_L1, 24.0 if ball else 0.1, 0.05, None, 0,
+                                               0.0, C.byref(h)))
     return lp.ADMM(ctx, h)
 
 
@@ -83,7 +86,7 @@ t_all = torch.tensor([mss], device=torch.device("cuda", local))
 dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"workload": ("cfg4_group_lasso" if big else "group_lasso_640") if lpv else
-                      ("cfg3_l1_admm" if full else "l1_admm_4095"), "n_gpus": world, "iters": iters,
+                      ("cfg3_l1_admm" if full else ("ball_l0_admm_4095" if ball else "l1_admm_4095")), "n_gpus": world, "iters": iters,
                       "one_gpu_it_per_s": iters / ms1 * 1e3, "sharded_it_per_s": iters / t_all.item() * 1e3,
                       "speedup": ms1 / t_all.item(), "rel_err_z": err, "rel_err_x": errx, "iters_one": it1,
                       "iters_sharded": its, "same_support": supp, "ok": bool(flag.item() == 1.0)}))
