@@ -113,8 +113,10 @@ __device__ __forceinline__ void warp_mma_row(double* C, int ldc, const double* A
 // multiplier instead of to the column (an LDL'-style update), so the critical path per column is pivot -> rsqrt -> two
 // multiplies -> one FMA.  The inverse needs exactly that broadcast column: its running sums s[i] = sum_{k<=c} L[i][k] x[k]
 // advance by the same FMA with the multiplier rsqrt(pivot) * x[c], and x[c] = -s[c] rsqrt(pivot) is ready when column c is.
-// Both halves therefore execute ONE instruction stream (the inverse no longer runs as a second 16-step serial loop:
-// 5.7 K -> about 3 K cycles per panel, tools/potf2_probe.cu).
+// Both halves therefore execute ONE instruction stream.  Measured (tools/potf2_probe.cu): 5.9 K cycles per panel, the same as
+// the two-loop version -- the panel is a chain of dependent FP64 operations at ~365 cycles per column, not issue-bound.  A
+// reciprocal-only chain (MUFU.RCP64H seed + two Newton steps for the multiplier, rsqrt taken once after the loop) was also
+// measured and is SLOWER (7.1 K cycles): CUDA's rsqrt is the shorter dependent sequence on this pipe.
 __device__ __forceinline__ void warp_potf2_inv(double* D, int ldd, double* Di, int ldi, double* colbuf, int lane,
                                                int* info, int pivot_base, double tol) {
     const unsigned full = 0xffffffffu;
@@ -203,10 +205,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potf2(const __grid_constant__ C
         const int nt = (TB - j0 - PB) >> 3;  // 8-row tiles below the panel's diagonal block
         if (warp == 0) {
             warp_potf2_inv(S + j0 * LDS + j0, LDS, Di, LDP, colbuf, lane, &a.info[prob], k * TB + j0, tol);
-        } else if (nt > 0 && j0 > 0) {
+        } else if (nt > 0 && j0 > 0 && warp != 4) {
             // panel p+1 (columns j0+16 .. j0+31, rows >= j0+16) -= L[rows, 0:j0) * L[j0+16 .. j0+31, 0:j0)'
+            // Warp 4 shares warp 0's SM sub-partition, i.e. its FP64 pipe: every DMMA it issued here could hold one of the
+            // dependent FP64 operations of warp 0's pivot chain back by up to 16 cycles, so it sits this phase out
+            // (5.95 K -> 5.85 K cycles per panel, tools/potf2_probe.cu).
             const double* Brow = S + (j0 + PB) * LDS;
-            for (int ti = warp - 1; ti < nt; ti += NTHREADS / 32 - 1)
+            for (int ti = warp < 4 ? warp - 1 : warp - 2; ti < nt; ti += NTHREADS / 32 - 2)
                 warp_mma_row<true, 2>(S + (j0 + PB + 8 * ti) * LDS + j0 + PB, LDS, S + (j0 + PB + 8 * ti) * LDS, LDS, Brow,
                                       LDS, 0, j0, 2, -1.0, true, lane);
         }
