@@ -24,6 +24,9 @@ constexpr int STAGE_D = 2 * TILE_D;  // I tile, J tile (J = weighted copy)
 #ifndef SYNTH_BURST
 #define SYNTH_BURST 1
 #endif
+#ifndef GRAM_PAIR_SYNC
+#define GRAM_PAIR_SYNC 0
+#endif
 constexpr int NSTAGE = 3;             // smem ring of the 8-warp kernel (per-stage mbarriers, no __syncthreads)
 
 struct Pref {
@@ -261,6 +264,11 @@ __device__ __forceinline__ void gram_tile(const GramArgs& a, int I, int J, int p
                 } else if (SYNTH_BURST) {
                     // whole next chunk in one burst: fewer DMMA<->DFMA interleave points (79.1 -> 77.7 ms)
                     if (kk == burst_kk) {
+#if GRAM_PAIR_SYNC == 1  // the two warps of an SM sub-partition start their bursts together (named barrier per pair)
+                        asm volatile("bar.sync %0, 64;" ::"r"(1 + (w & 3)) : "memory");
+#elif GRAM_PAIR_SYNC == 2  // all eight warps start their bursts together
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+#endif
                         if (any_mask) {  // warp-uniform: the masked variant costs 128 selects per chunk
 #pragma unroll
                             for (int j = 0; j < GRP; j++) synth_step(std::true_type{}, p1, zI, zJ, j, nxt);
