@@ -204,8 +204,8 @@ int lpvs_admm_run(lpvs_admm* h, int64_t max_iters, double tol, int64_t* iters_do
  *   lpvs_admm_shard_connect(h, handles)     maps the peers' regions (world x 64 bytes, rank order).
  * After a host barrier, lpvs_admm_run (same max_iters / tol on every rank) iterates with device-initiated peer stores
  * over NVLink (LPVS_OPT_SHARD_EXCHANGE, default: one all-reduce of the partial products per iteration, prox computed
- * redundantly on every rank), no host or NCCL call inside the loop.  NormL1 / NormL0, and with the default exchange the
- * group prox of lpvs_admm_create_lpv.  lpvs_admm_get / _result are valid on every rank after a host barrier that follows
+ * redundantly on every rank), no host or NCCL call inside the loop.  NormL1 / NormL0, and with the default exchange
+ * IndBallL0 and the group prox of lpvs_admm_create_lpv.  lpvs_admm_get / _result are valid on every rank after a host barrier that follows
  * the run. */
 int lpvs_admm_shard_begin(lpvs_admm* h, int rank, int world);
 int lpvs_admm_shard_handle(lpvs_admm* h, void* handle64);
