@@ -804,6 +804,26 @@ def main():
                                              "phase rounding (tests/test_gpu_baseline_parity.py)"}
     finally:
         ctx.set_option(L.OPT_PHASE_MODE, L.PHASE_AUTO)
+    # Opt-in LPVS_PHASE_STRUCTURED: the windows' Gram matrices from their 3 Nf trigonometric sums (Toeplitz + Hankel in the
+    # frequency index, csrc/structured.cu) -- the exact-phase accuracy class again, O(n Nf) instead of O(n Nf^2) work.
+    ctx.set_option(L.OPT_PHASE_MODE, L.PHASE_STRUCTURED)
+    try:
+        step_resident()
+        barrier()
+        x_ms = x_gms = 0.0
+        for _ in range(3):
+            ms_, gms_, _gfl = step_resident()
+            x_ms, x_gms = x_ms + ms_, x_gms + gms_
+        barrier()
+        extra["structured_mode"] = {"ms_per_step": allmax(x_ms / 3), "gram_stage_ms_per_step": x_gms / 3,
+                                    "windows_per_s": world * K / (allmax(x_ms / 3) * 1e-3),
+                                    "note": "LPVS_PHASE_STRUCTURED (opt-in, not the headline): Gram stage = sum tables + "
+                                            "k_trig_sums + k_gram_fill + k_gram_rhs; the rest of the step is the batched "
+                                            "Cholesky; exact phase of the ideal grid, tests/test_gpu_structured.py"}
+    except Exception as e:  # never lose the headline line to an extra leg
+        extra["structured_mode"] = {"error": repr(e)[:300]}
+    finally:
+        ctx.set_option(L.OPT_PHASE_MODE, L.PHASE_AUTO)
     parity_ok = True
     if not args.no_extra:
         from lpvspectral_jl_b200 import _dist as D

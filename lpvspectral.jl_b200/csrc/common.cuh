@@ -116,4 +116,13 @@ __device__ __forceinline__ double2 cis_reference(double f, double t) {
     return cis_of_phase(phi);
 }
 
+// One step of the angle-addition chain with the contraction PINNED (one rounded product, one FMA per component), so every
+// tile and every kernel that synthesises a column produces bit-identical values: the Gram matrix and the right-hand side
+// are then those of ONE well-defined matrix A~.  (With compiler-chosen contraction the same column differed in the last
+// bit between the diagonal and off-diagonal instantiations; in a null direction of A that inconsistency is amplified by
+// 1/shift ~ 1e13 -- 1.6e-5 in the Nyquist coefficient of the reference's 1000 x 1001 KAT, profiles/r02_rankdef.md.)
+__device__ __forceinline__ double2 chain_rotate(double2 z, double2 d) {
+    return make_double2(__fma_rn(z.x, d.x, -__dmul_rn(z.y, d.y)), __fma_rn(z.x, d.y, __dmul_rn(z.y, d.x)));
+}
+
 }  // namespace lpvs

@@ -22,7 +22,7 @@ struct DevBuf {
 enum BufSlot {
     BUF_T = 0, BUF_Y, BUF_U, BUF_W, BUF_F, BUF_ANC, BUF_DEL, BUF_G, BUF_B, BUF_LINV, BUF_INFO, BUF_PART, BUF_SUMS,
     BUF_X, BUF_MISC, BUF_YINV, BUF_E, BUF_K, BUF_V, BUF_CENT, BUF_LSQ_R, BUF_LSQ_V, BUF_LSQ_Y, BUF_LSQ_LI, BUF_LSQ_A,
-    BUF_LSQ_BT, BUF_LSQ_G2, BUF_WTAB, BUF_FLAGS, BUF_PSD, BUF_TRSM, BUF_WIN_ITS, BUF_WIN_RES, BUF_COUNT
+    BUF_LSQ_BT, BUF_LSQ_G2, BUF_WTAB, BUF_FLAGS, BUF_PSD, BUF_TRSM, BUF_WIN_ITS, BUF_WIN_RES, BUF_SFREQ, BUF_SANC, BUF_ZSUM, BUF_ZPART, BUF_COUNT
 };
 
 }  // namespace lpvs
@@ -56,6 +56,7 @@ struct lpvs_ctx {
     int call_depth = 0;
     int* d_nonfinite = nullptr;  // set by the upload-time scan of host inputs
     std::vector<double> wtab_host;      // staging of the GRAM_CHAINREF phase table (kept alive across the async upload)
+    std::vector<double> sfreq_host;     // staging of the LPVS_PHASE_STRUCTURED row frequencies
     std::vector<lpvs_admm*> live_admm;  // handles created on this context and not yet freed
 };
 
@@ -102,6 +103,8 @@ struct FourierPlan {
     double f0 = 0.0, df = 0.0, dd = 1.0;
     const double* d_f = nullptr;
     const double2* d_wtab = nullptr;  // GRAM_CHAINREF: (fl(2 pi f), fl(2 pi f) - 2 pi (f_anchor + j df)) per complex column
+    bool structured = false;          // LPVS_PHASE_STRUCTURED: Gram matrices from trigonometric sums (structured.cu); mode = GRAM_CHAIN
+    const double2* d_sfreq = nullptr; // ... double-double frequencies of the sum-table rows
 };
 int make_fourier_plan(lpvs_ctx* c, const double* f, int Nf, FourierPlan* plan);
 inline int pcol(int k) { return (k >> 6) * 128 + (k & 63); }

@@ -39,15 +39,6 @@ struct Pref {
     bool valid;  // the weight is zeroed for invalid samples at the point of USE (no stall on the prefetch)
 };
 
-// One step of the angle-addition chain with the contraction PINNED (one rounded product, one FMA per component), so every
-// tile and every kernel that synthesises a column produces bit-identical values: the Gram matrix and the right-hand side
-// are then those of ONE well-defined matrix A~.  (With compiler-chosen contraction the same column differed in the last
-// bit between the diagonal and off-diagonal instantiations; in a null direction of A that inconsistency is amplified by
-// 1/shift ~ 1e13 -- 1.6e-5 in the Nyquist coefficient of the reference's 1000 x 1001 KAT, profiles/r02_rankdef.md.)
-__device__ __forceinline__ double2 chain_rotate(double2 z, double2 d) {
-    return make_double2(__fma_rn(z.x, d.x, -__dmul_rn(z.y, d.y)), __fma_rn(z.x, d.y, __dmul_rn(z.y, d.x)));
-}
-
 // GRAM_CHAINREF: z = e^{-i theta} with the exact phase theta = 2 pi (f_anchor + j df) t -> e^{-i phi}, phi = fl(w t) the
 // reference's rounded phase.  phi - theta = dw t - (w t - fl(w t)); the product error is exact through one FMA, and the
 // rotation by that angle (<= ~1e-8 rad) is first order: second-order terms are < 1e-16.  Pinned arithmetic (see above).

@@ -75,4 +75,38 @@ void launch_lpv_tables(const double* X, const double* V, long long N, const doub
                        const double* centers, double gamma, int coulomb, int normalize, double2* E, double* Kt,
                        int* nonfinite /* device flag, bit 2 set on a 0/0 normalisation; nullable */, cudaStream_t st);
 
+// ---- LPVS_PHASE_STRUCTURED (structured.cu): Gram matrix of a uniform-grid Fourier basis from its 3 Nf trigonometric sums ----
+struct SumArgs {
+    const double* t;
+    const double* W;  // nullable = 1
+    int w_abs;        // as GramArgs
+    long long start0, hop;
+    int n;
+    long long s_end;
+    const double2* tab;  // rows [0, nbm): block anchors of Z-, [nbm, nbm + nbp): of Z+, then GRP group powers; [row][tbl_ns]
+    const double2* del;  // e^{-i 2 pi df t}
+    long long tbl_base, tbl_ns;
+    int nbm, nbp;        // 64-blocks of Z- (m = 0 .. Nf-1) and Z+ (m = 0 .. 2Nf-2)
+    double2* Z;          // per problem (nbm + nbp) * 64 sums
+    long long strideZ;
+};
+struct FillArgs {
+    const double2* Z;
+    long long strideZ;
+    int nbm;
+    int ncc, nblk, zero_first;
+    double gscale;
+    double* G;  // per problem Np x Np, every lower 128-tile written in full
+    long long strideG;
+};
+constexpr int structured_nbm(int Nf) { return (Nf + FB - 1) / FB; }
+constexpr int structured_nbp(int Nf) { return (2 * Nf - 1 + FB - 1) / FB; }
+void structured_row_freqs(double f0, double df, int nbm, int nbp, double* out /* 2 * (nbm + nbp + GRP) doubles */);
+void launch_sum_tables(const double* t, long long s0, long long ns, const double2* frow_dev, int nrows, double2* tab,
+                       cudaStream_t st);
+int launch_trig_sums(const SumArgs& a, int nproblems, cudaStream_t st);
+void launch_sum_parts(double2* out, const double2* parts, int count, long long stride, int nparts, int accumulate,
+                      cudaStream_t st);
+int launch_gram_fill(const FillArgs& a, int nproblems, cudaStream_t st);
+
 }  // namespace lpvs

@@ -22,7 +22,7 @@ def signal(N, seed, tones=((20.0, 1.0, 0.0), (55.0, 0.5, 1.0)), noise=0.1, T=10.
     return t, y
 
 
-@pytest.mark.parametrize("phase", [1, 2, 3])
+@pytest.mark.parametrize("phase", [1, 2, 3, 4])
 @pytest.mark.parametrize("N,Nf,zero", [(1000, 100, True), (777, 70, False), (300, 129, True)])
 def test_gram_matches_oracle(ctx, phase, N, Nf, zero):
     import lpvspectral_jl_b200 as lp
