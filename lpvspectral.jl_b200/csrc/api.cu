@@ -107,13 +107,13 @@ int make_fourier_plan(lpvs_ctx* c, const double* f, int Nf, FourierPlan* pl) {
     pl->structured = mode == LPVS_PHASE_STRUCTURED;
     if (pl->structured) mode = LPVS_PHASE_CHAIN;  // right-hand sides and operators: the exact-phase chains
     pl->mode = mode == LPVS_PHASE_CHAIN ? GRAM_CHAIN : (mode == LPVS_PHASE_CHAIN_REF ? GRAM_CHAINREF : GRAM_DIRECT);
-    if (pl->structured) {
-        const int nbm = structured_nbm(Nf), nbp = structured_nbp(Nf), nrows = nbm + nbp + GRP;
-        c->sfreq_host.assign((size_t)2 * nrows, 0.0);
-        structured_row_freqs(pl->f0, pl->df, nbm, nbp, c->sfreq_host.data());
-        double* d_sf = ws<double>(c, BUF_SFREQ, (size_t)2 * nrows);
+    if (pl->structured) {  // table-row frequencies of the two-right-hand-side layout (a call with fewer uses a prefix)
+        const StructuredLayout lay = structured_layout(pl->f0, Nf, 2);
+        c->sfreq_host.assign((size_t)2 * lay.nrows, 0.0);
+        structured_row_freqs(pl->f0, pl->df, Nf, 2, c->sfreq_host.data());
+        double* d_sf = ws<double>(c, BUF_SFREQ, (size_t)2 * lay.nrows);
         if (!d_sf) return fail(c, LPVS_E_NOMEM, "out of device memory (sum-table frequencies)");
-        LPVS_CU(c, cudaMemcpyAsync(d_sf, c->sfreq_host.data(), sizeof(double) * 2 * nrows, cudaMemcpyHostToDevice, c->st));
+        LPVS_CU(c, cudaMemcpyAsync(d_sf, c->sfreq_host.data(), sizeof(double) * 2 * lay.nrows, cudaMemcpyHostToDevice, c->st));
         pl->d_sfreq = reinterpret_cast<const double2*>(d_sf);
     }
     double* d_f = ws<double>(c, BUF_F, Nf);
@@ -300,36 +300,43 @@ void fill_basis_args(const FourierPlan& pl, GramArgs& g) {
     g.lpv_nf = 1;
 }
 
-// LPVS_PHASE_STRUCTURED: Z-/Z+ sums of `nprob` problems described by g (samples, weights, problem ranges, step table) into Z
-static int structured_sums(lpvs_ctx* c, const FourierPlan& pl, const GramArgs& g, int nprob, double2* Z) {
-    const int nbm = structured_nbm(pl.Nf), nbp = structured_nbp(pl.Nf), nrows = nbm + nbp + GRP;
-    double2* tab = ws<double2>(c, BUF_SANC, (size_t)nrows * g.tbl_ns);
+// LPVS_PHASE_STRUCTURED: the sums of `nprob` problems described by g (samples, weights, right-hand sides, problem ranges) into Z
+static int structured_sums(lpvs_ctx* c, const FourierPlan& pl, const StructuredLayout& lay, const GramArgs& g, int nprob,
+                           double2* Z) {
+    double2* tab = ws<double2>(c, BUF_SANC, (size_t)lay.nrows * g.tbl_ns);
     if (!tab) return fail(c, LPVS_E_NOMEM, "out of device memory (sum tables)");
-    launch_sum_tables(g.t, g.tbl_base, g.tbl_ns, pl.d_sfreq, nrows, tab, c->st);
+    launch_sum_tables(g.t, g.tbl_base, g.tbl_ns, pl.d_sfreq, lay.nzb, structured_layout(pl.f0, pl.Nf, 2).nzb, tab, c->st);
     SumArgs a{};
     a.t = g.t;
     a.W = g.W;
+    a.y = g.y;
+    a.u = g.u;
     a.w_abs = g.w_abs;
     a.start0 = g.start0;
     a.hop = g.hop;
     a.n = g.n;
     a.s_end = g.s_end;
     a.tab = tab;
-    a.del = g.del;
     a.tbl_base = g.tbl_base;
     a.tbl_ns = g.tbl_ns;
-    a.nbm = nbm;
-    a.nbp = nbp;
+    a.nzg = lay.nzg;
+    a.nby = lay.nby;
+    a.nzb = lay.nzb;
     a.Z = Z;
-    a.strideZ = (long long)(nbm + nbp) * FB;
+    a.strideZ = (long long)lay.nzb * FB;
     c->launches += 1 + launch_trig_sums(a, nprob, c->st);
     return LPVS_OK;
 }
-static void structured_fill(lpvs_ctx* c, const FourierPlan& pl, const double2* Z, double* G, long long strideG, int nprob) {
+// G (and b when B is given) of `nprob` problems from their sums
+static void structured_fill(lpvs_ctx* c, const FourierPlan& pl, const StructuredLayout& lay, const double2* Z, double* G,
+                            long long strideG, double* B, long long strideB, int nrhs, int nprob) {
     FillArgs fa{};
     fa.Z = Z;
-    fa.nbm = structured_nbm(pl.Nf);
-    fa.strideZ = (long long)(fa.nbm + structured_nbp(pl.Nf)) * FB;
+    fa.strideZ = (long long)lay.nzb * FB;
+    fa.zm_off = lay.zm_off;
+    fa.zp_off = lay.zp_off;
+    fa.zy_off[0] = lay.zy_off[0];
+    fa.zy_off[1] = lay.zy_off[1];
     fa.ncc = pl.Nf;
     fa.nblk = pl.nblk;
     fa.zero_first = pl.zero_first;
@@ -337,40 +344,39 @@ static void structured_fill(lpvs_ctx* c, const FourierPlan& pl, const double2* Z
     fa.G = G;
     fa.strideG = strideG;
     c->launches += launch_gram_fill(fa, nprob, c->st);
+    if (B && nrhs > 0) {
+        launch_rhs_from_sums(fa, nrhs, pl.dd, B, strideB, nprob, c->st);
+        c->launches++;
+    }
 }
 
-// gram_single for LPVS_PHASE_STRUCTURED: the sums are additive over sample splits (and over table segments), G is filled once
+// gram_single for LPVS_PHASE_STRUCTURED: the sums are additive over sample splits (and over table segments); G and b are
+// filled once from the totals
 static int gram_single_structured(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const double* d_y,
                                   const double* d_u, const double* d_W, int64_t N, int nrhs, double* d_G, double* d_B) {
-    const long long Np = pl.Np;
-    const int nz = structured_nbm(pl.Nf) + structured_nbp(pl.Nf);
-    const long long nz64 = (long long)nz * FB;
-    const long long per_sample = (long long)(nz + GRP + pl.ngroups + 1) * sizeof(double2);
+    if (!d_B || !d_y) nrhs = 0;
+    if (nrhs > 1 && !d_u) nrhs = 1;
+    const StructuredLayout lay = structured_layout(pl.f0, pl.Nf, nrhs);
+    const long long nz64 = (long long)lay.nzb * FB;
+    const long long per_sample = (long long)lay.nrows * sizeof(double2);
     const long long seg_cap = std::max<long long>(65536, (8LL << 30) / per_sample);
     const int nseg = (int)std::max<long long>(1, (N + seg_cap - 1) / seg_cap);
     const long long seg_len = (N + nseg - 1) / nseg;
-    // enough CTAs (nz per split) to fill the machine a few times over, each split >= 2048 samples
-    const long long want = (8LL * c->sms + nz - 1) / nz, maxs = std::max<long long>(1, seg_len / 2048);
+    // enough CTAs (nzb per split) to fill the machine a few times over, each split >= 2048 samples
+    const long long want = (8LL * c->sms + lay.nzb - 1) / lay.nzb, maxs = std::max<long long>(1, seg_len / 2048);
     const int nsplit = (int)std::min(want, maxs);
     double2* Zacc = ws<double2>(c, BUF_ZSUM, (size_t)nz64);
     double2* Zparts = ws<double2>(c, BUF_ZPART, (size_t)nsplit * nz64);
-    double* Bparts = d_B ? ws<double>(c, BUF_PART, (size_t)nsplit * 2 * Np) : nullptr;
-    if (!Zacc || !Zparts || (d_B && !Bparts)) return fail(c, LPVS_E_NOMEM, "out of device memory (structured Gram)");
+    if (!Zacc || !Zparts) return fail(c, LPVS_E_NOMEM, "out of device memory (structured Gram)");
     gram_timer_begin(c);
     for (int sgi = 0; sgi < nseg; sgi++) {
         const long long s0 = sgi * seg_len, s1 = std::min<long long>(N, s0 + seg_len);
         if (s1 <= s0) break;
         const long long ns = s1 - s0;
-        double2* anc = ws<double2>(c, BUF_ANC, (size_t)pl.ngroups * ns);
-        double2* del = ws<double2>(c, BUF_DEL, (size_t)ns);
-        if (!anc || !del) return fail(c, LPVS_E_NOMEM, "out of device memory (anchor table)");
-        launch_anchor_table(d_t, s0, ns, pl.d_f, pl.nblk, pl.df, anc, del, c->st);
-        c->launches++;
         long long n_split = (ns + nsplit - 1) / nsplit;
         n_split = (n_split + KC - 1) / KC * KC;
         const int nprob = (int)((ns + n_split - 1) / n_split);
         GramArgs g{};
-        fill_basis_args(pl, g);
         g.t = d_t;
         g.y = d_y;
         g.u = d_u;
@@ -380,25 +386,14 @@ static int gram_single_structured(lpvs_ctx* c, const FourierPlan& pl, const doub
         g.hop = n_split;
         g.n = (int)n_split;
         g.s_end = s1;
-        g.nrhs = nrhs;
-        g.anc = anc;
-        g.del = del;
         g.tbl_base = s0;
         g.tbl_ns = ns;
-        int rc = structured_sums(c, pl, g, nprob, Zparts);
+        int rc = structured_sums(c, pl, lay, g, nprob, Zparts);
         if (rc) return rc;
         launch_sum_parts(Zacc, Zparts, (int)nz64, nz64, nprob, sgi > 0, c->st);
         c->launches++;
-        if (d_B && nrhs > 0 && d_y) {
-            LPVS_CU(c, cudaMemsetAsync(Bparts, 0, sizeof(double) * nprob * 2 * Np, c->st));
-            g.B = Bparts;
-            g.strideB = 2 * Np;
-            c->launches += launch_gram_rhs(GRAM_CHAIN, g, nprob, c->st);
-            k_reduce_parts<<<(unsigned)((2 * Np + 255) / 256), 256, 0, c->st>>>(d_B, Bparts, 2 * Np, 2 * Np, nprob, sgi > 0);
-            c->launches++;
-        }
     }
-    structured_fill(c, pl, Zacc, d_G, 0, 1);
+    structured_fill(c, pl, lay, Zacc, d_G, 0, d_B, 0, nrhs, 1);
     gram_timer_end(c, (double)N * nz64 * 8.0, 1);  // executed: one complex rotation + accumulation per (sample, sum)
     LPVS_CU(c, cudaGetLastError());
     return LPVS_OK;
@@ -1012,7 +1007,7 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
         if (!d_G || !d_B) return fail(c, LPVS_E_NOMEM, "out of device memory (window batch of %d)", nw);
         GramArgs g{};
         fill_basis_args(pl, g);
-        if (gram_is_chain(pl.mode)) {
+        auto chain_tables = [&]() -> int {  // anchors + step of this batch's sample range for the chain kernels
             double2* anc = ws<double2>(c, BUF_ANC, (size_t)pl.ngroups * ns);
             double2* del = ws<double2>(c, BUF_DEL, (size_t)ns);
             if (!anc || !del) return fail(c, LPVS_E_NOMEM, "out of device memory (anchor table)");
@@ -1020,7 +1015,10 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
             c->launches++;
             g.anc = anc;
             g.del = del;
-        }
+            return LPVS_OK;
+        };
+        // (the structured mode has its own tables; the chain ones are only built if a window has to be re-done alone)
+        if (gram_is_chain(pl.mode) && !pl.structured && (rc = chain_tables())) return rc;
         g.t = d_t;
         g.y = d_y;
         g.u = nrhs > 1 ? d_u : nullptr;
@@ -1039,14 +1037,13 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
         g.strideB = 2 * Np;
         gram_timer_begin(c);
         if (pl.structured) {
-            // Gram matrices from the windows' trigonometric sums, right-hand sides by the exact-phase chains
-            const long long nz64 = (long long)(structured_nbm(Nf) + structured_nbp(Nf)) * FB;
-            double2* Z = ws<double2>(c, BUF_ZSUM, (size_t)nw * nz64);
+            // Gram matrices and right-hand sides from the windows' trigonometric sums
+            const StructuredLayout lay = structured_layout(pl.f0, Nf, nrhs);
+            double2* Z = ws<double2>(c, BUF_ZSUM, (size_t)nw * lay.nzb * FB);
             if (!Z) return fail(c, LPVS_E_NOMEM, "out of device memory (window sums)");
-            if ((rc = structured_sums(c, pl, g, nw, Z))) return rc;
-            structured_fill(c, pl, Z, d_G, Np * Np, nw);
-            c->launches += launch_gram_rhs(GRAM_CHAIN, g, nw, c->st);
-            gram_timer_end(c, (double)nw * n * nz64 * 8.0, 1);
+            if ((rc = structured_sums(c, pl, lay, g, nw, Z))) return rc;
+            structured_fill(c, pl, lay, Z, d_G, Np * Np, d_B, 2 * Np, nrhs, nw);
+            gram_timer_end(c, (double)nw * n * lay.nzb * FB * 8.0, 1);
         } else {
             c->launches += launch_gram(pl.mode, g, nw, c->st);  // k_gram (+ k_gram_rhs when there are two channels)
             gram_timer_end(c, (double)nw * n * pl.Nreg * (pl.Nreg + 1.0), 1);
@@ -1069,6 +1066,7 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
             if (!d_g1) return fail(c, LPVS_E_NOMEM, "out of device memory (window retry)");
             double* d_b1 = d_g1 + Np * Np;
             double* d_md = d_b1 + 2 * Np;
+            if (pl.structured && !g.anc && (rc = chain_tables())) return rc;
             GramArgs g1 = g;
             g1.start0 = g.start0 + (long long)i * hop;
             g1.G = d_g1;

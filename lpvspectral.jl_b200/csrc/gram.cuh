@@ -75,38 +75,50 @@ void launch_lpv_tables(const double* X, const double* V, long long N, const doub
                        const double* centers, double gamma, int coulomb, int normalize, double2* E, double* Kt,
                        int* nonfinite /* device flag, bit 2 set on a 0/0 normalisation; nullable */, cudaStream_t st);
 
-// ---- LPVS_PHASE_STRUCTURED (structured.cu): Gram matrix of a uniform-grid Fourier basis from its 3 Nf trigonometric sums ----
+// ---- LPVS_PHASE_STRUCTURED (structured.cu): Gram matrix and right-hand sides of a uniform-grid Fourier basis from
+// trigonometric sums.  Per problem the sums live in one array of 64-blocks: [0, nzg) the blocks for G (Z-, Z+; one family when
+// f0 = 0), then nby blocks per right-hand side; the table has one row per block, then GRP group powers, then the step.
+struct StructuredLayout {
+    bool alias;         // f0 == 0: Z- is the head of Z+
+    int zm_off, zp_off; // offsets (in sums) of Z-(0) and Z+(0)
+    int zy_off[2];      // offsets of Zy(0), Zu(0)
+    int nzg, nby, nzb;  // blocks for G, blocks per right-hand side, all blocks
+    int nrows;          // table rows: nzb + GRP + 1
+};
+StructuredLayout structured_layout(double f0, int Nf, int nrhs);
+void structured_row_freqs(double f0, double df, int Nf, int nrhs, double* out /* 2 * nrows doubles: (hi, lo) per row */);
 struct SumArgs {
     const double* t;
     const double* W;  // nullable = 1
+    const double* y;  // right-hand sides (weights W y, W u of the last 2 * nby blocks); nullable with nby = 0
+    const double* u;
     int w_abs;        // as GramArgs
     long long start0, hop;
     int n;
     long long s_end;
-    const double2* tab;  // rows [0, nbm): block anchors of Z-, [nbm, nbm + nbp): of Z+, then GRP group powers; [row][tbl_ns]
-    const double2* del;  // e^{-i 2 pi df t}
+    const double2* tab;  // [row][tbl_ns]
     long long tbl_base, tbl_ns;
-    int nbm, nbp;        // 64-blocks of Z- (m = 0 .. Nf-1) and Z+ (m = 0 .. 2Nf-2)
-    double2* Z;          // per problem (nbm + nbp) * 64 sums
+    int nzg, nby, nzb;
+    double2* Z;          // per problem nzb * 64 sums
     long long strideZ;
 };
 struct FillArgs {
     const double2* Z;
     long long strideZ;
-    int nbm;
+    int zm_off, zp_off, zy_off[2];
     int ncc, nblk, zero_first;
     double gscale;
     double* G;  // per problem Np x Np, every lower 128-tile written in full
     long long strideG;
 };
-constexpr int structured_nbm(int Nf) { return (Nf + FB - 1) / FB; }
-constexpr int structured_nbp(int Nf) { return (2 * Nf - 1 + FB - 1) / FB; }
-void structured_row_freqs(double f0, double df, int nbm, int nbp, double* out /* 2 * (nbm + nbp + GRP) doubles */);
-void launch_sum_tables(const double* t, long long s0, long long ns, const double2* frow_dev, int nrows, double2* tab,
-                       cudaStream_t st);
+// frow_dev holds the rows of the nrhs = 2 layout; the table gets the first nzb block rows + the GRP + 1 trailing rows
+void launch_sum_tables(const double* t, long long s0, long long ns, const double2* frow_dev, int nzb, int nzb_full,
+                       double2* tab, cudaStream_t st);
 int launch_trig_sums(const SumArgs& a, int nproblems, cudaStream_t st);
 void launch_sum_parts(double2* out, const double2* parts, int count, long long stride, int nparts, int accumulate,
                       cudaStream_t st);
 int launch_gram_fill(const FillArgs& a, int nproblems, cudaStream_t st);
+void launch_rhs_from_sums(const FillArgs& a, int nrhs, double bscale, double* B, long long strideB, int nproblems,
+                          cudaStream_t st);
 
 }  // namespace lpvs

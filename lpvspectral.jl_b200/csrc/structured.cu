@@ -13,9 +13,13 @@
 // the reference's fl(fl(2 pi f) t) -- that rounding is not a function of i +- j, which is why this is an opt-in mode and the
 // default stays the DMMA kernel with the reference's phase.
 //
-// k_sum_tables   per-sample table rows e^{-i 2 pi F_r t_s} for the block anchors of Z-, Z+ and the 8 group powers
-// k_trig_sums    one CTA per (64 sums, problem): warp = 8 consecutive m (angle-addition chain), lane = sample of a chunk
-// k_gram_fill    one CTA per (lower 128 x 128 tile, problem): the identities above, internal column layout of gram.cuh
+// The right-hand sides are sums of the same kind, Zy(k) = sum_s W_s y_s e^{-i 2 pi (f0 + k df) t_s}: A'Wy = (Re Zy, Im Zy).  With
+// f0 = 0 (the reference's default grids) Z- is the head of Z+, so a problem costs 2 Nf sums for G and Nf per right-hand side.
+//
+// k_sum_tables     per-sample table rows e^{-i 2 pi F_r t_s}: block anchors of every sum family, the 8 group powers, the step
+// k_trig_sums      one CTA per (64 sums, problem): warp = 8 consecutive m (angle-addition chain), lane = sample of a chunk
+// k_gram_fill      one CTA per (lower 128 x 128 tile, problem): the identities above, internal column layout of gram.cuh
+// k_rhs_from_sums  b in the internal layout
 #include "gram.cuh"
 
 namespace lpvs {
@@ -32,13 +36,14 @@ __device__ __forceinline__ double2 cis_turns_exact_dd(double hi, double lo, doub
     return make_double2(c, -s);
 }
 
+// table row r < nzb: block anchor r; rows nzb .. nzb + GRP: group powers and the step, which sit behind the block rows of the
+// FULL layout (two right-hand sides) in frow
 __global__ void k_sum_tables(const double* __restrict__ t, long long s0, long long ns, const double2* __restrict__ frow,
-                             int nrows, double2* __restrict__ tab) {
+                             int nzb, int nzb_full, double2* __restrict__ tab) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= ns) return;
     const int r = blockIdx.y;
-    if (r >= nrows) return;
-    const double2 F = frow[r];
+    const double2 F = frow[r < nzb ? r : r - nzb + nzb_full];
     tab[(long long)r * ns + s] = cis_turns_exact_dd(F.x, F.y, t[s0 + s]);
 }
 
@@ -52,7 +57,8 @@ __global__ void __launch_bounds__(NTHREADS) k_trig_sums(const __grid_constant__ 
     const int zb = blockIdx.x, prob = blockIdx.y;
     const long long s_begin = a.start0 + (long long)prob * a.hop;
     const int nchunks = (a.n + KC - 1) / KC;
-    const int nzb = a.nbm + a.nbp;
+    // blocks [0, nzg) are sums for G (weight W), then nby blocks per right-hand side (weight W y, W u)
+    const double* ysrc = zb < a.nzg ? nullptr : (zb < a.nzg + a.nby ? a.y : a.u);
     auto load = [&](int c) {
         Pre p;
         const int idx = c * KC + lane;
@@ -61,10 +67,11 @@ __global__ void __launch_bounds__(NTHREADS) k_trig_sums(const __grid_constant__ 
         if (!valid) s = min(s_begin + (long long)a.n, a.s_end) - 1;
         const long long si = s - a.tbl_base;
         p.a = a.tab[(long long)zb * a.tbl_ns + si];
-        p.pw = a.tab[(long long)(nzb + w) * a.tbl_ns + si];
-        p.d = a.del[si];
+        p.pw = a.tab[(long long)(a.nzb + w) * a.tbl_ns + si];
+        p.d = a.tab[(long long)(a.nzb + GRP) * a.tbl_ns + si];
         double wt = 1.0;
         if (a.W) wt = a.W[a.w_abs ? s : (s - s_begin)];
+        if (ysrc) wt *= ysrc[s];
         p.wt = valid ? wt : 0.0;
         return p;
     };
@@ -116,8 +123,8 @@ __global__ void __launch_bounds__(NTHREADS) k_gram_fill(const __grid_constant__ 
     int I, J;
     tile_ij(blockIdx.x, I, J);
     const int prob = blockIdx.y;
-    const double2* Zm = a.Z + (long long)prob * a.strideZ;
-    const double2* Zp = Zm + (long long)a.nbm * FB;
+    const double2* Zm = a.Z + (long long)prob * a.strideZ + a.zm_off;
+    const double2* Zp = a.Z + (long long)prob * a.strideZ + a.zp_off;
     const int Np = a.nblk * TB;
     double* Gp = a.G + (long long)prob * a.strideG;
     const double h = 0.5 * a.gscale;
@@ -142,12 +149,42 @@ __global__ void __launch_bounds__(NTHREADS) k_gram_fill(const __grid_constant__ 
     }
 }
 
+// b = A' diag(W) [y u] from the Zy / Zu sums: internal layout, dummies zero
+__global__ void k_rhs_from_sums(const __grid_constant__ FillArgs a, int nrhs, double bscale, double* __restrict__ B,
+                                long long strideB) {
+    const int Np = a.nblk * TB;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Np) return;
+    const int prob = blockIdx.y;
+    const int part = (p >> 6) & 1, k = (p >> 7) * FB + (p & (FB - 1));
+    const bool dummy = k >= a.ncc || (a.zero_first && part == 1 && k == 0);
+    for (int r = 0; r < nrhs; r++) {
+        double v = 0.0;
+        if (!dummy) {
+            const double2 z = a.Z[(long long)prob * a.strideZ + a.zy_off[r] + k];
+            v = bscale * (part == 0 ? z.x : z.y);
+        }
+        B[(long long)prob * strideB + (long long)r * Np + p] = v;
+    }
+}
+
 }  // namespace
 
-void launch_sum_tables(const double* t, long long s0, long long ns, const double2* frow_dev, int nrows, double2* tab,
-                       cudaStream_t st) {
-    dim3 grid((unsigned)((ns + 255) / 256), nrows);
-    k_sum_tables<<<grid, 256, 0, st>>>(t, s0, ns, frow_dev, nrows, tab);
+void launch_rhs_from_sums(const FillArgs& a, int nrhs, double bscale, double* B, long long strideB, int nproblems,
+                          cudaStream_t st) {
+    const int Np = a.nblk * TB;
+    for (int p0 = 0; p0 < nproblems; p0 += 32768) {
+        const int np = nproblems - p0 < 32768 ? nproblems - p0 : 32768;
+        FillArgs b = a;
+        b.Z = a.Z + (long long)p0 * a.strideZ;
+        k_rhs_from_sums<<<dim3((Np + 255) / 256, np), 256, 0, st>>>(b, nrhs, bscale, B + (long long)p0 * strideB, strideB);
+    }
+}
+
+void launch_sum_tables(const double* t, long long s0, long long ns, const double2* frow_dev, int nzb, int nzb_full,
+                       double2* tab, cudaStream_t st) {
+    dim3 grid((unsigned)((ns + 255) / 256), nzb + GRP + 1);
+    k_sum_tables<<<grid, 256, 0, st>>>(t, s0, ns, frow_dev, nzb, nzb_full, tab);
 }
 
 int launch_trig_sums(const SumArgs& a, int nproblems, cudaStream_t st) {
@@ -157,7 +194,7 @@ int launch_trig_sums(const SumArgs& a, int nproblems, cudaStream_t st) {
         SumArgs b = a;
         b.start0 = a.start0 + (long long)p0 * a.hop;
         b.Z = a.Z + (long long)p0 * a.strideZ;
-        k_trig_sums<<<dim3(a.nbm + a.nbp, np), NTHREADS, 0, st>>>(b);
+        k_trig_sums<<<dim3(a.nzb, np), NTHREADS, 0, st>>>(b);
         launched++;
     }
     return launched;
@@ -182,9 +219,25 @@ int launch_gram_fill(const FillArgs& a, int nproblems, cudaStream_t st) {
     return launched;
 }
 
-// Frequencies of the table rows as double-double (hi, lo): [0, nbm) -> (64 b) df; [nbm, nbm + nbp) -> 2 f0 + (64 b) df;
-// then GRP rows (8 g) df.  Integer x double products and the sum with 2 f0 are carried exactly.
-void structured_row_freqs(double f0, double df, int nbm, int nbp, double* out /* 2 * (nbm + nbp + GRP) */) {
+// Layout of the sums of one problem for a grid f0 + k df with nrhs right-hand sides, and the double-double (hi, lo) frequencies
+// of the table rows: one row per 64-sum block (first frequency of the block), then GRP rows (8 g) df, then the step df.
+// Integer x double products and the sums with f0 / 2 f0 are carried exactly.
+StructuredLayout structured_layout(double f0, int Nf, int nrhs) {
+    StructuredLayout L{};
+    const int nbm = (Nf + FB - 1) / FB, nbp = (2 * Nf - 1 + FB - 1) / FB;
+    L.alias = f0 == 0.0;  // Z-(m) = Z+(m): one family serves both
+    L.zm_off = 0;
+    L.zp_off = L.alias ? 0 : nbm * FB;
+    L.nzg = L.alias ? nbp : nbm + nbp;
+    L.nby = nrhs > 0 ? nbm : 0;
+    L.zy_off[0] = L.nzg * FB;
+    L.zy_off[1] = (L.nzg + L.nby) * FB;
+    L.nzb = L.nzg + (nrhs > 0 ? nrhs : 0) * L.nby;
+    L.nrows = L.nzb + GRP + 1;
+    return L;
+}
+
+void structured_row_freqs(double f0, double df, int Nf, int nrhs, double* out /* 2 * nrows */) {
     auto two_prod = [](double a, double b, double& lo) {
         const double p = a * b;
         lo = fma(a, b, -p);
@@ -195,15 +248,23 @@ void structured_row_freqs(double f0, double df, int nbm, int nbp, double* out /*
         lo = (a - (s - bb)) + (b - bb);
         return s;
     };
+    const StructuredLayout L = structured_layout(f0, Nf, nrhs);
+    const int nbm = (Nf + FB - 1) / FB, nbp = (2 * Nf - 1 + FB - 1) / FB;
     int r = 0;
-    for (int b = 0; b < nbm; b++, r++) out[2 * r] = two_prod((double)(FB * b), df, out[2 * r + 1]);
-    for (int b = 0; b < nbp; b++, r++) {
-        double pl, sl;
-        const double ph = two_prod((double)(FB * b), df, pl);
-        out[2 * r] = two_sum(2.0 * f0, ph, sl);
-        out[2 * r + 1] = sl + pl;
-    }
+    auto family = [&](double base, int nblocks) {
+        for (int b = 0; b < nblocks; b++, r++) {
+            double pl, sl;
+            const double ph = two_prod((double)(FB * b), df, pl);
+            out[2 * r] = two_sum(base, ph, sl);
+            out[2 * r + 1] = sl + pl;
+        }
+    };
+    if (!L.alias) family(0.0, nbm);
+    family(2.0 * f0, nbp);
+    for (int q = 0; q < (nrhs > 0 ? nrhs : 0); q++) family(f0, nbm);
     for (int g = 0; g < GRP; g++, r++) out[2 * r] = two_prod((double)(GRP * g), df, out[2 * r + 1]);
+    out[2 * r] = df;
+    out[2 * r + 1] = 0.0;
 }
 
 }  // namespace lpvs

@@ -10,3 +10,4 @@ import json
 d=json.loads(open("gpurun_out/bench_structured.json").read().strip().splitlines()[-1])
 print("headline ms/step", d["ms_per_step"], "structured", json.dumps(d["extra"].get("structured_mode")))
 P
+bash tools/structured_profile.sh
