@@ -818,7 +818,7 @@ def main():
         extra["structured_mode"] = {"ms_per_step": allmax(x_ms / 3), "gram_stage_ms_per_step": x_gms / 3,
                                     "windows_per_s": world * K / (allmax(x_ms / 3) * 1e-3),
                                     "note": "LPVS_PHASE_STRUCTURED (opt-in, not the headline): Gram stage = sum tables + "
-                                            "k_trig_sums + k_gram_fill + k_gram_rhs; the rest of the step is the batched "
+                                            "k_trig_sums + k_gram_fill + k_rhs_from_sums; the rest of the step is the batched "
                                             "Cholesky; exact phase of the ideal grid, tests/test_gpu_structured.py"}
     except Exception as e:  # never lose the headline line to an extra leg
         extra["structured_mode"] = {"error": repr(e)[:300]}
