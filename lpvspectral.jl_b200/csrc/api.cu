@@ -1201,7 +1201,7 @@ int lpvs_ls_window_sparse_sums(lpvs_ctx* c, int kind, const double* y, const dou
         }
         GramArgs g{};
         fill_basis_args(pl, g);
-        if (gram_is_chain(pl.mode)) {
+        if (gram_is_chain(pl.mode) && !pl.structured) {
             double2* anc = ws<double2>(c, BUF_ANC, (size_t)pl.ngroups * ns);
             double2* del = ws<double2>(c, BUF_DEL, (size_t)ns);
             if (!anc || !del) {
@@ -1230,8 +1230,19 @@ int lpvs_ls_window_sparse_sums(lpvs_ctx* c, int kind, const double* y, const dou
         g.B = d_B;
         g.strideB = 2 * Np;
         gram_timer_begin(c);
-        c->launches += launch_gram(pl.mode, g, nw, c->st);
-        gram_timer_end(c, (double)nw * n * pl.Nreg * (pl.Nreg + 1.0), 1);
+        if (pl.structured) {  // Gram matrices and right-hand sides from the windows' trigonometric sums (structured.cu)
+            const StructuredLayout lay = structured_layout(pl.f0, Nf, nrhs);
+            double2* Z = ws<double2>(c, BUF_ZSUM, (size_t)nw * lay.nzb * FB);
+            if (!Z || (rc = structured_sums(c, pl, lay, g, nw, Z))) {
+                cleanup();
+                return Z ? rc : fail(c, LPVS_E_NOMEM, "out of device memory (window sums)");
+            }
+            structured_fill(c, pl, lay, Z, d_G, Np * Np, d_B, 2 * Np, nrhs, nw);
+            gram_timer_end(c, (double)nw * n * lay.nzb * FB * 8.0, 1);
+        } else {
+            c->launches += launch_gram(pl.mode, g, nw, c->st);
+            gram_timer_end(c, (double)nw * n * pl.Nreg * (pl.Nreg + 1.0), 1);
+        }
         // M = (A'WA + I/mu)^-1 per window
         CholArgs ca{};
         ca.G = d_G;

@@ -79,6 +79,13 @@ def test_estimators_through_the_structured_gram(sctx):
     assert rel(Cxy, Cr) <= 1e-9
     Cyy, _ = lp.ls_cohere(y, y, t, fw, nw=12, ctx=sctx)
     assert np.all(Cyy == 1)
+    # windowed estimator with estimator = ls_sparse_spectral (batched ADMM on the windows' Gram matrices)
+    kw = dict(tol=1e-9, iters=1500, mu=0.05)
+    est = lambda yi, ti, fr, W, **k: o.ls_sparse_spectral(yi, ti, fr, W, mode="gram", printerval=10 ** 9, **k)  # noqa: E731
+    Cs, _ = lp.ls_cohere(y, u, t, fw, nw=12, estimator=lp.ls_sparse_spectral, proxg=lp.NormL1(0.05), ctx=sctx, **kw)
+    Csr, _ = o.ls_cohere(y, u, t, fw, nw=12, estimator=est, proxg=o.NormL1(0.05), **kw)
+    ok = np.isfinite(Csr)
+    assert np.array_equal(ok, np.isfinite(Cs)) and rel(Cs[ok], Csr[ok]) <= 1e-8
     fs = np.arange(1, 129) * 0.5
     z, _ = lp.ls_sparse_spectral(y[:1024], t[:1024], fs, lam=0.2, iters=400, tol=1e-9, ctx=sctx)
     zr, _ = o.ls_sparse_spectral(y[:1024], t[:1024], fs, lam=0.2, iters=400, tol=1e-9, printerval=10 ** 9)
