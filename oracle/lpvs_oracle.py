@@ -168,6 +168,51 @@ def get_fourier_regressor(t: np.ndarray, f: np.ndarray) -> Tuple[np.ndarray, Opt
     return np.concatenate([C, S], axis=1), zerofreq
 
 
+def gram_from_trig_sums(t: np.ndarray, f: np.ndarray, W: Optional[np.ndarray] = None,
+                        y: Optional[np.ndarray] = None) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+    """A'WA and A'Wy of get_fourier_regressor on a UNIFORM grid f_k = f0 + k df from the 3 Nf trigonometric sums
+    Z-(m) = sum_s W_s e^{-i 2 pi m df t_s}, Z+(m) = sum_s W_s e^{-i 2 pi (2 f0 + m df) t_s} and Zy(k) = sum_s W_s y_s e^{-i a_k(s)}
+    (product-to-sum identities: the matrix is Toeplitz + Hankel in the frequency index).  CPU restatement of the opt-in
+    LPVS_PHASE_STRUCTURED mode of the library (csrc/structured.cu) -- not a reference algorithm: src/lsfft.jl:77 forms the
+    product A'*Wd*A.  Phases are those of the ideal grid f0 + k df (long double), not the reference's fl(fl(2 pi f) t)."""
+    t = np.asarray(t, dtype=np.float64)
+    f = np.asarray(f, dtype=np.float64)
+    zerofreq = check_freq(f)
+    N, Nf = len(t), len(f)
+    Wv = np.ones(N) if W is None else np.asarray(W, dtype=np.float64)
+    LD = np.longdouble
+    f0 = LD(f[0])
+    df = LD((f[-1] - f[0]) / (Nf - 1)) if Nf > 1 else LD(0.0)
+    tl = t.astype(LD)
+
+    def zsum(freqs, weights):  # sum_s w_s (cos, sin)(2 pi F t_s), the phase reduced in turns in long double
+        turns = np.outer(freqs, tl)
+        r = (turns - np.rint(turns)).astype(np.float64)
+        return np.cos(2.0 * np.pi * r) @ weights, np.sin(2.0 * np.pi * r) @ weights
+
+    m_minus = np.arange(Nf).astype(LD)
+    m_plus = np.arange(2 * Nf - 1).astype(LD)
+    Cm, Sm = zsum(m_minus * df, Wv)
+    Cp, Sp = zsum(2 * f0 + m_plus * df, Wv)
+    i = np.arange(Nf)[:, None]
+    j = np.arange(Nf)[None, :]
+    d, sgn = np.abs(i - j), np.sign(i - j)
+    cc = 0.5 * (Cm[d] + Cp[i + j])
+    ss = 0.5 * (Cm[d] - Cp[i + j])
+    sc = -0.5 * (Sp[i + j] + sgn * Sm[d])  # rows -sin_i, columns cos_j
+    cs = -0.5 * (Sp[i + j] - sgn * Sm[d])  # rows cos_i, columns -sin_j
+    G = np.block([[cc, cs], [sc, ss]]) / (2 * Nf)
+    b = None
+    if y is not None:
+        Cy, Sy = zsum(f0 + m_minus * df, Wv * np.asarray(y, dtype=np.float64))
+        b = np.concatenate([Cy, -Sy]) / math.sqrt(2 * Nf)
+    if zerofreq is not None:  # the -sin column of the zero frequency does not exist
+        keep = np.r_[0:Nf, Nf + 1:2 * Nf]
+        G = G[np.ix_(keep, keep)]
+        b = None if b is None else b[keep]
+    return G, b
+
+
 def fourier2complex(x: np.ndarray, zerofreq: Optional[int]) -> np.ndarray:
     """src/utilities.jl:62-73."""
     x = np.asarray(x)

@@ -277,3 +277,20 @@ def test_literal_and_gram_modes_agree_over_random_shapes():
         assert np.all(one == 1.0)
 
     run()
+
+
+@pytest.mark.parametrize("N,Nf,f0,df", [(700, 33, 0.0, 0.31), (512, 20, 0.7, 0.45), (300, 1, 0.0, 1.0), (900, 65, 2.0, 0.05)])
+def test_gram_from_trig_sums_is_the_product_form(N, Nf, f0, df):
+    """The Toeplitz + Hankel identities behind the library's opt-in LPVS_PHASE_STRUCTURED mode (csrc/structured.cu), restated in
+    the oracle: A'WA and A'Wy from 3 Nf trigonometric sums equal the products formed from get_fourier_regressor."""
+    rng = np.random.default_rng(N + Nf)
+    t = np.sort(10 * rng.random(N))
+    y = rng.standard_normal(N)
+    f = f0 + df * np.arange(Nf)
+    A, _ = o.get_fourier_regressor(t, f)
+    for W in (None, 0.5 + rng.random(N)):
+        Aw = A if W is None else A * W[:, None]
+        G, b = o.gram_from_trig_sums(t, f, W, y)
+        assert G.shape == (A.shape[1], A.shape[1])
+        assert np.abs(G - Aw.T @ A).max() <= 1e-13 * np.abs(Aw.T @ A).max()
+        assert np.abs(b - Aw.T @ y).max() <= 1e-13 * np.abs(Aw.T @ y).max()
