@@ -47,10 +47,15 @@ enum lpvs_phase_mode {
     LPVS_PHASE_DIRECT = 2,   /* per-element sincos of fl(fl(2*pi*f)*t), the reference's rounding (src/lsfft.jl:34,41) */
     LPVS_PHASE_CHAIN_REF = 3, /* the chains of mode 1, each element turned by fl(fl(2*pi*f)*t) - 2*pi*f*t (5 FP64 ops): the
                                  reference's rounding at chain speed */
-    LPVS_PHASE_STRUCTURED = 4 /* uniform grids, opt-in: the Gram matrix from its 3 Nf trigonometric sums (Toeplitz + Hankel in
+    LPVS_PHASE_STRUCTURED = 4, /* uniform grids, opt-in: the Gram matrix from its 3 Nf trigonometric sums (Toeplitz + Hankel in
                                  the frequency index, O(n Nf) instead of O(n Nf^2) work) with the exact phase of the ideal grid
                                  f0 + k df -- the accuracy class of mode 1, not the reference's rounding; everything that is
                                  not a Gram matrix (right-hand sides, operators) runs as in mode 1 */
+    LPVS_PHASE_STRUCTURED_REF = 5 /* mode 4 plus the first-order correction of G and b for the reference's phase rounding
+                                 eps = fl(fl(2*pi*f)*t) - 2*pi*(f0 + k df)*t: G += D'B + B'D, b += D'y by a half-precision
+                                 tensor-core GEMM whose operands are synthesised in registers, eps taken exactly in FP64
+                                 (csrc/corr.cu) -- the reference's rounding (the class of mode 3) at a third of its cost;
+                                 opt-in; everything that is not a Gram matrix runs as in mode 3 */
 };
 enum lpvs_option {
     LPVS_OPT_PHASE_MODE = 0,   /* lpvs_phase_mode */

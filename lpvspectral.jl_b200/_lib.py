@@ -16,7 +16,7 @@ OK = 0
 E_BAD_ARG, E_NOT_SPD, E_NONFINITE, E_CUDA, E_NCCL, E_UNSUPPORTED, E_NOMEM = -1, -2, -3, -4, -5, -6, -7
 WIN_PSD, WIN_CSD, WIN_COHERE = 0, 1, 2
 PROX_L1, PROX_L0, PROX_BALL_L0, PROX_GROUP_L2 = 0, 1, 2, 3
-PHASE_AUTO, PHASE_CHAIN, PHASE_DIRECT, PHASE_CHAIN_REF, PHASE_STRUCTURED = 0, 1, 2, 3, 4
+PHASE_AUTO, PHASE_CHAIN, PHASE_DIRECT, PHASE_CHAIN_REF, PHASE_STRUCTURED, PHASE_STRUCTURED_REF = 0, 1, 2, 3, 4, 5
 OPT_PHASE_MODE, OPT_WINDOW_BATCH, OPT_JITTER, OPT_ADMM_CHECK_EVERY, OPT_ADMM_SYMV, OPT_TRSV_FLOW, OPT_SHARD_EXCHANGE, OPT_ADMM_M32 = 0, 1, 2, 3, 4, 5, 6, 7
 INFO_JITTER = 1
 INFO_QR = 2

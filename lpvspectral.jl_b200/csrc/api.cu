@@ -101,11 +101,14 @@ int make_fourier_plan(lpvs_ctx* c, const double* f, int Nf, FourierPlan* pl) {
     bool uniform = dev <= 8.0 * 2.220446049250313e-16 * fmaxabs;
     int mode = c->phase_mode;
     if (mode == LPVS_PHASE_AUTO) mode = uniform ? LPVS_PHASE_CHAIN_REF : LPVS_PHASE_DIRECT;
-    if ((mode == LPVS_PHASE_CHAIN || mode == LPVS_PHASE_CHAIN_REF || mode == LPVS_PHASE_STRUCTURED) && !uniform)
+    if ((mode == LPVS_PHASE_CHAIN || mode == LPVS_PHASE_CHAIN_REF || mode == LPVS_PHASE_STRUCTURED ||
+         mode == LPVS_PHASE_STRUCTURED_REF) && !uniform)
         return fail(c, LPVS_E_BAD_ARG,
-                    "LPVS_PHASE_CHAIN / LPVS_PHASE_CHAIN_REF / LPVS_PHASE_STRUCTURED require a uniformly spaced frequency grid");
-    pl->structured = mode == LPVS_PHASE_STRUCTURED;
-    if (pl->structured) mode = LPVS_PHASE_CHAIN;  // right-hand sides and operators: the exact-phase chains
+                    "LPVS_PHASE_CHAIN / LPVS_PHASE_CHAIN_REF / LPVS_PHASE_STRUCTURED[_REF] require a uniformly spaced frequency grid");
+    pl->structured_ref = mode == LPVS_PHASE_STRUCTURED_REF;
+    pl->structured = mode == LPVS_PHASE_STRUCTURED || pl->structured_ref;
+    // right-hand sides and operators (and windows re-done alone): the chains, with the phase class of the Gram matrices
+    if (pl->structured) mode = pl->structured_ref ? LPVS_PHASE_CHAIN_REF : LPVS_PHASE_CHAIN;
     pl->mode = mode == LPVS_PHASE_CHAIN ? GRAM_CHAIN : (mode == LPVS_PHASE_CHAIN_REF ? GRAM_CHAINREF : GRAM_DIRECT);
     if (pl->structured) {  // table-row frequencies of the two-right-hand-side layout (a call with fewer uses a prefix)
         const StructuredLayout lay = structured_layout(pl->f0, Nf, 2);
@@ -115,6 +118,15 @@ int make_fourier_plan(lpvs_ctx* c, const double* f, int Nf, FourierPlan* pl) {
         if (!d_sf) return fail(c, LPVS_E_NOMEM, "out of device memory (sum-table frequencies)");
         LPVS_CU(c, cudaMemcpyAsync(d_sf, c->sfreq_host.data(), sizeof(double) * 2 * lay.nrows, cudaMemcpyHostToDevice, c->st));
         pl->d_sfreq = reinterpret_cast<const double2*>(d_sf);
+    }
+    if (pl->structured_ref) {  // (w, dw) against the ideal grid f0 + k df the sums realise
+        const int ncol = pl->nblk * FB;
+        c->cwtab_host.assign((size_t)2 * ncol, 0.0);
+        structured_ref_wtab(pl->f0, pl->df, f, Nf, ncol, c->cwtab_host.data(), &pl->cw_max, &pl->cdw_max);
+        double* d_cw = ws<double>(c, BUF_CWTAB, (size_t)2 * ncol);
+        if (!d_cw) return fail(c, LPVS_E_NOMEM, "out of device memory (correction phase table)");
+        LPVS_CU(c, cudaMemcpyAsync(d_cw, c->cwtab_host.data(), sizeof(double) * 2 * ncol, cudaMemcpyHostToDevice, c->st));
+        pl->d_cwtab = reinterpret_cast<const double2*>(d_cw);
     }
     double* d_f = ws<double>(c, BUF_F, Nf);
     if (!d_f) return fail(c, LPVS_E_NOMEM, "out of device memory (f)");
@@ -350,6 +362,37 @@ static void structured_fill(lpvs_ctx* c, const FourierPlan& pl, const Structured
     }
 }
 
+// LPVS_PHASE_STRUCTURED_REF: G += D'B + B'D, b += D'[y u] for the `nprob` problems described by g (corr.cu); G / B as filled
+// by structured_fill
+static void structured_correct(lpvs_ctx* c, const FourierPlan& pl, const GramArgs& g, double* G, long long strideG,
+                               double* B, long long strideB, int nrhs, int nprob) {
+    CorrArgs a{};
+    a.t = g.t;
+    a.W = g.W;
+    a.y = g.y;
+    a.u = g.u;
+    a.w_abs = g.w_abs;
+    a.start0 = g.start0;
+    a.hop = g.hop;
+    a.n = g.n;
+    a.s_end = g.s_end;
+    a.ncc = pl.Nf;
+    a.nblk = pl.nblk;
+    a.nrhs = nrhs;
+    a.wtab = pl.d_cwtab;
+    a.wmax = pl.cw_max;
+    a.dwmax = pl.cdw_max;
+    a.df = pl.df;
+    a.gscale = pl.dd * pl.dd;
+    a.bscale = pl.dd;
+    a.G = G;
+    a.strideG = strideG;
+    a.B = B;
+    a.strideB = strideB;
+    c->launches += launch_gram_corr(a, nprob, c->st);
+    if (B && nrhs > 0 && g.y) c->launches += launch_rhs_corr(a, nprob, c->st);
+}
+
 // gram_single for LPVS_PHASE_STRUCTURED: the sums are additive over sample splits (and over table segments); G and b are
 // filled once from the totals
 static int gram_single_structured(lpvs_ctx* c, const FourierPlan& pl, const double* d_t, const double* d_y,
@@ -394,6 +437,36 @@ static int gram_single_structured(lpvs_ctx* c, const FourierPlan& pl, const doub
         c->launches++;
     }
     structured_fill(c, pl, lay, Zacc, d_G, 0, d_B, 0, nrhs, 1);
+    if (pl.structured_ref) {
+        // sample splits into zeroed partial buffers (each CTA read-modify-writes its own tile), added in split order
+        const long long Np = pl.Np, part_stride = Np * Np + 2 * Np;
+        const int ntiles = pl.nblk * (pl.nblk + 1) / 2;
+        const long long wantc = (4LL * c->sms + ntiles - 1) / ntiles, maxc = std::max<long long>(1, N / 2048);
+        const int ncs = (int)std::min(wantc, maxc);
+        long long n_split = (N + ncs - 1) / ncs;
+        n_split = (n_split + KC - 1) / KC * KC;
+        const int nprob = (int)((N + n_split - 1) / n_split);
+        GramArgs g{};
+        g.t = d_t;
+        g.y = nrhs > 0 ? d_y : nullptr;
+        g.u = nrhs > 1 ? d_u : nullptr;
+        g.W = d_W;
+        g.w_abs = 1;
+        g.start0 = 0;
+        g.hop = n_split;
+        g.n = (int)n_split;
+        g.s_end = N;
+        if (nprob == 1) {
+            structured_correct(c, pl, g, d_G, 0, d_B, 0, nrhs, 1);
+        } else {
+            double* parts = ws<double>(c, BUF_CPART, (size_t)nprob * part_stride);
+            if (!parts) return fail(c, LPVS_E_NOMEM, "out of device memory (correction partials)");
+            LPVS_CU(c, cudaMemsetAsync(parts, 0, sizeof(double) * nprob * part_stride, c->st));
+            structured_correct(c, pl, g, parts, part_stride, parts + Np * Np, part_stride, nrhs, nprob);
+            reduce_parts(c, d_G, parts, Np * Np, part_stride, nprob, 1);
+            if (d_B && nrhs > 0) reduce_parts(c, d_B, parts + Np * Np, 2 * Np, part_stride, nprob, 1);
+        }
+    }
     gram_timer_end(c, (double)N * nz64 * 8.0, 1);  // executed: one complex rotation + accumulation per (sample, sum)
     LPVS_CU(c, cudaGetLastError());
     return LPVS_OK;
@@ -1043,6 +1116,7 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
             if (!Z) return fail(c, LPVS_E_NOMEM, "out of device memory (window sums)");
             if ((rc = structured_sums(c, pl, lay, g, nw, Z))) return rc;
             structured_fill(c, pl, lay, Z, d_G, Np * Np, d_B, 2 * Np, nrhs, nw);
+            if (pl.structured_ref) structured_correct(c, pl, g, d_G, Np * Np, d_B, 2 * Np, nrhs, nw);
             gram_timer_end(c, (double)nw * n * lay.nzb * FB * 8.0, 1);
         } else {
             c->launches += launch_gram(pl.mode, g, nw, c->st);  // k_gram (+ k_gram_rhs when there are two channels)
@@ -1238,6 +1312,7 @@ int lpvs_ls_window_sparse_sums(lpvs_ctx* c, int kind, const double* y, const dou
                 return Z ? rc : fail(c, LPVS_E_NOMEM, "out of device memory (window sums)");
             }
             structured_fill(c, pl, lay, Z, d_G, Np * Np, d_B, 2 * Np, nrhs, nw);
+            if (pl.structured_ref) structured_correct(c, pl, g, d_G, Np * Np, d_B, 2 * Np, nrhs, nw);
             gram_timer_end(c, (double)nw * n * lay.nzb * FB * 8.0, 1);
         } else {
             c->launches += launch_gram(pl.mode, g, nw, c->st);

@@ -22,7 +22,7 @@ struct DevBuf {
 enum BufSlot {
     BUF_T = 0, BUF_Y, BUF_U, BUF_W, BUF_F, BUF_ANC, BUF_DEL, BUF_G, BUF_B, BUF_LINV, BUF_INFO, BUF_PART, BUF_SUMS,
     BUF_X, BUF_MISC, BUF_YINV, BUF_E, BUF_K, BUF_V, BUF_CENT, BUF_LSQ_R, BUF_LSQ_V, BUF_LSQ_Y, BUF_LSQ_LI, BUF_LSQ_A,
-    BUF_LSQ_BT, BUF_LSQ_G2, BUF_WTAB, BUF_FLAGS, BUF_PSD, BUF_TRSM, BUF_WIN_ITS, BUF_WIN_RES, BUF_SFREQ, BUF_SANC, BUF_ZSUM, BUF_ZPART, BUF_COUNT
+    BUF_LSQ_BT, BUF_LSQ_G2, BUF_WTAB, BUF_FLAGS, BUF_PSD, BUF_TRSM, BUF_WIN_ITS, BUF_WIN_RES, BUF_SFREQ, BUF_SANC, BUF_ZSUM, BUF_ZPART, BUF_CWTAB, BUF_CPART, BUF_COUNT
 };
 
 }  // namespace lpvs
@@ -57,6 +57,7 @@ struct lpvs_ctx {
     int* d_nonfinite = nullptr;  // set by the upload-time scan of host inputs
     std::vector<double> wtab_host;      // staging of the GRAM_CHAINREF phase table (kept alive across the async upload)
     std::vector<double> sfreq_host;     // staging of the LPVS_PHASE_STRUCTURED row frequencies
+    std::vector<double> cwtab_host;     // staging of the LPVS_PHASE_STRUCTURED_REF (w, dw) table
     std::vector<lpvs_admm*> live_admm;  // handles created on this context and not yet freed
 };
 
@@ -105,6 +106,9 @@ struct FourierPlan {
     const double2* d_wtab = nullptr;  // GRAM_CHAINREF: (fl(2 pi f), fl(2 pi f) - 2 pi (f_anchor + j df)) per complex column
     bool structured = false;          // LPVS_PHASE_STRUCTURED: Gram matrices from trigonometric sums (structured.cu); mode = GRAM_CHAIN
     const double2* d_sfreq = nullptr; // ... double-double frequencies of the sum-table rows
+    bool structured_ref = false;      // LPVS_PHASE_STRUCTURED_REF: + first-order correction for the reference's phase (corr.cu); mode = GRAM_CHAINREF
+    const double2* d_cwtab = nullptr; // ... (fl(2 pi f_k), fl(2 pi f_k) - 2 pi (f0 + k df)) per complex column
+    double cw_max = 0.0, cdw_max = 0.0;
 };
 int make_fourier_plan(lpvs_ctx* c, const double* f, int Nf, FourierPlan* plan);
 inline int pcol(int k) { return (k >> 6) * 128 + (k & 63); }

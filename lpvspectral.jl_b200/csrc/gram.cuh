@@ -121,4 +121,30 @@ int launch_gram_fill(const FillArgs& a, int nproblems, cudaStream_t st);
 void launch_rhs_from_sums(const FillArgs& a, int nrhs, double bscale, double* B, long long strideB, int nproblems,
                           cudaStream_t st);
 
+// ---- LPVS_PHASE_STRUCTURED_REF (corr.cu): first-order correction of the structured Gram matrix / right-hand sides for the
+// reference's phase rounding, G += D'B + B'D, b += D'[y u], by a half-precision tensor-core GEMM (see corr.cu)
+struct CorrArgs {
+    const double* t;
+    const double* W;  // nullable = 1
+    const double* y;  // right-hand sides (launch_rhs_corr only)
+    const double* u;
+    int w_abs;        // as GramArgs
+    long long start0, hop;
+    int n;
+    long long s_end;
+    int ncc, nblk, nrhs;
+    const double2* wtab;  // per complex column (fl(2 pi f_k), fl(2 pi f_k) - 2 pi (f0 + k df)), zero beyond ncc
+    double wmax, dwmax;   // max |w|, max |dw| over the columns
+    double df;
+    double gscale, bscale;
+    double* G;  // per problem Np x Np, lower 128-tiles (read-modify-write, every tile in full)
+    long long strideG;
+    double* B;  // per problem [2][Np] (read-modify-write)
+    long long strideB;
+};
+int launch_gram_corr(const CorrArgs& a, int nproblems, cudaStream_t st);  // returns the number of kernels launched
+int launch_rhs_corr(const CorrArgs& a, int nproblems, cudaStream_t st);
+void structured_ref_wtab(double f0, double df, const double* f, int Nf, int ncol, double* out /* 2 ncol */, double* wmax,
+                         double* dwmax);
+
 }  // namespace lpvs

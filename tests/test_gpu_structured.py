@@ -15,11 +15,14 @@ def rel(a, b):
     return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(b)
 
 
-@pytest.fixture()
-def sctx(ctx):
+@pytest.fixture(params=["structured", "structured_ref"])
+def sctx(ctx, request):
+    """Both opt-in modes: the plain sums, and the sums + the first-order correction for the reference's phase rounding
+    (LPVS_PHASE_STRUCTURED_REF, csrc/corr.cu) -- on ordinary phases the correction is far below every bar used here, so the
+    same tests exercise its plumbing (scales, padding columns, ragged chunks, sample splits, two right-hand sides)."""
     from lpvspectral_jl_b200 import _lib as L
 
-    ctx.set_option(L.OPT_PHASE_MODE, L.PHASE_STRUCTURED)
+    ctx.set_option(L.OPT_PHASE_MODE, L.PHASE_STRUCTURED if request.param == "structured" else L.PHASE_STRUCTURED_REF)
     yield ctx
     ctx.set_option(L.OPT_PHASE_MODE, L.PHASE_AUTO)
 
@@ -124,3 +127,67 @@ def test_cfg2_windows_meet_the_parity_bar(sctx):
     Sd, _ = lp.ls_windowpsd(y, t, f, nw=1024, window_func=lp.hanning, ctx=sctx)
     print(f"cfg2 structured: worst sampled-window error / bar {worst:.3f}; whole PSD vs the default mode {rel(S, Sd):.2e}")
     assert rel(S, Sd) <= 1e-9
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_structured_ref_reproduces_reference_phase_rounding(ctx, weighted):
+    """The setting of test_chain_ref_reproduces_reference_phase_rounding (phi ~ 2.6e7 rad: the reference's fl(fl(2 pi f) t) is off
+    the ideal phase by up to 2.9e-9 rad).  The plain structured Gram matrix differs from the oracle's by about that; with the
+    first-order correction G += D'B + B'D, b += D'y (half-precision tensor-core GEMM, eps exact in FP64) what is left is the
+    f16 operand rounding: <= 1e-3 of the difference (measured 3e-4), i.e. the class of the per-element modes."""
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+
+    rng = np.random.default_rng(12)
+    N, Nf = 4096, 200
+    t = 9.99 + np.sort(2.4e-3 * rng.random(N))
+    fs = N / 2.4e-3
+    f = np.arange(Nf) * (fs / N) * 5.0
+    W = 3.0 * o.hanning(N) if weighted else None
+    y = rng.standard_normal(N)
+    A, _ = o.get_fourier_regressor(t, f)
+    Aw = A if W is None else A * W[:, None]
+    Gr, br = Aw.T @ A, Aw.T @ y
+    err = {}
+    for mode in (L.PHASE_STRUCTURED, L.PHASE_STRUCTURED_REF, L.PHASE_DIRECT):
+        ctx.set_option(L.OPT_PHASE_MODE, mode)
+        try:
+            G, b = lp.gram_fourier(t, f, W, y, ctx=ctx)
+        finally:
+            ctx.set_option(L.OPT_PHASE_MODE, 0)
+        err[mode] = (np.abs(G - Gr).max() / np.abs(Gr).max(), np.abs(b - br).max() / np.abs(br).max())
+    print(f"Gram / rhs error vs the oracle (reference rounding): structured {err[L.PHASE_STRUCTURED][0]:.1e} / "
+          f"{err[L.PHASE_STRUCTURED][1]:.1e}, structured_ref {err[L.PHASE_STRUCTURED_REF][0]:.1e} / "
+          f"{err[L.PHASE_STRUCTURED_REF][1]:.1e}, direct {err[L.PHASE_DIRECT][0]:.1e} / {err[L.PHASE_DIRECT][1]:.1e}")
+    assert err[L.PHASE_STRUCTURED][0] > 1e-11  # the effect is there to be corrected
+    for q in (0, 1):
+        assert err[L.PHASE_STRUCTURED_REF][q] <= 5e-13 + 2e-3 * err[L.PHASE_STRUCTURED][q]
+
+
+def test_structured_ref_large_problem_with_sample_splits(ctx):
+    """One tall problem (sample splits -> partial buffers, added in split order) at large phases, two right-hand sides through
+    ls_spectral's weighted path: structured_ref vs the per-element reference-phase mode."""
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+
+    rng = np.random.default_rng(21)
+    N, Nf = 300000, 100
+    t = 5.0e4 + np.sort(50.0 * rng.random(N))
+    f = np.arange(Nf) * 0.37
+    W = 0.5 + rng.random(N)
+    y = np.sin(2 * np.pi * 3.7 * t) + 0.1 * rng.standard_normal(N)
+    out = {}
+    for mode in (L.PHASE_STRUCTURED, L.PHASE_STRUCTURED_REF, L.PHASE_DIRECT):
+        ctx.set_option(L.OPT_PHASE_MODE, mode)
+        try:
+            out[mode] = lp.gram_fourier(t, f, W, y, ctx=ctx)
+        finally:
+            ctx.set_option(L.OPT_PHASE_MODE, 0)
+    Gd, bd = out[L.PHASE_DIRECT]
+    e0 = np.abs(out[L.PHASE_STRUCTURED][0] - Gd).max() / np.abs(Gd).max()
+    e1 = np.abs(out[L.PHASE_STRUCTURED_REF][0] - Gd).max() / np.abs(Gd).max()
+    b0 = np.abs(out[L.PHASE_STRUCTURED][1] - bd).max() / np.abs(bd).max()
+    b1 = np.abs(out[L.PHASE_STRUCTURED_REF][1] - bd).max() / np.abs(bd).max()
+    print(f"tall problem: G structured {e0:.1e} -> structured_ref {e1:.1e}; b {b0:.1e} -> {b1:.1e} (vs direct mode)")
+    assert e1 <= 5e-13 + 2e-3 * e0 and b1 <= 5e-13 + 2e-3 * b0
+    assert np.array_equal(out[L.PHASE_STRUCTURED_REF][0], out[L.PHASE_STRUCTURED_REF][0].T)

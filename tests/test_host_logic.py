@@ -184,7 +184,8 @@ def test_python_enums_match_header():
                       ("PROX_BALL_L0", "LPVS_PROX_BALL_L0"), ("PROX_GROUP_L2", "LPVS_PROX_GROUP_L2"),
                       ("PHASE_AUTO", "LPVS_PHASE_AUTO"), ("PHASE_CHAIN", "LPVS_PHASE_CHAIN"),
                       ("PHASE_DIRECT", "LPVS_PHASE_DIRECT"), ("PHASE_CHAIN_REF", "LPVS_PHASE_CHAIN_REF"),
-                      ("PHASE_STRUCTURED", "LPVS_PHASE_STRUCTURED"), ("OPT_PHASE_MODE", "LPVS_OPT_PHASE_MODE"),
+                      ("PHASE_STRUCTURED", "LPVS_PHASE_STRUCTURED"),
+                      ("PHASE_STRUCTURED_REF", "LPVS_PHASE_STRUCTURED_REF"), ("OPT_PHASE_MODE", "LPVS_OPT_PHASE_MODE"),
                       ("OPT_WINDOW_BATCH", "LPVS_OPT_WINDOW_BATCH"), ("OPT_JITTER", "LPVS_OPT_JITTER"),
                       ("OPT_ADMM_CHECK_EVERY", "LPVS_OPT_ADMM_CHECK_EVERY"), ("OPT_ADMM_SYMV", "LPVS_OPT_ADMM_SYMV")):
         cval = int(re.search(rf"\b{cname}\s*=\s*(-?\d+)", hdr).group(1))
