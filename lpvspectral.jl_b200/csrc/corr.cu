@@ -25,6 +25,7 @@ namespace {
 
 constexpr int LDH = 72;            // smem row stride in halves: 64 k' + 8 pad = 144 B, conflict-free ldmatrix and STS.32
 constexpr int PANEL_H = TB * LDH;  // halves per panel buffer
+constexpr int LDM = TB + 1;        // row stride of the FP32 accumulator tile the epilogue stages in shared memory
 constexpr double CF = 6755399441055744.0;  // 1.5 * 2^52: x + CF has round(x) in its low word (|x| < 2^31)
 
 // per-problem powers of two: S with |eps| S <= 2^21 for every element, wsc with max|W| wsc < 2^-6 (so |D| < 2^15 in f16), and
@@ -40,9 +41,10 @@ __device__ __forceinline__ int exp_above(double x) {  // x < 2^result (x >= 0; z
 }
 __device__ __forceinline__ double pow2i(int e) { return __hiloint2double((1023 + e) << 20, 0); }  // |e| <= 1022
 
-__device__ CorrScales corr_scales(const CorrArgs& a, long long s_begin, double* red /* 16 doubles of smem */) {
+__device__ CorrScales corr_scales(const CorrArgs& a, long long s_begin, double* red /* 32 doubles of smem */) {
+    const int nwarps = blockDim.x >> 5;
     double tm = 0.0, wm = 0.0;
-    for (int idx = threadIdx.x; idx < a.n; idx += NTHREADS) {
+    for (int idx = threadIdx.x; idx < a.n; idx += blockDim.x) {
         const long long s = s_begin + idx;
         if (s < a.s_end) {
             tm = fmax(tm, fabs(a.t[s]));
@@ -56,15 +58,14 @@ __device__ CorrScales corr_scales(const CorrArgs& a, long long s_begin, double* 
     }
     if ((threadIdx.x & 31) == 0) {
         red[threadIdx.x >> 5] = tm;
-        red[8 + (threadIdx.x >> 5)] = wm;
+        red[16 + (threadIdx.x >> 5)] = wm;
     }
     __syncthreads();
     tm = 0.0;
     wm = 0.0;
-#pragma unroll
-    for (int i = 0; i < NTHREADS / 32; i++) {
+    for (int i = 0; i < nwarps; i++) {
         tm = fmax(tm, red[i]);
-        wm = fmax(wm, red[8 + i]);
+        wm = fmax(wm, red[16 + i]);
     }
     CorrScales sc;
     // |w t - fl(w t)| <= |w t| 2^-53, |dw t| <= dwmax tmax
@@ -88,23 +89,30 @@ __device__ __forceinline__ float2 cis_turns_f32(double q_plus_cq, int shl) {
 }
 
 // The 8 consecutive columns (one chain group) of one sample: emit(j, Bc, Bs, Dc, Ds) with B = (cos, -sin) of the phase and
-// D = W eps S wsc (-sin, -cos).  wt: (w, dw S) of the 8 columns; kvalid: how many of them exist.
+// D = W eps S wsc (-sin, -cos).  wt: (w, dw S) of the 8 columns.  Columns beyond ncc have w = dw = 0, so their D is zero; their B
+// is not (the consumers of G / b skip those rows and columns).  The FP64 part of all 8 elements is issued first (independent
+// chains: latency hidden), then the FP32 angle-addition chain.
 template <class Emit>
-__device__ __forceinline__ void corr_group(const double2* __restrict__ wt, int kvalid, double t, float wg, double S,
-                                           const CorrScales& sc, float2 step, Emit&& emit) {
-    float2 z = cis_turns_f32(__fma_rn(__dmul_rn(wt[0].x, t), 0.15915494309189535, sc.cq), sc.shl);  // the reference's own phase
+__device__ __forceinline__ void corr_group(const double2* __restrict__ wt, double t, float wg, const CorrScales& sc, float2 step,
+                                           Emit&& emit) {
+    int ei[GRP];
+    const double negS = -sc.S;
+    double p0 = 0.0;
 #pragma unroll
     for (int j = 0; j < GRP; j++) {
         const double2 wj = wt[j];
-        const double p = __dmul_rn(wj.x, t);       // fl(w t)
-        const double e = __fma_rn(wj.x, t, -p);    // w t - fl(w t), exact
-        const double g = __fma_rn(e, -S, CF);      // fixed point: -(w t - p) S
-        const double m = __fma_rn(wj.y, t, g);     // + (w - w_ideal) S t  =  eps S
-        const float ef = __int_as_float(0x4B400000 + __double2loint(m)) - 12582912.0f;  // int -> float, exact below 2^22
+        const double p = __dmul_rn(wj.x, t);         // fl(w t)
+        const double e = __fma_rn(wj.x, t, -p);      // w t - fl(w t), exact
+        const double g = __fma_rn(e, negS, CF);      // fixed point: -(w t - p) S
+        ei[j] = __double2loint(__fma_rn(wj.y, t, g));  // + (w - w_ideal) S t  =  eps S
+        if (j == 0) p0 = p;
+    }
+    float2 z = cis_turns_f32(__fma_rn(p0, 0.15915494309189535, sc.cq), sc.shl);  // anchor: the reference's own phase
+#pragma unroll
+    for (int j = 0; j < GRP; j++) {
+        const float ef = __int_as_float(0x4B400000 + ei[j]) - 12582912.0f;  // int -> float, exact below 2^22
         const float de = ef * wg;
-        const bool valid = j < kvalid;
-        const float bc = valid ? z.x : 0.f, bs = valid ? z.y : 0.f;
-        emit(j, bc, bs, de * bs, -de * bc);
+        emit(j, z.x, z.y, de * z.y, -de * z.x);
         z = make_float2(fmaf(z.x, step.x, -z.y * step.y), fmaf(z.x, step.y, z.y * step.x));
     }
 }
@@ -121,27 +129,37 @@ __device__ __forceinline__ void hmma16816(float (&c)[4], const unsigned (&a)[4],
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// one sample of a chunk as loaded (the conversion of the weight waits until the chunk is synthesised: the loads run two chunks
+// ahead and nothing may depend on them earlier)
 struct Sample {
-    double t;
-    float wg;
+    double t, w;
+    bool valid;
 };
 
-__device__ __forceinline__ Sample load_sample(const CorrArgs& a, long long s_begin, int c, int lane, double wsc) {
+__device__ __forceinline__ Sample load_sample(const CorrArgs& a, long long s_begin, int c, int lane) {
     const int idx = c * KC + lane;
-    const bool valid = idx < a.n && s_begin + idx < a.s_end;
-    long long s = s_begin + idx;
-    if (!valid) s = min(s_begin + (long long)a.n, a.s_end) - 1;
     Sample r;
-    r.t = a.t[s];
-    const double w = a.W ? a.W[a.w_abs ? s : (s - s_begin)] : 1.0;
-    r.wg = valid ? (float)(w * wsc) : 0.f;
+    r.valid = idx < a.n && s_begin + idx < a.s_end;
+    long long s = s_begin + idx;
+    if (!r.valid) s = min(s_begin + (long long)a.n, a.s_end) - 1;
+    r.t = __ldg(a.t + s);
+    r.w = a.W ? __ldg(a.W + (a.w_abs ? s : (s - s_begin))) : 1.0;
     return r;
 }
+__device__ __forceinline__ float sample_weight(const Sample& sm, double wsc) { return sm.valid ? (float)(sm.w * wsc) : 0.f; }
 
-__global__ void __launch_bounds__(NTHREADS, 2) k_gram_corr(const __grid_constant__ CorrArgs a) {
+constexpr int CORR_THREADS = 512;  // warps 0-7: MMA consumers (4 x 2, warp tile 32 x 64); warps 8-15: operand producers
+__device__ __forceinline__ void bar_chunk() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 2, 256;\n" ::: "memory"); }
+
+// Warp-specialised: the producers synthesise chunk c + 1 into one panel buffer while the consumers run the MMAs of chunk c
+// from the other; one 512-thread named barrier per chunk publishes a buffer and releases the other.
+// Off-diagonal tile (I > J): K' = 2 per sample, P = [D_I | B_I], Q = [B_J | D_J]  ->  acc = D_I'B_J + B_I'D_J.
+// Diagonal tile: K' = 1 per sample, P = D_I, Q = B_I -> acc = M = D_I'B_I; the epilogue adds M + M' through shared memory.
+__global__ void __launch_bounds__(CORR_THREADS, 1) k_gram_corr(const __grid_constant__ CorrArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __half* sP = reinterpret_cast<__half*>(smem_raw);      // [2][TB][LDH]: rows = functions of block I, k' = (sample, D | B)
-    __half* sQ = sP + 2 * PANEL_H;                          // [2][TB][LDH]: rows = functions of block J, k' = (sample, B | D)
+    __half* sP = reinterpret_cast<__half*>(smem_raw);            // [2][TB][LDH]: rows = functions of block I
+    __half* sQ = sP + 2 * PANEL_H;                                // [2][TB][LDH]: rows = functions of block J
     double2* sW = reinterpret_cast<double2*>(sQ + 2 * PANEL_H);  // [2][FB]: (w, dw S) of block I, block J
     double* red = reinterpret_cast<double*>(sW + 2 * FB);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -158,88 +176,107 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_gram_corr(const __grid_constant
     }
     __syncthreads();
     const bool diag = I == J;
-    const int kvI = min(GRP, max(0, a.ncc - (I * FB + GRP * warp))), kvJ = min(GRP, max(0, a.ncc - (J * FB + GRP * warp)));
     const int nchunks = (a.n + KC - 1) / KC;
-    float acc[2][8][4];
-#pragma unroll
-    for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-#pragma unroll
-            for (int q = 0; q < 4; q++) acc[i][j][q] = 0.f;
-    // ldmatrix lane addresses: A = P rows (16 x 16: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)), B = Q rows ((n 0-7 | 8-15) x k)
-    const int wm = warp & 3, wn = warp >> 2, mi = lane >> 3;
-    const int a_off = (wm * 32 + (mi & 1) * 8 + (lane & 7)) * LDH + (mi >> 1) * 8;
-    const int b_off = (wn * 64 + (mi >> 1) * 8 + (lane & 7)) * LDH + (mi & 1) * 8;
-    Sample cur = load_sample(a, s_begin, 0, lane, sc.wsc);
-    for (int c = 0; c < nchunks; c++) {
-        __half* P = sP + (c & 1) * PANEL_H;
-        __half* Q = sQ + (c & 1) * PANEL_H;
-        Sample nxt = cur;
-        if (c + 1 < nchunks) nxt = load_sample(a, s_begin, c + 1, lane, sc.wsc);
-        const float2 step = cis_turns_f32(__fma_rn(a.df, cur.t, sc.cq), sc.shl);
-        // this warp: columns 8 warp .. 8 warp + 7 of the block; this lane: sample `lane` of the chunk
-        __half* p0 = P + (GRP * warp) * LDH + 2 * lane;
-        __half* q0 = Q + (GRP * warp) * LDH + 2 * lane;
-        if (diag) {
-            corr_group(sW + GRP * warp, kvI, cur.t, cur.wg, sc.S, sc, step, [&](int j, float bc, float bs, float dc, float ds) {
-                *reinterpret_cast<__half2*>(p0 + j * LDH) = __floats2half2_rn(dc, bc);
-                *reinterpret_cast<__half2*>(p0 + (j + FB) * LDH) = __floats2half2_rn(ds, bs);
-                *reinterpret_cast<__half2*>(q0 + j * LDH) = __floats2half2_rn(bc, dc);
-                *reinterpret_cast<__half2*>(q0 + (j + FB) * LDH) = __floats2half2_rn(bs, ds);
-            });
-        } else {
-            corr_group(sW + GRP * warp, kvI, cur.t, cur.wg, sc.S, sc, step, [&](int j, float bc, float bs, float dc, float ds) {
-                *reinterpret_cast<__half2*>(p0 + j * LDH) = __floats2half2_rn(dc, bc);
-                *reinterpret_cast<__half2*>(p0 + (j + FB) * LDH) = __floats2half2_rn(ds, bs);
-            });
-            corr_group(sW + FB + GRP * warp, kvJ, cur.t, cur.wg, sc.S, sc, step, [&](int j, float bc, float bs, float dc, float ds) {
-                *reinterpret_cast<__half2*>(q0 + j * LDH) = __floats2half2_rn(bc, dc);
-                *reinterpret_cast<__half2*>(q0 + (j + FB) * LDH) = __floats2half2_rn(bs, ds);
-            });
+    if (warp >= 8) {
+        // ---- producers: warp = chain group (columns 8 g .. 8 g + 7 of a block), lane = sample of the chunk
+        const int g8 = GRP * (warp - 8);
+        Sample cur = load_sample(a, s_begin, 0, lane), nxt = load_sample(a, s_begin, nchunks > 1 ? 1 : 0, lane);
+        for (int c = 0; c < nchunks; c++) {
+            __half* P = sP + (c & 1) * PANEL_H + g8 * LDH;
+            __half* Q = sQ + (c & 1) * PANEL_H + g8 * LDH;
+            const Sample nx2 = load_sample(a, s_begin, c + 2 < nchunks ? c + 2 : c, lane);
+            const float wg = sample_weight(cur, sc.wsc);
+            const float2 step = cis_turns_f32(__fma_rn(a.df, cur.t, sc.cq), sc.shl);
+            if (diag) {
+                corr_group(sW + g8, cur.t, wg, sc, step, [&](int j, float bc, float bs, float dc, float ds) {
+                    P[j * LDH + lane] = __float2half_rn(dc);
+                    P[(j + FB) * LDH + lane] = __float2half_rn(ds);
+                    Q[j * LDH + lane] = __float2half_rn(bc);
+                    Q[(j + FB) * LDH + lane] = __float2half_rn(bs);
+                });
+            } else {
+                corr_group(sW + g8, cur.t, wg, sc, step, [&](int j, float bc, float bs, float dc, float ds) {
+                    *reinterpret_cast<__half2*>(P + j * LDH + 2 * lane) = __floats2half2_rn(dc, bc);
+                    *reinterpret_cast<__half2*>(P + (j + FB) * LDH + 2 * lane) = __floats2half2_rn(ds, bs);
+                });
+                corr_group(sW + FB + g8, cur.t, wg, sc, step, [&](int j, float bc, float bs, float dc, float ds) {
+                    *reinterpret_cast<__half2*>(Q + j * LDH + 2 * lane) = __floats2half2_rn(bc, dc);
+                    *reinterpret_cast<__half2*>(Q + (j + FB) * LDH + 2 * lane) = __floats2half2_rn(bs, ds);
+                });
+            }
+            bar_chunk();  // chunk c published; the consumers have finished chunk c - 1 (the buffer chunk c + 1 goes to)
+            cur = nxt;
+            nxt = nx2;
         }
-        __syncthreads();  // double-buffered panels: the next chunk's stores go to the other buffer
+    } else {
+        // ---- consumers
+        float acc[2][8][4];
 #pragma unroll
-        for (int ks = 0; ks < 2 * KC / 16; ks++) {
-            unsigned af[2][4], bf[4][4];
+        for (int i = 0; i < 2; i++)
 #pragma unroll
-            for (int i = 0; i < 2; i++) ldsm_x4(af[i], P + a_off + i * 16 * LDH + ks * 16);
+            for (int j = 0; j < 8; j++)
 #pragma unroll
-            for (int jj = 0; jj < 4; jj++) ldsm_x4(bf[jj], Q + b_off + jj * 16 * LDH + ks * 16);
+                for (int q = 0; q < 4; q++) acc[i][j][q] = 0.f;
+        // ldmatrix lane addresses: A = P rows (16 x 16: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)), B = Q rows ((n 0-7 | 8-15) x k)
+        const int wm = warp & 3, wn = warp >> 2, mi = lane >> 3;
+        const int a_off = (wm * 32 + (mi & 1) * 8 + (lane & 7)) * LDH + (mi >> 1) * 8;
+        const int b_off = (wn * 64 + (mi >> 1) * 8 + (lane & 7)) * LDH + (mi & 1) * 8;
+        const int ksteps = diag ? KC / 16 : 2 * KC / 16;
+        for (int c = 0; c < nchunks; c++) {
+            bar_chunk();
+            const __half* P = sP + (c & 1) * PANEL_H;
+            const __half* Q = sQ + (c & 1) * PANEL_H;
+            for (int ks = 0; ks < ksteps; ks++) {
+                unsigned af[2][4];
 #pragma unroll
-            for (int i = 0; i < 2; i++)
+                for (int i = 0; i < 2; i++) ldsm_x4(af[i], P + a_off + i * 16 * LDH + ks * 16);
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) {
-                    hmma16816(acc[i][2 * jj], af[i], bf[jj][0], bf[jj][1]);
-                    hmma16816(acc[i][2 * jj + 1], af[i], bf[jj][2], bf[jj][3]);
+                    unsigned bf[4];
+                    ldsm_x4(bf, Q + b_off + jj * 16 * LDH + ks * 16);
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        hmma16816(acc[i][2 * jj], af[i], bf[0], bf[1]);
+                        hmma16816(acc[i][2 * jj + 1], af[i], bf[2], bf[3]);
+                    }
                 }
-        }
-        cur = nxt;
-    }
-    // G += gscale / (S wsc) * acc   (accumulator fragment: rows g, g + 8; columns 2 t, 2 t + 1)
-    const int Np = a.nblk * TB;
-    const double scl = a.gscale * sc.unscale;
-    double* Gp = a.G + (long long)prob * a.strideG;
-#pragma unroll
-    for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int row = I * TB + wm * 32 + i * 16 + (lane >> 2) + 8 * h;
-                const int col = J * TB + wn * 64 + j * 8 + 2 * (lane & 3);
-                double2* ptr = reinterpret_cast<double2*>(Gp + (long long)row * Np + col);
-                double2 v = *ptr;
-                v.x += scl * (double)acc[i][j][2 * h];
-                v.y += scl * (double)acc[i][j][2 * h + 1];
-                *ptr = v;
             }
+        }
+        // the accumulators go through shared memory (over the panel buffers) so that all 16 warps write G, coalesced
+        bar_consumers();  // every consumer is done with the panels
+        float* sM = reinterpret_cast<float*>(smem_raw);
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    sM[(wm * 32 + i * 16 + (lane >> 2) + 8 * (q >> 1)) * LDM + wn * 64 + j * 8 + 2 * (lane & 3) + (q & 1)] =
+                        acc[i][j][q];
+    }
+    __syncthreads();
+    // G += gscale / (S wsc) * acc (diagonal tiles: M + M'); rows / columns of columns that do not exist (k >= ncc) stay as filled
+    {
+        const float* sM = reinterpret_cast<const float*>(smem_raw);
+        const int Np = a.nblk * TB;
+        const double scl = a.gscale * sc.unscale;
+        double* Gt = a.G + (long long)prob * a.strideG + (long long)I * TB * Np + J * TB;
+        const int cl = tid & (TB - 1);
+        const bool cok = J * FB + (cl & (FB - 1)) < a.ncc;
+#pragma unroll 8
+        for (int r0 = 0; r0 < TB; r0 += CORR_THREADS / TB) {
+            const int rl = r0 + (tid >> 7);
+            float v = sM[rl * LDM + cl];
+            if (diag) v += sM[cl * LDM + rl];
+            if (cok && I * FB + (rl & (FB - 1)) < a.ncc) Gt[(long long)rl * Np + cl] += scl * (double)v;
+        }
+    }
 }
 
 // b += D'[y u]: thread = (sample of the chunk, chain group), FP32 accumulation over the chunks, fixed-order lane reduction
 __global__ void __launch_bounds__(NTHREADS) k_rhs_corr(const __grid_constant__ CorrArgs a) {
     __shared__ double2 sW[FB];
-    __shared__ double red[16];
+    __shared__ double red[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int I = blockIdx.x, prob = blockIdx.y;
     const long long s_begin = a.start0 + (long long)prob * a.hop;
@@ -259,13 +296,14 @@ __global__ void __launch_bounds__(NTHREADS) k_rhs_corr(const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < GRP; j++) ac[r][j] = as[r][j] = 0.f;
     for (int c = 0; c < nchunks; c++) {
-        const Sample cur = load_sample(a, s_begin, c, lane, sc.wsc);
+        const Sample cur = load_sample(a, s_begin, c, lane);
         const int idx = c * KC + lane;
         long long s = s_begin + idx;
-        if (!(idx < a.n && s < a.s_end)) s = min(s_begin + (long long)a.n, a.s_end) - 1;  // weight 0 there
+        if (!cur.valid) s = min(s_begin + (long long)a.n, a.s_end) - 1;  // weight 0 there
         const float y0 = (float)a.y[s], y1 = a.nrhs > 1 ? (float)a.u[s] : 0.f;
+        const float wg = sample_weight(cur, sc.wsc);
         const float2 step = cis_turns_f32(__fma_rn(a.df, cur.t, sc.cq), sc.shl);
-        corr_group(sW + GRP * warp, kv, cur.t, cur.wg, sc.S, sc, step, [&](int j, float, float, float dc, float ds) {
+        corr_group(sW + GRP * warp, cur.t, wg, sc, step, [&](int j, float, float, float dc, float ds) {
             ac[0][j] = fmaf(dc, y0, ac[0][j]);
             as[0][j] = fmaf(ds, y0, as[0][j]);
             ac[1][j] = fmaf(dc, y1, ac[1][j]);
@@ -293,7 +331,7 @@ __global__ void __launch_bounds__(NTHREADS) k_rhs_corr(const __grid_constant__ C
         }
 }
 
-constexpr size_t CORR_SMEM = (size_t)4 * PANEL_H * sizeof(__half) + 2 * FB * sizeof(double2) + 16 * sizeof(double);
+constexpr size_t CORR_SMEM = (size_t)4 * PANEL_H * sizeof(__half) + 2 * FB * sizeof(double2) + 32 * sizeof(double);
 
 }  // namespace
 
@@ -310,7 +348,7 @@ int launch_gram_corr(const CorrArgs& a, int nproblems, cudaStream_t st) {
         CorrArgs b = a;
         b.start0 = a.start0 + (long long)p0 * a.hop;
         b.G = a.G + (long long)p0 * a.strideG;
-        k_gram_corr<<<dim3(ntiles, np), NTHREADS, CORR_SMEM, st>>>(b);
+        k_gram_corr<<<dim3(ntiles, np), CORR_THREADS, CORR_SMEM, st>>>(b);
         launched++;
     }
     return launched;
