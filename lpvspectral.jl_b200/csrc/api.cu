@@ -363,9 +363,9 @@ static void structured_fill(lpvs_ctx* c, const FourierPlan& pl, const Structured
 }
 
 // LPVS_PHASE_STRUCTURED_REF: G += D'B + B'D, b += D'[y u] for the `nprob` problems described by g (corr.cu); G / B as filled
-// by structured_fill
-static void structured_correct(lpvs_ctx* c, const FourierPlan& pl, const GramArgs& g, double* G, long long strideG,
-                               double* B, long long strideB, int nrhs, int nprob) {
+// by structured_fill.  The per-sample tables cover g's table range [g.tbl_base, g.tbl_base + g.tbl_ns).
+static int structured_correct(lpvs_ctx* c, const FourierPlan& pl, const GramArgs& g, double* G, long long strideG, double* B,
+                              long long strideB, int nrhs, int nprob) {
     CorrArgs a{};
     a.t = g.t;
     a.W = g.W;
@@ -383,14 +383,26 @@ static void structured_correct(lpvs_ctx* c, const FourierPlan& pl, const GramArg
     a.wmax = pl.cw_max;
     a.dwmax = pl.cdw_max;
     a.df = pl.df;
+    a.tbl_base = g.tbl_base;
+    a.tbl_ns = g.tbl_ns;
+    const long long ngr = (long long)pl.nblk * (FB / GRP);
+    const long long w0 = g.w_abs ? g.tbl_base : 0, nw = g.w_abs ? g.tbl_ns : g.n;
+    a.scal = ws<double>(c, BUF_CSCAL, 2);
+    a.eps = ws<uint4>(c, BUF_CEPS, (size_t)ngr * g.tbl_ns);
+    a.anc = ws<float2>(c, BUF_CANC, (size_t)ngr * g.tbl_ns);
+    a.step = ws<float2>(c, BUF_CSTEP, (size_t)g.tbl_ns);
+    a.wf = ws<float>(c, BUF_CWF, (size_t)nw);
+    if (!a.scal || !a.eps || !a.anc || !a.step || !a.wf) return fail(c, LPVS_E_NOMEM, "out of device memory (correction tables)");
     a.gscale = pl.dd * pl.dd;
     a.bscale = pl.dd;
     a.G = G;
     a.strideG = strideG;
     a.B = B;
     a.strideB = strideB;
+    c->launches += launch_corr_tables(a, w0, nw, c->st);
     c->launches += launch_gram_corr(a, nprob, c->st);
     if (B && nrhs > 0 && g.y) c->launches += launch_rhs_corr(a, nprob, c->st);
+    return LPVS_OK;
 }
 
 // gram_single for LPVS_PHASE_STRUCTURED: the sums are additive over sample splits (and over table segments); G and b are
@@ -438,33 +450,49 @@ static int gram_single_structured(lpvs_ctx* c, const FourierPlan& pl, const doub
     }
     structured_fill(c, pl, lay, Zacc, d_G, 0, d_B, 0, nrhs, 1);
     if (pl.structured_ref) {
-        // sample splits into zeroed partial buffers (each CTA read-modify-writes its own tile), added in split order
+        // Sample splits into zeroed partial buffers (each CTA read-modify-writes its own tile), added in split order.  The
+        // per-sample tables are built segment by segment (<= 4 GiB); every segment accumulates into the same partials.
         const long long Np = pl.Np, part_stride = Np * Np + 2 * Np;
         const int ntiles = pl.nblk * (pl.nblk + 1) / 2;
-        const long long wantc = (4LL * c->sms + ntiles - 1) / ntiles, maxc = std::max<long long>(1, N / 2048);
+        const long long per_s = (long long)corr_table_bytes_per_sample(pl.nblk) + 4;
+        const long long cseg_cap = std::max<long long>(65536, (4LL << 30) / per_s);
+        const int ncseg = (int)std::max<long long>(1, (N + cseg_cap - 1) / cseg_cap);
+        const long long cseg_len = (N + ncseg - 1) / ncseg;
+        const long long wantc = (4LL * c->sms + ntiles - 1) / ntiles, maxc = std::max<long long>(1, cseg_len / 2048);
         const int ncs = (int)std::min(wantc, maxc);
-        long long n_split = (N + ncs - 1) / ncs;
+        long long n_split = (cseg_len + ncs - 1) / ncs;
         n_split = (n_split + KC - 1) / KC * KC;
-        const int nprob = (int)((N + n_split - 1) / n_split);
-        GramArgs g{};
-        g.t = d_t;
-        g.y = nrhs > 0 ? d_y : nullptr;
-        g.u = nrhs > 1 ? d_u : nullptr;
-        g.W = d_W;
-        g.w_abs = 1;
-        g.start0 = 0;
-        g.hop = n_split;
-        g.n = (int)n_split;
-        g.s_end = N;
-        if (nprob == 1) {
-            structured_correct(c, pl, g, d_G, 0, d_B, 0, nrhs, 1);
-        } else {
-            double* parts = ws<double>(c, BUF_CPART, (size_t)nprob * part_stride);
+        const int nprob_max = (int)((cseg_len + n_split - 1) / n_split);
+        const bool direct = ncseg == 1 && nprob_max == 1;
+        double* parts = nullptr;
+        if (!direct) {
+            parts = ws<double>(c, BUF_CPART, (size_t)nprob_max * part_stride);
             if (!parts) return fail(c, LPVS_E_NOMEM, "out of device memory (correction partials)");
-            LPVS_CU(c, cudaMemsetAsync(parts, 0, sizeof(double) * nprob * part_stride, c->st));
-            structured_correct(c, pl, g, parts, part_stride, parts + Np * Np, part_stride, nrhs, nprob);
-            reduce_parts(c, d_G, parts, Np * Np, part_stride, nprob, 1);
-            if (d_B && nrhs > 0) reduce_parts(c, d_B, parts + Np * Np, 2 * Np, part_stride, nprob, 1);
+            LPVS_CU(c, cudaMemsetAsync(parts, 0, sizeof(double) * nprob_max * part_stride, c->st));
+        }
+        for (int sgi = 0; sgi < ncseg; sgi++) {
+            const long long s0 = sgi * cseg_len, s1 = std::min<long long>(N, s0 + cseg_len);
+            if (s1 <= s0) break;
+            GramArgs g{};
+            g.t = d_t;
+            g.y = nrhs > 0 ? d_y : nullptr;
+            g.u = nrhs > 1 ? d_u : nullptr;
+            g.W = d_W;
+            g.w_abs = 1;
+            g.start0 = s0;
+            g.hop = n_split;
+            g.n = (int)n_split;
+            g.s_end = s1;
+            g.tbl_base = s0;
+            g.tbl_ns = s1 - s0;
+            const int nprob = (int)((s1 - s0 + n_split - 1) / n_split);
+            int rc = direct ? structured_correct(c, pl, g, d_G, 0, d_B, 0, nrhs, 1)
+                            : structured_correct(c, pl, g, parts, part_stride, parts + Np * Np, part_stride, nrhs, nprob);
+            if (rc) return rc;
+        }
+        if (!direct) {
+            reduce_parts(c, d_G, parts, Np * Np, part_stride, nprob_max, 1);
+            if (d_B && nrhs > 0) reduce_parts(c, d_B, parts + Np * Np, 2 * Np, part_stride, nprob_max, 1);
         }
     }
     gram_timer_end(c, (double)N * nz64 * 8.0, 1);  // executed: one complex rotation + accumulation per (sample, sum)
@@ -1116,7 +1144,7 @@ int lpvs_ls_window_sums_dev(lpvs_ctx* c, int kind, const double* d_y, const doub
             if (!Z) return fail(c, LPVS_E_NOMEM, "out of device memory (window sums)");
             if ((rc = structured_sums(c, pl, lay, g, nw, Z))) return rc;
             structured_fill(c, pl, lay, Z, d_G, Np * Np, d_B, 2 * Np, nrhs, nw);
-            if (pl.structured_ref) structured_correct(c, pl, g, d_G, Np * Np, d_B, 2 * Np, nrhs, nw);
+            if (pl.structured_ref && (rc = structured_correct(c, pl, g, d_G, Np * Np, d_B, 2 * Np, nrhs, nw))) return rc;
             gram_timer_end(c, (double)nw * n * lay.nzb * FB * 8.0, 1);
         } else {
             c->launches += launch_gram(pl.mode, g, nw, c->st);  // k_gram (+ k_gram_rhs when there are two channels)
@@ -1312,7 +1340,10 @@ int lpvs_ls_window_sparse_sums(lpvs_ctx* c, int kind, const double* y, const dou
                 return Z ? rc : fail(c, LPVS_E_NOMEM, "out of device memory (window sums)");
             }
             structured_fill(c, pl, lay, Z, d_G, Np * Np, d_B, 2 * Np, nrhs, nw);
-            if (pl.structured_ref) structured_correct(c, pl, g, d_G, Np * Np, d_B, 2 * Np, nrhs, nw);
+            if (pl.structured_ref && (rc = structured_correct(c, pl, g, d_G, Np * Np, d_B, 2 * Np, nrhs, nw))) {
+                cleanup();
+                return rc;
+            }
             gram_timer_end(c, (double)nw * n * lay.nzb * FB * 8.0, 1);
         } else {
             c->launches += launch_gram(pl.mode, g, nw, c->st);

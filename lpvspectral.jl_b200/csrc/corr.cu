@@ -6,15 +6,21 @@
 // but it is tiny, and to first order (the eps^2 terms are < 1e-17)
 //     G_ref = G0 + D'B + B'D,     b_ref = b0 + D'y,     B = A0 (cos, -sin),  D = diag(W) (dA/dphi o eps) = W eps (-sin, -cos).
 // dG is 1e-10 of G and is needed to ~3 digits: a HALF-PRECISION tensor-core GEMM (mma.sync m16n8k16, f16 operands, f32
-// accumulation) with the operands synthesised in registers -- eps exactly in FP64 (the rounding error of the product by one
-// FMA, w t - fl(w t); plus (fl(2 pi f_k) - 2 pi f_k) t), then scaled by a power of two and rounded to f16; the cos / sin factors
-// from an FP32 angle-addition chain anchored on the reference phase itself.  Nothing is read from HBM but t, W (and y, u).
+// accumulation).  eps is taken exactly in FP64 -- the rounding error of the product by one FMA, w t - fl(w t), plus
+// (fl(2 pi f_k) - 2 pi f_k) t -- scaled by a power of two and rounded to f16.
 //
-// k_gram_corr  one CTA per (lower 128 x 128 tile, problem): K' = 2 n (per sample the pair (D_i B_j, B_i D_j)), G += scale * acc
-// k_rhs_corr   one CTA per (64-frequency block, problem): b += D'[y u] in FP32
+// FP64 instructions stall behind HMMA bursts on this SM (ncu, profiles/r02_summary.md: `math pipe throttle` on the first DMUL of
+// every synthesis phase), so the FP64 part runs ONCE per (column, sample) in a table pass and the GEMM kernel is FP64-free:
+//   k_corr_max      max |t|, max |W| of the sample range -> the power-of-two scales (computed identically by every kernel)
+//   k_corr_tables   per (8-column chain group, sample): eps S as 8 halves (16 B), the group's anchor (cos, -sin) of the
+//                   reference phase (float2), per sample the step rotation e^{-i 2 pi df t} (float2); Wf = float(W wsc)
+//   k_gram_corr     one CTA per (lower 128 x 128 tile, problem), warp-specialised: 8 producer warps turn table entries into f16
+//                   operand panels (FP32 angle-addition chain from the anchor), 8 consumer warps run the MMAs; G += scale * acc
+//   k_rhs_corr      one CTA per (64-frequency block, problem): b += D'[y u] in FP32
+// 3 bytes of table per (column, sample), window-independent (overlapping windows and all tiles of a window share them).
 //
 // Accuracy (tests/test_gpu_structured.py, tools/corr_emulation.py): dG to 3e-4 of itself; cfg5a window 4166 (phase 2.6e7 rad,
-// cond(A) 2e5): 4e-9 -> 2e-11 against the reference-rounded solve.
+// cond(A) 2e5): 4e-9 -> 5e-11 against the literal oracle.
 #include <cuda_fp16.h>
 
 #include "gram.cuh"
@@ -28,10 +34,11 @@ constexpr int PANEL_H = TB * LDH;  // halves per panel buffer
 constexpr int LDM = TB + 1;        // row stride of the FP32 accumulator tile the epilogue stages in shared memory
 constexpr double CF = 6755399441055744.0;  // 1.5 * 2^52: x + CF has round(x) in its low word (|x| < 2^31)
 
-// per-problem powers of two: S with |eps| S <= 2^21 for every element, wsc with max|W| wsc < 2^-6 (so |D| < 2^15 in f16), and
-// the magic constant / shift that leave the fraction of a phase in turns in the low word of a double
+// powers of two of one sample range: S with |eps| S <= 2^21 for every element (the table keeps eps S 2^-7 <= 2^14 as f16), wsc with
+// max|W| wsc < 1 (so |D| < 2^14 in f16), and the magic constant / shift that leave the fraction of a phase in turns in the
+// low word of a double
 struct CorrScales {
-    double S, wsc, unscale;  // unscale = 1 / (S wsc)
+    double S, wsc, unscale;  // unscale = 1 / (S 2^-7 wsc)
     double cq;               // 1.5 * 2^(52 - fb): q + cq has frac(q) 2^fb in its low word
     int shl;                 // 32 - fb
 };
@@ -41,44 +48,40 @@ __device__ __forceinline__ int exp_above(double x) {  // x < 2^result (x >= 0; z
 }
 __device__ __forceinline__ double pow2i(int e) { return __hiloint2double((1023 + e) << 20, 0); }  // |e| <= 1022
 
-__device__ CorrScales corr_scales(const CorrArgs& a, long long s_begin, double* red /* 32 doubles of smem */) {
-    const int nwarps = blockDim.x >> 5;
-    double tm = 0.0, wm = 0.0;
-    for (int idx = threadIdx.x; idx < a.n; idx += blockDim.x) {
-        const long long s = s_begin + idx;
-        if (s < a.s_end) {
-            tm = fmax(tm, fabs(a.t[s]));
-            wm = fmax(wm, a.W ? fabs(a.W[a.w_abs ? s : (long long)idx]) : 1.0);
-        }
-    }
+__device__ __forceinline__ CorrScales corr_scales(const CorrArgs& a) {
+    const double tm = a.scal[0], wm = a.scal[1];  // max |t|, max |W| (k_corr_max)
+    CorrScales sc;
+    // |w t - fl(w t)| <= |w t| 2^-53, |dw t| <= dwmax tmax
+    const double epsmax = a.wmax * tm * 1.1102230246251565e-16 + a.dwmax * tm;
+    const int sexp = min(21 - exp_above(epsmax), 600), wexp = min(-exp_above(wm), 600);
+    sc.S = pow2i(sexp);
+    sc.wsc = pow2i(wexp);
+    sc.unscale = pow2i(7 - sexp) * pow2i(-wexp);
+    const int tb = exp_above(a.wmax * tm * 0.15915494309189535);  // |phase| < 2^tb turns
+    const int fb = max(1, min(24, 51 - tb));
+    sc.cq = 1.5 * pow2i(52 - fb);
+    sc.shl = 32 - fb;
+    return sc;
+}
+
+// scal[0] = max |t_s| over [s0, s0 + ns), scal[1] = max |W_i| over [w0, w0 + nw) (1 without weights); non-negative doubles order
+// like their bit patterns
+__global__ void k_corr_max(const double* __restrict__ t, long long s0, long long ns, const double* __restrict__ W, long long w0,
+                           long long nw, unsigned long long* __restrict__ scal) {
+    double tm = 0.0, wm = W ? 0.0 : 1.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += stride) tm = fmax(tm, fabs(t[s0 + i]));
+    if (W)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += stride) wm = fmax(wm, fabs(W[w0 + i]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         tm = fmax(tm, __shfl_xor_sync(0xffffffffu, tm, o));
         wm = fmax(wm, __shfl_xor_sync(0xffffffffu, wm, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        red[threadIdx.x >> 5] = tm;
-        red[16 + (threadIdx.x >> 5)] = wm;
+        atomicMax(scal, (unsigned long long)__double_as_longlong(tm));
+        atomicMax(scal + 1, (unsigned long long)__double_as_longlong(wm));
     }
-    __syncthreads();
-    tm = 0.0;
-    wm = 0.0;
-    for (int i = 0; i < nwarps; i++) {
-        tm = fmax(tm, red[i]);
-        wm = fmax(wm, red[16 + i]);
-    }
-    CorrScales sc;
-    // |w t - fl(w t)| <= |w t| 2^-53, |dw t| <= dwmax tmax
-    const double epsmax = a.wmax * tm * 1.1102230246251565e-16 + a.dwmax * tm;
-    const int sexp = min(21 - exp_above(epsmax), 600), wexp = min(-6 - exp_above(wm), 600);
-    sc.S = pow2i(sexp);
-    sc.wsc = pow2i(wexp);
-    sc.unscale = pow2i(-sexp) * pow2i(-wexp);
-    const int tb = exp_above(a.wmax * tm * 0.15915494309189535);  // |phase| < 2^tb turns
-    const int fb = max(1, min(24, 51 - tb));
-    sc.cq = 1.5 * pow2i(52 - fb);
-    sc.shl = 32 - fb;
-    return sc;
 }
 
 // (cos, -sin)(2 pi q) in FP32 for a phase of q turns given as a double (|q| < 2^(51 - fb))
@@ -88,30 +91,59 @@ __device__ __forceinline__ float2 cis_turns_f32(double q_plus_cq, int shl) {
     return make_float2(__cosf(ang), -__sinf(ang));
 }
 
-// The 8 consecutive columns (one chain group) of one sample: emit(j, Bc, Bs, Dc, Ds) with B = (cos, -sin) of the phase and
-// D = W eps S wsc (-sin, -cos).  wt: (w, dw S) of the 8 columns.  Columns beyond ncc have w = dw = 0, so their D is zero; their B
-// is not (the consumers of G / b skip those rows and columns).  The FP64 part of all 8 elements is issued first (independent
-// chains: latency hidden), then the FP32 angle-addition chain.
-template <class Emit>
-__device__ __forceinline__ void corr_group(const double2* __restrict__ wt, double t, float wg, const CorrScales& sc, float2 step,
-                                           Emit&& emit) {
-    int ei[GRP];
+// grid (ceil(ns / 256), groups): thread = one sample of one 8-column chain group
+__global__ void __launch_bounds__(256) k_corr_tables(const __grid_constant__ CorrArgs a) {
+    const long long si = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= a.tbl_ns) return;
+    const int g = blockIdx.y;
+    const CorrScales sc = corr_scales(a);
+    const double t = a.t[a.tbl_base + si];
     const double negS = -sc.S;
+    float ef[GRP];
     double p0 = 0.0;
 #pragma unroll
     for (int j = 0; j < GRP; j++) {
-        const double2 wj = wt[j];
+        const double2 wj = a.wtab[g * GRP + j];      // (w, dw); zero beyond ncc
         const double p = __dmul_rn(wj.x, t);         // fl(w t)
         const double e = __fma_rn(wj.x, t, -p);      // w t - fl(w t), exact
-        const double g = __fma_rn(e, negS, CF);      // fixed point: -(w t - p) S
-        ei[j] = __double2loint(__fma_rn(wj.y, t, g));  // + (w - w_ideal) S t  =  eps S
+        const double q = __fma_rn(e, negS, CF);      // fixed point: -(w t - p) S
+        const int ei = __double2loint(__fma_rn(wj.y * sc.S, t, q));  // + (w - w_ideal) S t  =  eps S,  |.| <= 2^21
+        ef[j] = (__int_as_float(0x4B400000 + ei) - 12582912.0f) * 0.0078125f;  // int -> float (exact below 2^22), 2^-7
         if (j == 0) p0 = p;
     }
-    float2 z = cis_turns_f32(__fma_rn(p0, 0.15915494309189535, sc.cq), sc.shl);  // anchor: the reference's own phase
+    uint4 pk;
+    __half2 h;
+    h = __floats2half2_rn(ef[0], ef[1]);
+    pk.x = *reinterpret_cast<unsigned*>(&h);
+    h = __floats2half2_rn(ef[2], ef[3]);
+    pk.y = *reinterpret_cast<unsigned*>(&h);
+    h = __floats2half2_rn(ef[4], ef[5]);
+    pk.z = *reinterpret_cast<unsigned*>(&h);
+    h = __floats2half2_rn(ef[6], ef[7]);
+    pk.w = *reinterpret_cast<unsigned*>(&h);
+    a.eps[(long long)g * a.tbl_ns + si] = pk;
+    a.anc[(long long)g * a.tbl_ns + si] = cis_turns_f32(__fma_rn(p0, 0.15915494309189535, sc.cq), sc.shl);  // reference phase
+    if (g == 0) a.step[si] = cis_turns_f32(__fma_rn(a.df, t, sc.cq), sc.shl);
+}
+
+// Wf[i] = float(W[w0 + i] wsc)  (wsc alone without weights)
+__global__ void k_corr_weights(const __grid_constant__ CorrArgs a, long long w0, long long nw) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nw) return;
+    const CorrScales sc = corr_scales(a);
+    a.wf[i] = (float)((a.W ? a.W[w0 + i] : 1.0) * sc.wsc);
+}
+
+// The 8 consecutive columns (one chain group) of one sample from their table entries: emit(j, Bc, Bs, Dc, Ds) with
+// B = (cos, -sin) of the phase (FP32 angle-addition chain from the group's anchor) and D = W eps (-sin, -cos), scaled.  Columns
+// beyond ncc have eps = 0, so their D is zero; their B is not (the consumers of G / b skip those rows and columns).
+template <class Emit>
+__device__ __forceinline__ void corr_group(const uint4& eps, float2 z, float wf, float2 step, Emit&& emit) {
+    const unsigned w[4] = {eps.x, eps.y, eps.z, eps.w};
 #pragma unroll
     for (int j = 0; j < GRP; j++) {
-        const float ef = __int_as_float(0x4B400000 + ei[j]) - 12582912.0f;  // int -> float, exact below 2^22
-        const float de = ef * wg;
+        const __half2 h = *reinterpret_cast<const __half2*>(&w[j >> 1]);
+        const float de = ((j & 1) ? __high2float(h) : __low2float(h)) * wf;
         emit(j, z.x, z.y, de * z.y, -de * z.x);
         z = make_float2(fmaf(z.x, step.x, -z.y * step.y), fmaf(z.x, step.y, z.y * step.x));
     }
@@ -129,85 +161,130 @@ __device__ __forceinline__ void hmma16816(float (&c)[4], const unsigned (&a)[4],
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// one sample of a chunk as loaded (the conversion of the weight waits until the chunk is synthesised: the loads run two chunks
-// ahead and nothing may depend on them earlier)
-struct Sample {
-    double t, w;
-    bool valid;
+// table entries of one sample of a chunk for the chain groups gI (and gJ)
+struct Entry {
+    uint4 eI, eJ;
+    float2 aI, aJ, step;
+    float wf;
 };
 
-__device__ __forceinline__ Sample load_sample(const CorrArgs& a, long long s_begin, int c, int lane) {
+template <bool TWO>
+__device__ __forceinline__ Entry load_entry(const CorrArgs& a, long long s_begin, int c, int lane, int gI, int gJ) {
     const int idx = c * KC + lane;
-    Sample r;
-    r.valid = idx < a.n && s_begin + idx < a.s_end;
+    const bool valid = idx < a.n && s_begin + idx < a.s_end;
     long long s = s_begin + idx;
-    if (!r.valid) s = min(s_begin + (long long)a.n, a.s_end) - 1;
-    r.t = __ldg(a.t + s);
-    r.w = a.W ? __ldg(a.W + (a.w_abs ? s : (s - s_begin))) : 1.0;
-    return r;
+    if (!valid) s = min(s_begin + (long long)a.n, a.s_end) - 1;
+    const long long si = s - a.tbl_base;
+    Entry e;
+    e.eI = __ldg(a.eps + (long long)gI * a.tbl_ns + si);
+    e.aI = __ldg(a.anc + (long long)gI * a.tbl_ns + si);
+    if (TWO) {
+        e.eJ = __ldg(a.eps + (long long)gJ * a.tbl_ns + si);
+        e.aJ = __ldg(a.anc + (long long)gJ * a.tbl_ns + si);
+    }
+    e.step = __ldg(a.step + si);
+    e.wf = valid ? __ldg(a.wf + (a.w_abs ? si : (s - s_begin))) : 0.f;
+    return e;
 }
-__device__ __forceinline__ float sample_weight(const Sample& sm, double wsc) { return sm.valid ? (float)(sm.w * wsc) : 0.f; }
 
 constexpr int CORR_THREADS = 512;  // warps 0-7: MMA consumers (4 x 2, warp tile 32 x 64); warps 8-15: operand producers
 __device__ __forceinline__ void bar_chunk() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 2, 256;\n" ::: "memory"); }
 
-// Warp-specialised: the producers synthesise chunk c + 1 into one panel buffer while the consumers run the MMAs of chunk c
-// from the other; one 512-thread named barrier per chunk publishes a buffer and releases the other.
+// Warp-specialised: the producers build chunk c + 1 in one panel buffer while the consumers run the MMAs of chunk c from the
+// other; one 512-thread named barrier per chunk publishes a buffer and releases the other.
 // Off-diagonal tile (I > J): K' = 2 per sample, P = [D_I | B_I], Q = [B_J | D_J]  ->  acc = D_I'B_J + B_I'D_J.
-// Diagonal tile: K' = 1 per sample, P = D_I, Q = B_I -> acc = M = D_I'B_I; the epilogue adds M + M' through shared memory.
+// Diagonal tile: K' = 1 per sample, P = D_I, Q = B_I -> acc = M = D_I'B_I; the epilogue adds M + M'.
+template <bool DIAG>
+__device__ __forceinline__ void produce_chunk(const Entry& cur, int c, int lane, __half* sP, __half* sQ, int row0) {
+    __half* P = sP + (c & 1) * PANEL_H + row0 * LDH;
+    __half* Q = sQ + (c & 1) * PANEL_H + row0 * LDH;
+    if (DIAG) {
+        corr_group(cur.eI, cur.aI, cur.wf, cur.step, [&](int j, float bc, float bs, float dc, float ds) {
+            P[j * LDH + lane] = __float2half_rn(dc);
+            P[(j + FB) * LDH + lane] = __float2half_rn(ds);
+            Q[j * LDH + lane] = __float2half_rn(bc);
+            Q[(j + FB) * LDH + lane] = __float2half_rn(bs);
+        });
+    } else {
+        corr_group(cur.eI, cur.aI, cur.wf, cur.step, [&](int j, float bc, float bs, float dc, float ds) {
+            *reinterpret_cast<__half2*>(P + j * LDH + 2 * lane) = __floats2half2_rn(dc, bc);
+            *reinterpret_cast<__half2*>(P + (j + FB) * LDH + 2 * lane) = __floats2half2_rn(ds, bs);
+        });
+        corr_group(cur.eJ, cur.aJ, cur.wf, cur.step, [&](int j, float bc, float bs, float dc, float ds) {
+            *reinterpret_cast<__half2*>(Q + j * LDH + 2 * lane) = __floats2half2_rn(bc, dc);
+            *reinterpret_cast<__half2*>(Q + (j + FB) * LDH + 2 * lane) = __floats2half2_rn(bs, ds);
+        });
+    }
+    bar_chunk();  // chunk c published; the consumers have finished chunk c - 1 (the buffer chunk c + 1 goes to)
+}
+
+// table entries run two chunks ahead of their use; the loop is unrolled by three so that the three entries in flight keep
+// their registers (a rotating copy would wait for the newest load at the end of every chunk)
+template <bool DIAG>
+__device__ __forceinline__ void produce(const CorrArgs& a, long long s_begin, int nchunks, int lane, int gI, int gJ, __half* sP,
+                                        __half* sQ, int row0) {
+    const int last = nchunks - 1;
+    Entry e0 = load_entry<!DIAG>(a, s_begin, 0, lane, gI, gJ);
+    Entry e1 = load_entry<!DIAG>(a, s_begin, min(1, last), lane, gI, gJ);
+    Entry e2;
+    for (int c = 0; c < nchunks; c += 3) {
+        e2 = load_entry<!DIAG>(a, s_begin, min(c + 2, last), lane, gI, gJ);
+        produce_chunk<DIAG>(e0, c, lane, sP, sQ, row0);
+        if (c + 1 >= nchunks) break;
+        e0 = load_entry<!DIAG>(a, s_begin, min(c + 3, last), lane, gI, gJ);
+        produce_chunk<DIAG>(e1, c + 1, lane, sP, sQ, row0);
+        if (c + 2 >= nchunks) break;
+        e1 = load_entry<!DIAG>(a, s_begin, min(c + 4, last), lane, gI, gJ);
+        produce_chunk<DIAG>(e2, c + 2, lane, sP, sQ, row0);
+    }
+}
+
+// consumers: the MMAs of every chunk, warp tile 32 x 64 (A fragments from P, B fragments from Q)
+template <bool DIAG>
+__device__ __forceinline__ void consume(int nchunks, const __half* sP, const __half* sQ, int a_off, int b_off,
+                                        float (&acc)[2][8][4]) {
+    constexpr int KS = DIAG ? KC / 16 : 2 * KC / 16;
+    for (int c = 0; c < nchunks; c++) {
+        bar_chunk();
+        const __half* P = sP + (c & 1) * PANEL_H + a_off;
+        const __half* Q = sQ + (c & 1) * PANEL_H + b_off;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            unsigned af[2][4], bf[4][4];
+#pragma unroll
+            for (int i = 0; i < 2; i++) ldsm_x4(af[i], P + i * 16 * LDH + ks * 16);
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) ldsm_x4(bf[jj], Q + jj * 16 * LDH + ks * 16);
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    hmma16816(acc[i][2 * jj], af[i], bf[jj][0], bf[jj][1]);
+                    hmma16816(acc[i][2 * jj + 1], af[i], bf[jj][2], bf[jj][3]);
+                }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(CORR_THREADS, 1) k_gram_corr(const __grid_constant__ CorrArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __half* sP = reinterpret_cast<__half*>(smem_raw);            // [2][TB][LDH]: rows = functions of block I
-    __half* sQ = sP + 2 * PANEL_H;                                // [2][TB][LDH]: rows = functions of block J
-    double2* sW = reinterpret_cast<double2*>(sQ + 2 * PANEL_H);  // [2][FB]: (w, dw S) of block I, block J
-    double* red = reinterpret_cast<double*>(sW + 2 * FB);
+    __half* sP = reinterpret_cast<__half*>(smem_raw);  // [2][TB][LDH]: rows = functions of block I
+    __half* sQ = sP + 2 * PANEL_H;                      // [2][TB][LDH]: rows = functions of block J
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int I, J;
     tile_ij(blockIdx.x, I, J);
     const int prob = blockIdx.y;
     const long long s_begin = a.start0 + (long long)prob * a.hop;
-    const CorrScales sc = corr_scales(a, s_begin, red);
-    if (tid < 2 * FB) {
-        const int k = (tid < FB ? I : J) * FB + (tid & (FB - 1));
-        double2 v = k < a.ncc ? a.wtab[k] : make_double2(0.0, 0.0);
-        v.y *= sc.S;
-        sW[tid] = v;
-    }
-    __syncthreads();
     const bool diag = I == J;
     const int nchunks = (a.n + KC - 1) / KC;
     if (warp >= 8) {
         // ---- producers: warp = chain group (columns 8 g .. 8 g + 7 of a block), lane = sample of the chunk
-        const int g8 = GRP * (warp - 8);
-        Sample cur = load_sample(a, s_begin, 0, lane), nxt = load_sample(a, s_begin, nchunks > 1 ? 1 : 0, lane);
-        for (int c = 0; c < nchunks; c++) {
-            __half* P = sP + (c & 1) * PANEL_H + g8 * LDH;
-            __half* Q = sQ + (c & 1) * PANEL_H + g8 * LDH;
-            const Sample nx2 = load_sample(a, s_begin, c + 2 < nchunks ? c + 2 : c, lane);
-            const float wg = sample_weight(cur, sc.wsc);
-            const float2 step = cis_turns_f32(__fma_rn(a.df, cur.t, sc.cq), sc.shl);
-            if (diag) {
-                corr_group(sW + g8, cur.t, wg, sc, step, [&](int j, float bc, float bs, float dc, float ds) {
-                    P[j * LDH + lane] = __float2half_rn(dc);
-                    P[(j + FB) * LDH + lane] = __float2half_rn(ds);
-                    Q[j * LDH + lane] = __float2half_rn(bc);
-                    Q[(j + FB) * LDH + lane] = __float2half_rn(bs);
-                });
-            } else {
-                corr_group(sW + g8, cur.t, wg, sc, step, [&](int j, float bc, float bs, float dc, float ds) {
-                    *reinterpret_cast<__half2*>(P + j * LDH + 2 * lane) = __floats2half2_rn(dc, bc);
-                    *reinterpret_cast<__half2*>(P + (j + FB) * LDH + 2 * lane) = __floats2half2_rn(ds, bs);
-                });
-                corr_group(sW + FB + g8, cur.t, wg, sc, step, [&](int j, float bc, float bs, float dc, float ds) {
-                    *reinterpret_cast<__half2*>(Q + j * LDH + 2 * lane) = __floats2half2_rn(bc, dc);
-                    *reinterpret_cast<__half2*>(Q + (j + FB) * LDH + 2 * lane) = __floats2half2_rn(bs, ds);
-                });
-            }
-            bar_chunk();  // chunk c published; the consumers have finished chunk c - 1 (the buffer chunk c + 1 goes to)
-            cur = nxt;
-            nxt = nx2;
-        }
+        const int g = warp - 8;
+        if (diag)
+            produce<true>(a, s_begin, nchunks, lane, I * (FB / GRP) + g, 0, sP, sQ, GRP * g);
+        else
+            produce<false>(a, s_begin, nchunks, lane, I * (FB / GRP) + g, J * (FB / GRP) + g, sP, sQ, GRP * g);
     } else {
         // ---- consumers
         float acc[2][8][4];
@@ -221,27 +298,10 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) k_gram_corr(const __grid_cons
         const int wm = warp & 3, wn = warp >> 2, mi = lane >> 3;
         const int a_off = (wm * 32 + (mi & 1) * 8 + (lane & 7)) * LDH + (mi >> 1) * 8;
         const int b_off = (wn * 64 + (mi >> 1) * 8 + (lane & 7)) * LDH + (mi & 1) * 8;
-        const int ksteps = diag ? KC / 16 : 2 * KC / 16;
-        for (int c = 0; c < nchunks; c++) {
-            bar_chunk();
-            const __half* P = sP + (c & 1) * PANEL_H;
-            const __half* Q = sQ + (c & 1) * PANEL_H;
-            for (int ks = 0; ks < ksteps; ks++) {
-                unsigned af[2][4];
-#pragma unroll
-                for (int i = 0; i < 2; i++) ldsm_x4(af[i], P + a_off + i * 16 * LDH + ks * 16);
-#pragma unroll
-                for (int jj = 0; jj < 4; jj++) {
-                    unsigned bf[4];
-                    ldsm_x4(bf, Q + b_off + jj * 16 * LDH + ks * 16);
-#pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        hmma16816(acc[i][2 * jj], af[i], bf[0], bf[1]);
-                        hmma16816(acc[i][2 * jj + 1], af[i], bf[2], bf[3]);
-                    }
-                }
-            }
-        }
+        if (diag)
+            consume<true>(nchunks, sP, sQ, a_off, b_off, acc);
+        else
+            consume<false>(nchunks, sP, sQ, a_off, b_off, acc);
         // the accumulators go through shared memory (over the panel buffers) so that all 16 warps write G, coalesced
         bar_consumers();  // every consumer is done with the panels
         float* sM = reinterpret_cast<float*>(smem_raw);
@@ -256,39 +316,36 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) k_gram_corr(const __grid_cons
     }
     __syncthreads();
     // G += gscale / (S wsc) * acc (diagonal tiles: M + M'); rows / columns of columns that do not exist (k >= ncc) stay as filled
-    {
-        const float* sM = reinterpret_cast<const float*>(smem_raw);
-        const int Np = a.nblk * TB;
-        const double scl = a.gscale * sc.unscale;
-        double* Gt = a.G + (long long)prob * a.strideG + (long long)I * TB * Np + J * TB;
-        const int cl = tid & (TB - 1);
-        const bool cok = J * FB + (cl & (FB - 1)) < a.ncc;
-#pragma unroll 8
-        for (int r0 = 0; r0 < TB; r0 += CORR_THREADS / TB) {
-            const int rl = r0 + (tid >> 7);
+    const float* sM = reinterpret_cast<const float*>(smem_raw);
+    const int Np = a.nblk * TB;
+    const double scl = a.gscale * corr_scales(a).unscale;
+    double* Gt = a.G + (long long)prob * a.strideG + (long long)I * TB * Np + J * TB;
+    const int cl = tid & (TB - 1);
+    const bool cok = J * FB + (cl & (FB - 1)) < a.ncc;
+    for (int r0 = 0; r0 < TB; r0 += 8 * (CORR_THREADS / TB)) {  // 8 rows per thread at a time: all loads, then all stores
+        double gv[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int rl = r0 + q * (CORR_THREADS / TB) + (tid >> 7);
+            gv[q] = (cok && I * FB + (rl & (FB - 1)) < a.ncc) ? Gt[(long long)rl * Np + cl] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int rl = r0 + q * (CORR_THREADS / TB) + (tid >> 7);
             float v = sM[rl * LDM + cl];
             if (diag) v += sM[cl * LDM + rl];
-            if (cok && I * FB + (rl & (FB - 1)) < a.ncc) Gt[(long long)rl * Np + cl] += scl * (double)v;
+            if (cok && I * FB + (rl & (FB - 1)) < a.ncc) Gt[(long long)rl * Np + cl] = gv[q] + scl * (double)v;
         }
     }
 }
 
 // b += D'[y u]: thread = (sample of the chunk, chain group), FP32 accumulation over the chunks, fixed-order lane reduction
 __global__ void __launch_bounds__(NTHREADS) k_rhs_corr(const __grid_constant__ CorrArgs a) {
-    __shared__ double2 sW[FB];
-    __shared__ double red[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int I = blockIdx.x, prob = blockIdx.y;
     const long long s_begin = a.start0 + (long long)prob * a.hop;
-    const CorrScales sc = corr_scales(a, s_begin, red);
-    if (tid < FB) {
-        const int k = I * FB + tid;
-        double2 v = k < a.ncc ? a.wtab[k] : make_double2(0.0, 0.0);
-        v.y *= sc.S;
-        sW[tid] = v;
-    }
-    __syncthreads();
-    const int kv = min(GRP, max(0, a.ncc - (I * FB + GRP * warp)));
+    const int g = I * (FB / GRP) + warp;
+    const int kv = min(GRP, max(0, a.ncc - g * GRP));
     const int nchunks = (a.n + KC - 1) / KC;
     float ac[2][GRP], as[2][GRP];
 #pragma unroll
@@ -296,14 +353,12 @@ __global__ void __launch_bounds__(NTHREADS) k_rhs_corr(const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < GRP; j++) ac[r][j] = as[r][j] = 0.f;
     for (int c = 0; c < nchunks; c++) {
-        const Sample cur = load_sample(a, s_begin, c, lane);
+        const Entry cur = load_entry<false>(a, s_begin, c, lane, g, g);
         const int idx = c * KC + lane;
         long long s = s_begin + idx;
-        if (!cur.valid) s = min(s_begin + (long long)a.n, a.s_end) - 1;  // weight 0 there
+        if (!(idx < a.n && s < a.s_end)) s = min(s_begin + (long long)a.n, a.s_end) - 1;  // weight 0 there
         const float y0 = (float)a.y[s], y1 = a.nrhs > 1 ? (float)a.u[s] : 0.f;
-        const float wg = sample_weight(cur, sc.wsc);
-        const float2 step = cis_turns_f32(__fma_rn(a.df, cur.t, sc.cq), sc.shl);
-        corr_group(sW + GRP * warp, cur.t, wg, sc, step, [&](int j, float, float, float dc, float ds) {
+        corr_group(cur.eI, cur.aI, cur.wf, cur.step, [&](int j, float, float, float dc, float ds) {
             ac[0][j] = fmaf(dc, y0, ac[0][j]);
             as[0][j] = fmaf(ds, y0, as[0][j]);
             ac[1][j] = fmaf(dc, y1, ac[1][j]);
@@ -311,7 +366,7 @@ __global__ void __launch_bounds__(NTHREADS) k_rhs_corr(const __grid_constant__ C
         });
     }
     const int Np = a.nblk * TB;
-    const double scl = a.bscale * sc.unscale;
+    const double scl = a.bscale * corr_scales(a).unscale;
     double* Bp = a.B + (long long)prob * a.strideB;
 #pragma unroll
     for (int r = 0; r < 2; r++)
@@ -331,9 +386,20 @@ __global__ void __launch_bounds__(NTHREADS) k_rhs_corr(const __grid_constant__ C
         }
 }
 
-constexpr size_t CORR_SMEM = (size_t)4 * PANEL_H * sizeof(__half) + 2 * FB * sizeof(double2) + 32 * sizeof(double);
+constexpr size_t CORR_SMEM = (size_t)4 * PANEL_H * sizeof(__half);
 
 }  // namespace
+
+size_t corr_table_bytes_per_sample(int nblk) { return (size_t)nblk * (FB / GRP) * (sizeof(uint4) + sizeof(float2)) + sizeof(float2); }
+
+// scales + tables of the sample range [a.tbl_base, a.tbl_base + a.tbl_ns) (a.scal zeroed here); weights W[w0 .. w0 + nw) -> a.wf
+int launch_corr_tables(const CorrArgs& a, long long w0, long long nw, cudaStream_t st) {
+    cudaMemsetAsync(a.scal, 0, 2 * sizeof(double), st);
+    k_corr_max<<<296, 256, 0, st>>>(a.t, a.tbl_base, a.tbl_ns, a.W, w0, nw, reinterpret_cast<unsigned long long*>(a.scal));
+    k_corr_tables<<<dim3((unsigned)((a.tbl_ns + 255) / 256), a.nblk * (FB / GRP)), 256, 0, st>>>(a);
+    k_corr_weights<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(a, w0, nw);
+    return 3;
+}
 
 int launch_gram_corr(const CorrArgs& a, int nproblems, cudaStream_t st) {
     static bool attr = false;

@@ -122,7 +122,7 @@ void launch_rhs_from_sums(const FillArgs& a, int nrhs, double bscale, double* B,
                           cudaStream_t st);
 
 // ---- LPVS_PHASE_STRUCTURED_REF (corr.cu): first-order correction of the structured Gram matrix / right-hand sides for the
-// reference's phase rounding, G += D'B + B'D, b += D'[y u], by a half-precision tensor-core GEMM (see corr.cu)
+// reference's phase rounding, G += D'B + B'D, b += D'[y u], by a half-precision tensor-core GEMM over per-sample tables
 struct CorrArgs {
     const double* t;
     const double* W;  // nullable = 1
@@ -136,12 +136,22 @@ struct CorrArgs {
     const double2* wtab;  // per complex column (fl(2 pi f_k), fl(2 pi f_k) - 2 pi (f0 + k df)), zero beyond ncc
     double wmax, dwmax;   // max |w|, max |dw| over the columns
     double df;
+    // tables of the sample range [tbl_base, tbl_base + tbl_ns) (launch_corr_tables), rows of tbl_ns entries
+    long long tbl_base, tbl_ns;
+    double* scal;   // [2]: max |t|, max |W| of the range -> the power-of-two scales
+    uint4* eps;     // [8 nblk][tbl_ns]: eps S 2^-7 of the 8 columns of a chain group, f16
+    float2* anc;    // [8 nblk][tbl_ns]: (cos, -sin) of the reference phase of the group's first column
+    float2* step;   // [tbl_ns]: (cos, -sin)(2 pi df t)
+    float* wf;      // float(W wsc): by in-problem sample index (w_abs = 0) or by table index (w_abs = 1)
     double gscale, bscale;
     double* G;  // per problem Np x Np, lower 128-tiles (read-modify-write, every tile in full)
     long long strideG;
     double* B;  // per problem [2][Np] (read-modify-write)
     long long strideB;
 };
+size_t corr_table_bytes_per_sample(int nblk);
+// fills a.scal, a.eps, a.anc, a.step for the table range and a.wf from W[w0 .. w0 + nw); returns the number of kernels launched
+int launch_corr_tables(const CorrArgs& a, long long w0, long long nw, cudaStream_t st);
 int launch_gram_corr(const CorrArgs& a, int nproblems, cudaStream_t st);  // returns the number of kernels launched
 int launch_rhs_corr(const CorrArgs& a, int nproblems, cudaStream_t st);
 void structured_ref_wtab(double f0, double df, const double* f, int Nf, int ncol, double* out /* 2 ncol */, double* wmax,
