@@ -188,17 +188,24 @@ __device__ __forceinline__ Entry load_entry(const CorrArgs& a, long long s_begin
 }
 
 constexpr int CORR_THREADS = 512;  // warps 0-7: MMA consumers (4 x 2, warp tile 32 x 64); warps 8-15: operand producers
-__device__ __forceinline__ void bar_chunk() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+constexpr int NSTAGE = 3;          // ring of operand panel pairs between producers and consumers
+constexpr int STAGE_H = 2 * PANEL_H;  // halves per stage: P then Q
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 2, 256;\n" ::: "memory"); }
 
-// Warp-specialised: the producers build chunk c + 1 in one panel buffer while the consumers run the MMAs of chunk c from the
-// other; one 512-thread named barrier per chunk publishes a buffer and releases the other.
+// Warp-specialised: the producers fill a ring of NSTAGE operand panel pairs, the consumers run the MMAs of a stage as soon as it
+// is full and hand it back when their fragment loads are done (full / empty mbarriers): neither side waits for the other
+// in lock-step.
 // Off-diagonal tile (I > J): K' = 2 per sample, P = [D_I | B_I], Q = [B_J | D_J]  ->  acc = D_I'B_J + B_I'D_J.
 // Diagonal tile: K' = 1 per sample, P = D_I, Q = B_I -> acc = M = D_I'B_I; the epilogue adds M + M'.
+// full[s]: the 256 producer threads have written stage s; empty[s]: the 256 consumer threads have read it (mbarriers: arrive
+// releases, the parity wait acquires)
 template <bool DIAG>
-__device__ __forceinline__ void produce_chunk(const Entry& cur, int c, int lane, __half* sP, __half* sQ, int row0) {
-    __half* P = sP + (c & 1) * PANEL_H + row0 * LDH;
-    __half* Q = sQ + (c & 1) * PANEL_H + row0 * LDH;
+__device__ __forceinline__ void produce_chunk(const Entry& cur, int c, int lane, __half* ring, int row0, uint64_t* full,
+                                              uint64_t* empty) {
+    const int st = c % NSTAGE;
+    __half* P = ring + st * STAGE_H + row0 * LDH;
+    __half* Q = P + PANEL_H;
+    mbar_wait(empty + st, ((c / NSTAGE) + 1) & 1);  // first round: passes at once
     if (DIAG) {
         corr_group(cur.eI, cur.aI, cur.wf, cur.step, [&](int j, float bc, float bs, float dc, float ds) {
             P[j * LDH + lane] = __float2half_rn(dc);
@@ -216,39 +223,40 @@ __device__ __forceinline__ void produce_chunk(const Entry& cur, int c, int lane,
             *reinterpret_cast<__half2*>(Q + (j + FB) * LDH + 2 * lane) = __floats2half2_rn(bs, ds);
         });
     }
-    bar_chunk();  // chunk c published; the consumers have finished chunk c - 1 (the buffer chunk c + 1 goes to)
+    mbar_arrive(full + st);
 }
 
 // table entries run two chunks ahead of their use; the loop is unrolled by three so that the three entries in flight keep
 // their registers (a rotating copy would wait for the newest load at the end of every chunk)
 template <bool DIAG>
-__device__ __forceinline__ void produce(const CorrArgs& a, long long s_begin, int nchunks, int lane, int gI, int gJ, __half* sP,
-                                        __half* sQ, int row0) {
+__device__ __forceinline__ void produce(const CorrArgs& a, long long s_begin, int nchunks, int lane, int gI, int gJ, __half* ring,
+                                        int row0, uint64_t* full, uint64_t* empty) {
     const int last = nchunks - 1;
     Entry e0 = load_entry<!DIAG>(a, s_begin, 0, lane, gI, gJ);
     Entry e1 = load_entry<!DIAG>(a, s_begin, min(1, last), lane, gI, gJ);
     Entry e2;
     for (int c = 0; c < nchunks; c += 3) {
         e2 = load_entry<!DIAG>(a, s_begin, min(c + 2, last), lane, gI, gJ);
-        produce_chunk<DIAG>(e0, c, lane, sP, sQ, row0);
+        produce_chunk<DIAG>(e0, c, lane, ring, row0, full, empty);
         if (c + 1 >= nchunks) break;
         e0 = load_entry<!DIAG>(a, s_begin, min(c + 3, last), lane, gI, gJ);
-        produce_chunk<DIAG>(e1, c + 1, lane, sP, sQ, row0);
+        produce_chunk<DIAG>(e1, c + 1, lane, ring, row0, full, empty);
         if (c + 2 >= nchunks) break;
         e1 = load_entry<!DIAG>(a, s_begin, min(c + 4, last), lane, gI, gJ);
-        produce_chunk<DIAG>(e2, c + 2, lane, sP, sQ, row0);
+        produce_chunk<DIAG>(e2, c + 2, lane, ring, row0, full, empty);
     }
 }
 
 // consumers: the MMAs of every chunk, warp tile 32 x 64 (A fragments from P, B fragments from Q)
 template <bool DIAG>
-__device__ __forceinline__ void consume(int nchunks, const __half* sP, const __half* sQ, int a_off, int b_off,
+__device__ __forceinline__ void consume(int nchunks, const __half* ring, int a_off, int b_off, uint64_t* full, uint64_t* empty,
                                         float (&acc)[2][8][4]) {
     constexpr int KS = DIAG ? KC / 16 : 2 * KC / 16;
     for (int c = 0; c < nchunks; c++) {
-        bar_chunk();
-        const __half* P = sP + (c & 1) * PANEL_H + a_off;
-        const __half* Q = sQ + (c & 1) * PANEL_H + b_off;
+        const int st = c % NSTAGE;
+        mbar_wait(full + st, (c / NSTAGE) & 1);
+        const __half* P = ring + st * STAGE_H + a_off;
+        const __half* Q = ring + st * STAGE_H + PANEL_H + b_off;
 #pragma unroll
         for (int ks = 0; ks < KS; ks++) {
             unsigned af[2][4], bf[4][4];
@@ -256,6 +264,7 @@ __device__ __forceinline__ void consume(int nchunks, const __half* sP, const __h
             for (int i = 0; i < 2; i++) ldsm_x4(af[i], P + i * 16 * LDH + ks * 16);
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) ldsm_x4(bf[jj], Q + jj * 16 * LDH + ks * 16);
+            if (ks == KS - 1) mbar_arrive(empty + st);  // this thread has read all it needs of the stage
 #pragma unroll
             for (int jj = 0; jj < 4; jj++)
 #pragma unroll
@@ -269,8 +278,12 @@ __device__ __forceinline__ void consume(int nchunks, const __half* sP, const __h
 
 __global__ void __launch_bounds__(CORR_THREADS, 1) k_gram_corr(const __grid_constant__ CorrArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __half* sP = reinterpret_cast<__half*>(smem_raw);  // [2][TB][LDH]: rows = functions of block I
-    __half* sQ = sP + 2 * PANEL_H;                      // [2][TB][LDH]: rows = functions of block J
+    __half* ring = reinterpret_cast<__half*>(smem_raw);  // [NSTAGE][P | Q][TB][LDH]: rows = functions of block I | block J
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + NSTAGE * STAGE_H);
+    uint64_t* empty = full + NSTAGE;
+    if (threadIdx.x < 2 * NSTAGE) mbar_init(full + threadIdx.x, CORR_THREADS / 2);  // full[] and empty[] are contiguous
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int I, J;
     tile_ij(blockIdx.x, I, J);
@@ -282,9 +295,9 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) k_gram_corr(const __grid_cons
         // ---- producers: warp = chain group (columns 8 g .. 8 g + 7 of a block), lane = sample of the chunk
         const int g = warp - 8;
         if (diag)
-            produce<true>(a, s_begin, nchunks, lane, I * (FB / GRP) + g, 0, sP, sQ, GRP * g);
+            produce<true>(a, s_begin, nchunks, lane, I * (FB / GRP) + g, 0, ring, GRP * g, full, empty);
         else
-            produce<false>(a, s_begin, nchunks, lane, I * (FB / GRP) + g, J * (FB / GRP) + g, sP, sQ, GRP * g);
+            produce<false>(a, s_begin, nchunks, lane, I * (FB / GRP) + g, J * (FB / GRP) + g, ring, GRP * g, full, empty);
     } else {
         // ---- consumers
         float acc[2][8][4];
@@ -299,9 +312,9 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) k_gram_corr(const __grid_cons
         const int a_off = (wm * 32 + (mi & 1) * 8 + (lane & 7)) * LDH + (mi >> 1) * 8;
         const int b_off = (wn * 64 + (mi >> 1) * 8 + (lane & 7)) * LDH + (mi & 1) * 8;
         if (diag)
-            consume<true>(nchunks, sP, sQ, a_off, b_off, acc);
+            consume<true>(nchunks, ring, a_off, b_off, full, empty, acc);
         else
-            consume<false>(nchunks, sP, sQ, a_off, b_off, acc);
+            consume<false>(nchunks, ring, a_off, b_off, full, empty, acc);
         // the accumulators go through shared memory (over the panel buffers) so that all 16 warps write G, coalesced
         bar_consumers();  // every consumer is done with the panels
         float* sM = reinterpret_cast<float*>(smem_raw);
@@ -386,7 +399,7 @@ __global__ void __launch_bounds__(NTHREADS) k_rhs_corr(const __grid_constant__ C
         }
 }
 
-constexpr size_t CORR_SMEM = (size_t)4 * PANEL_H * sizeof(__half);
+constexpr size_t CORR_SMEM = (size_t)NSTAGE * STAGE_H * sizeof(__half) + 2 * NSTAGE * sizeof(uint64_t);
 
 }  // namespace
 

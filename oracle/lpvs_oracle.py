@@ -213,6 +213,66 @@ def gram_from_trig_sums(t: np.ndarray, f: np.ndarray, W: Optional[np.ndarray] = 
     return G, b
 
 
+def _two_prod_err(a: np.ndarray, b: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """p = fl(a b) and e = a b - p exactly (Dekker / Veltkamp splitting: what one FMA gives on the device)."""
+    p = a * b
+    c = 134217729.0  # 2^27 + 1
+    ah = (a * c) - ((a * c) - a)
+    al = a - ah
+    bh = (b * c) - ((b * c) - b)
+    bl = b - bh
+    e = ((ah * bh - p) + ah * bl + al * bh) + al * bl
+    return p, e
+
+
+def gram_phase_correction(t: np.ndarray, f: np.ndarray, W: Optional[np.ndarray] = None, y: Optional[np.ndarray] = None,
+                          half: bool = True) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+    """First-order correction that takes gram_from_trig_sums (ideal phases theta = 2 pi (f0 + k df) t) to the reference's basis
+    at phi = fl(fl(2 pi f) t) (src/lsfft.jl:34,41): with eps = phi - theta, B = (cos, -sin)(phi) and D = W eps (-sin, -cos)(phi),
+        dG = (D'B + B'D) / (2 Nf),   db = D'y / sqrt(2 Nf).
+    CPU restatement of LPVS_PHASE_STRUCTURED_REF (csrc/corr.cu) -- not a reference algorithm.  eps is exact: the rounding error
+    of the product w t (two-product) plus (fl(2 pi f_k) - 2 pi f_k) t; `half` rounds eps and the operands to float16 as the
+    tensor-core kernel does (float32 accumulation)."""
+    t = np.asarray(t, dtype=np.float64)
+    f = np.asarray(f, dtype=np.float64)
+    zerofreq = check_freq(f)
+    N, Nf = len(t), len(f)
+    Wv = np.ones(N) if W is None else np.asarray(W, dtype=np.float64)
+    LD = np.longdouble
+    twopi = LD("6.283185307179586476925286766559005768")
+    df = LD((f[-1] - f[0]) / (Nf - 1)) if Nf > 1 else LD(0.0)
+    w = 2.0 * np.pi * f  # fl(2 pi f), src/lsfft.jl:34
+    dw = (w.astype(LD) - twopi * (LD(f[0]) + df * np.arange(Nf).astype(LD))).astype(np.float64)
+    p, e = _two_prod_err(t[:, None], w[None, :])  # p = fl(w t), e = w t - p
+    eps = dw[None, :] * t[:, None] - e
+    c, ms = np.cos(p), -np.sin(p)
+    if half:
+        scale = 2.0 ** (14 - math.frexp(max(np.abs(eps).max(), 1e-300))[1])
+        wsc = 2.0 ** (-math.frexp(np.abs(Wv).max())[1])
+        ef = (eps * scale).astype(np.float16).astype(np.float32)
+        de = ef * (Wv * wsc).astype(np.float32)[:, None]
+        q = lambda a: a.astype(np.float16).astype(np.float32)  # noqa: E731
+        D = np.hstack([q(de * ms.astype(np.float32)), q(-de * c.astype(np.float32))])
+        B = np.hstack([q(c), q(ms)])
+        M = (D.T @ B).astype(np.float64) / (scale * wsc)
+        db = None if y is None else (np.hstack([de * ms.astype(np.float32), -de * c.astype(np.float32)]).T.astype(np.float64)
+                                     @ np.asarray(y, dtype=np.float64)) / (scale * wsc)
+    else:
+        de = eps * Wv[:, None]
+        D = np.hstack([de * ms, -de * c])
+        B = np.hstack([c, ms])
+        M = D.T @ B
+        db = None if y is None else D.T @ np.asarray(y, dtype=np.float64)
+    dG = (M + M.T) / (2 * Nf)
+    if db is not None:
+        db = db / math.sqrt(2 * Nf)
+    if zerofreq is not None:
+        keep = np.r_[0:Nf, Nf + 1:2 * Nf]
+        dG = dG[np.ix_(keep, keep)]
+        db = None if db is None else db[keep]
+    return dG, db
+
+
 def fourier2complex(x: np.ndarray, zerofreq: Optional[int]) -> np.ndarray:
     """src/utilities.jl:62-73."""
     x = np.asarray(x)

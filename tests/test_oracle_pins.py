@@ -294,3 +294,27 @@ def test_gram_from_trig_sums_is_the_product_form(N, Nf, f0, df):
         assert G.shape == (A.shape[1], A.shape[1])
         assert np.abs(G - Aw.T @ A).max() <= 1e-13 * np.abs(Aw.T @ A).max()
         assert np.abs(b - Aw.T @ y).max() <= 1e-13 * np.abs(Aw.T @ y).max()
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_first_order_phase_correction_recovers_the_reference_gram(half):
+    """LPVS_PHASE_STRUCTURED_REF (csrc/corr.cu) restated: at large phases (2.6e7 rad: the reference's fl(fl(2 pi f) t) is off the
+    ideal phase by up to 2.9e-9 rad) the Gram matrix / right-hand side of the ideal grid differ from the reference's products by
+    ~1e-10; adding the first-order terms D'B + B'D, D'y leaves <= 1e-3 of that -- with float16 operands too (what the tensor-core
+    kernel uses), because only the DIFFERENCE goes through half precision."""
+    rng = np.random.default_rng(12)
+    N, Nf = 2048, 48
+    t = 9.99 + np.sort(2.4e-3 * rng.random(N))
+    f = np.arange(Nf) * (4096 / 2.4e-3 / 4096) * 5.0
+    W = 3.0 * o.hanning(N)
+    y = rng.standard_normal(N)
+    A, _ = o.get_fourier_regressor(t, f)
+    Gr, br = (A.T * W) @ A, (A.T * W) @ y
+    G0, b0 = o.gram_from_trig_sums(t, f, W, y)
+    dG, db = o.gram_phase_correction(t, f, W, y, half=half)
+    e0 = np.abs(G0 - Gr).max() / np.abs(Gr).max()
+    e1 = np.abs(G0 + dG - Gr).max() / np.abs(Gr).max()
+    f0 = np.abs(b0 - br).max() / np.abs(br).max()
+    f1 = np.abs(b0 + db - br).max() / np.abs(br).max()
+    assert e0 > 1e-11 and f0 > 1e-11  # the effect is there
+    assert e1 <= 1e-3 * e0 + 2e-14 and f1 <= 1e-3 * f0 + 2e-14, (e0, e1, f0, f1)
