@@ -873,9 +873,10 @@ def main():
             "rel_l2_vs_default_mode": float(_np.linalg.norm(sums_ref - sums_default) / _np.linalg.norm(sums_default)),
             "correction_flop_per_step": float(K) * (NF // 64 + (NF % 64 > 0)) * ((NF // 64 + (NF % 64 > 0)) + 1) / 2
                                         * 2.0 * 128 * 128 * 2 * n,
-            "note": "LPVS_PHASE_STRUCTURED_REF (opt-in, not the headline): structured Gram stage + k_gram_corr (f16 mma.sync "
-                    "m16n8k16, f32 accumulation, K' = 2 n per lower 128-tile) + k_rhs_corr; reference phase rounding to first "
-                    "order, tests/test_gpu_structured.py"}
+            "note": "LPVS_PHASE_STRUCTURED_REF (opt-in, not the headline): structured Gram stage + k_corr_tables (eps exact in "
+                    "FP64, once per (column, sample)) + k_gram_corr (f16 mma.sync m16n8k16, f32 accumulation, warp-specialised "
+                    "producers / consumers over a 3-stage mbarrier ring) + k_rhs_corr; the reference's phase rounding to first "
+                    "order: the default mode's parity class (tests/test_gpu_structured.py, tests/test_gpu_baseline_parity.py)"}
     except Exception as e:  # never lose the headline line to an extra leg
         extra["structured_ref_mode"] = {"error": repr(e)[:300]}
     finally:

@@ -365,12 +365,22 @@ __global__ void __launch_bounds__(NTHREADS) k_rhs_corr(const __grid_constant__ C
     for (int r = 0; r < 2; r++)
 #pragma unroll
         for (int j = 0; j < GRP; j++) ac[r][j] = as[r][j] = 0.f;
-    for (int c = 0; c < nchunks; c++) {
-        const Entry cur = load_entry<false>(a, s_begin, c, lane, g, g);
+    auto load_y = [&](int c, float& y0, float& y1) {
         const int idx = c * KC + lane;
         long long s = s_begin + idx;
         if (!(idx < a.n && s < a.s_end)) s = min(s_begin + (long long)a.n, a.s_end) - 1;  // weight 0 there
-        const float y0 = (float)a.y[s], y1 = a.nrhs > 1 ? (float)a.u[s] : 0.f;
+        y0 = (float)__ldg(a.y + s);
+        y1 = a.nrhs > 1 ? (float)__ldg(a.u + s) : 0.f;
+    };
+    Entry nxt = load_entry<false>(a, s_begin, 0, lane, g, g);
+    float ny0, ny1;
+    load_y(0, ny0, ny1);
+    for (int c = 0; c < nchunks; c++) {
+        const Entry cur = nxt;
+        const float y0 = ny0, y1 = ny1;
+        const int cn = c + 1 < nchunks ? c + 1 : c;  // the next chunk's entries load while this one is accumulated
+        nxt = load_entry<false>(a, s_begin, cn, lane, g, g);
+        load_y(cn, ny0, ny1);
         corr_group(cur.eI, cur.aI, cur.wf, cur.step, [&](int j, float, float, float dc, float ds) {
             ac[0][j] = fmaf(dc, y0, ac[0][j]);
             as[0][j] = fmaf(ds, y0, as[0][j]);
