@@ -20,7 +20,7 @@
 // 3 bytes of table per (column, sample), window-independent (overlapping windows and all tiles of a window share them).
 //
 // Accuracy (tests/test_gpu_structured.py, tools/corr_emulation.py): dG to 3e-4 of itself; cfg5a window 4166 (phase 2.6e7 rad,
-// cond(A) 2e5): 4e-9 -> 5e-11 against the literal oracle.
+// cond(A) 2e5): 4e-9 -> 5e-11 against the reference-literal N-rhs LU solve on the CPU.
 #include <cuda_fp16.h>
 
 #include "gram.cuh"
