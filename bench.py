@@ -903,6 +903,13 @@ def main():
                     "FP64, once per (column, sample)) + k_gram_corr (f16 mma.sync m16n8k16, f32 accumulation, warp-specialised "
                     "producers / consumers over a 3-stage mbarrier ring) + k_rhs_corr; the reference's phase rounding to first "
                     "order: the default mode's parity class (tests/test_gpu_structured.py, tests/test_gpu_baseline_parity.py)"}
+        sm_ = extra.get("structured_mode", {}).get("gram_stage_ms_per_step")
+        if sm_:  # tables + k_gram_corr + k_rhs_corr: what the correction adds to the structured Gram stage
+            r_ = extra["structured_ref_mode"]
+            r_["correction_stage_ms_per_step"] = r_["gram_stage_ms_per_step"] - sm_
+            r_["correction_f16_tflops_over_stage"] = r_["correction_flop_per_step"] / (r_["correction_stage_ms_per_step"] * 1e-3) / 1e12
+            r_["f16_peaks_tflops"] = {"mma_sync_m16n8k16_issue_peak_this_pool": 554.0, "source": "tools/mma_probe.cu; k_gram_corr "
+                                      "alone: profiles/r02_summary.md (14.0 ms = 314 TFLOP/s = 57 %)"}
     except Exception as e:  # never lose the headline line to an extra leg
         extra["structured_ref_mode"] = {"error": repr(e)[:300]}
     finally:

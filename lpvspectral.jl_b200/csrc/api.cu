@@ -402,6 +402,7 @@ static int structured_correct(lpvs_ctx* c, const FourierPlan& pl, const GramArgs
     c->launches += launch_corr_tables(a, w0, nw, c->st);
     c->launches += launch_gram_corr(a, nprob, c->st);
     if (B && nrhs > 0 && g.y) c->launches += launch_rhs_corr(a, nprob, c->st);
+    LPVS_CU(c, cudaGetLastError());
     return LPVS_OK;
 }
 

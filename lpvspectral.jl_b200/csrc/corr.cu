@@ -425,10 +425,12 @@ int launch_corr_tables(const CorrArgs& a, long long w0, long long nw, cudaStream
 }
 
 int launch_gram_corr(const CorrArgs& a, int nproblems, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr_done[64] = {};  // per device: function attributes belong to the device's context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
         cudaFuncSetAttribute(k_gram_corr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CORR_SMEM);
-        attr = true;
+        attr_done[dev & 63] = true;
     }
     int launched = 0;
     const int ntiles = a.nblk * (a.nblk + 1) / 2;
