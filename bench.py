@@ -508,32 +508,39 @@ def cfg5_legs(ctx, lp, L, C, D, torch, dist, rank, world, local, allmax, barrier
                              "CUDA events on the launching stream, max over ranks; busbw = 2(P-1)/P bytes/time against the "
                              "725 GB/s measured 8-GPU bus bandwidth"},
         "peak_power_yy": float((x[0].real ** 2 + x[0].imag ** 2).max())}
-    # the same problem with the Gram matrix from its trigonometric sums (opt-in LPVS_PHASE_STRUCTURED, exact-phase class)
-    try:
-        ctx.set_option(L.OPT_PHASE_MODE, L.PHASE_STRUCTURED)
-        xs = np.empty((2, Nf), dtype=np.complex128)
-        best_s = None
-        for rep in range(2):
-            barrier()
-            w0 = time.perf_counter()
-            ctx.check(ctx.lib.lpvs_gram_partial_dev(ctx.h, p(d_y), p(d_u), p(d_t), p(d_W), r1 - r0, vp(f), Nf, p(packed)))
-            g_ms = ctx.last_call_ms()
-            if world > 1:
-                dist.all_reduce(packed)
-                torch.cuda.synchronize()
-            ctx.check(ctx.lib.lpvs_solve_packed_dev(ctx.h, p(packed), vp(f), Nf, 2, LAMBDA, vp(xs), C.byref(info)))
-            wall = allmax(time.perf_counter() - w0)
-            if best_s is None or wall < best_s[0]:
-                best_s = (wall, allmax(g_ms))
-        out["cfg5b_rowsharded"]["structured_mode"] = {
-            "ms_total_resident": best_s[0] * 1e3, "gram_ms": best_s[1],
-            "rel_l2_vs_default_mode": float(np.linalg.norm(xs - x) / np.linalg.norm(x)),
-            "note": "opt-in LPVS_PHASE_STRUCTURED: 3 Nf sums over the rows instead of the DMMA Gram; the difference to the default "
-                    "mode is the reference's phase rounding at phases up to 2.6e7 rad (DESIGN.md 1b / 3a)"}
-    except Exception as e:  # never lose the headline line to an extra leg
-        out["cfg5b_rowsharded"]["structured_mode"] = {"error": repr(e)[:300]}
-    finally:
-        ctx.set_option(L.OPT_PHASE_MODE, L.PHASE_AUTO)
+    # the same problem with the Gram matrix from its trigonometric sums (opt-in LPVS_PHASE_STRUCTURED, exact-phase class) and
+    # with the first-order correction to the reference's phase rounding on top (LPVS_PHASE_STRUCTURED_REF: per-sample tables
+    # built segment by segment, half-precision tensor-core GEMM over sample splits)
+    for key, mode, note in (
+            ("structured_mode", L.PHASE_STRUCTURED,
+             "opt-in LPVS_PHASE_STRUCTURED: 3 Nf sums over the rows instead of the DMMA Gram; the difference to the default "
+             "mode is the reference's phase rounding at phases up to 2.6e7 rad (DESIGN.md 1b / 3a)"),
+            ("structured_ref_mode", L.PHASE_STRUCTURED_REF,
+             "opt-in LPVS_PHASE_STRUCTURED_REF: the sums + the first-order phase-rounding correction (DESIGN.md 3b): the "
+             "default mode's class")):
+        try:
+            ctx.set_option(L.OPT_PHASE_MODE, mode)
+            xs = np.empty((2, Nf), dtype=np.complex128)
+            best_s = None
+            for rep in range(2):
+                barrier()
+                w0 = time.perf_counter()
+                ctx.check(ctx.lib.lpvs_gram_partial_dev(ctx.h, p(d_y), p(d_u), p(d_t), p(d_W), r1 - r0, vp(f), Nf, p(packed)))
+                g_ms = ctx.last_call_ms()
+                if world > 1:
+                    dist.all_reduce(packed)
+                    torch.cuda.synchronize()
+                ctx.check(ctx.lib.lpvs_solve_packed_dev(ctx.h, p(packed), vp(f), Nf, 2, LAMBDA, vp(xs), C.byref(info)))
+                wall = allmax(time.perf_counter() - w0)
+                if best_s is None or wall < best_s[0]:
+                    best_s = (wall, allmax(g_ms))
+            out["cfg5b_rowsharded"][key] = {
+                "ms_total_resident": best_s[0] * 1e3, "gram_ms": best_s[1],
+                "rel_l2_vs_default_mode": float(np.linalg.norm(xs - x) / np.linalg.norm(x)), "note": note}
+        except Exception as e:  # never lose the headline line to an extra leg
+            out["cfg5b_rowsharded"][key] = {"error": repr(e)[:300]}
+        finally:
+            ctx.set_option(L.OPT_PHASE_MODE, L.PHASE_AUTO)
     del d_t, d_y, d_u, d_W, packed
     torch.cuda.empty_cache()
     return out

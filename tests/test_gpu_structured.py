@@ -191,3 +191,33 @@ def test_structured_ref_large_problem_with_sample_splits(ctx):
     print(f"tall problem: G structured {e0:.1e} -> structured_ref {e1:.1e}; b {b0:.1e} -> {b1:.1e} (vs direct mode)")
     assert e1 <= 5e-13 + 2e-3 * e0 and b1 <= 5e-13 + 2e-3 * b0
     assert np.array_equal(out[L.PHASE_STRUCTURED_REF][0], out[L.PHASE_STRUCTURED_REF][0].T)
+
+
+def test_structured_ref_table_segments(ctx):
+    """A problem whose correction tables exceed one 4 GiB segment (2048 frequencies: 6 KB of table per sample, 800 k samples ->
+    two segments, each with its own power-of-two scales, accumulating into the same sample-split partials): structured_ref vs
+    the per-element reference-phase mode at large phases."""
+    import lpvspectral_jl_b200 as lp
+    from lpvspectral_jl_b200 import _lib as L
+
+    rng = np.random.default_rng(33)
+    N, Nf = 800_000, 2048
+    t = 2.0e4 + np.sort(40.0 * rng.random(N))
+    f = np.arange(Nf) * 0.21
+    W = 0.5 + rng.random(N)
+    y = np.sin(2 * np.pi * 37.8 * t) + 0.1 * rng.standard_normal(N)
+    out = {}
+    for mode in (L.PHASE_STRUCTURED, L.PHASE_STRUCTURED_REF, L.PHASE_DIRECT):
+        ctx.set_option(L.OPT_PHASE_MODE, mode)
+        try:
+            out[mode] = lp.gram_fourier(t, f, W, y, ctx=ctx)
+        finally:
+            ctx.set_option(L.OPT_PHASE_MODE, 0)
+    Gd, bd = out[L.PHASE_DIRECT]
+    e0 = np.abs(out[L.PHASE_STRUCTURED][0] - Gd).max() / np.abs(Gd).max()
+    e1 = np.abs(out[L.PHASE_STRUCTURED_REF][0] - Gd).max() / np.abs(Gd).max()
+    b0 = np.abs(out[L.PHASE_STRUCTURED][1] - bd).max() / np.abs(bd).max()
+    b1 = np.abs(out[L.PHASE_STRUCTURED_REF][1] - bd).max() / np.abs(bd).max()
+    print(f"two table segments: G structured {e0:.1e} -> structured_ref {e1:.1e}; b {b0:.1e} -> {b1:.1e} (vs direct mode)")
+    assert e1 <= 5e-13 + 2e-3 * e0 and b1 <= 5e-13 + 2e-3 * b0
+    ctx.release_workspace()
