@@ -16,7 +16,7 @@
 //                   reference phase (float2), per sample the step rotation e^{-i 2 pi df t} (float2); Wf = float(W wsc)
 //   k_gram_corr     one CTA per (lower 128 x 128 tile, problem), warp-specialised: 8 producer warps turn table entries into f16
 //                   operand panels (FP32 angle-addition chain from the anchor), 8 consumer warps run the MMAs; G += scale * acc
-//   k_rhs_corr      one CTA per (64-frequency block, problem): b += D'[y u] in FP32
+//   k_rhs_corr      one CTA per (64-frequency block, problem): b += D'[y u], eps in FP64 (21 bits), products / sums in FP32
 // 3 bytes of table per (column, sample), window-independent (overlapping windows and all tiles of a window share them).
 //
 // Accuracy (tests/test_gpu_structured.py, tools/corr_emulation.py): dG to 3e-4 of itself; cfg5a window 4166 (phase 2.6e7 rad,
@@ -352,7 +352,31 @@ __global__ void __launch_bounds__(CORR_THREADS, 1) k_gram_corr(const __grid_cons
     }
 }
 
-// b += D'[y u]: thread = (sample of the chunk, chain group), FP32 accumulation over the chunks, fixed-order lane reduction
+// b += D'[y u]: thread = (sample of the chunk, chain group), FP32 accumulation over the chunks, fixed-order lane reduction.
+// eps is taken in FP64 here (this kernel has no HMMAs to wait behind) and enters the products with 21 bits instead of the
+// table's 11: b carries the residual of the correction at full weight (dx = G^-1 (db - dG x)), and with the f16 eps it was the
+// larger of the two (8e-13 of b against 5e-14 of G at 2.6e7 rad).  Anchors, steps and weights still come from the tables.
+struct RhsEntry {
+    float2 anc, step;
+    float wf, y0, y1;
+    double t;
+};
+__device__ __forceinline__ RhsEntry load_rhs_entry(const CorrArgs& a, long long s_begin, int c, int lane, int g) {
+    const int idx = c * KC + lane;
+    const bool valid = idx < a.n && s_begin + idx < a.s_end;
+    long long s = s_begin + idx;
+    if (!valid) s = min(s_begin + (long long)a.n, a.s_end) - 1;  // weight 0 there
+    const long long si = s - a.tbl_base;
+    RhsEntry e;
+    e.anc = __ldg(a.anc + (long long)g * a.tbl_ns + si);
+    e.step = __ldg(a.step + si);
+    e.wf = valid ? __ldg(a.wf + (a.w_abs ? si : (s - s_begin))) : 0.f;
+    e.t = __ldg(a.t + s);
+    e.y0 = (float)__ldg(a.y + s);
+    e.y1 = a.nrhs > 1 ? (float)__ldg(a.u + s) : 0.f;
+    return e;
+}
+
 __global__ void __launch_bounds__(NTHREADS) k_rhs_corr(const __grid_constant__ CorrArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int I = blockIdx.x, prob = blockIdx.y;
@@ -360,36 +384,41 @@ __global__ void __launch_bounds__(NTHREADS) k_rhs_corr(const __grid_constant__ C
     const int g = I * (FB / GRP) + warp;
     const int kv = min(GRP, max(0, a.ncc - g * GRP));
     const int nchunks = (a.n + KC - 1) / KC;
+    const CorrScales sc = corr_scales(a);
+    const double negS = -sc.S;
+    double2 wt[GRP];  // (w, dw S) of this warp's columns; zero beyond ncc
+#pragma unroll
+    for (int j = 0; j < GRP; j++) {
+        wt[j] = a.wtab[g * GRP + j];
+        wt[j].y *= sc.S;
+    }
     float ac[2][GRP], as[2][GRP];
 #pragma unroll
     for (int r = 0; r < 2; r++)
 #pragma unroll
         for (int j = 0; j < GRP; j++) ac[r][j] = as[r][j] = 0.f;
-    auto load_y = [&](int c, float& y0, float& y1) {
-        const int idx = c * KC + lane;
-        long long s = s_begin + idx;
-        if (!(idx < a.n && s < a.s_end)) s = min(s_begin + (long long)a.n, a.s_end) - 1;  // weight 0 there
-        y0 = (float)__ldg(a.y + s);
-        y1 = a.nrhs > 1 ? (float)__ldg(a.u + s) : 0.f;
-    };
-    Entry nxt = load_entry<false>(a, s_begin, 0, lane, g, g);
-    float ny0, ny1;
-    load_y(0, ny0, ny1);
+    RhsEntry nxt = load_rhs_entry(a, s_begin, 0, lane, g);
     for (int c = 0; c < nchunks; c++) {
-        const Entry cur = nxt;
-        const float y0 = ny0, y1 = ny1;
-        const int cn = c + 1 < nchunks ? c + 1 : c;  // the next chunk's entries load while this one is accumulated
-        nxt = load_entry<false>(a, s_begin, cn, lane, g, g);
-        load_y(cn, ny0, ny1);
-        corr_group(cur.eI, cur.aI, cur.wf, cur.step, [&](int j, float, float, float dc, float ds) {
-            ac[0][j] = fmaf(dc, y0, ac[0][j]);
-            as[0][j] = fmaf(ds, y0, as[0][j]);
-            ac[1][j] = fmaf(dc, y1, ac[1][j]);
-            as[1][j] = fmaf(ds, y1, as[1][j]);
-        });
+        const RhsEntry cur = nxt;
+        nxt = load_rhs_entry(a, s_begin, c + 1 < nchunks ? c + 1 : c, lane, g);  // loads while this chunk is accumulated
+        float2 z = cur.anc;
+#pragma unroll
+        for (int j = 0; j < GRP; j++) {
+            const double p = __dmul_rn(wt[j].x, cur.t);       // fl(w t)
+            const double e = __fma_rn(wt[j].x, cur.t, -p);    // w t - fl(w t), exact
+            const double q = __fma_rn(e, negS, CF);
+            const int ei = __double2loint(__fma_rn(wt[j].y, cur.t, q));  // eps S, |.| <= 2^21
+            const float de = (__int_as_float(0x4B400000 + ei) - 12582912.0f) * 0.0078125f * cur.wf;  // the table's scaling
+            const float dc = de * z.y, ds = -de * z.x;
+            ac[0][j] = fmaf(dc, cur.y0, ac[0][j]);
+            as[0][j] = fmaf(ds, cur.y0, as[0][j]);
+            ac[1][j] = fmaf(dc, cur.y1, ac[1][j]);
+            as[1][j] = fmaf(ds, cur.y1, as[1][j]);
+            z = make_float2(fmaf(z.x, cur.step.x, -z.y * cur.step.y), fmaf(z.x, cur.step.y, z.y * cur.step.x));
+        }
     }
     const int Np = a.nblk * TB;
-    const double scl = a.bscale * corr_scales(a).unscale;
+    const double scl = a.bscale * sc.unscale;
     double* Bp = a.B + (long long)prob * a.strideB;
 #pragma unroll
     for (int r = 0; r < 2; r++)

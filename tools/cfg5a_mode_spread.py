@@ -27,8 +27,12 @@ vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
 info = C.c_int(0)
 res = {}
 coh = {}
-for name, mode in (("default_chain_ref", L.PHASE_AUTO), ("direct", L.PHASE_DIRECT), ("structured_ref", L.PHASE_STRUCTURED_REF),
-                   ("chain_exact_phase", L.PHASE_CHAIN), ("structured", L.PHASE_STRUCTURED)):
+MODES = (("default_chain_ref", L.PHASE_AUTO), ("direct", L.PHASE_DIRECT), ("structured_ref", L.PHASE_STRUCTURED_REF),
+         ("chain_exact_phase", L.PHASE_CHAIN), ("structured", L.PHASE_STRUCTURED))
+want = set(sys.argv[1:])  # optional subset of mode names (the default mode always runs: it is the yardstick)
+for name, mode in MODES:
+    if want and name not in want and name != "default_chain_ref":
+        continue
     ctx.set_option(L.OPT_PHASE_MODE, mode)
     sums = np.zeros(4 * Nf)
     w0 = time.perf_counter()
