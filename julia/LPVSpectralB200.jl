@@ -55,7 +55,7 @@ const OPT_ADMM_M32 = Cint(7)
 setopt(key, v) = check(ccall((:lpvs_set_option, liblpvs), Cint, (Ptr{Cvoid}, Cint, Float64), ctx(), key, Float64(v)))
 # LPVS_OPT_PHASE_MODE (include/lpvs.h, enum lpvs_phase_mode): how the Fourier basis / its Gram matrix is formed.  The default
 # (:auto) reproduces the reference's phase rounding fl(fl(2 pi f) t) (src/lsfft.jl:34,41); :structured_ref gives the same
-# results from the trigonometric-sum Gram matrix + a half-precision tensor-core correction, 2.7x faster on uniform grids.
+# results from the trigonometric-sum Gram matrix + a half-precision tensor-core correction, 2.6x faster on uniform grids.
 const OPT_PHASE_MODE = Cint(0)
 const PHASE_MODES = (auto = 0, chain = 1, direct = 2, chain_ref = 3, structured = 4, structured_ref = 5)
 "phase_mode!(:auto | :chain | :direct | :chain_ref | :structured | :structured_ref) -- applies to every later call."
