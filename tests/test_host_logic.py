@@ -316,3 +316,67 @@ def test_julia_shim_phase_modes_match_header():
         assert cval == val, name
     assert re.search(r"const OPT_PHASE_MODE = Cint\((\d+)\)", shim).group(1) == re.search(
         r"\bLPVS_OPT_PHASE_MODE\s*=\s*(\d+)", hdr).group(1)
+
+
+def test_corr_fixed_point_tricks_restated():
+    """The FP64 arithmetic of csrc/corr.cu (k_corr_tables / k_rhs_corr), restated with exact rationals for the FMAs: (i) the
+    double-double (w, dw) table of structured_ref_wtab, (ii) eps S = round((fl(w t) - w t + dw t) S) read from the low word of
+    fma(dw S, t, fma(e, -S, 1.5 2^52)), bounded by 2^21 by the power-of-two scale, (iii) the fraction of the phase in turns from
+    the low word of fma(p, 1/(2 pi), 1.5 2^(52 - fb)) -- all against 60-digit arithmetic."""
+    import math
+    import struct
+    from fractions import Fraction as Fr
+
+    import mpmath as mp
+
+    mp.mp.dps = 60
+
+    def fma(a, b, c):
+        return float(Fr(a) * Fr(b) + Fr(c))
+
+    def loint(x):
+        lo = struct.unpack("<q", struct.pack("<d", x))[0] & 0xFFFFFFFF
+        return lo - (1 << 32) if lo >= (1 << 31) else lo
+
+    P_HI, P_LO = 6.283185307179586, 2.4492935982947064e-16
+    rng = np.random.default_rng(1)
+    Nf, n, fs = 64, 4096, 1.6e6
+    f = np.arange(Nf) * 2 * fs / n
+    f0, df = float(f[0]), float((f[-1] - f[0]) / (Nf - 1))
+    tab = []
+    for k in range(Nf):  # structured_ref_wtab
+        w = P_HI * f[k]
+        kd = float(k) * df
+        kd_lo = fma(float(k), df, -kd)
+        s_hi = f0 + kd
+        bb = s_hi - f0
+        s_lo = ((f0 - (s_hi - bb)) + (kd - bb)) + kd_lo
+        ph = P_HI * s_hi
+        pe = fma(P_HI, s_hi, -ph)
+        p_lo = fma(P_LO, s_hi, pe) + P_HI * s_lo
+        tab.append((w, (w - ph) - p_lo))
+    for k in (1, 7, 33, 63):
+        exact = mp.mpf(tab[k][0]) - 2 * mp.pi * (mp.mpf(f0) + k * mp.mpf(df))
+        assert abs(tab[k][1] - float(exact)) <= 1e-12 * abs(float(exact))
+    ts = np.sort(5 + 5 * rng.random(6))
+    wmax, dwmax, tm = max(abs(w) for w, _ in tab), max(abs(d) for _, d in tab), float(ts.max())
+    epsmax = wmax * tm * 1.1102230246251565e-16 + dwmax * tm
+    S = 2.0 ** (21 - math.frexp(epsmax)[1])
+    fb = max(1, min(24, 51 - math.frexp(wmax * tm * 0.15915494309189535)[1]))
+    cq, shl, CF = 1.5 * 2.0 ** (52 - fb), 32 - fb, 6755399441055744.0
+    for t in ts:
+        t = float(t)
+        for k in (1, 7, 33, 63):
+            w, dw = tab[k]
+            p = w * t
+            e = fma(w, t, -p)
+            ei = loint(fma(dw * S, t, fma(e, -S, CF)))
+            eps = mp.mpf(p) - 2 * mp.pi * (mp.mpf(f0) + k * mp.mpf(df)) * mp.mpf(t)  # phi_ref - theta_ideal
+            assert abs(ei) < 2 ** 21 and abs(ei - float(eps * S)) <= 1.01
+            fr = (loint(fma(p, 0.15915494309189535, cq)) << shl) & 0xFFFFFFFF
+            fr = fr - (1 << 32) if fr >= (1 << 31) else fr
+            ang = np.float32(fr) * np.float32(1.4629180792671596e-9)
+            assert abs(float(np.cos(ang)) - float(mp.cos(mp.mpf(p)))) <= 2e-6
+            ef = np.float32(0).view(np.int32)  # int -> float through the 1.5 * 2^23 bit pattern
+            ef = (np.int32(0x4B400000 + ei).view(np.float32) - np.float32(12582912.0))
+            assert float(ef) == float(ei)
