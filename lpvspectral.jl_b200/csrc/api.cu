@@ -741,7 +741,11 @@ int lpvs_set_option(lpvs_ctx* c, int key, double value) {
     if (!c) return LPVS_E_BAD_ARG;
     Lock lk(c->mu);
     switch (key) {
-        case LPVS_OPT_PHASE_MODE: c->phase_mode = (int)value; break;
+        case LPVS_OPT_PHASE_MODE:
+            if ((int)value < LPVS_PHASE_AUTO || (int)value > LPVS_PHASE_STRUCTURED_REF)
+                return fail(c, LPVS_E_BAD_ARG, "LPVS_OPT_PHASE_MODE must be one of lpvs_phase_mode (0 .. %d)", (int)LPVS_PHASE_STRUCTURED_REF);
+            c->phase_mode = (int)value;
+            break;
         case LPVS_OPT_WINDOW_BATCH: c->window_batch = (int)value; break;
         case LPVS_OPT_JITTER: c->jitter = (int)value; break;
         case LPVS_OPT_ADMM_CHECK_EVERY: c->admm_check_every = std::max(1, (int)value); break;

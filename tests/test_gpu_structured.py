@@ -221,3 +221,13 @@ def test_structured_ref_table_segments(ctx):
     print(f"two table segments: G structured {e0:.1e} -> structured_ref {e1:.1e}; b {b0:.1e} -> {b1:.1e} (vs direct mode)")
     assert e1 <= 5e-13 + 2e-3 * e0 and b1 <= 5e-13 + 2e-3 * b0
     ctx.release_workspace()
+
+
+def test_unknown_phase_mode_is_rejected(ctx):
+    """lpvs_set_option validates LPVS_OPT_PHASE_MODE (an unknown value used to fall through to the per-element mode silently)."""
+    from lpvspectral_jl_b200 import _lib as L
+
+    for bad in (6, -1, 99):
+        with pytest.raises(Exception, match="PHASE_MODE"):
+            ctx.set_option(L.OPT_PHASE_MODE, bad)
+    ctx.set_option(L.OPT_PHASE_MODE, L.PHASE_AUTO)
