@@ -318,3 +318,24 @@ def test_first_order_phase_correction_recovers_the_reference_gram(half):
     f1 = np.abs(b0 + db - br).max() / np.abs(br).max()
     assert e0 > 1e-11 and f0 > 1e-11  # the effect is there
     assert e1 <= 1e-3 * e0 + 2e-14 and f1 <= 1e-3 * f0 + 2e-14, (e0, e1, f0, f1)
+
+
+@pytest.mark.parametrize("f0,df,Nf,toff", [(3.1e3, 977.3, 33, 9.99), (0.0, 1234.5, 20, 55.0), (512.25, 2048.0, 65, 3.0)])
+def test_first_order_phase_correction_on_other_grids(f0, df, Nf, toff):
+    """The same statement for grids that do not start at zero (no dropped -sin column, Z+ != Z-) and other phase magnitudes:
+    sums + first-order terms reproduce the reference-rounded products to <= 1e-3 of the uncorrected difference."""
+    rng = np.random.default_rng(int(f0) + Nf)
+    N = 1500
+    t = toff + np.sort(3.0e-3 * rng.random(N))
+    f = f0 + df * np.arange(Nf)
+    W = 0.25 + rng.random(N)
+    y = rng.standard_normal(N)
+    A, _ = o.get_fourier_regressor(t, f)
+    Gr, br = (A.T * W) @ A, (A.T * W) @ y
+    G0, b0 = o.gram_from_trig_sums(t, f, W, y)
+    dG, db = o.gram_phase_correction(t, f, W, y, half=True)
+    e0 = np.abs(G0 - Gr).max() / np.abs(Gr).max()
+    e1 = np.abs(G0 + dG - Gr).max() / np.abs(Gr).max()
+    f0e = np.abs(b0 - br).max() / np.abs(br).max()
+    f1e = np.abs(b0 + db - br).max() / np.abs(br).max()
+    assert e1 <= 1e-3 * e0 + 3e-14 and f1e <= 1e-3 * f0e + 3e-14, (e0, e1, f0e, f1e)
