@@ -7,6 +7,7 @@ Julia shim in ``julia/LPVSpectralB200.jl`` does before its ``ccall``.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
 import os
@@ -69,6 +70,10 @@ def _preserve_eltype(fn):
     return wrapper
 
 
+PHASE_MODES = {"auto": L.PHASE_AUTO, "chain": L.PHASE_CHAIN, "direct": L.PHASE_DIRECT, "chain_ref": L.PHASE_CHAIN_REF,
+               "structured": L.PHASE_STRUCTURED, "structured_ref": L.PHASE_STRUCTURED_REF}
+
+
 class Context:
     """One liblpvs context = one GPU (one process per GPU)."""
 
@@ -88,6 +93,16 @@ class Context:
 
     def set_option(self, key, value):
         self.check(self.lib.lpvs_set_option(self.h, key, float(value)))
+
+    @contextlib.contextmanager
+    def phase_mode(self, mode):
+        """``with ctx.phase_mode("structured_ref"): ...`` -- LPVS_OPT_PHASE_MODE for the calls inside, then back to "auto".
+        Names as in the Julia shim's ``phase_mode!``: auto, chain, direct, chain_ref, structured, structured_ref."""
+        self.set_option(L.OPT_PHASE_MODE, PHASE_MODES[mode] if isinstance(mode, str) else int(mode))
+        try:
+            yield self
+        finally:
+            self.set_option(L.OPT_PHASE_MODE, L.PHASE_AUTO)
 
     def set_stream(self, cuda_stream_ptr):
         """Run on the caller's CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``); 0/None = own stream."""

@@ -314,6 +314,9 @@ def test_julia_shim_phase_modes_match_header():
     for name, val in pairs.items():
         cval = int(re.search(rf"\bLPVS_PHASE_{name.upper()}\s*=\s*(\d+)", hdr).group(1))
         assert cval == val, name
+    from lpvspectral_jl_b200 import _api
+
+    assert _api.PHASE_MODES == pairs  # the Python twin's ``ctx.phase_mode(name)`` uses the same names and values
     assert re.search(r"const OPT_PHASE_MODE = Cint\((\d+)\)", shim).group(1) == re.search(
         r"\bLPVS_OPT_PHASE_MODE\s*=\s*(\d+)", hdr).group(1)
 
